@@ -1,0 +1,178 @@
+/*
+ * laser_b200.h -- C ABI of the B200-native strided GEMM that drops in for
+ * mratsim/laser's `gemm_strided` hot path.
+ *
+ * Every entry point below states the reference interface it replaces
+ * (paths relative to the reference checkout, mratsim/laser @ d310294).
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.
+ * The Nim binding a maintainer would add is in INTEGRATION.md and nim/laser_b200.nim.
+ *
+ * Conventions (identical to the reference):
+ *   - A is M x K, B is K x N, C is M x N;  C <- alpha * A*B + beta * C
+ *   - element (i, j) of a matrix X lives at X[i*rowStrideX + j*colStrideX]
+ *     (laser/primitives/matrix_multiplication/gemm_utils.nim:36-60); strides are
+ *     in ELEMENTS, may be any int64 (transposed, sliced, non-unit, negative)
+ *   - beta == 0 overwrites C without reading it (NaN/garbage in C never
+ *     propagates)                      gemm_ukernel_generic.nim:53-76,97-126
+ *   - beta is applied once             gemm.nim:158
+ *   - the callee never retains A, B, C past return (host variants) or past
+ *     completion of the work queued on `stream` (`_dev` variants); A, B must
+ *     not alias C
+ *
+ * Return value: 0 on success, non-zero LASER_B200_E* otherwise;
+ * laser_b200_last_error() gives a thread-local message.  The reference
+ * returns void and validates nothing (gemm.nim:184-247); the Nim wrapper turns
+ * non-zero into an exception.  There is NO CPU fallback: if no sm_100 device
+ * is usable every compute entry point fails with LASER_B200_ENODEVICE.
+ */
+#ifndef LASER_B200_H
+#define LASER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LASER_B200_OK 0
+#define LASER_B200_EINVAL 1     /* bad argument (negative size, null pointer) */
+#define LASER_B200_ENODEVICE 2  /* no usable sm_100 GPU / driver */
+#define LASER_B200_ECUDA 3      /* CUDA runtime or driver error */
+#define LASER_B200_ENOMEM 4     /* device allocation failed */
+#define LASER_B200_EUNSUPPORTED 5
+
+/* Which kernel family executes a float32 gemm_strided call.
+ * AUTO: tensor cores (fp32-faithful 3xTF32) when the problem is large enough,
+ *       exact SIMT otherwise.  The reference's analogue of this switch is its
+ *       run-time ISA dispatch, gemm.nim:228-247. */
+#define LASER_B200_PATH_AUTO 0
+#define LASER_B200_PATH_SIMT 1    /* exact fp32 FFMA chain, bit-equal to the CPU reference order */
+#define LASER_B200_PATH_TF32X1 2  /* tcgen05 kind::tf32, one pass (fast, ~1e-3 relative)      */
+#define LASER_B200_PATH_TF32X3 3  /* tcgen05 kind::tf32, hi/lo split, three passes (fp32-faithful) */
+#define LASER_B200_PATH_BF16 4    /* tcgen05 kind::f16 (bf16 inputs, fp32 accumulate)         */
+
+/* ---- life cycle -------------------------------------------------------
+ * The reference has one piece of import-time state, cpuinfo_initialize()
+ * (laser/cpuinfo.nim:358-360).  Here a per-device context (stream, TMA
+ * descriptor cache, split workspace) is created lazily; init/shutdown are
+ * optional. */
+int laser_b200_init(void);
+void laser_b200_shutdown(void);
+const char *laser_b200_last_error(void);
+int laser_b200_version(void);
+/* number of kernels this library has launched on the calling thread's device
+ * context since init (used by bench.py's "gpu_launches"). */
+int64_t laser_b200_launch_count(void);
+/* LASER_B200_PATH_* actually taken by the calling thread's last gemm call. */
+int laser_b200_last_path(void);
+/* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32X3 (default),
+ * _TF32X1 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32x1|simt. */
+int laser_b200_set_f32_mode(int path);
+int laser_b200_get_f32_mode(void);
+
+/* ---- THE drop-in entry: host pointers ----------------------------------
+ * Replaces  proc gemm_strided*[T: SomeNumber](M, N, K: int, alpha: T, A: ptr T,
+ *   rowStrideA, colStrideA: int, B: ptr T, rowStrideB, colStrideB: int, beta: T,
+ *   C: ptr T, rowStrideC, colStrideC: int)
+ *   laser/primitives/matrix_multiplication/gemm.nim:184-193
+ * Same argument order and meaning.  A, B, C are HOST pointers: the call stages
+ * the touched spans to the GPU, runs, copies C back and returns when C is valid
+ * on the host (synchronous, like the reference). */
+int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha,
+                                const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                const float *B, int64_t rowStrideB, int64_t colStrideB,
+                                float beta, float *C, int64_t rowStrideC, int64_t colStrideC);
+int laser_b200_gemm_strided_f64(int64_t M, int64_t N, int64_t K, double alpha,
+                                const double *A, int64_t rowStrideA, int64_t colStrideA,
+                                const double *B, int64_t rowStrideB, int64_t colStrideB,
+                                double beta, double *C, int64_t rowStrideC, int64_t colStrideC);
+int laser_b200_gemm_strided_i32(int64_t M, int64_t N, int64_t K, int32_t alpha,
+                                const int32_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                const int32_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                int32_t beta, int32_t *C, int64_t rowStrideC, int64_t colStrideC);
+int laser_b200_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alpha,
+                                const int64_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                const int64_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                int64_t beta, int64_t *C, int64_t rowStrideC, int64_t colStrideC);
+/* bf16 (new dtype, BASELINE.json config 4): buffers hold bf16 bit patterns,
+ * alpha/beta and accumulation are fp32, C is rounded RNE to bf16. */
+int laser_b200_gemm_strided_bf16(int64_t M, int64_t N, int64_t K, float alpha,
+                                 const uint16_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                 const uint16_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                 float beta, uint16_t *C, int64_t rowStrideC, int64_t colStrideC);
+
+/* ---- device-resident variants (what the metric is measured on) ---------
+ * Same contract as above (gemm.nim:184-193) with DEVICE pointers on the
+ * current device, asynchronous on `stream` (a cudaStream_t passed as void*;
+ * NULL = the library's own stream, synchronised before return).
+ * `path` is a LASER_B200_PATH_* value. */
+int laser_b200_gemm_strided_f32_dev(int64_t M, int64_t N, int64_t K, float alpha,
+                                    const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                    const float *B, int64_t rowStrideB, int64_t colStrideB,
+                                    float beta, float *C, int64_t rowStrideC, int64_t colStrideC,
+                                    int path, void *stream);
+int laser_b200_gemm_strided_f64_dev(int64_t M, int64_t N, int64_t K, double alpha,
+                                    const double *A, int64_t rowStrideA, int64_t colStrideA,
+                                    const double *B, int64_t rowStrideB, int64_t colStrideB,
+                                    double beta, double *C, int64_t rowStrideC, int64_t colStrideC,
+                                    void *stream);
+int laser_b200_gemm_strided_i32_dev(int64_t M, int64_t N, int64_t K, int32_t alpha,
+                                    const int32_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                    const int32_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                    int32_t beta, int32_t *C, int64_t rowStrideC, int64_t colStrideC,
+                                    void *stream);
+int laser_b200_gemm_strided_i64_dev(int64_t M, int64_t N, int64_t K, int64_t alpha,
+                                    const int64_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                    const int64_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                    int64_t beta, int64_t *C, int64_t rowStrideC, int64_t colStrideC,
+                                    void *stream);
+int laser_b200_gemm_strided_bf16_dev(int64_t M, int64_t N, int64_t K, float alpha,
+                                     const uint16_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                     const uint16_t *B, int64_t rowStrideB, int64_t colStrideB,
+                                     float beta, uint16_t *C, int64_t rowStrideC, int64_t colStrideC,
+                                     void *stream);
+
+/* ---- device storage for the Tensor contract ----------------------------
+ * Device analogue of allocCpuStorage (laser/tensor/allocator.nim:17-29: 64-byte
+ * aligned, owned by the storage object) and of copyFromRaw / setZero
+ * (laser/tensor/initialization.nim:80-154).  Pointers returned are >= 256-byte
+ * aligned device addresses. */
+int laser_b200_malloc(void **dev_ptr, size_t bytes);
+int laser_b200_free(void *dev_ptr);
+int laser_b200_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int laser_b200_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int laser_b200_memset_zero(void *dst_dev, size_t bytes);
+int laser_b200_synchronize(void);
+
+/* POD view of a Tensor: what laser/tensor/datatypes.nim:18-22 exposes through
+ * rank / shape / strides / offset / unsafe_raw_data (strides and offset in
+ * elements, LASER_MAXRANK = 6, laser/dynamic_stack_arrays.nim:6). */
+#define LASER_B200_MAXRANK 6
+typedef struct {
+  int32_t rank;
+  int32_t dtype; /* 0 f32, 1 f64, 2 i32, 3 i64, 4 bf16 */
+  int64_t shape[LASER_B200_MAXRANK];
+  int64_t strides[LASER_B200_MAXRANK];
+  int64_t offset;
+  void *storage; /* device base pointer; unsafe_raw_data = storage + offset */
+} laser_b200_tensor_view;
+
+/* C <- alpha * A x B + beta * C on rank-2 device tensor views (any strides):
+ * the tensor-level caller of gemm_strided, as gemm_prepacked.nim:306-307 does
+ * with `cast[ptr T](t.unsafe_raw_data)`. */
+int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_tensor_view *B,
+                            laser_b200_tensor_view *C, double alpha, double beta, int path,
+                            void *stream);
+
+/* ---- synthetic inputs ---------------------------------------------------
+ * Counter-based uniform generator, bit-identical to the CPU oracle's
+ * (oracle_fill_uniform_f32); stands in for the reference bench's
+ * randomize(42) + rand(-0.1..0.1) (benchmarks/gemm/gemm_bench_float32.nim:329,343-344). */
+int laser_b200_fill_uniform_f32_dev(float *dst_dev, int64_t n, uint64_t seed, float lo, float hi,
+                                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASER_B200_H */

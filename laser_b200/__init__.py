@@ -1,0 +1,13 @@
+"""laser_b200 -- B200-native (sm_100a) drop-in for mratsim/laser's strided GEMM hot path.
+
+The product is the C-ABI shared library laser_b200/lib/liblaser_b200.so (hand-written CUDA:
+tcgen05/TMEM/TMA tensor-core kernels + an exact SIMT kernel); this package is the thin
+host-side mirror of the reference interface on top of it.  See DESIGN.md / INTEGRATION.md.
+"""
+from ._capi import (PATH_AUTO, PATH_BF16, PATH_NAMES, PATH_SIMT, PATH_TF32X1, PATH_TF32X3,
+                    LaserB200Error, lib, lib_path)
+from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, get_f32_mode, init, last_path,
+                   launch_count, set_f32_mode, shutdown, synchronize)
+from .tensor import LASER_MAXRANK, Storage, Tensor, matmul, newTensor, toTensor
+
+__version__ = "0.1.0"

@@ -1,0 +1,716 @@
+// capi.cu -- host side of liblaser_b200.so: the C ABI declared in include/laser_b200.h.
+//
+// Mirrors the host half of the reference's gemm_strided (gemm.nim:184-247): build the
+// three matrix views, pick a kernel family (the reference picks an ISA micro-kernel at
+// run time, gemm.nim:228-247; here: exact SIMT vs tcgen05), prepare the operands
+// (the reference allocates packing Tiles per call, gemm_tiling.nim:312-341; here: TMA
+// tensor maps, plus the hi/lo split workspace for the fp32-faithful mode) and launch.
+// There is no CPU fallback anywhere in this file.
+#include "../../include/laser_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <type_traits>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "split.cuh"
+
+namespace {
+
+using namespace lb200;
+
+thread_local std::string g_last_error;
+thread_local int g_last_path = 0;
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_f32_mode{-1};
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      cudaGetLastError();                                                                   \
+      return set_error(_e == cudaErrorMemoryAllocation ? LASER_B200_ENOMEM : LASER_B200_ECUDA, \
+                       "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                       __LINE__);                                                           \
+    }                                                                                       \
+  } while (0)
+
+struct Buffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  int dev = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  Buffer ws[4];      // A_hi/A_lo/B_hi/B_lo (or packed operands)
+  Buffer stage[3];   // device staging of host A, B, C spans
+  cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
+  std::mutex mu;       // workspace + tensor-map construction
+  std::mutex host_mu;  // staging buffers of the host-pointer entry points
+  bool ready = false;
+};
+
+constexpr int kMaxDevices = 32;
+Ctx g_ctx[kMaxDevices];
+std::mutex g_ctx_mu;
+
+int get_ctx(Ctx **out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(LASER_B200_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  if (dev < 0 || dev >= kMaxDevices) return set_error(LASER_B200_ENODEVICE, "device index %d", dev);
+  Ctx &c = g_ctx[dev];
+  if (!c.ready) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!c.ready) {
+      cudaDeviceProp prop;
+      CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+      if (prop.major != 10)
+        return set_error(LASER_B200_ENODEVICE,
+                         "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)",
+                         dev, prop.major, prop.minor);
+      c.dev = dev;
+      c.sm_count = prop.multiProcessorCount;
+      CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&c.ws_free, cudaEventDisableTiming));
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess)
+        return set_error(LASER_B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+      c.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+      const char *mode = getenv("LASER_B200_F32_MODE");
+      if (g_f32_mode.load() < 0) {
+        int m = LASER_B200_PATH_TF32X3;
+        if (mode) {
+          if (!strcmp(mode, "tf32x1")) m = LASER_B200_PATH_TF32X1;
+          else if (!strcmp(mode, "simt")) m = LASER_B200_PATH_SIMT;
+        }
+        g_f32_mode.store(m);
+      }
+      c.ready = true;
+    }
+  }
+  *out = &c;
+  return LASER_B200_OK;
+}
+
+int ensure(Buffer &b, size_t bytes) {
+  if (b.bytes >= bytes) return LASER_B200_OK;
+  if (b.ptr) CUDA_TRY(cudaFree(b.ptr));
+  b.ptr = nullptr;
+  b.bytes = 0;
+  size_t want = bytes + (bytes >> 3);  // slack: avoid re-allocation on slightly larger calls
+  want = (want + 255) & ~static_cast<size_t>(255);
+  CUDA_TRY(cudaMalloc(&b.ptr, want));
+  b.bytes = want;
+  return LASER_B200_OK;
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
+  int64_t g = static_cast<int64_t>(c.sm_count) * per_sm;
+  if (work_items < g) g = work_items > 0 ? work_items : 1;
+  return static_cast<int>(g);
+}
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+#define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------
+//                                   exact SIMT path
+// ---------------------------------------------------------------------------------------
+template <typename T, int TM, int TN, int BK>
+int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
+                int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
+                int64_t csC, cudaStream_t s) {
+  SimtParams<T> p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
+  p.A = A; p.rsA = rsA; p.csA = csA;
+  p.B = B; p.rsB = rsB; p.csB = csB;
+  p.C = C; p.rsC = rsC; p.csC = csC;
+  p.a_along_m = (llabs(rsA) < llabs(csA)) ? 1 : 0;
+  p.b_along_k = (llabs(rsB) < llabs(csB)) ? 1 : 0;
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  p.num_m_blocks = static_cast<int>((M + BM - 1) / BM);
+  p.num_n_blocks = static_cast<int>((N + BN - 1) / BN);
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  if (tiles > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
+  const int grid = grid_for(c, tiles, 2);
+  gemm_simt_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+
+template <typename T>
+int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
+              int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
+              int64_t csC, cudaStream_t s) {
+  if constexpr (sizeof(T) == 4)
+    return launch_simt<T, 8, 8, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+  else
+    return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+}
+
+// ---------------------------------------------------------------------------------------
+//                                  tensor-core path
+// ---------------------------------------------------------------------------------------
+// An operand of the contraction seen as [mn][k]: for A mn = M (s_mn = rowStrideA,
+// s_k = colStrideA), for B mn = N (s_mn = colStrideB, s_k = rowStrideB).
+struct Operand {
+  const void *ptr;
+  int64_t mn, k, s_mn, s_k;
+};
+enum Major { K_MAJOR = 0, MN_MAJOR = 1, GENERAL = 2 };
+
+Major classify(const Operand &o, int esz) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+  if (!aligned) return GENERAL;
+  const int64_t lim = (static_cast<int64_t>(1) << 40) / esz;
+  if (o.s_k == 1 && o.s_mn > 0 && (o.s_mn * esz) % 16 == 0 && o.s_mn < lim) return K_MAJOR;
+  if (o.s_mn == 1 && o.s_k > 0 && (o.s_k * esz) % 16 == 0 && o.s_k < lim) return MN_MAJOR;
+  return GENERAL;
+}
+
+int encode_map(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer,
+               int64_t outer_stride_elems, int box_inner, int box_outer) {
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(outer_stride_elems) * esz};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = c.encode(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LASER_B200_ECUDA,
+                     "cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld stride=%lld box=%dx%d",
+                     static_cast<int>(r), base, (long long)inner, (long long)outer,
+                     (long long)outer_stride_elems, box_inner, box_outer);
+  return LASER_B200_OK;
+}
+
+// tensor map for one operand given as compact/strided [mn][k] data with the stated major-ness
+int operand_map(Ctx &c, CUtensorMap *map, int esz, const void *base, Major major, int64_t mn,
+                int64_t k, int64_t ld, int block_mn) {
+  const int block_k = TC_ROW_BYTES / esz;
+  const int mn_atom = TC_ROW_BYTES / esz;
+  if (major == K_MAJOR) return encode_map(c, map, esz, base, k, mn, ld, block_k, block_mn);
+  return encode_map(c, map, esz, base, mn, k, ld, mn_atom, block_k);
+}
+
+template <int ESZ, typename OutT>
+int launch_tc(Ctx &c, bool a_mn, bool b_mn, const CUtensorMap &a0, const CUtensorMap &a1,
+              const CUtensorMap &b0, const CUtensorMap &b1, const TcParams &p, cudaStream_t s) {
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int grid = static_cast<int>(tiles < c.sm_count ? tiles : c.sm_count);
+#define LB200_LAUNCH(AMN, BMN)                                                                   \
+  do {                                                                                           \
+    auto kfn = gemm_tc_kernel<ESZ, AMN, BMN, OutT>;                                              \
+    static bool attr_set = false;                                                                \
+    if (!attr_set) {                                                                             \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      attr_set = true;                                                                           \
+    }                                                                                            \
+    kfn<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(a0, a1, b0, b1, p);                              \
+  } while (0)
+  if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
+  else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
+  else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
+  else LB200_LAUNCH(true, true);
+#undef LB200_LAUNCH
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+
+// Prepare one fp32/bf16 operand for the tensor-core kernel.  Outputs up to two maps
+// (hi, lo) and the major-ness the kernel must be instantiated with.
+template <int ESZ>
+int prepare_operand(Ctx &c, const Operand &o, bool split, Buffer &w_hi, Buffer &w_lo, int block_mn,
+                    CUtensorMap *m_hi, CUtensorMap *m_lo, bool *mn_major, bool *used_ws,
+                    cudaStream_t s) {
+  using ET = typename std::conditional<ESZ == 4, float, uint16_t>::type;
+  const Major mj = classify(o, ESZ);
+  const int64_t vec = 16 / ESZ;
+  if (mj != GENERAL && !split) {
+    const int64_t ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
+    *mn_major = (mj == MN_MAJOR);
+    int rc = operand_map(c, m_hi, ESZ, o.ptr, mj, o.mn, o.k, ld, block_mn);
+    if (rc) return rc;
+    *m_lo = *m_hi;
+    return LASER_B200_OK;
+  }
+  *used_ws = true;
+  if (mj != GENERAL) {
+    // TMA-addressable: elementwise hi/lo split that keeps the operand's major-ness
+    if constexpr (ESZ == 4) {
+      const int64_t R = (mj == K_MAJOR) ? o.mn : o.k;
+      const int64_t Cc = (mj == K_MAJOR) ? o.k : o.mn;
+      const int64_t src_ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
+      const int64_t ld = round_up(Cc, vec);
+      const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
+      int rc = ensure(w_hi, bytes);
+      if (rc) return rc;
+      rc = ensure(w_lo, bytes);
+      if (rc) return rc;
+      const int64_t items = R * ((Cc + 3) / 4);
+      split_rows_tf32_kernel<<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(
+          static_cast<const float *>(o.ptr), R, Cc, src_ld, static_cast<float *>(w_hi.ptr),
+          static_cast<float *>(w_lo.ptr), ld);
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      *mn_major = (mj == MN_MAJOR);
+      rc = operand_map(c, m_hi, ESZ, w_hi.ptr, mj, o.mn, o.k, ld, block_mn);
+      if (rc) return rc;
+      return operand_map(c, m_lo, ESZ, w_lo.ptr, mj, o.mn, o.k, ld, block_mn);
+    }
+  }
+  // general strides: one coalesced gather into a compact K-major [mn][ld] array
+  const int64_t ld = round_up(o.k, vec);
+  const size_t bytes = static_cast<size_t>(o.mn) * ld * ESZ;
+  int rc = ensure(w_hi, bytes);
+  if (rc) return rc;
+  if (split) {
+    rc = ensure(w_lo, bytes);
+    if (rc) return rc;
+  }
+  const int64_t tiles = ((o.mn + 31) / 32) * ((o.k + 31) / 32);
+  const int read_along_r = (llabs(o.s_mn) < llabs(o.s_k)) ? 1 : 0;
+  const int grid = grid_for(c, tiles, 8);
+  if constexpr (ESZ == 4) {
+    if (split)
+      pack_general_kernel<float, true><<<grid, 256, 0, s>>>(
+          static_cast<const float *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<float *>(w_hi.ptr),
+          static_cast<float *>(w_lo.ptr), ld, read_along_r);
+    else
+      pack_general_kernel<float, false><<<grid, 256, 0, s>>>(
+          static_cast<const float *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<float *>(w_hi.ptr),
+          nullptr, ld, read_along_r);
+  } else {
+    pack_general_kernel<ET, false><<<grid, 256, 0, s>>>(
+        static_cast<const ET *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<ET *>(w_hi.ptr), nullptr,
+        ld, read_along_r);
+  }
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  *mn_major = false;
+  rc = operand_map(c, m_hi, ESZ, w_hi.ptr, K_MAJOR, o.mn, o.k, ld, block_mn);
+  if (rc) return rc;
+  if (split) return operand_map(c, m_lo, ESZ, w_lo.ptr, K_MAJOR, o.mn, o.k, ld, block_mn);
+  *m_lo = *m_hi;
+  return LASER_B200_OK;
+}
+
+template <int ESZ, typename OutT>
+int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
+            int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
+            int64_t csC, int npass, cudaStream_t s) {
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
+    return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
+  std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
+  const bool split = (npass == 3);
+  Operand oa{A, M, K, rsA, csA};
+  Operand ob{B, N, K, csB, rsB};
+  CUtensorMap a0, a1, b0, b1;
+  bool a_mn = false, b_mn = false, used_ws = false;
+  // the previous call may still be reading the workspace on another stream
+  CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
+  int rc = prepare_operand<ESZ>(c, oa, split, c.ws[0], c.ws[1], TC_BLOCK_M, &a0, &a1, &a_mn, &used_ws, s);
+  if (rc) return rc;
+  rc = prepare_operand<ESZ>(c, ob, split, c.ws[2], c.ws[3], TC_BLOCK_N, &b0, &b1, &b_mn, &used_ws, s);
+  if (rc) return rc;
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
+  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass;
+  p.num_m_blocks = static_cast<int>((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
+  p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
+  rc = launch_tc<ESZ, OutT>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
+  if (rc) return rc;
+  if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
+  return LASER_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+//                                      dispatch
+// ---------------------------------------------------------------------------------------
+int check_args(int64_t M, int64_t N, int64_t K, const void *A, const void *B, const void *C) {
+  if (M < 0 || N < 0 || K < 0) return set_error(LASER_B200_EINVAL, "negative extent M=%lld N=%lld K=%lld",
+                                                (long long)M, (long long)N, (long long)K);
+  if (M == 0 || N == 0 || K == 0) return -1;  // nothing to do (gemm.nim:150: C untouched)
+  if (!A || !B || !C) return set_error(LASER_B200_EINVAL, "null matrix pointer");
+  return LASER_B200_OK;
+}
+
+int finish(Ctx &c, cudaStream_t user, cudaStream_t s) {
+  if (!user) CUDA_TRY(cudaStreamSynchronize(s));
+  return LASER_B200_OK;
+}
+
+int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
+            const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
+            int path, void *stream) {
+  int rc = check_args(M, N, K, A, B, C);
+  if (rc == -1) return LASER_B200_OK;
+  if (rc) return rc;
+  Ctx *c;
+  rc = get_ctx(&c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  if (path == LASER_B200_PATH_AUTO) {
+    // the reference switches behaviour at M*N*K > 128^3 (gemm.nim:140-141); below that
+    // a 128x256 tensor-core tile is mostly padding and the exact kernel is used
+    const double work = static_cast<double>(M) * N * K;
+    if (work <= 128.0 * 128.0 * 128.0) path = LASER_B200_PATH_SIMT;
+    else if (N <= 4 && M >= 1024) path = -1;  // skinny: warp-shuffle GEMV
+    else path = g_f32_mode.load();
+  }
+  switch (path) {
+    case -1: {
+      const int grid = grid_for(*c, (M + 7) / 8, 8);
+#define LB200_GEMV(NV) gemv_warp_kernel<NV><<<grid, 256, 0, s>>>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC)
+      if (N == 1) LB200_GEMV(1); else if (N == 2) LB200_GEMV(2); else if (N == 3) LB200_GEMV(3); else LB200_GEMV(4);
+#undef LB200_GEMV
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      g_last_path = LASER_B200_PATH_SIMT;
+      break;
+    }
+    case LASER_B200_PATH_SIMT:
+      rc = gemm_simt<float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+      if (rc) return rc;
+      g_last_path = LASER_B200_PATH_SIMT;
+      break;
+    case LASER_B200_PATH_TF32X1:
+    case LASER_B200_PATH_TF32X3:
+      rc = gemm_tc<4, float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC,
+                             path == LASER_B200_PATH_TF32X3 ? 3 : 1, s);
+      if (rc) return rc;
+      g_last_path = path;
+      break;
+    default:
+      return set_error(LASER_B200_EINVAL, "unknown path %d for float32", path);
+  }
+  return finish(*c, static_cast<cudaStream_t>(stream), s);
+}
+
+template <typename T>
+int simt_dev(int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA, int64_t csA,
+             const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC, int64_t csC,
+             void *stream) {
+  int rc = check_args(M, N, K, A, B, C);
+  if (rc == -1) return LASER_B200_OK;
+  if (rc) return rc;
+  Ctx *c;
+  rc = get_ctx(&c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  rc = gemm_simt<T>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+  if (rc) return rc;
+  g_last_path = LASER_B200_PATH_SIMT;
+  return finish(*c, static_cast<cudaStream_t>(stream), s);
+}
+
+int bf16_dev(int64_t M, int64_t N, int64_t K, float alpha, const uint16_t *A, int64_t rsA,
+             int64_t csA, const uint16_t *B, int64_t rsB, int64_t csB, float beta, uint16_t *C,
+             int64_t rsC, int64_t csC, void *stream) {
+  int rc = check_args(M, N, K, A, B, C);
+  if (rc == -1) return LASER_B200_OK;
+  if (rc) return rc;
+  Ctx *c;
+  rc = get_ctx(&c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  rc = gemm_tc<2, uint16_t>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 1, s);
+  if (rc) return rc;
+  g_last_path = LASER_B200_PATH_BF16;
+  return finish(*c, static_cast<cudaStream_t>(stream), s);
+}
+
+// ---------------------------------------------------------------------------------------
+//                         host-pointer (drop-in) variants
+// ---------------------------------------------------------------------------------------
+struct Span {
+  int64_t lo, hi;   // element offsets relative to the base pointer, inclusive
+  bool dense;       // every element of [lo, hi] belongs to the view
+};
+Span span_of(int64_t rows, int64_t cols, int64_t rs, int64_t cs) {
+  Span sp;
+  const int64_t r = (rows - 1) * rs, q = (cols - 1) * cs;
+  sp.lo = (r < 0 ? r : 0) + (q < 0 ? q : 0);
+  sp.hi = (r > 0 ? r : 0) + (q > 0 ? q : 0);
+  const int64_t ars = llabs(rs), acs = llabs(cs);
+  sp.dense = (acs == 1 && (ars == cols || rows == 1)) || (ars == 1 && (acs == rows || cols == 1)) ||
+             (rows == 1 && cols == 1);
+  return sp;
+}
+
+template <typename T, typename Fn>
+int host_gemm(int64_t M, int64_t N, int64_t K, const T *A, int64_t rsA, int64_t csA, const T *B,
+              int64_t rsB, int64_t csB, bool beta_zero, T *C, int64_t rsC, int64_t csC, Fn run) {
+  int rc = check_args(M, N, K, A, B, C);
+  if (rc == -1) return LASER_B200_OK;
+  if (rc) return rc;
+  Ctx *c;
+  rc = get_ctx(&c);
+  if (rc) return rc;
+  const Span sa = span_of(M, K, rsA, csA), sb = span_of(K, N, rsB, csB), sc = span_of(M, N, rsC, csC);
+  const size_t na = static_cast<size_t>(sa.hi - sa.lo + 1) * sizeof(T);
+  const size_t nb = static_cast<size_t>(sb.hi - sb.lo + 1) * sizeof(T);
+  const size_t nc = static_cast<size_t>(sc.hi - sc.lo + 1) * sizeof(T);
+  std::lock_guard<std::mutex> host_lk(c->host_mu);  // one host-pointer call at a time per device
+  if ((rc = ensure(c->stage[0], na + 256))) return rc;
+  if ((rc = ensure(c->stage[1], nb + 256))) return rc;
+  if ((rc = ensure(c->stage[2], nc + 256))) return rc;
+  T *dA = static_cast<T *>(c->stage[0].ptr);
+  T *dB = static_cast<T *>(c->stage[1].ptr);
+  T *dC = static_cast<T *>(c->stage[2].ptr);
+  cudaStream_t s = c->stream;
+  CUDA_TRY(cudaMemcpyAsync(dA, A + sa.lo, na, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(dB, B + sb.lo, nb, cudaMemcpyHostToDevice, s));
+  // C travels to the device only if it is read (beta != 0) or if the span holds
+  // elements outside the view that must survive the round trip
+  if (!beta_zero || !sc.dense) CUDA_TRY(cudaMemcpyAsync(dC, C + sc.lo, nc, cudaMemcpyHostToDevice, s));
+  rc = run(dA - sa.lo, dB - sb.lo, dC - sc.lo, static_cast<void *>(s));
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(C + sc.lo, dC, nc, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return LASER_B200_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+//                                     extern "C"
+// =======================================================================================
+extern "C" {
+
+int laser_b200_init(void) {
+  Ctx *c;
+  return get_ctx(&c);
+}
+
+void laser_b200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    Ctx &c = g_ctx[d];
+    if (!c.ready) continue;
+    cudaSetDevice(d);
+    cudaStreamSynchronize(c.stream);
+    for (auto &b : c.ws) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
+    for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
+    cudaEventDestroy(c.ws_free);
+    cudaStreamDestroy(c.stream);
+    c.ready = false;
+  }
+  cudaSetDevice(cur);
+}
+
+const char *laser_b200_last_error(void) { return g_last_error.c_str(); }
+int laser_b200_version(void) { return 100; }
+int64_t laser_b200_launch_count(void) { return g_launches.load(); }
+int laser_b200_last_path(void) { return g_last_path; }
+int laser_b200_set_f32_mode(int path) {
+  if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3)
+    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1 or TF32X3");
+  g_f32_mode.store(path);
+  return LASER_B200_OK;
+}
+int laser_b200_get_f32_mode(void) {
+  const int m = g_f32_mode.load();
+  return m < 0 ? LASER_B200_PATH_TF32X3 : m;
+}
+
+// ---- device-resident -----------------------------------------------------------------
+int laser_b200_gemm_strided_f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                    int64_t rsA, int64_t csA, const float *B, int64_t rsB,
+                                    int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
+                                    int path, void *stream) {
+  return f32_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, path, stream);
+}
+int laser_b200_gemm_strided_f64_dev(int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                                    int64_t rsA, int64_t csA, const double *B, int64_t rsB,
+                                    int64_t csB, double beta, double *C, int64_t rsC, int64_t csC,
+                                    void *stream) {
+  return simt_dev<double>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, stream);
+}
+int laser_b200_gemm_strided_i32_dev(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t *A,
+                                    int64_t rsA, int64_t csA, const int32_t *B, int64_t rsB,
+                                    int64_t csB, int32_t beta, int32_t *C, int64_t rsC, int64_t csC,
+                                    void *stream) {
+  return simt_dev<int32_t>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, stream);
+}
+int laser_b200_gemm_strided_i64_dev(int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t *A,
+                                    int64_t rsA, int64_t csA, const int64_t *B, int64_t rsB,
+                                    int64_t csB, int64_t beta, int64_t *C, int64_t rsC, int64_t csC,
+                                    void *stream) {
+  return simt_dev<int64_t>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, stream);
+}
+int laser_b200_gemm_strided_bf16_dev(int64_t M, int64_t N, int64_t K, float alpha, const uint16_t *A,
+                                     int64_t rsA, int64_t csA, const uint16_t *B, int64_t rsB,
+                                     int64_t csB, float beta, uint16_t *C, int64_t rsC, int64_t csC,
+                                     void *stream) {
+  return bf16_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, stream);
+}
+
+// ---- host pointers (the drop-in signature, gemm.nim:184-193) ---------------------------
+int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
+                                float beta, float *C, int64_t rsC, int64_t csC) {
+  return host_gemm<float>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0f, C, rsC, csC,
+                          [&](const float *a, const float *b, float *c, void *s) {
+                            return f32_dev(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c, rsC, csC,
+                                           LASER_B200_PATH_AUTO, s);
+                          });
+}
+int laser_b200_gemm_strided_f64(int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                                int64_t rsA, int64_t csA, const double *B, int64_t rsB, int64_t csB,
+                                double beta, double *C, int64_t rsC, int64_t csC) {
+  return host_gemm<double>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0, C, rsC, csC,
+                           [&](const double *a, const double *b, double *c, void *s) {
+                             return simt_dev<double>(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c,
+                                                     rsC, csC, s);
+                           });
+}
+int laser_b200_gemm_strided_i32(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t *A,
+                                int64_t rsA, int64_t csA, const int32_t *B, int64_t rsB, int64_t csB,
+                                int32_t beta, int32_t *C, int64_t rsC, int64_t csC) {
+  return host_gemm<int32_t>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0, C, rsC, csC,
+                            [&](const int32_t *a, const int32_t *b, int32_t *c, void *s) {
+                              return simt_dev<int32_t>(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c,
+                                                       rsC, csC, s);
+                            });
+}
+int laser_b200_gemm_strided_i64(int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t *A,
+                                int64_t rsA, int64_t csA, const int64_t *B, int64_t rsB, int64_t csB,
+                                int64_t beta, int64_t *C, int64_t rsC, int64_t csC) {
+  return host_gemm<int64_t>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0, C, rsC, csC,
+                            [&](const int64_t *a, const int64_t *b, int64_t *c, void *s) {
+                              return simt_dev<int64_t>(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c,
+                                                       rsC, csC, s);
+                            });
+}
+int laser_b200_gemm_strided_bf16(int64_t M, int64_t N, int64_t K, float alpha, const uint16_t *A,
+                                 int64_t rsA, int64_t csA, const uint16_t *B, int64_t rsB,
+                                 int64_t csB, float beta, uint16_t *C, int64_t rsC, int64_t csC) {
+  return host_gemm<uint16_t>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0f, C, rsC, csC,
+                             [&](const uint16_t *a, const uint16_t *b, uint16_t *c, void *s) {
+                               return bf16_dev(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c, rsC,
+                                               csC, s);
+                             });
+}
+
+// ---- storage -----------------------------------------------------------------------------
+int laser_b200_malloc(void **dev_ptr, size_t bytes) {
+  if (!dev_ptr) return set_error(LASER_B200_EINVAL, "null out pointer");
+  Ctx *c;
+  int rc = get_ctx(&c);
+  if (rc) return rc;
+  *dev_ptr = nullptr;
+  CUDA_TRY(cudaMalloc(dev_ptr, bytes ? bytes : 1));
+  return LASER_B200_OK;
+}
+int laser_b200_free(void *dev_ptr) {
+  if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+  return LASER_B200_OK;
+}
+int laser_b200_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
+  CUDA_TRY(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return LASER_B200_OK;
+}
+int laser_b200_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes) {
+  CUDA_TRY(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return LASER_B200_OK;
+}
+int laser_b200_memset_zero(void *dst_dev, size_t bytes) {
+  CUDA_TRY(cudaMemset(dst_dev, 0, bytes));
+  return LASER_B200_OK;
+}
+int laser_b200_synchronize(void) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  return LASER_B200_OK;
+}
+
+int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_tensor_view *B,
+                            laser_b200_tensor_view *C, double alpha, double beta, int path,
+                            void *stream) {
+  if (!A || !B || !C) return set_error(LASER_B200_EINVAL, "null view");
+  if (A->rank != 2 || B->rank != 2 || C->rank != 2)
+    return set_error(LASER_B200_EINVAL, "matmul needs rank-2 views (got %d, %d, %d)", A->rank, B->rank, C->rank);
+  if (A->dtype != B->dtype || A->dtype != C->dtype) return set_error(LASER_B200_EINVAL, "dtype mismatch");
+  const int64_t M = A->shape[0], K = A->shape[1], N = B->shape[1];
+  if (B->shape[0] != K || C->shape[0] != M || C->shape[1] != N)
+    return set_error(LASER_B200_EINVAL, "shape mismatch: A %lldx%lld B %lldx%lld C %lldx%lld", (long long)M,
+                     (long long)K, (long long)B->shape[0], (long long)N, (long long)C->shape[0],
+                     (long long)C->shape[1]);
+#define LB200_RAW(T, v) (static_cast<T *>((v)->storage) + (v)->offset)
+  switch (A->dtype) {
+    case 0:
+      return f32_dev(M, N, K, (float)alpha, LB200_RAW(float, A), A->strides[0], A->strides[1],
+                     LB200_RAW(float, B), B->strides[0], B->strides[1], (float)beta, LB200_RAW(float, C),
+                     C->strides[0], C->strides[1], path, stream);
+    case 1:
+      return simt_dev<double>(M, N, K, alpha, LB200_RAW(double, A), A->strides[0], A->strides[1],
+                              LB200_RAW(double, B), B->strides[0], B->strides[1], beta,
+                              LB200_RAW(double, C), C->strides[0], C->strides[1], stream);
+    case 2:
+      return simt_dev<int32_t>(M, N, K, (int32_t)alpha, LB200_RAW(int32_t, A), A->strides[0],
+                               A->strides[1], LB200_RAW(int32_t, B), B->strides[0], B->strides[1],
+                               (int32_t)beta, LB200_RAW(int32_t, C), C->strides[0], C->strides[1], stream);
+    case 3:
+      return simt_dev<int64_t>(M, N, K, (int64_t)alpha, LB200_RAW(int64_t, A), A->strides[0],
+                               A->strides[1], LB200_RAW(int64_t, B), B->strides[0], B->strides[1],
+                               (int64_t)beta, LB200_RAW(int64_t, C), C->strides[0], C->strides[1], stream);
+    case 4:
+      return bf16_dev(M, N, K, (float)alpha, LB200_RAW(uint16_t, A), A->strides[0], A->strides[1],
+                      LB200_RAW(uint16_t, B), B->strides[0], B->strides[1], (float)beta,
+                      LB200_RAW(uint16_t, C), C->strides[0], C->strides[1], stream);
+    default:
+      return set_error(LASER_B200_EINVAL, "unknown dtype %d", A->dtype);
+  }
+#undef LB200_RAW
+}
+
+int laser_b200_fill_uniform_f32_dev(float *dst_dev, int64_t n, uint64_t seed, float lo, float hi,
+                                    void *stream) {
+  if (n <= 0) return LASER_B200_OK;
+  if (!dst_dev) return set_error(LASER_B200_EINVAL, "null pointer");
+  Ctx *c;
+  int rc = get_ctx(&c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  fill_uniform_f32_kernel<<<grid_for(*c, (n + 255) / 256, 8), 256, 0, s>>>(dst_dev, n, seed, lo, hi);
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return finish(*c, static_cast<cudaStream_t>(stream), s);
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// gemm_simt.cuh -- exact CUDA-core strided GEMM (fp32 FFMA; also f64 / i32 / i64).
+//
+// The non-tensor-core path: any strides, any alignment, any size.  For float
+// types every C[i,j] is produced by the SAME sequence of operations as the
+// reference CPU path, so results are bit-identical to it (and to oracle/):
+//   - k-sequential FMA chain from 0 inside blocks of kc = min(2048/sizeof(T), K)
+//       (gemm_tiling.nim:309-310, gemm_ukernel_generator.nim:196-250)
+//   - after every kc block the reference epilogue runs on C itself, with
+//       beta' = beta on the first block and 1 afterwards   (gemm.nim:150-158,
+//       gemm_ukernel_generic.nim:53-76): beta'==0 -> C not read.
+// Integer types wrap (the reference uses mullo + add).
+//
+// Tiling: (16*TM) x (16*TN) x BK block tile, 256 threads, TM x TN outputs per thread
+// in two strided halves so that shared-memory reads are 16-byte broadcasts and the
+// C accesses of a warp are contiguous along N.  Global loads of the next k-tile are
+// issued into registers before the FMAs of the current one (software pipelining);
+// the thread -> element mapping of the loads follows whichever stride of the operand
+// is smaller so that HBM accesses coalesce for row-major, transposed and sliced views.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb200 {
+
+template <typename T> struct SimtOps;
+template <> struct SimtOps<float> {
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <> struct SimtOps<double> {
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+template <> struct SimtOps<int32_t> {
+  static __device__ __forceinline__ int32_t fma(int32_t a, int32_t b, int32_t c) {
+    return static_cast<int32_t>(static_cast<uint32_t>(a) * static_cast<uint32_t>(b) + static_cast<uint32_t>(c));
+  }
+  static __device__ __forceinline__ int32_t mul(int32_t a, int32_t b) {
+    return static_cast<int32_t>(static_cast<uint32_t>(a) * static_cast<uint32_t>(b));
+  }
+  static __device__ __forceinline__ int32_t add(int32_t a, int32_t b) {
+    return static_cast<int32_t>(static_cast<uint32_t>(a) + static_cast<uint32_t>(b));
+  }
+};
+template <> struct SimtOps<int64_t> {
+  static __device__ __forceinline__ int64_t fma(int64_t a, int64_t b, int64_t c) {
+    return static_cast<int64_t>(static_cast<uint64_t>(a) * static_cast<uint64_t>(b) + static_cast<uint64_t>(c));
+  }
+  static __device__ __forceinline__ int64_t mul(int64_t a, int64_t b) {
+    return static_cast<int64_t>(static_cast<uint64_t>(a) * static_cast<uint64_t>(b));
+  }
+  static __device__ __forceinline__ int64_t add(int64_t a, int64_t b) {
+    return static_cast<int64_t>(static_cast<uint64_t>(a) + static_cast<uint64_t>(b));
+  }
+};
+
+template <typename T>
+struct SimtParams {
+  int64_t M, N, K;
+  T alpha, beta;
+  const T *A; int64_t rsA, csA;
+  const T *B; int64_t rsB, csB;
+  T *C; int64_t rsC, csC;
+  int a_along_m;  // 1: consecutive loader threads walk m (|rsA| < |csA|), 0: walk k
+  int b_along_k;  // 1: consecutive loader threads walk k (|rsB| < |csB|), 0: walk n
+  int num_m_blocks, num_n_blocks;
+};
+
+template <typename T, int TM, int TN, int BK>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const SimtParams<T> p) {
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  constexpr int HM = TM / 2, HN = TN / 2;       // the two halves of the micro-tile
+  constexpr int A_PER_T = BM * BK / 256, B_PER_T = BN * BK / 256;
+  static_assert(TM % 2 == 0 && TN % 2 == 0, "micro tile halves");
+  static_assert((BM * BK) % 256 == 0 && (BN * BK) % 256 == 0, "loader mapping");
+  using Op = SimtOps<T>;
+  constexpr int64_t KC = 2048 / static_cast<int64_t>(sizeof(T));  // gemm_tiling.nim:310
+
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int mb = tile % p.num_m_blocks, nb = tile / p.num_m_blocks;
+    const int64_t m0 = static_cast<int64_t>(mb) * BM, n0 = static_cast<int64_t>(nb) * BN;
+
+    T ra[A_PER_T], rb[B_PER_T];
+    auto load_tiles = [&](int64_t k0, int64_t kend) {
+#pragma unroll
+      for (int i = 0; i < A_PER_T; ++i) {
+        const int idx = tid + i * 256;
+        const int m = p.a_along_m ? (idx % BM) : (idx / BK);
+        const int k = p.a_along_m ? (idx / BM) : (idx % BK);
+        const int64_t gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < p.M && gk < kend) ? p.A[gm * p.rsA + gk * p.csA] : T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER_T; ++i) {
+        const int idx = tid + i * 256;
+        const int n = p.b_along_k ? (idx / BK) : (idx % BN);
+        const int k = p.b_along_k ? (idx % BK) : (idx / BN);
+        const int64_t gn = n0 + n, gk = k0 + k;
+        rb[i] = (gn < p.N && gk < kend) ? p.B[gk * p.rsB + gn * p.csB] : T(0);
+      }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+      for (int i = 0; i < A_PER_T; ++i) {
+        const int idx = tid + i * 256;
+        const int m = p.a_along_m ? (idx % BM) : (idx / BK);
+        const int k = p.a_along_m ? (idx / BM) : (idx % BK);
+        As[k][m] = ra[i];
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER_T; ++i) {
+        const int idx = tid + i * 256;
+        const int n = p.b_along_k ? (idx / BK) : (idx % BN);
+        const int k = p.b_along_k ? (idx % BK) : (idx / BN);
+        Bs[k][n] = rb[i];
+      }
+    };
+
+    for (int64_t pc = 0; pc < p.K; pc += KC) {  // reference loop 2 (gemm.nim:150)
+      const int64_t kend = (pc + KC < p.K) ? pc + KC : p.K;
+      T acc[TM][TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+      load_tiles(pc, kend);
+      for (int64_t k0 = pc; k0 < kend; k0 += BK) {
+        __syncthreads();  // previous tile fully consumed
+        store_tiles();
+        __syncthreads();
+        if (k0 + BK < kend) load_tiles(k0 + BK, kend);  // in flight during the FMAs below
+        const int kmax = (kend - k0 < BK) ? static_cast<int>(kend - k0) : BK;
+#pragma unroll 4
+        for (int k = 0; k < kmax; ++k) {
+          T a[TM], b[TN];
+#pragma unroll
+          for (int i = 0; i < HM; ++i) {
+            a[i] = As[k][ty * HM + i];
+            a[HM + i] = As[k][BM / 2 + ty * HM + i];
+          }
+#pragma unroll
+          for (int j = 0; j < HN; ++j) {
+            b[j] = Bs[k][tx * HN + j];
+            b[HN + j] = Bs[k][BN / 2 + tx * HN + j];
+          }
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = Op::fma(a[i], b[j], acc[i][j]);
+        }
+      }
+
+      // reference epilogue for this kc block (gemm_ukernel_generic.nim:53-76)
+      const T beta1 = (pc == 0) ? p.beta : T(1);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int64_t gm = m0 + ((i < HM) ? (ty * HM + i) : (BM / 2 + ty * HM + (i - HM)));
+        if (gm >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int64_t gn = n0 + ((j < HN) ? (tx * HN + j) : (BN / 2 + tx * HN + (j - HN)));
+          if (gn >= p.N) continue;
+          T *c = p.C + gm * p.rsC + gn * p.csC;
+          T v;
+          if (beta1 == T(0)) v = T(0);
+          else if (beta1 != T(1)) v = Op::mul(*c, beta1);
+          else v = *c;
+          if (p.alpha == T(1)) v = Op::add(v, acc[i][j]);
+          else v = Op::add(v, Op::mul(p.alpha, acc[i][j]));
+          *c = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Skinny GEMM: N <= 4 (matrix x few vectors).  One warp per output row: lanes stride
+// over K with coalesced loads of A's row, partial dot products are combined with
+// warp shuffles.  Not bit-identical to the reference's k-sequential chain (the
+// reduction tree differs) - used only when the caller asks for PATH_AUTO on a
+// skinny problem; PATH_SIMT always takes the exact kernel above.
+// ---------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+gemv_warp_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A, int64_t rsA,
+                 int64_t csA, const float *__restrict__ B, int64_t rsB, int64_t csB, float beta,
+                 float *__restrict__ C, int64_t rsC, int64_t csC) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M;
+       row += warps_total) {
+    float acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
+    const float *a = A + row * rsA;
+    for (int64_t k = lane; k < K; k += 32) {
+      const float av = a[k * csA];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[j] = fmaf(av, B[k * rsB + j * csB], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float *c = C + row * rsC + j * csC;
+        const float v = alpha * acc[j];
+        *c = (beta == 0.0f) ? v : fmaf(beta, *c, v);
+      }
+    }
+  }
+}
+
+}  // namespace lb200

@@ -1,0 +1,308 @@
+// gemm_tc.cuh -- the tcgen05 / TMEM / TMA strided GEMM for sm_100a.
+//
+// What it replaces in the reference (mratsim/laser, paths relative to
+// laser/primitives/matrix_multiplication/):
+//   pack_A_mc_kc / pack_B_kc_nc (gemm_packing.nim:24-94)  -> TMA tensor maps: the
+//       copy engine resolves the operand's strides and lands 128-byte-swizzled
+//       tiles in shared memory; no packing buffers exist.
+//   gebb_ukernel register micro-kernel (gemm_ukernel_generator.nim:140-250)
+//       -> tcgen05.mma (kind::tf32 / kind::f16) issued by ONE thread per CTA,
+//       accumulators in TMEM (128 lanes x 256 columns fp32 per tile).
+//   gebp_mkernel loops jr/ir + gemm_impl loops pc/ic (gemm.nim:48-176)
+//       -> persistent CTAs walking 128 x 256 output tiles; the k loop is a
+//       4-deep mbarrier ring between the TMA producer thread and the MMA thread.
+//   epilogues (gemm_ukernel_generic.nim:53-126)
+//       -> tcgen05.ld TMEM -> registers, alpha/beta in fp32, beta == 0 never reads C.
+//
+// Operand "major-ness" (which of the two strides is 1) is a template parameter:
+// UMMA reads K-major and MN-major tiles natively, so A^T*B, A*B^T ... need no
+// data movement.  fp32-faithful mode runs three tf32 passes per k-block
+// (hi*hi + hi*lo + lo*hi) over hi/lo arrays produced by split_tf32 (split.cuh).
+#pragma once
+
+#include "ptx.cuh"
+
+namespace lb200 {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_N = 256;
+constexpr int TC_ROW_BYTES = 128;  // one swizzle row; BLOCK_K = 128 / sizeof(element)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_ROW_BYTES;  // 16 KB
+constexpr int TC_B_STAGE_BYTES = TC_BLOCK_N * TC_ROW_BYTES;  // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_STAGE_BYTES + TC_B_STAGE_BYTES;
+constexpr int TC_ACC_STAGES = 2;
+constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512: all of TMEM
+constexpr int TC_THREADS = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+  int64_t M, N, K;
+  float alpha, beta;
+  void *C;
+  int64_t rsC, csC;
+  int npass;          // 1, or 3 for the hi/lo split
+  int num_m_blocks, num_n_blocks;
+};
+
+// pass p of the 3xTF32 product uses (A[sel_a], B[sel_b]): hi*lo and lo*hi first, hi*hi last
+__device__ __forceinline__ int pass_sel_a(int p, int npass) { return (npass == 3 && p == 1) ? 1 : 0; }
+__device__ __forceinline__ int pass_sel_b(int p, int npass) { return (npass == 3 && p == 0) ? 1 : 0; }
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int &mb, int &nb) {
+  // groups of 8 m-blocks sweep n together so that concurrently resident CTAs
+  // share A and B tiles in L2
+  constexpr int G = 8;
+  const int per_group = G * num_n;
+  const int g = t / per_group;
+  const int first_m = g * G;
+  const int gsz = min(G, num_m - first_m);
+  const int r = t - g * per_group;
+  mb = first_m + r % gsz;
+  nb = r / gsz;
+}
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t h) {
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// ESZ: element size of A/B in bytes (4 = tf32 containers, 2 = bf16).
+// OutT: float or uint16_t (bf16 bits).
+template <int ESZ, bool A_MN, bool B_MN, typename OutT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const TcParams p) {
+  constexpr int BLOCK_K = TC_ROW_BYTES / ESZ;        // 32 (tf32) or 64 (bf16) elements
+  constexpr int UMMA_K = 32 / ESZ;                   // 8 or 16 elements = 32 bytes
+  constexpr int K_STEPS = BLOCK_K / UMMA_K;          // 4
+  constexpr int MN_ATOM = TC_ROW_BYTES / ESZ;        // elements per 128-byte MN chunk
+  constexpr int MN_BOX_BYTES = BLOCK_K * TC_ROW_BYTES;  // one [BLOCK_K][128 B] TMA box
+  constexpr uint32_t IDESC =
+      ptx::make_idesc(ESZ == 4 ? ptx::kFmtTF32 : ptx::kFmtBF16, A_MN ? 1 : 0, B_MN ? 1 : 0,
+                      TC_BLOCK_M, TC_BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + TC_STAGES * TC_A_STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t *full_bar = bars;                        // [TC_STAGES]
+  uint64_t *empty_bar = bars + TC_STAGES;           // [TC_STAGES]
+  uint64_t *tmem_full = bars + 2 * TC_STAGES;       // [TC_ACC_STAGES]
+  uint64_t *tmem_empty = tmem_full + TC_ACC_STAGES; // [TC_ACC_STAGES]
+  uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(tmem_empty + TC_ACC_STAGES);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_kb = static_cast<int>((p.K + BLOCK_K - 1) / BLOCK_K);
+  const int iters_per_tile = num_kb * p.npass;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    ptx::prefetch_tensormap(&mapB0);
+    if (p.npass == 3) {
+      ptx::prefetch_tensormap(&mapA1);
+      ptx::prefetch_tensormap(&mapB1);
+    }
+  }
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < TC_ACC_STAGES; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 2) ptx::tmem_alloc<TC_TMEM_COLS>(tmem_base_smem);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp_idx == 0 && lane == 0) {
+    // ===================== TMA producer (one thread) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mb, nb;
+      tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
+      const int m0 = mb * TC_BLOCK_M, n0 = nb * TC_BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int k0 = kb * BLOCK_K;
+        for (int ps = 0; ps < p.npass; ++ps) {
+          const CUtensorMap *ma = pass_sel_a(ps, p.npass) ? &mapA1 : &mapA0;
+          const CUtensorMap *mbp = pass_sel_b(ps, p.npass) ? &mapB1 : &mapB0;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+          uint8_t *sa = smem_a + stage * TC_A_STAGE_BYTES;
+          uint8_t *sb = smem_b + stage * TC_B_STAGE_BYTES;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BLOCK_M / MN_ATOM; ++c)  // boxes {MN_ATOM, BLOCK_K}
+              ptx::tma_load_2d(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, 256}
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BLOCK_N / MN_ATOM; ++c)
+              ptx::tma_load_2d(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
+          }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * TC_BLOCK_N;
+      for (int it = 0; it < iters_per_tile; ++it) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TC_B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < K_STEPS; ++k) {
+          // K-major: step 32 bytes inside the 128-byte swizzle row.
+          // MN-major: step UMMA_K k-rows of 128 bytes.
+          const uint64_t ad = A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES,
+                                                         MN_BOX_BYTES, 1024)
+                                   : ptx::make_smem_desc(a_addr + k * 32, 0, 1024);
+          const uint64_t bd = B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES,
+                                                         MN_BOX_BYTES, 1024)
+                                   : ptx::make_smem_desc(b_addr + k * 32, 0, 1024);
+          const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+          if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
+          else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+        }
+        ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue (4 warps, 32 TMEM lanes each) =====================
+    const int ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C);
+    const bool vec_ok = (p.csC == 1) && ((p.rsC * sizeof(OutT)) % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mb, nb;
+      tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
+      const int64_t row = static_cast<int64_t>(mb) * TC_BLOCK_M + ew * 32 + lane;
+      const int64_t n0 = static_cast<int64_t>(nb) * TC_BLOCK_N;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * TC_BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < TC_BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == TC_BLOCK_N / 32 - 1) {
+          // all of this thread's TMEM reads for the tile are done: hand the
+          // accumulator stage back to the MMA thread before the global stores
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        const int64_t col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          OutT *crow = C + row * p.rsC;
+          if (vec_ok && col0 + 32 <= p.N) {
+            if constexpr (sizeof(OutT) == 4) {
+              float4 *dst = reinterpret_cast<float4 *>(crow + col0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 v;
+                v.x = p.alpha * __uint_as_float(r[4 * q + 0]);
+                v.y = p.alpha * __uint_as_float(r[4 * q + 1]);
+                v.z = p.alpha * __uint_as_float(r[4 * q + 2]);
+                v.w = p.alpha * __uint_as_float(r[4 * q + 3]);
+                if (p.beta != 0.0f) {
+                  const float4 o = dst[q];
+                  v.x = fmaf(p.beta, o.x, v.x);
+                  v.y = fmaf(p.beta, o.y, v.y);
+                  v.z = fmaf(p.beta, o.z, v.z);
+                  v.w = fmaf(p.beta, o.w, v.w);
+                }
+                dst[q] = v;
+              }
+            } else {
+              uint4 *dst = reinterpret_cast<uint4 *>(crow + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = p.alpha * __uint_as_float(r[8 * q + e]);
+                if (p.beta != 0.0f) {
+                  const uint4 o = dst[q];
+                  const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    f[2 * e] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] & 0xffff)), f[2 * e]);
+                    f[2 * e + 1] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
+                  }
+                }
+                uint4 w;
+                w.x = f32_to_bf16_bits(f[0]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[1])) << 16);
+                w.y = f32_to_bf16_bits(f[2]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[3])) << 16);
+                w.z = f32_to_bf16_bits(f[4]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[5])) << 16);
+                w.w = f32_to_bf16_bits(f[6]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[7])) << 16);
+                dst[q] = w;
+              }
+            }
+          } else {
+            // any C strides / ragged right edge: scalar, predicated
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = col0 + j;
+              if (col < p.N) {
+                OutT *dst = crow + col * p.csC;
+                float v = p.alpha * __uint_as_float(r[j]);
+                if constexpr (sizeof(OutT) == 4) {
+                  if (p.beta != 0.0f) v = fmaf(p.beta, *dst, v);
+                  *dst = v;
+                } else {
+                  if (p.beta != 0.0f) v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
+                  *dst = f32_to_bf16_bits(v);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  if (warp_idx == 2) ptx::tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+}  // namespace lb200

@@ -1,0 +1,122 @@
+// split.cuh -- HBM-bound operand preparation kernels.
+//
+//  split_rows_tf32 : elementwise hi/lo split of an operand that TMA can read as is
+//                    (one stride == 1): hi = tf32_rna(x), lo = tf32_rna(x - hi).  The
+//                    operand keeps its major-ness; outputs are compact [R][ld].
+//  pack_general    : gather of an operand with arbitrary (row, col) element strides
+//                    (neither is 1, misaligned base, odd leading dimension, negative
+//                    strides ...) into a compact row-major [R][ld] array, optionally
+//                    hi/lo split on the way.  This is the one place where the
+//                    reference's pack_A_mc_kc / pack_B_kc_nc (gemm_packing.nim:24-94)
+//                    survives: as a single coalesced pass for the operands the TMA
+//                    engine cannot address.
+// Both are pure streaming kernels: grid = multiple of the SM count, 16-byte
+// accesses where alignment allows.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb200 {
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// src: R rows of Cc contiguous floats, leading dimension src_ld (16-byte aligned rows).
+// hi/lo: compact, leading dimension dst_ld (multiple of 4).
+__global__ void __launch_bounds__(256)
+split_rows_tf32_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
+                       float *__restrict__ hi, float *__restrict__ lo, int64_t dst_ld) {
+  const int64_t vec_per_row = (Cc + 3) >> 2;
+  const int64_t total = R * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int64_t c = (i - r * vec_per_row) << 2;
+    const float *s = src + r * src_ld + c;
+    float4 v;
+    if (c + 4 <= Cc) {
+      v = *reinterpret_cast<const float4 *>(s);
+    } else {
+      v.x = s[0];
+      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
+      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
+      v.w = 0.0f;
+    }
+    float4 h, l;
+    h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+    h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+    h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+    h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+    *reinterpret_cast<float4 *>(hi + r * dst_ld + c) = h;
+    *reinterpret_cast<float4 *>(lo + r * dst_ld + c) = l;
+  }
+}
+
+// dst[r*ld + c] = src[r*sr + c*sc] for r < R, c < Cc.  32 x 32 tiles through shared
+// memory so that both the gather (along whichever source stride is smaller) and the
+// store (along c) are coalesced.  SPLIT: also write lo (fp32 only).
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(256)
+pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr, int64_t sc,
+                    T *__restrict__ dst, T *__restrict__ dst_lo, int64_t ld, int read_along_r) {
+  __shared__ T tile[32][33];
+  const int64_t tiles_c = (Cc + 31) >> 5;
+  const int64_t tiles_r = (R + 31) >> 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int64_t t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const int64_t r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 5;
+    if (read_along_r) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t c = c0 + ty + i * 8, r = r0 + tx;
+        if (r < R && c < Cc) tile[tx][ty + i * 8] = src[r * sr + c * sc];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + i * 8, c = c0 + tx;
+        if (r < R && c < Cc) tile[ty + i * 8][tx] = src[r * sr + c * sc];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty + i * 8, c = c0 + tx;
+      if (r < R && c < Cc) {
+        const T v = tile[ty + i * 8][tx];
+        if constexpr (SPLIT) {
+          const float h = tf32_rna(v);
+          dst[r * ld + c] = h;
+          dst_lo[r * ld + c] = tf32_rna(v - h);
+        } else {
+          dst[r * ld + c] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// counter-based uniform fill, bit-identical to oracle_fill_uniform_f32
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256)
+fill_uniform_f32_kernel(float *__restrict__ dst, int64_t n, uint64_t seed, float lo, float hi) {
+  const float span = __fsub_rn(hi, lo);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t h = splitmix64_dev(seed * 0xD1342543DE82EF95ull + static_cast<uint64_t>(i));
+    const float u = __fmul_rn(static_cast<float>(static_cast<uint32_t>(h >> 40)), 1.0f / 16777216.0f);
+    dst[i] = __fmaf_rn(u, span, lo);
+  }
+}
+
+}  // namespace lb200

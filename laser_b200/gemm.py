@@ -1,0 +1,152 @@
+"""Host-side mirror of the reference's operator for the hot path.
+
+    gemm_strided(M, N, K, alpha, A, rowStrideA, colStrideA, B, rowStrideB, colStrideB,
+                 beta, C, rowStrideC, colStrideC)
+
+has the reference's name, argument order and meaning
+(laser/primitives/matrix_multiplication/gemm.nim:184-193).  A, B, C are "pointers":
+  * numpy arrays          -> HOST pointers (address of element [0]); the call goes through
+                             the drop-in C entry laser_b200_gemm_strided_<T>, which stages
+                             H2D, runs on the GPU, copies C back and returns synchronously;
+  * torch CUDA tensors, laser_b200.Tensor, or DevPtr(int, dtype)
+                          -> DEVICE pointers; the call goes through ..._dev, asynchronous
+                             on the given (default: torch current) stream.
+All arithmetic happens in liblaser_b200.so (CUDA).  Nothing here computes.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, LaserB200Error,
+                    check, lib)
+
+__all__ = ["gemm_strided", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",
+           "fill_uniform_f32", "init", "shutdown", "synchronize"]
+
+_NP_DTYPES = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.int32): "i32",
+              np.dtype(np.int64): "i64", np.dtype(np.uint16): "bf16"}
+
+
+class DevPtr:
+    """A raw device address plus element type ('f32', 'f64', 'i32', 'i64', 'bf16')."""
+
+    def __init__(self, ptr, dtype):
+        self.ptr = int(ptr)
+        self.dtype = dtype
+
+
+def _torch_dtype_name(t):
+    import torch
+    return {torch.float32: "f32", torch.float64: "f64", torch.int32: "i32", torch.int64: "i64",
+            torch.bfloat16: "bf16"}.get(t.dtype)
+
+
+def _resolve(x):
+    """-> (address, dtype name, is_device)"""
+    from .tensor import Tensor
+    if isinstance(x, np.ndarray):
+        name = _NP_DTYPES.get(x.dtype)
+        if name is None:
+            raise TypeError("unsupported numpy dtype %s" % x.dtype)
+        return x.ctypes.data, name, False
+    if isinstance(x, DevPtr):
+        return x.ptr, x.dtype, True
+    if isinstance(x, Tensor):
+        return x.unsafe_raw_data(), x.dtype, True
+    if type(x).__module__.startswith("torch"):
+        name = _torch_dtype_name(x)
+        if name is None:
+            raise TypeError("unsupported torch dtype %s" % x.dtype)
+        if not x.is_cuda:
+            raise TypeError("torch CPU tensors are not accepted: pass t.numpy() for the host-pointer "
+                            "entry or a CUDA tensor for the device entry")
+        return x.data_ptr(), name, True
+    raise TypeError("A, B, C must be numpy arrays (host), torch CUDA tensors, laser_b200.Tensor or DevPtr")
+
+
+def _current_stream():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_stream().cuda_stream)
+    except Exception:  # torch absent: the library's own stream is used
+        pass
+    return 0
+
+
+def _scalar(name, v):
+    if name in ("f32", "bf16"):
+        return ctypes.c_float(float(v))
+    if name == "f64":
+        return ctypes.c_double(float(v))
+    if name == "i32":
+        return ctypes.c_int32(int(v))
+    return ctypes.c_int64(int(v))
+
+
+def gemm_strided(M, N, K, alpha, A, rowStrideA, colStrideA, B, rowStrideB, colStrideB, beta, C,
+                 rowStrideC, colStrideC, path=PATH_AUTO, stream=None):
+    """C <- alpha * A(MxK) * B(KxN) + beta * C; strides in elements (see module docstring)."""
+    pa, ta, da = _resolve(A)
+    pb, tb, db = _resolve(B)
+    pc, tc, dc = _resolve(C)
+    if not (ta == tb == tc):
+        raise TypeError("A, B, C element types differ: %s, %s, %s" % (ta, tb, tc))
+    if not (da == db == dc):
+        raise TypeError("A, B, C must all be host pointers or all be device pointers")
+    L = lib()
+    args = [M, N, K, _scalar(ta, alpha), pa, rowStrideA, colStrideA, pb, rowStrideB, colStrideB,
+            _scalar(ta, beta), pc, rowStrideC, colStrideC]
+    if not da:
+        if path != PATH_AUTO:
+            raise ValueError("the host-pointer entry has the reference's exact signature (no path "
+                             "argument); use set_f32_mode() or device pointers")
+        check(getattr(L, "laser_b200_gemm_strided_" + ta)(*args))
+        return
+    if stream is None:
+        stream = _current_stream()
+    if ta == "f32":
+        check(L.laser_b200_gemm_strided_f32_dev(*args, path, stream))
+    else:
+        if path not in (PATH_AUTO, PATH_SIMT if ta != "bf16" else PATH_BF16):
+            raise ValueError("path %d is not available for %s" % (path, ta))
+        check(getattr(L, "laser_b200_gemm_strided_%s_dev" % ta)(*args, stream))
+
+
+def last_path():
+    return lib().laser_b200_last_path()
+
+
+def launch_count():
+    return int(lib().laser_b200_launch_count())
+
+
+def set_f32_mode(path):
+    check(lib().laser_b200_set_f32_mode(path))
+
+
+def get_f32_mode():
+    return lib().laser_b200_get_f32_mode()
+
+
+def init():
+    check(lib().laser_b200_init())
+
+
+def shutdown():
+    lib().laser_b200_shutdown()
+
+
+def synchronize():
+    check(lib().laser_b200_synchronize())
+
+
+def fill_uniform_f32(dst, n, seed, lo, hi, stream=None):
+    """Counter-based U[lo,hi) fill of a device buffer (bit-identical to the CPU oracle's)."""
+    p, t, d = _resolve(dst)
+    if not d or t != "f32":
+        raise TypeError("fill_uniform_f32 needs a float32 device buffer")
+    if stream is None:
+        stream = _current_stream()
+    check(lib().laser_b200_fill_uniform_f32_dev(p, int(n), int(seed), float(lo), float(hi), stream))

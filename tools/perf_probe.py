@@ -1,0 +1,62 @@
+"""Quick GPU probe (not the bench): TF32 operand rounding behaviour + raw kernel timings."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import laser_b200 as L
+
+torch.cuda.set_device(0)
+L.init()
+
+def probe_rounding():
+    # value v = 1 + 2^-11 + 2^-12: tf32 truncation -> 1.0, round-to-nearest -> 1 + 2^-10
+    M, N, K = 128, 256, 32
+    for name, v in (("1+2^-11+2^-12", 1 + 2**-11 + 2**-12), ("1+2^-11 (tie)", 1 + 2**-11), ("1+2^-10", 1 + 2**-10)):
+        a = torch.full((M, K), v, dtype=torch.float32, device="cuda"); b = torch.ones((K, N), dtype=torch.float32, device="cuda")
+        c = torch.zeros((M, N), dtype=torch.float32, device="cuda")
+        L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1, path=L.PATH_TF32X1)
+        torch.cuda.synchronize()
+        print("rounding probe A=%s: C/K = %.10f  (trunc -> 1.0, rn -> %.10f)" % (name, c[0, 0].item() / K, 1 + 2**-10))
+        c.zero_()
+        L.gemm_strided(M, N, K, 1.0, b.t().contiguous(), K, 1, a.t().contiguous(), N, 1, 0.0, c, N, 1, path=L.PATH_TF32X1)
+        torch.cuda.synchronize()
+        print("               B=%s: C/K = %.10f" % (name, c[0, 0].item() / K))
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sum(ts) / len(ts)
+
+def perf():
+    out = {}
+    for n in (4096, 8192):
+        a = torch.rand(n, n, device="cuda"); b = torch.rand(n, n, device="cuda"); c = torch.empty(n, n, device="cuda")
+        at = a.t().contiguous()
+        for pname, path in (("tf32x1", L.PATH_TF32X1), ("tf32x3", L.PATH_TF32X3)) + ((("simt", L.PATH_SIMT),) if n == 4096 else ()):
+            mn, av = timeit(lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1, path=path), iters=3 if pname == "simt" else 5)
+            print("n=%d %-7s row,row     best %.3f ms  %.1f TFLOP/s (avg %.3f ms)" % (n, pname, mn, 2 * n**3 / mn / 1e9, av)); out["%d_%s" % (n, pname)] = mn
+        for pname, path in (("tf32x1", L.PATH_TF32X1), ("tf32x3", L.PATH_TF32X3)):
+            mn, av = timeit(lambda: L.gemm_strided(n, n, n, 1.0, at, 1, n, b, n, 1, 0.0, c, n, 1, path=path))
+            print("n=%d %-7s A^T(col),row best %.3f ms  %.1f TFLOP/s" % (n, pname, mn, 2 * n**3 / mn / 1e9))
+            bt = b.t().contiguous()
+            mn, av = timeit(lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, bt, 1, n, 0.0, c, n, 1, path=path))
+            print("n=%d %-7s row,B^T(col) best %.3f ms  %.1f TFLOP/s  (both K-major)" % (n, pname, mn, 2 * n**3 / mn / 1e9))
+        ab = a.to(torch.bfloat16); bb = b.to(torch.bfloat16); cb = torch.empty(n, n, device="cuda", dtype=torch.bfloat16)
+        mn, av = timeit(lambda: L.gemm_strided(n, n, n, 1.0, ab, n, 1, bb, n, 1, 0.0, cb, n, 1))
+        print("n=%d bf16   row,row      best %.3f ms  %.1f TFLOP/s" % (n, mn, 2 * n**3 / mn / 1e9))
+        torch.backends.cuda.matmul.allow_tf32 = True
+        mn, av = timeit(lambda: torch.matmul(a, b, out=c))
+        print("n=%d cuBLAS tf32 (informal ceiling) best %.3f ms %.1f TFLOP/s" % (n, mn, 2 * n**3 / mn / 1e9))
+        mn, av = timeit(lambda: torch.matmul(ab, bb, out=cb))
+        print("n=%d cuBLAS bf16 (informal ceiling) best %.3f ms %.1f TFLOP/s" % (n, mn, 2 * n**3 / mn / 1e9))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/perf_probe.json", "w"))
+
+if __name__ == "__main__":
+    probe_rounding()
+    perf()
