@@ -66,6 +66,14 @@ int laser_b200_version(void);
 int64_t laser_b200_launch_count(void);
 /* LASER_B200_PATH_* actually taken by the calling thread's last gemm call. */
 int laser_b200_last_path(void);
+/* Device-side timing of the library's own kernels (bench.py's roofline numbers):
+ * between profile_begin() and profile_end() every tensor-core GEMM launch and every
+ * operand-preparation (hi/lo split, pack) launch sequence is bracketed by CUDA events on
+ * the stream it is launched on.  profile_end() synchronises and returns the summed
+ * durations in milliseconds and the number of bracketed launches. */
+int laser_b200_profile_begin(void);
+int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
+                           int64_t *prep_launches);
 /* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32X3 (default),
  * _TF32X1 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32x1|simt. */
 int laser_b200_set_f32_mode(int path);

@@ -7,7 +7,8 @@ host-side mirror of the reference interface on top of it.  See DESIGN.md / INTEG
 from ._capi import (PATH_AUTO, PATH_BF16, PATH_NAMES, PATH_SIMT, PATH_TF32X1, PATH_TF32X3,
                     LaserB200Error, lib, lib_path)
 from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, get_f32_mode, init, last_path,
-                   launch_count, set_f32_mode, shutdown, synchronize)
+                   launch_count, profile_begin, profile_end, set_f32_mode, shutdown,
+                   synchronize)
 from .tensor import LASER_MAXRANK, Storage, Tensor, matmul, newTensor, toTensor
 
 __version__ = "0.1.0"

@@ -39,6 +39,9 @@ SIGNATURES = {
     "laser_b200_version": (ctypes.c_int, []),
     "laser_b200_launch_count": (i64, []),
     "laser_b200_last_path": (ctypes.c_int, []),
+    "laser_b200_profile_begin": (ctypes.c_int, []),
+    "laser_b200_profile_end": (ctypes.c_int, [ctypes.POINTER(f64), ctypes.POINTER(i64),
+                                              ctypes.POINTER(f64), ctypes.POINTER(i64)]),
     "laser_b200_set_f32_mode": (ctypes.c_int, [ctypes.c_int]),
     "laser_b200_get_f32_mode": (ctypes.c_int, []),
     "laser_b200_gemm_strided_f32": (ctypes.c_int, _gemm_sig(f32)),

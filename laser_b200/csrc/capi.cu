@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -60,7 +61,15 @@ struct Buffer {
   size_t bytes = 0;
 };
 
+struct EventPair {
+  cudaEvent_t a, b;
+  int kind;  // 0 = tensor-core GEMM kernel, 1 = operand preparation kernels
+  int launches;
+};
+
 struct Ctx {
+  bool profiling = false;
+  std::vector<EventPair> prof;
   int dev = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -133,6 +142,23 @@ int ensure(Buffer &b, size_t bytes) {
   return LASER_B200_OK;
 }
 
+int prof_open(Ctx &c, cudaStream_t s, EventPair *ep, int kind) {
+  if (!c.profiling) return LASER_B200_OK;
+  ep->kind = kind;
+  ep->launches = 0;
+  CUDA_TRY(cudaEventCreate(&ep->a));
+  CUDA_TRY(cudaEventCreate(&ep->b));
+  CUDA_TRY(cudaEventRecord(ep->a, s));
+  return LASER_B200_OK;
+}
+int prof_close(Ctx &c, cudaStream_t s, EventPair *ep, int launches) {
+  if (!c.profiling) return LASER_B200_OK;
+  CUDA_TRY(cudaEventRecord(ep->b, s));
+  ep->launches = launches;
+  c.prof.push_back(*ep);
+  return LASER_B200_OK;
+}
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
   int64_t g = static_cast<int64_t>(c.sm_count) * per_sm;
@@ -199,14 +225,14 @@ Major classify(const Operand &o, int esz) {
 }
 
 int encode_map(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer,
-               int64_t outer_stride_elems, int box_inner, int box_outer) {
+               int64_t outer_stride_elems, int box_inner, int box_outer, CUtensorMapSwizzle swz) {
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(outer_stride_elems) * esz};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = c.encode(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(LASER_B200_ECUDA,
@@ -221,8 +247,11 @@ int operand_map(Ctx &c, CUtensorMap *map, int esz, const void *base, Major major
                 int64_t k, int64_t ld, int block_mn) {
   const int block_k = TC_ROW_BYTES / esz;
   const int mn_atom = TC_ROW_BYTES / esz;
-  if (major == K_MAJOR) return encode_map(c, map, esz, base, k, mn, ld, block_k, block_mn);
-  return encode_map(c, map, esz, base, mn, k, ld, mn_atom, block_k);
+  if (major == K_MAJOR)
+    return encode_map(c, map, esz, base, k, mn, ld, block_k, block_mn, CU_TENSOR_MAP_SWIZZLE_128B);
+  // MN-major fp32/tf32 tiles need the 32-byte-atom flavour of the 128B swizzle (see ptx.cuh)
+  return encode_map(c, map, esz, base, mn, k, ld, mn_atom, block_k,
+                    esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int ESZ, typename OutT>
@@ -342,16 +371,26 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   bool a_mn = false, b_mn = false, used_ws = false;
   // the previous call may still be reading the workspace on another stream
   CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
-  int rc = prepare_operand<ESZ>(c, oa, split, c.ws[0], c.ws[1], TC_BLOCK_M, &a0, &a1, &a_mn, &used_ws, s);
+  EventPair ep;
+  const int64_t launches_before = g_launches.load();
+  int rc = prof_open(c, s, &ep, 1);
+  if (rc) return rc;
+  rc = prepare_operand<ESZ>(c, oa, split, c.ws[0], c.ws[1], TC_BLOCK_M, &a0, &a1, &a_mn, &used_ws, s);
   if (rc) return rc;
   rc = prepare_operand<ESZ>(c, ob, split, c.ws[2], c.ws[3], TC_BLOCK_N, &b0, &b1, &b_mn, &used_ws, s);
+  if (rc) return rc;
+  rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass;
   p.num_m_blocks = static_cast<int>((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
+  rc = prof_open(c, s, &ep, 0);
+  if (rc) return rc;
   rc = launch_tc<ESZ, OutT>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
+  if (rc) return rc;
+  rc = prof_close(c, s, &ep, 1);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;
@@ -532,6 +571,44 @@ void laser_b200_shutdown(void) {
     c.ready = false;
   }
   cudaSetDevice(cur);
+}
+
+int laser_b200_profile_begin(void) {
+  Ctx *c;
+  int rc = get_ctx(&c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (auto &e : c->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  c->prof.clear();
+  c->profiling = true;
+  return LASER_B200_OK;
+}
+int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
+                           int64_t *prep_launches) {
+  Ctx *c;
+  int rc = get_ctx(&c);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(c->mu);
+  double ms[2] = {0.0, 0.0};
+  int64_t n[2] = {0, 0};
+  for (auto &e : c->prof) {
+    float t = 0.0f;
+    if (e.launches > 0) {
+      CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+      ms[e.kind] += t;
+      n[e.kind] += e.launches;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  c->prof.clear();
+  c->profiling = false;
+  if (gemm_ms) *gemm_ms = ms[0];
+  if (gemm_launches) *gemm_launches = n[0];
+  if (prep_ms) *prep_ms = ms[1];
+  if (prep_launches) *prep_launches = n[1];
+  return LASER_B200_OK;
 }
 
 const char *laser_b200_last_error(void) { return g_last_error.c_str(); }

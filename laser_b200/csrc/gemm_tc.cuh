@@ -84,6 +84,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   constexpr int K_STEPS = BLOCK_K / UMMA_K;          // 4
   constexpr int MN_ATOM = TC_ROW_BYTES / ESZ;        // elements per 128-byte MN chunk
   constexpr int MN_BOX_BYTES = BLOCK_K * TC_ROW_BYTES;  // one [BLOCK_K][128 B] TMA box
+  // MN-major 32-bit operands must use the 128B-swizzle-with-32B-atoms layout (4 k-rows per atom)
+  constexpr uint32_t MN_LAYOUT = ESZ == 4 ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
+  constexpr uint32_t MN_SBO = ESZ == 4 ? 512 : 1024;
   constexpr uint32_t IDESC =
       ptx::make_idesc(ESZ == 4 ? ptx::kFmtTF32 : ptx::kFmtBF16, A_MN ? 1 : 0, B_MN ? 1 : 0,
                       TC_BLOCK_M, TC_BLOCK_N);
@@ -185,12 +188,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int k = 0; k < K_STEPS; ++k) {
           // K-major: step 32 bytes inside the 128-byte swizzle row.
           // MN-major: step UMMA_K k-rows of 128 bytes.
-          const uint64_t ad = A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES,
-                                                         MN_BOX_BYTES, 1024)
-                                   : ptx::make_smem_desc(a_addr + k * 32, 0, 1024);
-          const uint64_t bd = B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES,
-                                                         MN_BOX_BYTES, 1024)
-                                   : ptx::make_smem_desc(b_addr + k * 32, 0, 1024);
+          const uint64_t ad =
+              A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                   : ptx::make_smem_desc(a_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
+          const uint64_t bd =
+              B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                   : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
           const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
           if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
           else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
@@ -221,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int c = 0; c < TC_BLOCK_N / 32; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_wait(r);
         if (c == TC_BLOCK_N / 32 - 1) {
           // all of this thread's TMEM reads for the tile are done: hand the
           // accumulator stage back to the MMA thread before the global stores

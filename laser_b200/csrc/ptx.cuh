@@ -162,31 +162,41 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+// tcgen05.ld is asynchronous: the destination registers are only valid after
+// tcgen05.wait::ld.  The registers are threaded through the wait as "+r" operands so
+// that the compiler cannot schedule any use of them above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // ------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  start address >> 4          [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4 [46,48) version = 1 (Blackwell)
-//   [49,52) base offset = 0             [61,64) layout: 0 none, 2 = 128B swizzle,
-//                                                4 = 64B, 6 = 32B
-// All tiles here use the 128-byte swizzle written by TMA (CU_TENSOR_MAP_SWIZZLE_128B),
-// tile bases are 1024-byte aligned.
-//   K-major operand  : rows of 128 B (one swizzle row) along K, 8-row atoms 1024 B
-//                      apart along M/N  -> SBO = 1024, LBO unused.
-//   MN-major operand : 128 B along M/N per k row, 8 k-rows = 1024 B (SBO); the next
-//                      128-byte chunk of M/N is one TMA box further (LBO = box bytes).
-constexpr uint64_t kLayoutSw128 = 2;
+//   [49,52) base offset = 0             [61,64) layout: 0 none, 1 = 128B swizzle with 32B
+//                                                atoms, 2 = 128B swizzle, 4 = 64B, 6 = 32B
+// Tile bases are 1024-byte aligned; tiles are written by TMA with the matching swizzle.
+//   K-major operand  (CU_TENSOR_MAP_SWIZZLE_128B, layout 2): rows of 128 B (one swizzle
+//       row) along K, 8-row atoms 1024 B apart along M/N -> SBO = 1024, LBO unused.
+//   MN-major 16-bit  (CU_TENSOR_MAP_SWIZZLE_128B, layout 2): 128 B along M/N per k row,
+//       8 k-rows = one atom (SBO = 1024 between atoms); the next 128-byte chunk of M/N is
+//       one TMA box further (LBO = box bytes).
+//   MN-major tf32    (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, layout 1): the only MN-major
+//       layout the tensor core accepts for 32-bit operands: 32-byte chunks swizzled over
+//       4 k-rows -> atoms of 4 k-rows, SBO = 512; LBO = box bytes as above.
+constexpr uint32_t kLayoutSw128 = 2;
+constexpr uint32_t kLayoutSw128Base32 = 1;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= kLayoutSw128 << 61;
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
 

@@ -22,7 +22,7 @@ from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, L
                     check, lib)
 
 __all__ = ["gemm_strided", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",
-           "fill_uniform_f32", "init", "shutdown", "synchronize"]
+           "fill_uniform_f32", "init", "shutdown", "synchronize", "profile_begin", "profile_end"]
 
 _NP_DTYPES = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.int32): "i32",
               np.dtype(np.int64): "i64", np.dtype(np.uint16): "bf16"}
@@ -128,6 +128,19 @@ def set_f32_mode(path):
 
 def get_f32_mode():
     return lib().laser_b200_get_f32_mode()
+
+
+def profile_begin():
+    check(lib().laser_b200_profile_begin())
+
+
+def profile_end():
+    """-> dict(gemm_ms, gemm_launches, prep_ms, prep_launches): device time of the library's
+    own kernels since profile_begin(), from CUDA events on the launching stream."""
+    g, p = ctypes.c_double(), ctypes.c_double()
+    ng, npr = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().laser_b200_profile_end(ctypes.byref(g), ctypes.byref(ng), ctypes.byref(p), ctypes.byref(npr)))
+    return dict(gemm_ms=g.value, gemm_launches=ng.value, prep_ms=p.value, prep_launches=npr.value)
 
 
 def init():

@@ -1,0 +1,67 @@
+"""Row-panel sharding of a large GEMM across the GPUs of one box (one process per GPU).
+
+The reference parallelises exactly this way on a CPU: its `ic` loop hands each worker a
+row block of A and C while all workers share one packed panel of B per `pc` iteration, and
+beta is applied on the first K-panel only (gemm.nim:150-176).  Here:
+  * rank r owns rows [start_r, stop_r) of A and C (never moved);
+  * B lives on `src` and is broadcast once, as K-panels, over NCCL/NVLink
+    (torch.distributed); panel i+1 is in flight while the GEMM consumes panel i with
+    beta' = beta (i == 0) or 1 (i > 0) -- no collective inside the MMA loop, no reduction.
+The host logic is backend-agnostic (tested on CPU with gloo + the oracle as gemm_fn).
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["partition_rows", "k_panels", "gemm_rowsharded"]
+
+
+def partition_rows(M, world_size, align=128):
+    """[(start, stop)] per rank: ceil(M / world) rounded up to the CTA tile height; the
+    last ranks take what is left (possibly nothing)."""
+    per = -(-M // world_size)
+    per = -(-per // align) * align
+    out = []
+    for r in range(world_size):
+        lo = min(M, r * per)
+        out.append((lo, min(M, lo + per)))
+    return out
+
+
+def k_panels(K, n_panels, align=32):
+    """Split K in at most n_panels panels whose sizes are multiples of `align` (one TMA
+    k-block) except possibly the last."""
+    n_panels = max(1, min(int(n_panels), -(-K // align)))
+    per = -(-K // n_panels)
+    per = -(-per // align) * align
+    out, k0 = [], 0
+    while k0 < K:
+        out.append((k0, min(K, k0 + per)))
+        k0 += per
+    return out
+
+
+def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, group=None,
+                    n_panels=8, gemm_fn=None, broadcast=True):
+    """C_local <- alpha * A_local @ B + beta * C_local on every rank.
+
+    A_local: (M_local, K) tensor view (any strides), C_local: (M_local, N) view,
+    B: (K, N) row-major contiguous tensor on every rank, valid on `src` only (unless
+    broadcast=False).  gemm_fn has the gemm_strided signature (default: the CUDA library)."""
+    if gemm_fn is None:
+        from .gemm import gemm_strided as gemm_fn
+    assert B.dim() == 2 and B.shape[0] == K and B.shape[1] == N and B.is_contiguous()
+    panels = k_panels(K, n_panels)
+    works = []
+    if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for (k0, k1) in panels:  # all panels are queued now; NCCL streams them in order
+            works.append(dist.broadcast(B[k0:k1], src=src, group=group, async_op=True))
+    rsA, csA = (A_local.stride(0), A_local.stride(1)) if M_local > 0 else (K, 1)
+    rsC, csC = (C_local.stride(0), C_local.stride(1)) if M_local > 0 else (N, 1)
+    for i, (k0, k1) in enumerate(panels):
+        if works:
+            works[i].wait()  # NCCL: the current stream waits for panel i; gloo: host wait
+        if M_local == 0:
+            continue
+        gemm_fn(M_local, N, k1 - k0, alpha, A_local[:, k0:k1], rsA, csA, B[k0:k1], N, 1,
+                beta if i == 0 else 1.0, C_local, rsC, csC)
+    return C_local

@@ -20,9 +20,10 @@ def embed(mat, layout):
     Unused buffer slots are filled with a sentinel so that out-of-view reads/writes show."""
     R, C = mat.shape
     dt = mat.dtype
-    sentinel = np.array(-77, dtype=dt) if dt.kind in "iu" else np.array(-7777.0, dtype=dt)
     if dt == np.uint16:
         sentinel = np.array(0xC2FA, dtype=dt)  # bf16 -125
+    else:
+        sentinel = np.array(-77, dtype=dt) if dt.kind in "iu" else np.array(-7777.0, dtype=dt)
     if layout == "row":
         buf = mat.reshape(-1).copy(); off, rs, cs = 0, C, 1
     elif layout == "col":

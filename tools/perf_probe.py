@@ -10,15 +10,17 @@ L.init()
 
 def probe_rounding():
     # value v = 1 + 2^-11 + 2^-12: tf32 truncation -> 1.0, round-to-nearest -> 1 + 2^-10
+    # both operands K-major (A row-major, B given as B^T storage) so that TMA feeds the raw bits
     M, N, K = 128, 256, 32
     for name, v in (("1+2^-11+2^-12", 1 + 2**-11 + 2**-12), ("1+2^-11 (tie)", 1 + 2**-11), ("1+2^-10", 1 + 2**-10)):
-        a = torch.full((M, K), v, dtype=torch.float32, device="cuda"); b = torch.ones((K, N), dtype=torch.float32, device="cuda")
+        x = torch.full((M, K), v, dtype=torch.float32, device="cuda"); onesT = torch.ones((N, K), dtype=torch.float32, device="cuda")
         c = torch.zeros((M, N), dtype=torch.float32, device="cuda")
-        L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1, path=L.PATH_TF32X1)
+        L.gemm_strided(M, N, K, 1.0, x, K, 1, onesT, 1, K, 0.0, c, N, 1, path=L.PATH_TF32X1)
         torch.cuda.synchronize()
         print("rounding probe A=%s: C/K = %.10f  (trunc -> 1.0, rn -> %.10f)" % (name, c[0, 0].item() / K, 1 + 2**-10))
+        xT = torch.full((N, K), v, dtype=torch.float32, device="cuda"); ones = torch.ones((M, K), dtype=torch.float32, device="cuda")
         c.zero_()
-        L.gemm_strided(M, N, K, 1.0, b.t().contiguous(), K, 1, a.t().contiguous(), N, 1, 0.0, c, N, 1, path=L.PATH_TF32X1)
+        L.gemm_strided(M, N, K, 1.0, ones, K, 1, xT, 1, K, 0.0, c, N, 1, path=L.PATH_TF32X1)
         torch.cuda.synchronize()
         print("               B=%s: C/K = %.10f" % (name, c[0, 0].item() / K))
 
