@@ -68,6 +68,7 @@ struct EventPair {
 };
 
 struct Ctx {
+  int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
   std::vector<EventPair> prof;
   int dev = -1;
@@ -114,6 +115,10 @@ int get_ctx(Ctx **out) {
       if (!fn || qres != cudaDriverEntryPointSuccess)
         return set_error(LASER_B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
       c.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+      if (const char *kc = getenv("LASER_B200_KC")) {
+        const int v = atoi(kc);
+        if (v >= 32) c.kc_faithful = v;
+      }
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32X3;
@@ -383,7 +388,18 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   if (rc) return rc;
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
-  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass;
+  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0;
+  {
+    // K extent accumulated inside the tensor core before the epilogue warps add the block
+    // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
+    // Only the fp32-faithful mode needs short chains; see gemm_tc.cuh.
+    const int block_k = TC_ROW_BYTES / ESZ;
+    const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
+    int kc = (npass == 3) ? c.kc_faithful : 0;
+    p.kb_per_block = (kc > 0) ? (kc + block_k - 1) / block_k : num_kb;
+    if (p.kb_per_block < 1) p.kb_per_block = 1;
+    if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
+  }
   p.num_m_blocks = static_cast<int>((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
   rc = prof_open(c, s, &ep, 0);

@@ -8,16 +8,24 @@
 //   gebb_ukernel register micro-kernel (gemm_ukernel_generator.nim:140-250)
 //       -> tcgen05.mma (kind::tf32 / kind::f16) issued by ONE thread per CTA,
 //       accumulators in TMEM (128 lanes x 256 columns fp32 per tile).
-//   gebp_mkernel loops jr/ir + gemm_impl loops pc/ic (gemm.nim:48-176)
-//       -> persistent CTAs walking 128 x 256 output tiles; the k loop is a
-//       4-deep mbarrier ring between the TMA producer thread and the MMA thread.
+//   gemm_impl loop pc (gemm.nim:150-158: K is cut in kc blocks, every block's partial
+//       product is ADDED to C in fp32) -> K is cut in accumulation blocks of `kb_per_block`
+//       k-tiles: the tensor core accumulates one block in TMEM, the epilogue warps drain
+//       it and add it (IEEE round-to-nearest FADD) to running sums held in registers
+//       while the tensor core is already working on the next block in the other TMEM
+//       stage.  This matters numerically: the tensor core's own accumulator truncates
+//       (measured on B200: ~0.5 ulp of bias per MMA instruction, i.e. 8.6e-5 relative at
+//       K = 8192 for positive inputs), so long chains must not live in TMEM.
+//   gebp_mkernel loops jr/ir + loop ic (gemm.nim:48-176)
+//       -> persistent CTAs walking 128 x 256 output tiles; the k loop is a 4-deep
+//       mbarrier ring between the TMA producer thread and the MMA thread.
 //   epilogues (gemm_ukernel_generic.nim:53-126)
-//       -> tcgen05.ld TMEM -> registers, alpha/beta in fp32, beta == 0 never reads C.
+//       -> alpha/beta in fp32 from the running sums; beta == 0 never reads C.
 //
 // Operand "major-ness" (which of the two strides is 1) is a template parameter:
 // UMMA reads K-major and MN-major tiles natively, so A^T*B, A*B^T ... need no
-// data movement.  fp32-faithful mode runs three tf32 passes per k-block
-// (hi*hi + hi*lo + lo*hi) over hi/lo arrays produced by split_tf32 (split.cuh).
+// data movement.  fp32-faithful mode runs three tf32 passes per k-tile
+// (hi*lo, lo*hi, then hi*hi) over hi/lo arrays produced by split.cuh.
 #pragma once
 
 #include "ptx.cuh"
@@ -33,8 +41,13 @@ constexpr int TC_B_STAGE_BYTES = TC_BLOCK_N * TC_ROW_BYTES;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_STAGE_BYTES + TC_B_STAGE_BYTES;
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512: all of TMEM
-constexpr int TC_THREADS = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | warps 4-11: epilogue (2 warpgroups)
+constexpr int TC_THREADS = 384;
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_EPI_COLS = TC_BLOCK_N / 2;  // columns owned by one epilogue thread
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_REGS_CTRL = 56;   // setmaxnreg for the producer/MMA warpgroup
+constexpr int TC_REGS_EPI = 216;   // ... and for the epilogue warpgroups (running sums)
 
 struct TcParams {
   int64_t M, N, K;
@@ -42,12 +55,10 @@ struct TcParams {
   void *C;
   int64_t rsC, csC;
   int npass;          // 1, or 3 for the hi/lo split
+  int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
+  uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
   int num_m_blocks, num_n_blocks;
 };
-
-// pass p of the 3xTF32 product uses (A[sel_a], B[sel_b]): hi*lo and lo*hi first, hi*hi last
-__device__ __forceinline__ int pass_sel_a(int p, int npass) { return (npass == 3 && p == 1) ? 1 : 0; }
-__device__ __forceinline__ int pass_sel_b(int p, int npass) { return (npass == 3 && p == 0) ? 1 : 0; }
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int &mb, int &nb) {
   // groups of 8 m-blocks sweep n together so that concurrently resident CTAs
@@ -70,6 +81,15 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
   if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return static_cast<uint16_t>(u >> 16);
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ESZ: element size of A/B in bytes (4 = tf32 containers, 2 = bf16).
@@ -107,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_kb = static_cast<int>((p.K + BLOCK_K - 1) / BLOCK_K);
-  const int iters_per_tile = num_kb * p.npass;
+  const int num_blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&mapA0);
@@ -124,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int i = 0; i < TC_ACC_STAGES; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 128);
+      ptx::mbar_init(&tmem_empty[i], TC_EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -134,79 +154,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  if (warp_idx == 0 && lane == 0) {
-    // ===================== TMA producer (one thread) =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int mb, nb;
-      tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
-      const int m0 = mb * TC_BLOCK_M, n0 = nb * TC_BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int k0 = kb * BLOCK_K;
-        for (int ps = 0; ps < p.npass; ++ps) {
-          const CUtensorMap *ma = pass_sel_a(ps, p.npass) ? &mapA1 : &mapA0;
-          const CUtensorMap *mbp = pass_sel_b(ps, p.npass) ? &mapB1 : &mapB0;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-          uint8_t *sa = smem_a + stage * TC_A_STAGE_BYTES;
-          uint8_t *sb = smem_b + stage * TC_B_STAGE_BYTES;
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
-          } else {
+  if (warp_idx < 4) {
+    setmaxnreg_dec<TC_REGS_CTRL>();  // hand registers to the epilogue warpgroups
+    if (warp_idx == 0 && lane == 0) {
+      // ===================== TMA producer (one thread) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_stage = [&](const CUtensorMap *ma, const CUtensorMap *mbp, int m0, int n0, int k0) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        uint8_t *sa = smem_a + stage * TC_A_STAGE_BYTES;
+        uint8_t *sb = smem_b + stage * TC_B_STAGE_BYTES;
+        if constexpr (!A_MN) {
+          ptx::tma_load_2d(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
+        } else {
 #pragma unroll
-            for (int c = 0; c < TC_BLOCK_M / MN_ATOM; ++c)  // boxes {MN_ATOM, BLOCK_K}
-              ptx::tma_load_2d(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
-          }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, 256}
-          } else {
-#pragma unroll
-            for (int c = 0; c < TC_BLOCK_N / MN_ATOM; ++c)
-              ptx::tma_load_2d(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
-          }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          for (int c = 0; c < TC_BLOCK_M / MN_ATOM; ++c)  // boxes {MN_ATOM, BLOCK_K}
+            ptx::tma_load_2d(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
         }
-      }
-    }
-  } else if (warp_idx == 1 && lane == 0) {
-    // ===================== MMA issuer (one thread) =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * TC_BLOCK_N;
-      for (int it = 0; it < iters_per_tile; ++it) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t a_addr = ptx::smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
-        const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TC_B_STAGE_BYTES);
+        if constexpr (!B_MN) {
+          ptx::tma_load_2d(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, 256}
+        } else {
 #pragma unroll
-        for (int k = 0; k < K_STEPS; ++k) {
-          // K-major: step 32 bytes inside the 128-byte swizzle row.
-          // MN-major: step UMMA_K k-rows of 128 bytes.
-          const uint64_t ad =
-              A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
-                   : ptx::make_smem_desc(a_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
-          const uint64_t bd =
-              B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
-                   : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
-          const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-          if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
-          else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+          for (int c = 0; c < TC_BLOCK_N / MN_ATOM; ++c)
+            ptx::tma_load_2d(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
         }
-        ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mb, nb;
+        tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
+        const int m0 = mb * TC_BLOCK_M, n0 = nb * TC_BLOCK_N;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
+          const int kb1 = min(num_kb, kb0 + p.kb_per_block);
+          if (p.npass == 3) {
+            // the two small cross terms first (the accumulator is still small, so its
+            // truncation does not touch them), then the hi*hi chain
+            for (int kb = kb0; kb < kb1; ++kb) {
+              load_stage(&mapA0, &mapB1, m0, n0, kb * BLOCK_K);  // A_hi * B_lo
+              load_stage(&mapA1, &mapB0, m0, n0, kb * BLOCK_K);  // A_lo * B_hi
+            }
+          }
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(&mapA0, &mapB0, m0, n0, kb * BLOCK_K);
+        }
       }
-      ptx::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-      if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    } else if (warp_idx == 1 && lane == 0) {
+      // ===================== MMA issuer (one thread) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
+          const int iters = (min(num_kb, kb0 + p.kb_per_block) - kb0) * p.npass;
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * TC_BLOCK_N;
+          for (int it = 0; it < iters; ++it) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t a_addr = ptx::smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TC_B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < K_STEPS; ++k) {
+              // K-major: step 32 bytes inside the 128-byte swizzle row.
+              // MN-major: step UMMA_K k-rows of 128 bytes.
+              const uint64_t ad =
+                  A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                       : ptx::make_smem_desc(a_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
+              const uint64_t bd =
+                  B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                       : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
+              const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+              if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
+              else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+            }
+            ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          ptx::mma_commit(&tmem_full[acc]);  // block complete -> epilogue warps drain it
+          if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
     }
-  } else if (warp_idx >= 4) {
-    // ===================== epilogue (4 warps, 32 TMEM lanes each) =====================
-    const int ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+  } else {
+    // ============ epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and 128 columns ============
+    setmaxnreg_inc<TC_REGS_EPI>();
+    const int q = warp_idx & 3;          // TMEM lane quarter this warp may read
+    const int h = (warp_idx - 4) >> 2;   // column half
     int acc = 0;
     uint32_t acc_phase = 0;
     OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C);
@@ -215,89 +250,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int mb, nb;
       tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
-      const int64_t row = static_cast<int64_t>(mb) * TC_BLOCK_M + ew * 32 + lane;
-      const int64_t n0 = static_cast<int64_t>(nb) * TC_BLOCK_N;
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * TC_BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < TC_BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait(r);
-        if (c == TC_BLOCK_N / 32 - 1) {
-          // all of this thread's TMEM reads for the tile are done: hand the
-          // accumulator stage back to the MMA thread before the global stores
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&tmem_empty[acc]);
+      const int64_t row = static_cast<int64_t>(mb) * TC_BLOCK_M + q * 32 + lane;
+      const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
+      float run[TC_EPI_COLS];  // running sums of this thread's row segment (registers)
+#pragma unroll
+      for (int j = 0; j < TC_EPI_COLS; ++j) run[j] = 0.0f;
+      for (int blk = 0; blk < num_blocks; ++blk) {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * TC_BLOCK_N + h * TC_EPI_COLS;
+        // Eight 16-column chunks.  `dep` (always 0 at run time: p.zero is 0, but the compiler
+        // cannot know) makes the address of chunk c+1 depend on an addition of chunk c, so the
+        // scheduler cannot issue all eight loads first and keep 128 extra registers in flight.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int c = 0; c < TC_EPI_COLS / 16; ++c) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(t_addr + c * 16 + dep, r);
+          ptx::tmem_ld_wait(r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) run[c * 16 + j] = __fadd_rn(run[c * 16 + j], __uint_as_float(r[j]));
+          dep = (__float_as_uint(run[c * 16]) | __float_as_uint(run[c * 16 + 15])) & p.zero;
         }
-        const int64_t col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          OutT *crow = C + row * p.rsC;
-          if (vec_ok && col0 + 32 <= p.N) {
-            if constexpr (sizeof(OutT) == 4) {
-              float4 *dst = reinterpret_cast<float4 *>(crow + col0);
+        // this thread's TMEM reads of the block are done: hand the stage back to the MMA thread
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      // ---- C <- alpha * sum + beta * C  (gemm_ukernel_generic.nim:53-76 semantics) ----
+      if (row < p.M && col0 < p.N) {
+        OutT *crow = C + row * p.rsC;
+        if (vec_ok && col0 + TC_EPI_COLS <= p.N) {
+          if constexpr (sizeof(OutT) == 4) {
+            float4 *dst = reinterpret_cast<float4 *>(crow + col0);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float4 v;
-                v.x = p.alpha * __uint_as_float(r[4 * q + 0]);
-                v.y = p.alpha * __uint_as_float(r[4 * q + 1]);
-                v.z = p.alpha * __uint_as_float(r[4 * q + 2]);
-                v.w = p.alpha * __uint_as_float(r[4 * q + 3]);
-                if (p.beta != 0.0f) {
-                  const float4 o = dst[q];
-                  v.x = fmaf(p.beta, o.x, v.x);
-                  v.y = fmaf(p.beta, o.y, v.y);
-                  v.z = fmaf(p.beta, o.z, v.z);
-                  v.w = fmaf(p.beta, o.w, v.w);
-                }
-                dst[q] = v;
+            for (int v4 = 0; v4 < TC_EPI_COLS / 4; ++v4) {
+              float4 v;
+              v.x = p.alpha * run[4 * v4 + 0];
+              v.y = p.alpha * run[4 * v4 + 1];
+              v.z = p.alpha * run[4 * v4 + 2];
+              v.w = p.alpha * run[4 * v4 + 3];
+              if (p.beta != 0.0f) {
+                const float4 o = dst[v4];
+                v.x = fmaf(p.beta, o.x, v.x);
+                v.y = fmaf(p.beta, o.y, v.y);
+                v.z = fmaf(p.beta, o.z, v.z);
+                v.w = fmaf(p.beta, o.w, v.w);
               }
-            } else {
-              uint4 *dst = reinterpret_cast<uint4 *>(crow + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = p.alpha * __uint_as_float(r[8 * q + e]);
-                if (p.beta != 0.0f) {
-                  const uint4 o = dst[q];
-                  const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    f[2 * e] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] & 0xffff)), f[2 * e]);
-                    f[2 * e + 1] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
-                  }
-                }
-                uint4 w;
-                w.x = f32_to_bf16_bits(f[0]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[1])) << 16);
-                w.y = f32_to_bf16_bits(f[2]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[3])) << 16);
-                w.z = f32_to_bf16_bits(f[4]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[5])) << 16);
-                w.w = f32_to_bf16_bits(f[6]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[7])) << 16);
-                dst[q] = w;
-              }
+              dst[v4] = v;
             }
           } else {
-            // any C strides / ragged right edge: scalar, predicated
+            uint4 *dst = reinterpret_cast<uint4 *>(crow + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = col0 + j;
-              if (col < p.N) {
-                OutT *dst = crow + col * p.csC;
-                float v = p.alpha * __uint_as_float(r[j]);
-                if constexpr (sizeof(OutT) == 4) {
-                  if (p.beta != 0.0f) v = fmaf(p.beta, *dst, v);
-                  *dst = v;
-                } else {
-                  if (p.beta != 0.0f) v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
-                  *dst = f32_to_bf16_bits(v);
+            for (int v8 = 0; v8 < TC_EPI_COLS / 8; ++v8) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = p.alpha * run[8 * v8 + e];
+              if (p.beta != 0.0f) {
+                const uint4 o = dst[v8];
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[2 * e] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] & 0xffff)), f[2 * e]);
+                  f[2 * e + 1] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
                 }
               }
+              uint4 w;
+              w.x = f32_to_bf16_bits(f[0]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[1])) << 16);
+              w.y = f32_to_bf16_bits(f[2]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[3])) << 16);
+              w.z = f32_to_bf16_bits(f[4]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[5])) << 16);
+              w.w = f32_to_bf16_bits(f[6]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[7])) << 16);
+              dst[v8] = w;
             }
+          }
+        } else {
+          // any C strides / ragged right edge: scalar, predicated; one running pointer so
+          // that the unrolled loop does not keep 128 addresses live
+          OutT *dst = crow + col0 * p.csC;
+          const int64_t ncols = p.N - col0;
+#pragma unroll
+          for (int j = 0; j < TC_EPI_COLS; ++j) {
+            if (j < ncols) {
+              float v = p.alpha * run[j];
+              if constexpr (sizeof(OutT) == 4) {
+                if (p.beta != 0.0f) v = fmaf(p.beta, *dst, v);
+                *dst = v;
+              } else {
+                if (p.beta != 0.0f) v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
+                *dst = f32_to_bf16_bits(v);
+              }
+            }
+            dst += p.csC;
           }
         }
       }
-      if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
