@@ -105,13 +105,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------- reference arm
 def cpu_reference_sample(budget_s=12.0):
     """Times the structure-faithful C restatement of the reference's CPU gemm_strided
-    (oracle/laser_cpu_gemm.c: packing + 14x32 AVX-512 micro-kernel + OpenMP, all host threads)
-    on a bounded sample of the workload: the largest n in {2048, 4096, 8192} whose single run
-    is predicted to fit the budget.  Same flop accounting as the reference (gemm_common.nim:20-25)."""
+    (oracle/laser_cpu_gemm.c: packing + 14x32 AVX-512 micro-kernel + OpenMP) on a bounded
+    sample of the workload.  The OpenMP team size is calibrated first (all logical CPUs vs
+    one thread per physical core, whichever is faster on a 2048^3 probe: the reference's
+    ic/jr task structure collapses when hyper-threads oversubscribe it), then the largest n in
+    {2048, 4096, 8192} whose run is predicted to fit the budget is timed.  Flop accounting as
+    the reference's bench (gemm_common.nim:20-25)."""
     import numpy as np
     import oracle as O
-    threads = O.num_threads()
     isa = O.detect_isa()
+    logical = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = logical
+    logical = min(logical, aff)
 
     def run(n, reps):
         a = O.fill_uniform_f32(n * n, 42, -0.1, 0.1); b = O.fill_uniform_f32(n * n, 43, -0.1, 0.1)
@@ -125,21 +133,27 @@ def cpu_reference_sample(budget_s=12.0):
             ts.append(time.perf_counter() - t0)
         return sum(ts) / len(ts), min(ts)
 
-    mean, _ = run(2048, 2)
-    rate = 2 * 2048**3 / mean
+    cands = sorted({logical, max(1, logical // 2)}, reverse=True)
+    best_t, threads = None, cands[0]
+    for t in cands:
+        O.set_num_threads(t)
+        mean, _ = run(2048, 2)
+        if best_t is None or mean < best_t:
+            best_t, threads = mean, t
+    O.set_num_threads(threads)
+    rate = 2 * 2048**3 / best_t
     n = 2048
     for cand in (4096, 8192):
-        if 2 * cand**3 / rate * 2.5 <= budget_s:     # warm-up + >= 1 sample
+        # larger problems run at a higher rate (more ic blocks per thread): x2 is conservative
+        if 2 * cand**3 / (2 * rate) * 2.5 <= budget_s:
             n = cand
-    reps = 3 if n < 8192 else 1
-    if n != 2048:
-        mean, best = run(n, reps)
-    else:
-        mean, best = run(2048, 5)
+    reps = 3 if n < 8192 else 2
+    mean, best = run(n, reps) if n != 2048 else run(2048, 5)
     tflops = 2 * n**3 / mean / 1e12
     return dict(value=tflops, unit=UNIT, cores=threads, kind="port",
-                sample="SGEMM %d^3 fp32 row-major, mean of %d run(s) after 1 warm-up, %d OpenMP threads, %s micro-kernel; "
-                       "C restatement of the reference (Nim is not installable here)" % (n, reps, threads, O.ISA_NAMES[isa]),
+                sample="SGEMM %d^3 fp32 row-major, mean of %d run(s) after 1 warm-up, %d OpenMP threads (of %d logical CPUs; "
+                       "team size picked by a 2048^3 probe), %s micro-kernel; C restatement of the reference "
+                       "(Nim is not installable here)" % (n, reps, threads, logical, O.ISA_NAMES[isa]),
                 ms=mean * 1e3, n=n)
 
 
@@ -149,7 +163,7 @@ def run_reference(args):
         return
     import numpy as np
     import oracle as O
-    base = cpu_reference_sample(budget_s=10.0)
+    base = cpu_reference_sample(budget_s=20.0)
     n = base["n"]
     a = O.fill_uniform_f32(n * n, 42, -0.1, 0.1); b = O.fill_uniform_f32(n * n, 43, -0.1, 0.1)
     c = np.zeros(n * n, np.float32)
@@ -231,17 +245,29 @@ def run_ours(args):
 
     # ---- the metric: device-resident, default (fp32-faithful) mode --------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()       # before the warm-up so that nvidia-smi is already streaming
     for _ in range(args.warmup):
         step()
     barrier()
-    if sampler:
-        sampler.start()
     n0 = L.launch_count()
     L.profile_begin()
     ms_step = timed(step, args.steps, 0)
     prof = L.profile_end()
     launches = L.launch_count() - n0
+    # nvidia-smi samples every 100 ms; if the timed region was shorter than ~1.5 s keep the
+    # very same step running (untimed) so that the clock/throttle record is under this load
+    obs_steps = int(max(0.0, 1500.0 - ms_step * args.steps) / max(ms_step, 1e-3))
+    if world > 1:
+        t_obs = torch.tensor([obs_steps], device=dev)
+        dist.broadcast(t_obs, src=0)
+        obs_steps = int(t_obs.item())
+    for _ in range(obs_steps):
+        step()
+    barrier()
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["observed_over"] = "warm-up + %d timed + %d untimed identical steps" % (args.steps, obs_steps)
     flops_step = 2.0 * M * N * K * world
     value = flops_step / (ms_step * 1e-3) / 1e12
 

@@ -61,9 +61,9 @@ struct TcParams {
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int &mb, int &nb) {
-  // groups of 8 m-blocks sweep n together so that concurrently resident CTAs
-  // share A and B tiles in L2
-  constexpr int G = 8;
+  // groups of 16 m-blocks sweep n together: the ~148 concurrently resident tiles then cover
+  // a near-square 16 x 9 patch, which minimises the A + B panels one wave pulls through L2
+  constexpr int G = 16;
   const int per_group = G * num_n;
   const int g = t / per_group;
   const int first_m = g * G;

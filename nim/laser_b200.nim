@@ -1,0 +1,154 @@
+# laser_b200.nim -- the Nim side of the drop-in boundary.
+#
+# A thin {.importc.} shim over liblaser_b200.so (C ABI: include/laser_b200.h) that gives Nim
+# callers the reference's own API for the hot path:
+#
+#   gemm_strided(M, N, K, alpha, A, rowStrideA, colStrideA, B, rowStrideB, colStrideB,
+#                beta, C, rowStrideC, colStrideC)
+#
+# with exactly the signature of laser/primitives/matrix_multiplication/gemm.nim:184-193, so
+# that `import laser_b200` can replace `import laser/primitives/matrix_multiplication/gemm`
+# at a call site such as benchmarks/gemm/gemm_bench_float32.nim:184-189 without touching it.
+# FFI idiom: the reference's own (benchmarks/third_party/blas.nim:18-23: importc + dynlib).
+#
+# NOTE: no Nim toolchain exists in the build image, so this file is shipped untested; every
+# symbol it imports is exercised through the identical C ABI by tests/ (ctypes) instead.
+
+const laserB200Lib* {.strdefine.} = "liblaser_b200.so"
+
+type
+  LaserB200Error* = object of CatchableError   # cf. LibraryError in laser/cpuinfo.nim:358-359
+
+  GemmPath* {.size: sizeof(cint).} = enum      # LASER_B200_PATH_*
+    pathAuto = 0, pathSimt = 1, pathTf32x1 = 2, pathTf32x3 = 3, pathBf16 = 4
+
+{.push importc, cdecl, dynlib: laserB200Lib.}
+proc laser_b200_init*(): cint
+proc laser_b200_shutdown*()
+proc laser_b200_last_error*(): cstring
+proc laser_b200_set_f32_mode*(path: cint): cint
+proc laser_b200_gemm_strided_f32*(M, N, K: int64, alpha: float32,
+    A: ptr float32, rowStrideA, colStrideA: int64,
+    B: ptr float32, rowStrideB, colStrideB: int64,
+    beta: float32, C: ptr float32, rowStrideC, colStrideC: int64): cint
+proc laser_b200_gemm_strided_f64*(M, N, K: int64, alpha: float64,
+    A: ptr float64, rowStrideA, colStrideA: int64,
+    B: ptr float64, rowStrideB, colStrideB: int64,
+    beta: float64, C: ptr float64, rowStrideC, colStrideC: int64): cint
+proc laser_b200_gemm_strided_i32*(M, N, K: int64, alpha: int32,
+    A: ptr int32, rowStrideA, colStrideA: int64,
+    B: ptr int32, rowStrideB, colStrideB: int64,
+    beta: int32, C: ptr int32, rowStrideC, colStrideC: int64): cint
+proc laser_b200_gemm_strided_i64*(M, N, K: int64, alpha: int64,
+    A: ptr int64, rowStrideA, colStrideA: int64,
+    B: ptr int64, rowStrideB, colStrideB: int64,
+    beta: int64, C: ptr int64, rowStrideC, colStrideC: int64): cint
+proc laser_b200_gemm_strided_f32_dev*(M, N, K: int64, alpha: float32,
+    A: ptr float32, rowStrideA, colStrideA: int64,
+    B: ptr float32, rowStrideB, colStrideB: int64,
+    beta: float32, C: ptr float32, rowStrideC, colStrideC: int64,
+    path: cint, stream: pointer): cint
+proc laser_b200_malloc*(devPtr: ptr pointer, bytes: csize_t): cint
+proc laser_b200_free*(devPtr: pointer): cint
+proc laser_b200_memcpy_h2d*(dst, src: pointer, bytes: csize_t): cint
+proc laser_b200_memcpy_d2h*(dst, src: pointer, bytes: csize_t): cint
+proc laser_b200_memset_zero*(dst: pointer, bytes: csize_t): cint
+{.pop.}
+
+template check(code: cint) =
+  if code != 0:
+    raise newException(LaserB200Error, $laser_b200_last_error())
+
+# ---- the drop-in overloads: same parameter list as gemm.nim:184-193 -------------------
+proc gemm_strided*(M, N, K: int, alpha: float32,
+                   A: ptr float32, rowStrideA, colStrideA: int,
+                   B: ptr float32, rowStrideB, colStrideB: int,
+                   beta: float32,
+                   C: ptr float32, rowStrideC, colStrideC: int) =
+  check laser_b200_gemm_strided_f32(M, N, K, alpha, A, rowStrideA, colStrideA,
+                                    B, rowStrideB, colStrideB, beta, C, rowStrideC, colStrideC)
+
+proc gemm_strided*(M, N, K: int, alpha: float64,
+                   A: ptr float64, rowStrideA, colStrideA: int,
+                   B: ptr float64, rowStrideB, colStrideB: int,
+                   beta: float64,
+                   C: ptr float64, rowStrideC, colStrideC: int) =
+  check laser_b200_gemm_strided_f64(M, N, K, alpha, A, rowStrideA, colStrideA,
+                                    B, rowStrideB, colStrideB, beta, C, rowStrideC, colStrideC)
+
+proc gemm_strided*(M, N, K: int, alpha: int32,
+                   A: ptr int32, rowStrideA, colStrideA: int,
+                   B: ptr int32, rowStrideB, colStrideB: int,
+                   beta: int32,
+                   C: ptr int32, rowStrideC, colStrideC: int) =
+  check laser_b200_gemm_strided_i32(M, N, K, alpha, A, rowStrideA, colStrideA,
+                                    B, rowStrideB, colStrideB, beta, C, rowStrideC, colStrideC)
+
+proc gemm_strided*(M, N, K: int, alpha: int,
+                   A: ptr int, rowStrideA, colStrideA: int,
+                   B: ptr int, rowStrideB, colStrideB: int,
+                   beta: int,
+                   C: ptr int, rowStrideC, colStrideC: int) =
+  check laser_b200_gemm_strided_i64(M, N, K, alpha.int64, cast[ptr int64](A), rowStrideA, colStrideA,
+                                    cast[ptr int64](B), rowStrideB, colStrideB, beta.int64,
+                                    cast[ptr int64](C), rowStrideC, colStrideC)
+
+# ---- device tensor honouring laser/tensor's contract (datatypes.nim:12-88) -----------
+# Same fields and accessors as Tensor[T]; storage lives in HBM.  Metadata mirrors
+# DynamicStackArray[int] with LASER_MAXRANK = 6 (laser/dynamic_stack_arrays.nim:6,14-19).
+const LASER_MAXRANK* = 6
+type
+  Metadata* = object
+    data*: array[LASER_MAXRANK, int]
+    len*: int
+  CudaStorage*[T] = ref object
+    raw_buffer*: ptr UncheckedArray[T]   # device address
+    memowner*: bool
+  CudaTensor*[T] = object
+    shape*, strides*: Metadata           # strides in elements
+    offset*: int
+    storage*: CudaStorage[T]
+
+proc finalizer[T](s: CudaStorage[T]) =
+  if s.memowner and not s.raw_buffer.isNil: discard laser_b200_free(s.raw_buffer)
+
+func rank*(t: CudaTensor): int {.inline.} = t.shape.len
+func size*(t: CudaTensor): int =
+  result = 1
+  for i in 0 ..< t.shape.len: result *= t.shape.data[i]
+func is_C_contiguous*(t: CudaTensor): bool =
+  var cur = 1
+  for i in countdown(t.rank - 1, 0):
+    if t.shape.data[i] != 1 and t.strides.data[i] != cur: return false
+    cur *= t.shape.data[i]
+  true
+func unsafe_raw_data*[T](t: CudaTensor[T]): ptr T {.inline.} =
+  ## device address of element [0, ..., 0] (storage + offset), datatypes.nim:64-88
+  cast[ptr T](t.storage.raw_buffer[t.offset].addr)
+
+proc newCudaTensor*[T](shape: varargs[int]): CudaTensor[T] =
+  ## zero-initialised row-major device tensor (initialization.nim:156-170)
+  result.shape.len = shape.len
+  result.strides.len = shape.len
+  var acc = 1
+  for i in countdown(shape.len - 1, 0):
+    result.shape.data[i] = shape[i]
+    result.strides.data[i] = acc
+    acc *= shape[i]
+  new(result.storage, finalizer[T])
+  var p: pointer
+  check laser_b200_malloc(p.addr, csize_t(acc * sizeof(T)))
+  check laser_b200_memset_zero(p, csize_t(acc * sizeof(T)))
+  result.storage.raw_buffer = cast[ptr UncheckedArray[T]](p)
+  result.storage.memowner = true
+
+proc matmul*(a, b: CudaTensor[float32], c: var CudaTensor[float32],
+             alpha = 1'f32, beta = 0'f32, path = pathAuto) =
+  ## C <- alpha*A*B + beta*C on device tensors of any strides, as gemm_prepacked.nim:306-307
+  ## does with `cast[ptr T](t.unsafe_raw_data)`.
+  doAssert a.rank == 2 and b.rank == 2 and c.rank == 2
+  check laser_b200_gemm_strided_f32_dev(
+    a.shape.data[0], b.shape.data[1], a.shape.data[1], alpha,
+    a.unsafe_raw_data, a.strides.data[0], a.strides.data[1],
+    b.unsafe_raw_data, b.strides.data[0], b.strides.data[1],
+    beta, c.unsafe_raw_data, c.strides.data[0], c.strides.data[1], path.cint, nil)

@@ -56,6 +56,14 @@ int laser_cpu_num_threads(void) {
 #endif
 }
 
+void laser_cpu_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static microkernel_t select_ukernel(int isa) {
   microkernel_t u;
   switch (isa) {

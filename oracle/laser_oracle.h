@@ -81,6 +81,7 @@ int laser_cpu_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha,
                                int isa);
 int laser_cpu_detect_isa(void);
 int laser_cpu_num_threads(void);
+void laser_cpu_set_num_threads(int n);
 
 /* ---- error metrics (laser/private/error_functions.nim:6-34) ---- */
 double oracle_relative_error(double y, double y_true);

@@ -18,7 +18,7 @@ _lib = None
 __all__ = [
     "build", "lib", "gemm_strided", "cpu_gemm_strided_f32", "gemm_f32_in_f64",
     "fill_uniform_f32", "mean_relative_error", "max_relative_error",
-    "normwise_relative_error", "detect_isa", "num_threads", "ISA_NAMES",
+    "normwise_relative_error", "detect_isa", "num_threads", "set_num_threads", "ISA_NAMES",
 ]
 
 ISA_NAMES = {1: "generic 2x1", 2: "avx+fma 6x16", 3: "avx512 14x32"}
@@ -55,6 +55,8 @@ def lib():
         L.oracle_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32]
         L.laser_cpu_detect_isa.restype = ctypes.c_int
         L.laser_cpu_num_threads.restype = ctypes.c_int
+        L.laser_cpu_set_num_threads.restype = None
+        L.laser_cpu_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -127,3 +129,7 @@ def detect_isa():
 
 def num_threads():
     return lib().laser_cpu_num_threads()
+
+
+def set_num_threads(n):
+    lib().laser_cpu_set_num_threads(int(n))
