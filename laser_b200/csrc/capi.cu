@@ -68,6 +68,7 @@ struct EventPair {
 };
 
 struct Ctx {
+  bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
   std::vector<EventPair> prof;
@@ -119,6 +120,7 @@ int get_ctx(Ctx **out) {
         const int v = atoi(kc);
         if (v >= 32) c.kc_faithful = v;
       }
+      if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32X3;
@@ -259,20 +261,35 @@ int operand_map(Ctx &c, CUtensorMap *map, int esz, const void *base, Major major
                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int ESZ, typename OutT>
+template <int ESZ, typename OutT, bool PAIR>
 int launch_tc(Ctx &c, bool a_mn, bool b_mn, const CUtensorMap &a0, const CUtensorMap &a1,
               const CUtensorMap &b0, const CUtensorMap &b1, const TcParams &p, cudaStream_t s) {
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
-  const int grid = static_cast<int>(tiles < c.sm_count ? tiles : c.sm_count);
+  // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than tiles
+  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
+  const int sched = static_cast<int>(tiles < units ? tiles : units);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define LB200_LAUNCH(AMN, BMN)                                                                   \
   do {                                                                                           \
-    auto kfn = gemm_tc_kernel<ESZ, AMN, BMN, OutT>;                                              \
+    auto kfn = gemm_tc_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                        \
     static bool attr_set = false;                                                                \
     if (!attr_set) {                                                                             \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
       attr_set = true;                                                                           \
     }                                                                                            \
-    kfn<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(a0, a1, b0, b1, p);                              \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, p));                                  \
   } while (0)
   if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
   else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
@@ -382,7 +399,10 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   if (rc) return rc;
   rc = prepare_operand<ESZ>(c, oa, split, c.ws[0], c.ws[1], TC_BLOCK_M, &a0, &a1, &a_mn, &used_ws, s);
   if (rc) return rc;
-  rc = prepare_operand<ESZ>(c, ob, split, c.ws[2], c.ws[3], TC_BLOCK_N, &b0, &b1, &b_mn, &used_ws, s);
+  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
+  const bool pair = c.cta_pair && M > TC_BLOCK_M;
+  rc = prepare_operand<ESZ>(c, ob, split, c.ws[2], c.ws[3], pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &b0, &b1,
+                            &b_mn, &used_ws, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
@@ -400,11 +420,13 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
     if (p.kb_per_block < 1) p.kb_per_block = 1;
     if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
   }
-  p.num_m_blocks = static_cast<int>((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
+  const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+  p.num_m_blocks = static_cast<int>((M + tile_m - 1) / tile_m);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
   rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;
-  rc = launch_tc<ESZ, OutT>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
+  if (pair) rc = launch_tc<ESZ, OutT, true>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
+  else rc = launch_tc<ESZ, OutT, false>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, 1);
   if (rc) return rc;

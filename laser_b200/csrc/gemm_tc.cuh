@@ -35,17 +35,24 @@ namespace lb200 {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_N = 256;
 constexpr int TC_ROW_BYTES = 128;  // one swizzle row; BLOCK_K = 128 / sizeof(element)
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_ROW_BYTES;  // 16 KB
-constexpr int TC_B_STAGE_BYTES = TC_BLOCK_N * TC_ROW_BYTES;  // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_STAGE_BYTES + TC_B_STAGE_BYTES;
+// Single-CTA kernel: the CTA stages all 256 B columns (32 KB) -> 48 KB stages, 4 of them.
+// CTA-pair kernel (cta_group::2, 256 x 256 tile per pair): each CTA stages its own 128 rows
+// of A and HALF of the B columns (16 KB) -> 32 KB stages, 6 of them; the tensor cores of both
+// SMs read both halves.
+template <bool PAIR> struct TcCfg {
+  static constexpr int B_COLS = PAIR ? TC_BLOCK_N / 2 : TC_BLOCK_N;
+  static constexpr int B_STAGE_BYTES = B_COLS * TC_ROW_BYTES;
+  static constexpr int STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512: all of TMEM
 // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle | warps 4-11: epilogue (2 warpgroups)
 constexpr int TC_THREADS = 384;
 constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_EPI_COLS = TC_BLOCK_N / 2;  // columns owned by one epilogue thread
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_REGS_CTRL = 56;   // setmaxnreg for the producer/MMA warpgroup
 constexpr int TC_REGS_EPI = 216;   // ... and for the epilogue warpgroups (running sums)
 
@@ -57,7 +64,7 @@ struct TcParams {
   int npass;          // 1, or 3 for the hi/lo split
   int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
-  int num_m_blocks, num_n_blocks;
+  int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int &mb, int &nb) {
@@ -94,7 +101,8 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 
 // ESZ: element size of A/B in bytes (4 = tf32 containers, 2 = bf16).
 // OutT: float or uint16_t (bf16 bits).
-template <int ESZ, bool A_MN, bool B_MN, typename OutT>
+// PAIR: launched as clusters of 2 CTAs; CTA rank r owns rows [128r, 128r+128) of the 256-row tile.
+template <int ESZ, bool A_MN, bool B_MN, typename OutT, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -107,9 +115,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   // MN-major 32-bit operands must use the 128B-swizzle-with-32B-atoms layout (4 k-rows per atom)
   constexpr uint32_t MN_LAYOUT = ESZ == 4 ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
   constexpr uint32_t MN_SBO = ESZ == 4 ? 512 : 1024;
+  using Cfg = TcCfg<PAIR>;
+  constexpr int TC_STAGES = Cfg::STAGES;
+  constexpr int TC_B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
+  constexpr int TC_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int TILE_M = PAIR ? 2 * TC_BLOCK_M : TC_BLOCK_M;  // rows of one scheduled tile
   constexpr uint32_t IDESC =
       ptx::make_idesc(ESZ == 4 ? ptx::kFmtTF32 : ptx::kFmtBF16, A_MN ? 1 : 0, B_MN ? 1 : 0,
-                      TC_BLOCK_M, TC_BLOCK_N);
+                      TILE_M, TC_BLOCK_N);
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const int sched_id = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int sched_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -139,18 +155,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
   if (threadIdx.x == 32) {
     for (int i = 0; i < TC_STAGES; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
+      // pair: the leader's full barrier takes its own arrive.expect_tx plus the peer's arrive
+      ptx::mbar_init(&full_bar[i], PAIR ? 2 : 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < TC_ACC_STAGES; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], TC_EPI_THREADS);
+      // pair: the epilogue threads of BOTH CTAs release the leader's accumulator stage
+      ptx::mbar_init(&tmem_empty[i], PAIR ? 2 * TC_EPI_THREADS : TC_EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
-  if (warp_idx == 2) ptx::tmem_alloc<TC_TMEM_COLS>(tmem_base_smem);
+  if (warp_idx == 2) {
+    if constexpr (PAIR) ptx::tmem_alloc_pair<TC_TMEM_COLS>(tmem_base_smem);
+    else ptx::tmem_alloc<TC_TMEM_COLS>(tmem_base_smem);
+  }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // peer barriers must exist before any remote arrive
+  else __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -160,31 +182,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       // ===================== TMA producer (one thread) =====================
       int stage = 0;
       uint32_t phase = 0;
+      auto tma = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+        if constexpr (PAIR) ptx::tma_load_2d_pair(dst, m, bar, c0, c1);  // bytes -> leader's barrier
+        else ptx::tma_load_2d(dst, m, bar, c0, c1);
+      };
       auto load_stage = [&](const CUtensorMap *ma, const CUtensorMap *mbp, int m0, int n0, int k0) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        if constexpr (PAIR) {
+          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * TC_STAGE_BYTES);
+          else ptx::mbar_arrive_leader(&full_bar[stage]);
+        } else {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        }
         uint8_t *sa = smem_a + stage * TC_A_STAGE_BYTES;
         uint8_t *sb = smem_b + stage * TC_B_STAGE_BYTES;
         if constexpr (!A_MN) {
-          ptx::tma_load_2d(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
+          tma(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
         } else {
 #pragma unroll
           for (int c = 0; c < TC_BLOCK_M / MN_ATOM; ++c)  // boxes {MN_ATOM, BLOCK_K}
-            ptx::tma_load_2d(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
+            tma(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
         }
         if constexpr (!B_MN) {
-          ptx::tma_load_2d(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, 256}
+          tma(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, B_COLS}
         } else {
 #pragma unroll
-          for (int c = 0; c < TC_BLOCK_N / MN_ATOM; ++c)
-            ptx::tma_load_2d(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
+          for (int c = 0; c < Cfg::B_COLS / MN_ATOM; ++c)
+            tma(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
         }
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       };
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = sched_id; t < num_tiles; t += sched_stride) {
         int mb, nb;
         tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
-        const int m0 = mb * TC_BLOCK_M, n0 = nb * TC_BLOCK_N;
+        // pair: this CTA's 128 rows of A and its half of the B columns
+        const int m0 = mb * TILE_M + static_cast<int>(cta_rank) * TC_BLOCK_M;
+        const int n0 = nb * TC_BLOCK_N + static_cast<int>(cta_rank) * (TC_BLOCK_N - Cfg::B_COLS);
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
           const int kb1 = min(num_kb, kb0 + p.kb_per_block);
           if (p.npass == 3) {
@@ -198,13 +231,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int kb = kb0; kb < kb1; ++kb) load_stage(&mapA0, &mapB0, m0, n0, kb * BLOCK_K);
         }
       }
-    } else if (warp_idx == 1 && lane == 0) {
-      // ===================== MMA issuer (one thread) =====================
+    } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
+      // ===================== MMA issuer (one thread; pair: the leader CTA only) =============
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = sched_id; t < num_tiles; t += sched_stride) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
           const int iters = (min(num_kb, kb0 + p.kb_per_block) - kb0) * p.npass;
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -226,13 +259,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
                        : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
               const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-              if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
-              else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+              if constexpr (PAIR) {
+                if constexpr (ESZ == 4) ptx::mma_tf32_ss_pair(d_tmem, ad, bd, IDESC, accum);
+                else ptx::mma_f16_ss_pair(d_tmem, ad, bd, IDESC, accum);
+              } else {
+                if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
+                else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+              }
             }
-            ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if constexpr (PAIR) ptx::mma_commit_pair(&empty_bar[stage]);
+            else ptx::mma_commit(&empty_bar[stage]);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&tmem_full[acc]);  // block complete -> epilogue warps drain it
+          // block complete -> the epilogue warps (of both CTAs) drain it
+          if constexpr (PAIR) ptx::mma_commit_pair(&tmem_full[acc]);
+          else ptx::mma_commit(&tmem_full[acc]);
           if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -247,10 +289,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C);
     const bool vec_ok = (p.csC == 1) && ((p.rsC * sizeof(OutT)) % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = sched_id; t < num_tiles; t += sched_stride) {
       int mb, nb;
       tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
-      const int64_t row = static_cast<int64_t>(mb) * TC_BLOCK_M + q * 32 + lane;
+      const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
       float run[TC_EPI_COLS];  // running sums of this thread's row segment (registers)
 #pragma unroll
@@ -274,7 +316,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         // this thread's TMEM reads of the block are done: hand the stage back to the MMA thread
         ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&tmem_empty[acc]);
+        if constexpr (PAIR) ptx::mbar_arrive_leader(&tmem_empty[acc]);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       // ---- C <- alpha * sum + beta * C  (gemm_ukernel_generic.nim:53-76 semantics) ----
@@ -349,9 +392,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   __syncwarp();
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // neither CTA may leave while its peer still uses its smem/TMEM
+  else __syncthreads();
   ptx::tc_fence_after_sync();
-  if (warp_idx == 2) ptx::tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  if (warp_idx == 2) {
+    if constexpr (PAIR) ptx::tmem_dealloc_pair<TC_TMEM_COLS>(tmem_base);
+    else ptx::tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace lb200
