@@ -6,8 +6,8 @@
 
 A "step" is one pass of the hot path: C <- A x B, fp32, row-major, alpha=1, beta=0 (the call
 the reference's bench makes, benchmarks/gemm/gemm_bench_float32.nim:184-189), through the
-C ABI of liblaser_b200.so in its DEFAULT fp32-faithful mode (tcgen05 3xTF32, parity-gated at
-1e-4).  At N GPUs the problem is row-sharded (weak scaling: every rank owns 8192 rows of A
+C ABI of liblaser_b200.so in its DEFAULT fp32-faithful mode (tcgen05: one tf32 hi*hi pass + two
+bf16 passes for the hi*lo / lo*hi correction terms, parity-gated at 1e-4).  At N GPUs the problem is row-sharded (weak scaling: every rank owns 8192 rows of A
 and C, so N=4 is BASELINE.json's "M=32768, N=K=8192" case) and each step includes the
 K-panelled NCCL broadcast of B from rank 0.
 
@@ -28,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch at 8192^3 in the default
+# mode, from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc_8192.md); None until measured
+TRAFFIC_BYTES_PER_LAUNCH = None
 METRIC = "sgemm_tflops_m8192_n8192_k8192"
 UNIT = "TFLOP/s"
 MNK = 8192
@@ -278,17 +281,23 @@ def run_ours(args):
         flops_launch = 2.0 * M * N * K / max(1, prof["gemm_launches"] // args.steps)
         achieved = flops_launch / (gemm_ms * 1e-3) / 1e12
         tf32_peak = peaks["bf16"] / 2.0
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<tf32, 3 passes>", "achieved": achieved, "peak": tf32_peak,
-                    "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<fp32 in, CTA pair, mixed tf32+bf16c>", "achieved": achieved,
+                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                    "traffic": TRAFFIC_BYTES_PER_LAUNCH,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 2 = TF32 rate, of %s" % peaks["source"],
-                    "tensor_pipe_frac": 3.0 * achieved / tf32_peak,
-                    "note": "achieved counts ALGORITHMIC flops 2MNK; the fp32-faithful mode issues 3 TF32 MMAs per useful MAC, "
-                            "so frac <= 1/3 by construction and tensor_pipe_frac = 3*frac is the pipe utilisation",
+                    "tensor_pipe_frac": 2.0 * achieved / tf32_peak,
+                    "note": "achieved counts ALGORITHMIC flops 2MNK; the default fp32-faithful mode issues, per useful MAC, one TF32 "
+                            "MMA plus two bf16 MMAs at twice the rate (= 2 TF32-equivalents), so frac <= 1/2 by construction and "
+                            "tensor_pipe_frac = 2*frac is the tensor-pipe utilisation; traffic = ncu dram bytes read+written per "
+                            "launch (profiles/), algorithmic bytes = 805 MB",
                     "kernel_ms": gemm_ms, "prep_ms_per_step": prof["prep_ms"] / args.steps}
     # ---- informational: the other kernel families, device-resident, same shape ---------------
     modes = {}
     if world == 1:
         ms1 = timed(lambda: L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1, path=L.PATH_TF32X1), max(3, args.steps // 2), 2)
+        ms3 = timed(lambda: L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1, path=L.PATH_TF32X3), max(3, args.steps // 2), 2)
+        modes["tf32x3_max_accuracy"] = {"tflops": 2.0 * M * N * K / ms3 / 1e9, "ms": ms3,
+                                        "note": "three tf32 passes (hi*lo, lo*hi, hi*hi); normwise ~5.5e-7 vs 8.7e-7 for the default"}
         modes["tf32x1_fast_mode"] = {"tflops": 2.0 * M * N * K / ms1 / 1e9, "ms": ms1, "tolerance": "normwise 2e-3 (hardware truncates fp32 -> tf32)",
                                      "frac_of_tf32_peak": 2.0 * M * N * K / ms1 / 1e9 / (peaks["bf16"] / 2.0)}
         Ab = A.view(M, K).to(torch.bfloat16); Bb = B.view(K, N).to(torch.bfloat16); Cb = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
@@ -329,7 +338,7 @@ def run_ours(args):
             "config": {"workload": "SGEMM fp32 C=A*B, per-GPU M=8192 N=K=8192 row-major, alpha=1 beta=0"
                                    + ("" if world == 1 else "; row-sharded: total M=%d, B broadcast from rank 0 over NCCL in 8 K-panels every step" % (M * world)),
                        "global_M": M * world, "N": N, "K": K, "parallelism": "rowshard%d" % world,
-                       "f32_mode": "tf32x3 (fp32-faithful, default)", "l2": "inputs larger than L2 (A+B+C = 805 MB vs 126 MB)",
+                       "f32_mode": "tf32_bf16c (fp32-faithful, default)", "l2": "inputs larger than L2 (A+B+C = 805 MB vs 126 MB)",
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "modes": modes,
         }

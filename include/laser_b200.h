@@ -43,14 +43,16 @@ extern "C" {
 #define LASER_B200_EUNSUPPORTED 5
 
 /* Which kernel family executes a float32 gemm_strided call.
- * AUTO: tensor cores (fp32-faithful 3xTF32) when the problem is large enough,
- *       exact SIMT otherwise.  The reference's analogue of this switch is its
+ * AUTO: tensor cores in the default fp32-faithful mode (TF32_BF16C) when the problem is
+ *       large enough, exact SIMT otherwise.  The reference's analogue of this switch is its
  *       run-time ISA dispatch, gemm.nim:228-247. */
 #define LASER_B200_PATH_AUTO 0
 #define LASER_B200_PATH_SIMT 1    /* exact fp32 FFMA chain, bit-equal to the CPU reference order */
 #define LASER_B200_PATH_TF32X1 2  /* tcgen05 kind::tf32, one pass (fast, ~1e-3 relative)      */
 #define LASER_B200_PATH_TF32X3 3  /* tcgen05 kind::tf32, hi/lo split, three passes (fp32-faithful) */
 #define LASER_B200_PATH_BF16 4    /* tcgen05 kind::f16 (bf16 inputs, fp32 accumulate)         */
+#define LASER_B200_PATH_TF32_BF16C 5 /* fp32-faithful, mixed: tf32 hi*hi pass + two bf16 passes for the
+                                      * hi*lo / lo*hi correction terms (2 tf32-equivalents instead of 3) */
 
 /* ---- life cycle -------------------------------------------------------
  * The reference has one piece of import-time state, cpuinfo_initialize()
@@ -74,8 +76,8 @@ int laser_b200_last_path(void);
 int laser_b200_profile_begin(void);
 int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
                            int64_t *prep_launches);
-/* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32X3 (default),
- * _TF32X1 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32x1|simt. */
+/* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32_BF16C (default), _TF32X3,
+ * _TF32X1 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|simt. */
 int laser_b200_set_f32_mode(int path);
 int laser_b200_get_f32_mode(void);
 

@@ -76,7 +76,7 @@ struct Ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  Buffer ws[4];      // A_hi/A_lo/B_hi/B_lo (or packed operands)
+  Buffer ws[8];      // per operand: hi, lo (fp32) and xb, lb (bf16) -- A then B
   Buffer stage[3];   // device staging of host A, B, C spans
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
@@ -123,9 +123,11 @@ int get_ctx(Ctx **out) {
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
-        int m = LASER_B200_PATH_TF32X3;
+        int m = LASER_B200_PATH_TF32_BF16C;
         if (mode) {
+          if (!strcmp(mode, "tf32x3")) m = LASER_B200_PATH_TF32X3;
           if (!strcmp(mode, "tf32x1")) m = LASER_B200_PATH_TF32X1;
+          else if (!strcmp(mode, "tf32_bf16c")) m = LASER_B200_PATH_TF32_BF16C;
           else if (!strcmp(mode, "simt")) m = LASER_B200_PATH_SIMT;
         }
         g_f32_mode.store(m);
@@ -261,9 +263,22 @@ int operand_map(Ctx &c, CUtensorMap *map, int esz, const void *base, Major major
                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Tensor maps (and workspace arrays) of one operand for the tensor-core kernel.
+//   hi  : the operand itself (single pass) or tf32_rna(x) in fp32 containers
+//   lo  : tf32_rna(x - hi)                       (fp32, 3-pass mode)
+//   xb  : bf16(x),  lb : bf16(x - hi)            (bf16, mixed mode)
+struct OperandMaps {
+  CUtensorMap hi, lo, xb, lb;
+  bool mn_major = false;
+};
+struct OperandWs {
+  Buffer *hi, *lo, *xb, *lb;
+};
+enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2 };
+
 template <int ESZ, typename OutT, bool PAIR>
-int launch_tc(Ctx &c, bool a_mn, bool b_mn, const CUtensorMap &a0, const CUtensorMap &a1,
-              const CUtensorMap &b0, const CUtensorMap &b1, const TcParams &p, cudaStream_t s) {
+int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, cudaStream_t s) {
+  const bool a_mn = A.mn_major, b_mn = B.mn_major;
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than tiles
   const int units = PAIR ? c.sm_count / 2 : c.sm_count;
@@ -289,7 +304,7 @@ int launch_tc(Ctx &c, bool a_mn, bool b_mn, const CUtensorMap &a0, const CUtenso
                                     TcCfg<PAIR>::SMEM_BYTES));                                   \
       attr_set = true;                                                                           \
     }                                                                                            \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, a0, a1, b0, b1, p));                                  \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
   } while (0)
   if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
   else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
@@ -301,81 +316,86 @@ int launch_tc(Ctx &c, bool a_mn, bool b_mn, const CUtensorMap &a0, const CUtenso
   return LASER_B200_OK;
 }
 
-// Prepare one fp32/bf16 operand for the tensor-core kernel.  Outputs up to two maps
-// (hi, lo) and the major-ness the kernel must be instantiated with.
 template <int ESZ>
-int prepare_operand(Ctx &c, const Operand &o, bool split, Buffer &w_hi, Buffer &w_lo, int block_mn,
-                    CUtensorMap *m_hi, CUtensorMap *m_lo, bool *mn_major, bool *used_ws,
-                    cudaStream_t s) {
+int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w, int block_mn,
+                    OperandMaps *m, bool *used_ws, cudaStream_t s) {
   using ET = typename std::conditional<ESZ == 4, float, uint16_t>::type;
   const Major mj = classify(o, ESZ);
   const int64_t vec = 16 / ESZ;
-  if (mj != GENERAL && !split) {
+  int rc;
+  if (mj != GENERAL && mode == SPLIT_NONE) {
     const int64_t ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
-    *mn_major = (mj == MN_MAJOR);
-    int rc = operand_map(c, m_hi, ESZ, o.ptr, mj, o.mn, o.k, ld, block_mn);
-    if (rc) return rc;
-    *m_lo = *m_hi;
+    m->mn_major = (mj == MN_MAJOR);
+    if ((rc = operand_map(c, &m->hi, ESZ, o.ptr, mj, o.mn, o.k, ld, block_mn))) return rc;
+    m->lo = m->xb = m->lb = m->hi;
     return LASER_B200_OK;
   }
   *used_ws = true;
+  // layout of the prepared arrays: the operand's own major-ness when TMA can address it,
+  // compact K-major [mn][k] after a gather otherwise
+  const Major out_mj = (mj == GENERAL) ? K_MAJOR : mj;
+  const int64_t R = (out_mj == K_MAJOR) ? o.mn : o.k;    // rows of the prepared arrays
+  const int64_t Cc = (out_mj == K_MAJOR) ? o.k : o.mn;   // contiguous extent
+  const int64_t ld = round_up(Cc, vec);
+  const int64_t ld_b = round_up(Cc, 8);
+  const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
+  const size_t bytes_b = static_cast<size_t>(R) * ld_b * 2;
+  if ((rc = ensure(*w.hi, bytes))) return rc;
+  if (mode == SPLIT_TF32 && (rc = ensure(*w.lo, bytes))) return rc;
+  if (mode == SPLIT_MIXED) {
+    if ((rc = ensure(*w.xb, bytes_b))) return rc;
+    if ((rc = ensure(*w.lb, bytes_b))) return rc;
+  }
   if (mj != GENERAL) {
-    // TMA-addressable: elementwise hi/lo split that keeps the operand's major-ness
+    // TMA-addressable: elementwise split that keeps the operand's major-ness (fp32 only)
     if constexpr (ESZ == 4) {
-      const int64_t R = (mj == K_MAJOR) ? o.mn : o.k;
-      const int64_t Cc = (mj == K_MAJOR) ? o.k : o.mn;
       const int64_t src_ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
-      const int64_t ld = round_up(Cc, vec);
-      const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
-      int rc = ensure(w_hi, bytes);
-      if (rc) return rc;
-      rc = ensure(w_lo, bytes);
-      if (rc) return rc;
       const int64_t items = R * ((Cc + 3) / 4);
-      split_rows_tf32_kernel<<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(
-          static_cast<const float *>(o.ptr), R, Cc, src_ld, static_cast<float *>(w_hi.ptr),
-          static_cast<float *>(w_lo.ptr), ld);
-      COUNT_LAUNCH();
-      CHECK_LAUNCH();
-      *mn_major = (mj == MN_MAJOR);
-      rc = operand_map(c, m_hi, ESZ, w_hi.ptr, mj, o.mn, o.k, ld, block_mn);
-      if (rc) return rc;
-      return operand_map(c, m_lo, ESZ, w_lo.ptr, mj, o.mn, o.k, ld, block_mn);
+      const int grid = grid_for(c, (items + 255) / 256, 8);
+      if (mode == SPLIT_TF32)
+        split_rows_tf32_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
+                                                    static_cast<float *>(w.hi->ptr),
+                                                    static_cast<float *>(w.lo->ptr), ld);
+      else
+        split_rows_mixed_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
+                                                     static_cast<float *>(w.hi->ptr), ld,
+                                                     static_cast<uint16_t *>(w.xb->ptr),
+                                                     static_cast<uint16_t *>(w.lb->ptr), ld_b);
     }
-  }
-  // general strides: one coalesced gather into a compact K-major [mn][ld] array
-  const int64_t ld = round_up(o.k, vec);
-  const size_t bytes = static_cast<size_t>(o.mn) * ld * ESZ;
-  int rc = ensure(w_hi, bytes);
-  if (rc) return rc;
-  if (split) {
-    rc = ensure(w_lo, bytes);
-    if (rc) return rc;
-  }
-  const int64_t tiles = ((o.mn + 31) / 32) * ((o.k + 31) / 32);
-  const int read_along_r = (llabs(o.s_mn) < llabs(o.s_k)) ? 1 : 0;
-  const int grid = grid_for(c, tiles, 8);
-  if constexpr (ESZ == 4) {
-    if (split)
-      pack_general_kernel<float, true><<<grid, 256, 0, s>>>(
-          static_cast<const float *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<float *>(w_hi.ptr),
-          static_cast<float *>(w_lo.ptr), ld, read_along_r);
-    else
-      pack_general_kernel<float, false><<<grid, 256, 0, s>>>(
-          static_cast<const float *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<float *>(w_hi.ptr),
-          nullptr, ld, read_along_r);
   } else {
-    pack_general_kernel<ET, false><<<grid, 256, 0, s>>>(
-        static_cast<const ET *>(o.ptr), o.mn, o.k, o.s_mn, o.s_k, static_cast<ET *>(w_hi.ptr), nullptr,
-        ld, read_along_r);
+    // general strides: one coalesced gather (the surviving descendant of pack_A / pack_B)
+    const int64_t tiles = ((o.mn + 31) / 32) * ((o.k + 31) / 32);
+    const int read_along_r = (llabs(o.s_mn) < llabs(o.s_k)) ? 1 : 0;
+    const int grid = grid_for(c, tiles, 8);
+    const ET *src = static_cast<const ET *>(o.ptr);
+    ET *dhi = static_cast<ET *>(w.hi->ptr);
+    if constexpr (ESZ == 4) {
+      if (mode == SPLIT_TF32)
+        pack_general_kernel<float, 1><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi,
+                                                           static_cast<float *>(w.lo->ptr), ld,
+                                                           read_along_r, nullptr, nullptr, 0);
+      else if (mode == SPLIT_MIXED)
+        pack_general_kernel<float, 2><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
+                                                           read_along_r, static_cast<uint16_t *>(w.xb->ptr),
+                                                           static_cast<uint16_t *>(w.lb->ptr), ld_b);
+      else
+        pack_general_kernel<float, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
+                                                           read_along_r, nullptr, nullptr, 0);
+    } else {
+      pack_general_kernel<ET, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
+                                                      read_along_r, nullptr, nullptr, 0);
+    }
   }
   COUNT_LAUNCH();
   CHECK_LAUNCH();
-  *mn_major = false;
-  rc = operand_map(c, m_hi, ESZ, w_hi.ptr, K_MAJOR, o.mn, o.k, ld, block_mn);
-  if (rc) return rc;
-  if (split) return operand_map(c, m_lo, ESZ, w_lo.ptr, K_MAJOR, o.mn, o.k, ld, block_mn);
-  *m_lo = *m_hi;
+  m->mn_major = (out_mj == MN_MAJOR);
+  if ((rc = operand_map(c, &m->hi, ESZ, w.hi->ptr, out_mj, o.mn, o.k, ld, block_mn))) return rc;
+  m->lo = m->xb = m->lb = m->hi;
+  if (mode == SPLIT_TF32) return operand_map(c, &m->lo, ESZ, w.lo->ptr, out_mj, o.mn, o.k, ld, block_mn);
+  if (mode == SPLIT_MIXED) {
+    if ((rc = operand_map(c, &m->xb, 2, w.xb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
+    return operand_map(c, &m->lb, 2, w.lb->ptr, out_mj, o.mn, o.k, ld_b, block_mn);
+  }
   return LASER_B200_OK;
 }
 
@@ -386,23 +406,24 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
     return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
   std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
-  const bool split = (npass == 3);
+  const SplitMode mode = (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
   Operand oa{A, M, K, rsA, csA};
   Operand ob{B, N, K, csB, rsB};
-  CUtensorMap a0, a1, b0, b1;
-  bool a_mn = false, b_mn = false, used_ws = false;
+  OperandMaps ma, mb;
+  bool used_ws = false;
   // the previous call may still be reading the workspace on another stream
   CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
   EventPair ep;
   const int64_t launches_before = g_launches.load();
   int rc = prof_open(c, s, &ep, 1);
   if (rc) return rc;
-  rc = prepare_operand<ESZ>(c, oa, split, c.ws[0], c.ws[1], TC_BLOCK_M, &a0, &a1, &a_mn, &used_ws, s);
+  rc = prepare_operand<ESZ>(c, oa, mode, OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3]}, TC_BLOCK_M, &ma,
+                            &used_ws, s);
   if (rc) return rc;
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
   const bool pair = c.cta_pair && M > TC_BLOCK_M;
-  rc = prepare_operand<ESZ>(c, ob, split, c.ws[2], c.ws[3], pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &b0, &b1,
-                            &b_mn, &used_ws, s);
+  rc = prepare_operand<ESZ>(c, ob, mode, OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7]},
+                            pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
@@ -413,9 +434,9 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
     // K extent accumulated inside the tensor core before the epilogue warps add the block
     // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
     // Only the fp32-faithful mode needs short chains; see gemm_tc.cuh.
-    const int block_k = TC_ROW_BYTES / ESZ;
+    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;  // scheduling unit along K
     const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
-    int kc = (npass == 3) ? c.kc_faithful : 0;
+    int kc = (npass == 3 || npass == 2) ? c.kc_faithful : 0;
     p.kb_per_block = (kc > 0) ? (kc + block_k - 1) / block_k : num_kb;
     if (p.kb_per_block < 1) p.kb_per_block = 1;
     if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
@@ -425,8 +446,8 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
   rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;
-  if (pair) rc = launch_tc<ESZ, OutT, true>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
-  else rc = launch_tc<ESZ, OutT, false>(c, a_mn, b_mn, a0, a1, b0, b1, p, s);
+  if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, p, s);
+  else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, p, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, 1);
   if (rc) return rc;
@@ -486,8 +507,9 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
       break;
     case LASER_B200_PATH_TF32X1:
     case LASER_B200_PATH_TF32X3:
+    case LASER_B200_PATH_TF32_BF16C:
       rc = gemm_tc<4, float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC,
-                             path == LASER_B200_PATH_TF32X3 ? 3 : 1, s);
+                             path == LASER_B200_PATH_TF32X3 ? 3 : (path == LASER_B200_PATH_TF32_BF16C ? 2 : 1), s);
       if (rc) return rc;
       g_last_path = path;
       break;
@@ -654,14 +676,15 @@ int laser_b200_version(void) { return 100; }
 int64_t laser_b200_launch_count(void) { return g_launches.load(); }
 int laser_b200_last_path(void) { return g_last_path; }
 int laser_b200_set_f32_mode(int path) {
-  if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3)
-    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1 or TF32X3");
+  if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3 &&
+      path != LASER_B200_PATH_TF32_BF16C)
+    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3 or TF32_BF16C");
   g_f32_mode.store(path);
   return LASER_B200_OK;
 }
 int laser_b200_get_f32_mode(void) {
   const int m = g_f32_mode.load();
-  return m < 0 ? LASER_B200_PATH_TF32X3 : m;
+  return m < 0 ? LASER_B200_PATH_TF32_BF16C : m;
 }
 
 // ---- device-resident -----------------------------------------------------------------

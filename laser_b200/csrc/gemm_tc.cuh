@@ -28,6 +28,8 @@
 // (hi*lo, lo*hi, then hi*hi) over hi/lo arrays produced by split.cuh.
 #pragma once
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace lb200 {
@@ -61,7 +63,7 @@ struct TcParams {
   float alpha, beta;
   void *C;
   int64_t rsC, csC;
-  int npass;          // 1, or 3 for the hi/lo split
+  int npass;          // 1 single pass | 3 tf32 hi/lo split | 2 mixed: tf32 hi*hi + bf16 cross terms
   int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
@@ -106,23 +108,18 @@ template <int ESZ, bool A_MN, bool B_MN, typename OutT, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+               const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3,
                const TcParams p) {
-  constexpr int BLOCK_K = TC_ROW_BYTES / ESZ;        // 32 (tf32) or 64 (bf16) elements
-  constexpr int UMMA_K = 32 / ESZ;                   // 8 or 16 elements = 32 bytes
-  constexpr int K_STEPS = BLOCK_K / UMMA_K;          // 4
-  constexpr int MN_ATOM = TC_ROW_BYTES / ESZ;        // elements per 128-byte MN chunk
-  constexpr int MN_BOX_BYTES = BLOCK_K * TC_ROW_BYTES;  // one [BLOCK_K][128 B] TMA box
-  // MN-major 32-bit operands must use the 128B-swizzle-with-32B-atoms layout (4 k-rows per atom)
-  constexpr uint32_t MN_LAYOUT = ESZ == 4 ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
-  constexpr uint32_t MN_SBO = ESZ == 4 ? 512 : 1024;
+  // K extent of one scheduling unit: a 32-element k-tile (tf32 input), a 64-element k-tile
+  // (bf16 input) or, in the mixed mode, a 64-element group = 2 bf16 correction tiles + 2 tf32 tiles
+  const bool mixed = (ESZ == 4) && (p.npass == 2);
+  const int unit_k = mixed ? 64 : TC_ROW_BYTES / ESZ;
   using Cfg = TcCfg<PAIR>;
   constexpr int TC_STAGES = Cfg::STAGES;
   constexpr int TC_B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
   constexpr int TC_STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TILE_M = PAIR ? 2 * TC_BLOCK_M : TC_BLOCK_M;  // rows of one scheduled tile
-  constexpr uint32_t IDESC =
-      ptx::make_idesc(ESZ == 4 ? ptx::kFmtTF32 : ptx::kFmtBF16, A_MN ? 1 : 0, B_MN ? 1 : 0,
-                      TILE_M, TC_BLOCK_N);
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const int sched_id = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int sched_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -142,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  const int num_kb = static_cast<int>((p.K + BLOCK_K - 1) / BLOCK_K);
+  const int num_kb = static_cast<int>((p.K + unit_k - 1) / unit_k);       // scheduling units along K
   const int num_blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
 
   if (threadIdx.x == 0) {
@@ -151,6 +148,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.npass == 3) {
       ptx::prefetch_tensormap(&mapA1);
       ptx::prefetch_tensormap(&mapB1);
+    }
+    if (mixed) {
+      ptx::prefetch_tensormap(&mapA2);
+      ptx::prefetch_tensormap(&mapA3);
+      ptx::prefetch_tensormap(&mapB2);
+      ptx::prefetch_tensormap(&mapB3);
     }
   }
   if (threadIdx.x == 32) {
@@ -186,7 +189,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if constexpr (PAIR) ptx::tma_load_2d_pair(dst, m, bar, c0, c1);  // bytes -> leader's barrier
         else ptx::tma_load_2d(dst, m, bar, c0, c1);
       };
-      auto load_stage = [&](const CUtensorMap *ma, const CUtensorMap *mbp, int m0, int n0, int k0) {
+      // E = element size of the tiles of THIS stage (4: fp32/tf32, 2: bf16)
+      auto load_stage = [&](auto esz_tag, const CUtensorMap *ma, const CUtensorMap *mbp, int m0, int n0, int k0) {
+        constexpr int E = decltype(esz_tag)::value;
+        constexpr int BLOCK_K = TC_ROW_BYTES / E;             // 32 or 64 k-elements per tile
+        [[maybe_unused]] constexpr int MN_ATOM = TC_ROW_BYTES / E;             // elements per 128-byte MN chunk
+        [[maybe_unused]] constexpr int MN_BOX_BYTES = BLOCK_K * TC_ROW_BYTES;  // one [BLOCK_K][128 B] TMA box
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if constexpr (PAIR) {
           if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * TC_STAGE_BYTES);
@@ -212,6 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       };
+      using E_in = std::integral_constant<int, ESZ>;
+      using E_bf = std::integral_constant<int, 2>;
       for (int t = sched_id; t < num_tiles; t += sched_stride) {
         int mb, nb;
         tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
@@ -220,15 +230,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n0 = nb * TC_BLOCK_N + static_cast<int>(cta_rank) * (TC_BLOCK_N - Cfg::B_COLS);
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
           const int kb1 = min(num_kb, kb0 + p.kb_per_block);
+          // the small cross terms first (the accumulator is still small, so its truncation
+          // does not touch them), then the hi*hi chain
           if (p.npass == 3) {
-            // the two small cross terms first (the accumulator is still small, so its
-            // truncation does not touch them), then the hi*hi chain
             for (int kb = kb0; kb < kb1; ++kb) {
-              load_stage(&mapA0, &mapB1, m0, n0, kb * BLOCK_K);  // A_hi * B_lo
-              load_stage(&mapA1, &mapB0, m0, n0, kb * BLOCK_K);  // A_lo * B_hi
+              load_stage(E_in{}, &mapA0, &mapB1, m0, n0, kb * unit_k);  // A_hi * B_lo
+              load_stage(E_in{}, &mapA1, &mapB0, m0, n0, kb * unit_k);  // A_lo * B_hi
             }
           }
-          for (int kb = kb0; kb < kb1; ++kb) load_stage(&mapA0, &mapB0, m0, n0, kb * BLOCK_K);
+          if constexpr (ESZ == 4) {
+            if (mixed) {
+              for (int kb = kb0; kb < kb1; ++kb) {
+                load_stage(E_bf{}, &mapA2, &mapB3, m0, n0, kb * 64);  // bf16(A) * bf16(B_lo)
+                load_stage(E_bf{}, &mapA3, &mapB2, m0, n0, kb * 64);  // bf16(A_lo) * bf16(B)
+              }
+              for (int kb = kb0; kb < kb1; ++kb) {
+                load_stage(E_in{}, &mapA0, &mapB0, m0, n0, kb * 64);
+                if (kb * 64 + 32 < p.K) load_stage(E_in{}, &mapA0, &mapB0, m0, n0, kb * 64 + 32);
+              }
+              continue;
+            }
+          }
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(E_in{}, &mapA0, &mapB0, m0, n0, kb * unit_k);
         }
       }
     } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
@@ -237,41 +260,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      uint32_t d_tmem = 0;
+      bool fresh = true;  // next MMA overwrites the accumulator (start of an accumulation block)
+      auto mma_stage = [&](auto esz_tag) {
+        constexpr int E = decltype(esz_tag)::value;
+        constexpr int BLOCK_K = TC_ROW_BYTES / E;
+        constexpr int UMMA_K = 32 / E;                        // 8 or 16 elements = 32 bytes
+        constexpr int K_STEPS = BLOCK_K / UMMA_K;             // 4
+        constexpr int MN_BOX_BYTES = BLOCK_K * TC_ROW_BYTES;
+        // MN-major 32-bit operands must use the 128B-swizzle-with-32B-atoms layout (4 k-rows per atom)
+        constexpr uint32_t MN_LAYOUT = E == 4 ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
+        constexpr uint32_t MN_SBO = E == 4 ? 512 : 1024;
+        constexpr uint32_t IDESC = ptx::make_idesc(E == 4 ? ptx::kFmtTF32 : ptx::kFmtBF16, A_MN ? 1 : 0,
+                                                   B_MN ? 1 : 0, TILE_M, TC_BLOCK_N);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TC_B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < K_STEPS; ++k) {
+          // K-major: step 32 bytes inside the 128-byte swizzle row.
+          // MN-major: step UMMA_K k-rows of 128 bytes.
+          const uint64_t ad =
+              A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                   : ptx::make_smem_desc(a_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
+          const uint64_t bd =
+              B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
+                   : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
+          const uint32_t accum = (fresh && k == 0) ? 0u : 1u;
+          if constexpr (PAIR) {
+            if constexpr (E == 4) ptx::mma_tf32_ss_pair(d_tmem, ad, bd, IDESC, accum);
+            else ptx::mma_f16_ss_pair(d_tmem, ad, bd, IDESC, accum);
+          } else {
+            if constexpr (E == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
+            else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+          }
+        }
+        fresh = false;
+        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+        if constexpr (PAIR) ptx::mma_commit_pair(&empty_bar[stage]);
+        else ptx::mma_commit(&empty_bar[stage]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      };
+      using E_in = std::integral_constant<int, ESZ>;
+      using E_bf = std::integral_constant<int, 2>;
       for (int t = sched_id; t < num_tiles; t += sched_stride) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
-          const int iters = (min(num_kb, kb0 + p.kb_per_block) - kb0) * p.npass;
+          const int kb1 = min(num_kb, kb0 + p.kb_per_block);
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + acc * TC_BLOCK_N;
-          for (int it = 0; it < iters; ++it) {
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tc_fence_after_sync();
-            const uint32_t a_addr = ptx::smem_u32(smem_a + stage * TC_A_STAGE_BYTES);
-            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * TC_B_STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < K_STEPS; ++k) {
-              // K-major: step 32 bytes inside the 128-byte swizzle row.
-              // MN-major: step UMMA_K k-rows of 128 bytes.
-              const uint64_t ad =
-                  A_MN ? ptx::make_smem_desc(a_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
-                       : ptx::make_smem_desc(a_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
-              const uint64_t bd =
-                  B_MN ? ptx::make_smem_desc(b_addr + k * UMMA_K * TC_ROW_BYTES, MN_BOX_BYTES, MN_SBO, MN_LAYOUT)
-                       : ptx::make_smem_desc(b_addr + k * 32, 0, 1024, ptx::kLayoutSw128);
-              const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-              if constexpr (PAIR) {
-                if constexpr (ESZ == 4) ptx::mma_tf32_ss_pair(d_tmem, ad, bd, IDESC, accum);
-                else ptx::mma_f16_ss_pair(d_tmem, ad, bd, IDESC, accum);
-              } else {
-                if constexpr (ESZ == 4) ptx::mma_tf32_ss(d_tmem, ad, bd, IDESC, accum);
-                else ptx::mma_f16_ss(d_tmem, ad, bd, IDESC, accum);
+          d_tmem = tmem_base + acc * TC_BLOCK_N;
+          fresh = true;
+          bool done = false;
+          if (p.npass == 3)
+            for (int kb = kb0; kb < kb1; ++kb) { mma_stage(E_in{}); mma_stage(E_in{}); }
+          if constexpr (ESZ == 4) {
+            if (mixed) {
+              for (int kb = kb0; kb < kb1; ++kb) { mma_stage(E_bf{}); mma_stage(E_bf{}); }
+              for (int kb = kb0; kb < kb1; ++kb) {
+                mma_stage(E_in{});
+                if (kb * 64 + 32 < p.K) mma_stage(E_in{});
               }
+              done = true;
             }
-            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-            if constexpr (PAIR) ptx::mma_commit_pair(&empty_bar[stage]);
-            else ptx::mma_commit(&empty_bar[stage]);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
+          if (!done)
+            for (int kb = kb0; kb < kb1; ++kb) mma_stage(E_in{});
           // block complete -> the epilogue warps (of both CTAs) drain it
           if constexpr (PAIR) ptx::mma_commit_pair(&tmem_full[acc]);
           else ptx::mma_commit(&tmem_full[acc]);

@@ -56,13 +56,58 @@ split_rows_tf32_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int
   }
 }
 
+__device__ __forceinline__ uint16_t bf16_rn_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// Mixed-precision split: hi = tf32_rna(x) (fp32 container, feeds the tf32 hi*hi pass),
+// xb = bf16(x) and lb = bf16(x - hi) (feed the two bf16 cross-term passes, which run at twice
+// the tf32 rate).  Same addressing as split_rows_tf32_kernel; bf16 rows have pitch ld_b.
+__global__ void __launch_bounds__(256)
+split_rows_mixed_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
+                        float *__restrict__ hi, int64_t dst_ld, uint16_t *__restrict__ xb,
+                        uint16_t *__restrict__ lb, int64_t ld_b) {
+  const int64_t vec_per_row = (Cc + 3) >> 2;
+  const int64_t total = R * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int64_t c = (i - r * vec_per_row) << 2;
+    const float *s = src + r * src_ld + c;
+    float4 v;
+    if (c + 4 <= Cc) {
+      v = *reinterpret_cast<const float4 *>(s);
+    } else {
+      v.x = s[0];
+      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
+      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
+      v.w = 0.0f;
+    }
+    float4 h;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    *reinterpret_cast<float4 *>(hi + r * dst_ld + c) = h;
+    uint2 b, l;
+    b.x = bf16_rn_bits(v.x) | (static_cast<uint32_t>(bf16_rn_bits(v.y)) << 16);
+    b.y = bf16_rn_bits(v.z) | (static_cast<uint32_t>(bf16_rn_bits(v.w)) << 16);
+    l.x = bf16_rn_bits(v.x - h.x) | (static_cast<uint32_t>(bf16_rn_bits(v.y - h.y)) << 16);
+    l.y = bf16_rn_bits(v.z - h.z) | (static_cast<uint32_t>(bf16_rn_bits(v.w - h.w)) << 16);
+    *reinterpret_cast<uint2 *>(xb + r * ld_b + c) = b;
+    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
+  }
+}
+
 // dst[r*ld + c] = src[r*sr + c*sc] for r < R, c < Cc.  32 x 32 tiles through shared
 // memory so that both the gather (along whichever source stride is smaller) and the
 // store (along c) are coalesced.  SPLIT: also write lo (fp32 only).
-template <typename T, bool SPLIT>
+// MODE 0: plain copy; 1: fp32 hi/lo (dst, dst_lo); 2: mixed (dst = hi fp32, xb/lb = bf16 arrays).
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr, int64_t sc,
-                    T *__restrict__ dst, T *__restrict__ dst_lo, int64_t ld, int read_along_r) {
+                    T *__restrict__ dst, T *__restrict__ dst_lo, int64_t ld, int read_along_r,
+                    uint16_t *__restrict__ xb, uint16_t *__restrict__ lb, int64_t ld_b) {
   __shared__ T tile[32][33];
   const int64_t tiles_c = (Cc + 31) >> 5;
   const int64_t tiles_r = (R + 31) >> 5;
@@ -88,10 +133,15 @@ pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr
       const int64_t r = r0 + ty + i * 8, c = c0 + tx;
       if (r < R && c < Cc) {
         const T v = tile[ty + i * 8][tx];
-        if constexpr (SPLIT) {
+        if constexpr (MODE == 1) {
           const float h = tf32_rna(v);
           dst[r * ld + c] = h;
           dst_lo[r * ld + c] = tf32_rna(v - h);
+        } else if constexpr (MODE == 2) {
+          const float h = tf32_rna(v);
+          dst[r * ld + c] = h;
+          xb[r * ld_b + c] = bf16_rn_bits(v);
+          lb[r * ld_b + c] = bf16_rn_bits(v - h);
         } else {
           dst[r * ld + c] = v;
         }

@@ -18,8 +18,8 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, LaserB200Error,
-                    check, lib)
+from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32_BF16C, PATH_TF32X1, PATH_TF32X3,
+                    LaserB200Error, check, lib)
 
 __all__ = ["gemm_strided", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",
            "fill_uniform_f32", "init", "shutdown", "synchronize", "profile_begin", "profile_end"]

@@ -1,7 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
 oracle on identical inputs.  Bars:
   * integer / SIMT paths: BIT-EXACT with the oracle (same order of operations);
-  * fp32 tensor-core, 3xTF32 (default): max |ours-ref|/|ref| < 1e-4 on U(0,1) inputs
+  * fp32 tensor-core, fp32-faithful modes (TF32_BF16C = default, TF32X3): max |ours-ref|/|ref| < 1e-4 on U(0,1) inputs
     (BASELINE.json gate), normwise < 2e-6 and mean_relative_error <= 1e-5 (the reference's
     own gate, gemm_bench_float32.nim:365-367) on U(-0.1,0.1);
   * fp32 tensor-core, 1xTF32 (opt-in fast mode): normwise < 2e-3;
@@ -20,7 +20,8 @@ torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
 
 NP = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
-F32_PATHS = [L.PATH_SIMT, L.PATH_TF32X1, L.PATH_TF32X3]
+F32_PATHS = [L.PATH_SIMT, L.PATH_TF32X1, L.PATH_TF32X3, L.PATH_TF32_BF16C]
+FAITHFUL = (L.PATH_TF32X3, L.PATH_TF32_BF16C)   # fp32-faithful tensor-core modes (same gates)
 
 
 def dev(buf):
@@ -116,7 +117,7 @@ def test_every_stride_class(la, lb, lc, path):
     if path == L.PATH_SIMT:
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     else:
-        tol = 1e-4 if path == L.PATH_TF32X3 else 5e-3
+        tol = 1e-4 if path in FAITHFUL else 5e-3
         assert O.max_relative_error(got, want) < tol, O.max_relative_error(got, want)
     mask = np.ones(after.size, bool); mask[(oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc).ravel()] = False
     assert np.array_equal(after[mask], before[mask])
@@ -126,13 +127,14 @@ def test_every_stride_class(la, lb, lc, path):
 TC_SHAPES = [(128, 256, 32), (256, 512, 4096), (300, 500, 1000), (1000, 777, 513), (4096, 128, 64), (129, 257, 8200)]
 
 
+@pytest.mark.parametrize("path", FAITHFUL)
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_tf32x3_meets_fp32_gates(shape):
+def test_faithful_modes_meet_fp32_gates(shape, path):
     M, N, K = shape
     for seed, lo, hi in ((42, 0.0, 1.0), (42, -0.1, 0.1)):
         A = O.fill_uniform_f32(M * K, seed, lo, hi).reshape(M, K); B = O.fill_uniform_f32(K * N, seed + 1, lo, hi).reshape(K, N)
         want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, want, N, 1)
-        got, *_ = run_dev("f32", M, N, K, 1.0, A, "row", B, "row", 0.0, np.full((M, N), np.nan, np.float32), "row", L.PATH_TF32X3)
+        got, *_ = run_dev("f32", M, N, K, 1.0, A, "row", B, "row", 0.0, np.full((M, N), np.nan, np.float32), "row", path)
         assert O.normwise_relative_error(got, want) < 2e-6
         if lo >= 0:
             assert O.max_relative_error(got, want) < 1e-4     # BASELINE.json gate (P inputs)
@@ -193,7 +195,7 @@ def test_host_pointer_entry_strided(la, lb, lc):
         ba, oa, rsa, csa = embed(A, la); bb, ob, rsb, csb = embed(B, lb); bc, oc, rsc, csc = embed(C0, lc)
         before = bc.copy()
         L.gemm_strided(M, N, K, alpha, ba[oa:], rsa, csa, bb[ob:], rsb, csb, beta, bc[oc:], rsc, csc)
-        assert L.last_path() == L.PATH_TF32X3
+        assert L.last_path() == L.PATH_TF32_BF16C     # the default fp32-faithful mode
         got = extract(bc, oc, rsc, csc, M, N)
         assert O.max_relative_error(got, want) < 1e-4
         mask = np.ones(bc.size, bool); mask[(oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc).ravel()] = False
@@ -206,7 +208,7 @@ def test_auto_path_selection():
     assert L.last_path() == L.PATH_SIMT            # M*N*K <= 128^3: exact kernel (gemm.nim:140-141 threshold)
     a = dev(np.ones(256 * 256, np.float32)); c = dev(np.zeros(256 * 256, np.float32))
     L.gemm_strided(256, 256, 256, 1.0, a, 256, 1, a, 256, 1, 0.0, c, 256, 1)
-    assert L.last_path() == L.PATH_TF32X3
+    assert L.last_path() == L.PATH_TF32_BF16C
     torch.cuda.synchronize()
     assert np.all(c.cpu().numpy() == 256.0)
 
@@ -271,7 +273,7 @@ def test_full_size_sgemm_sampled_rows(n):
     L.fill_uniform_f32(tA, M * K, 42, 0, 1); L.fill_uniform_f32(tB, K * N, 43, 0, 1)
     tC = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
     L.gemm_strided(M, N, K, 1.0, tA, K, 1, tB, N, 1, 0.0, tC, N, 1)
-    assert L.last_path() == L.PATH_TF32X3
+    assert L.last_path() == L.PATH_TF32_BF16C
     torch.cuda.synchronize()
     assert not torch.isnan(tC).any()
     rows = np.unique(np.random.default_rng(0).integers(0, M, 48))
@@ -295,13 +297,13 @@ def test_full_size_transposed_a_4096():
     M = N = K = 4096
     tAt = torch.empty(K * M, dtype=torch.float32, device="cuda"); tB = torch.empty(K * N, dtype=torch.float32, device="cuda")
     L.fill_uniform_f32(tAt, K * M, 44, 0, 1); L.fill_uniform_f32(tB, K * N, 45, 0, 1)
-    for path in (L.PATH_TF32X3, L.PATH_TF32X1):
+    for path in (L.PATH_TF32_BF16C, L.PATH_TF32X3, L.PATH_TF32X1):
         tC = torch.empty((M, N), dtype=torch.float32, device="cuda")
         L.gemm_strided(M, N, K, 1.0, tAt, 1, M, tB, N, 1, 0.0, tC, N, 1, path=path)
         torch.cuda.synchronize()
         rows = np.unique(np.random.default_rng(1).integers(0, M, 32))
         A_logical = tAt.view(K, M).t()
-        _rows_check(M, N, K, A_logical, tB.view(K, N), tC, rows, 1e-4 if path == L.PATH_TF32X3 else 5e-3)
+        _rows_check(M, N, K, A_logical, tB.view(K, N), tC, rows, 1e-4 if path in FAITHFUL else 5e-3)
 
 
 def test_full_size_bf16_8192():
