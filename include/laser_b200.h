@@ -143,6 +143,35 @@ int laser_b200_gemm_strided_bf16_dev(int64_t M, int64_t N, int64_t K, float alph
                                      float beta, uint16_t *C, int64_t rowStrideC, int64_t colStrideC,
                                      void *stream);
 
+/* ---- pre-packed operands (device) -----------------------------------------
+ * Replaces  gemm_prepackA_mem_required / gemm_prepackB_mem_required, gemm_prepackA / gemm_prepackB
+ * and gemm_packed   (laser/primitives/matrix_multiplication/gemm_prepacked.nim:63-292).
+ * The reference packs an operand once into micro-panels so that repeated products with the same
+ * matrix skip the packing pass; here "packing" is the operand preparation of the default
+ * fp32-faithful mode (tf32 hi part + bf16 cross-term parts, K-major compact), so repeated
+ * products skip the split pre-pass and read TMA-friendly K-major tiles whatever the source
+ * strides were.  Packed buffers are opaque DEVICE memory owned by the caller, sized by
+ * *_mem_required (bytes), 256-byte aligned; like the reference's they are only meaningful to the
+ * library build that wrote them ("unsafe to store or serialize", gemm_prepacked.nim:120-123).
+ * M, N, K are the extents of the product the operand will take part in (A is M x K, B is K x N). */
+size_t laser_b200_gemm_prepackA_mem_required_f32(int64_t M, int64_t N, int64_t K);
+size_t laser_b200_gemm_prepackB_mem_required_f32(int64_t M, int64_t N, int64_t K);
+int laser_b200_gemm_prepackA_f32_dev(void *dst_packedA, int64_t M, int64_t N, int64_t K,
+                                     const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                     void *stream);
+int laser_b200_gemm_prepackB_f32_dev(void *dst_packedB, int64_t M, int64_t N, int64_t K,
+                                     const float *B, int64_t rowStrideB, int64_t colStrideB,
+                                     void *stream);
+/* C <- alpha * A*B + beta * C with both operands pre-packed (gemm_packed, gemm_prepacked.nim:275-292) */
+int laser_b200_gemm_packed_f32_dev(int64_t M, int64_t N, int64_t K, float alpha,
+                                   const void *packedA, const void *packedB, float beta, float *C,
+                                   int64_t rowStrideC, int64_t colStrideC, void *stream);
+/* the common case: a fixed (pre-packed) B, a fresh A with any strides */
+int laser_b200_gemm_packedB_f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                    int64_t rowStrideA, int64_t colStrideA, const void *packedB,
+                                    float beta, float *C, int64_t rowStrideC, int64_t colStrideC,
+                                    void *stream);
+
 /* ---- device storage for the Tensor contract ----------------------------
  * Device analogue of allocCpuStorage (laser/tensor/allocator.nim:17-29: 64-byte
  * aligned, owned by the storage object) and of copyFromRaw / setZero

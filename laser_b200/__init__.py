@@ -9,6 +9,8 @@ from ._capi import (PATH_AUTO, PATH_BF16, PATH_NAMES, PATH_SIMT, PATH_TF32_BF16C
 from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, get_f32_mode, init, last_path,
                    launch_count, profile_begin, profile_end, set_f32_mode, shutdown,
                    synchronize)
+from .prepacked import (alloc_packed, gemm_packed, gemm_packedB, gemm_prepackA, gemm_prepackA_mem_required,
+                        gemm_prepackB, gemm_prepackB_mem_required)
 from .tensor import LASER_MAXRANK, Storage, Tensor, matmul, newTensor, toTensor
 
 __version__ = "0.1.0"

@@ -54,6 +54,12 @@ SIGNATURES = {
     "laser_b200_gemm_strided_i32_dev": (ctypes.c_int, _gemm_sig(i32) + [vp]),
     "laser_b200_gemm_strided_i64_dev": (ctypes.c_int, _gemm_sig(i64) + [vp]),
     "laser_b200_gemm_strided_bf16_dev": (ctypes.c_int, _gemm_sig(f32) + [vp]),
+    "laser_b200_gemm_prepackA_mem_required_f32": (sz, [i64, i64, i64]),
+    "laser_b200_gemm_prepackB_mem_required_f32": (sz, [i64, i64, i64]),
+    "laser_b200_gemm_prepackA_f32_dev": (ctypes.c_int, [vp, i64, i64, i64, vp, i64, i64, vp]),
+    "laser_b200_gemm_prepackB_f32_dev": (ctypes.c_int, [vp, i64, i64, i64, vp, i64, i64, vp]),
+    "laser_b200_gemm_packed_f32_dev": (ctypes.c_int, [i64, i64, i64, f32, vp, vp, f32, vp, i64, i64, vp]),
+    "laser_b200_gemm_packedB_f32_dev": (ctypes.c_int, [i64, i64, i64, f32, vp, i64, i64, vp, f32, vp, i64, i64, vp]),
     "laser_b200_malloc": (ctypes.c_int, [ctypes.POINTER(vp), sz]),
     "laser_b200_free": (ctypes.c_int, [vp]),
     "laser_b200_memcpy_h2d": (ctypes.c_int, [vp, vp, sz]),

@@ -74,7 +74,9 @@ struct Ctx {
   std::vector<EventPair> prof;
   int dev = -1;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;          // compute (and default) stream of the library
+  cudaStream_t up = nullptr, down = nullptr;  // H2D / D2H streams of the pipelined host entry
+  std::vector<cudaEvent_t> panel_ev;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   Buffer ws[8];      // per operand: hi, lo (fp32) and xb, lb (bf16) -- A then B
   Buffer stage[3];   // device staging of host A, B, C spans
@@ -109,6 +111,8 @@ int get_ctx(Ctx **out) {
       c.dev = dev;
       c.sm_count = prop.multiProcessorCount;
       CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&c.up, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&c.down, cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&c.ws_free, cudaEventDisableTiming));
       void *fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
@@ -399,41 +403,24 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   return LASER_B200_OK;
 }
 
+inline SplitMode split_mode(int npass) {
+  return (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
+}
+inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3]}; }
+inline OperandWs ws_of_B(Ctx &c) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7]}; }
+
+// launch the tensor-core kernel on prepared operands (c.mu held by the caller)
 template <int ESZ, typename OutT>
-int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
-            int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
-            int64_t csC, int npass, cudaStream_t s) {
-  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
-    return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
-  std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
-  const SplitMode mode = (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
-  Operand oa{A, M, K, rsA, csA};
-  Operand ob{B, N, K, csB, rsB};
-  OperandMaps ma, mb;
-  bool used_ws = false;
-  // the previous call may still be reading the workspace on another stream
-  CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
-  EventPair ep;
-  const int64_t launches_before = g_launches.load();
-  int rc = prof_open(c, s, &ep, 1);
-  if (rc) return rc;
-  rc = prepare_operand<ESZ>(c, oa, mode, OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3]}, TC_BLOCK_M, &ma,
-                            &used_ws, s);
-  if (rc) return rc;
-  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
-  const bool pair = c.cta_pair && M > TC_BLOCK_M;
-  rc = prepare_operand<ESZ>(c, ob, mode, OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7]},
-                            pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
-  if (rc) return rc;
-  rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
-  if (rc) return rc;
+int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMaps &ma,
+           const OperandMaps &mb, float beta, OutT *C, int64_t rsC, int64_t csC, int npass, bool pair,
+           cudaStream_t s) {
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0;
   {
     // K extent accumulated inside the tensor core before the epilogue warps add the block
     // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
-    // Only the fp32-faithful mode needs short chains; see gemm_tc.cuh.
+    // Only the fp32-faithful modes need short chains; see gemm_tc.cuh.
     const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;  // scheduling unit along K
     const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
     int kc = (npass == 3 || npass == 2) ? c.kc_faithful : 0;
@@ -444,15 +431,140 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
   p.num_m_blocks = static_cast<int>((M + tile_m - 1) / tile_m);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
-  rc = prof_open(c, s, &ep, 0);
+  EventPair ep;
+  int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;
   if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, p, s);
   else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, p, s);
   if (rc) return rc;
-  rc = prof_close(c, s, &ep, 1);
+  return prof_close(c, s, &ep, 1);
+}
+
+template <int ESZ, typename OutT>
+int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
+            int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
+            int64_t csC, int npass, cudaStream_t s) {
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
+    return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
+  std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
+  const SplitMode mode = split_mode(npass);
+  Operand oa{A, M, K, rsA, csA};
+  Operand ob{B, N, K, csB, rsB};
+  OperandMaps ma, mb;
+  bool used_ws = false;
+  // the previous call may still be reading the workspace on another stream
+  CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
+  EventPair ep;
+  const int64_t launches_before = g_launches.load();
+  int rc = prof_open(c, s, &ep, 1);
+  if (rc) return rc;
+  rc = prepare_operand<ESZ>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
+  if (rc) return rc;
+  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
+  const bool pair = c.cta_pair && M > TC_BLOCK_M;
+  rc = prepare_operand<ESZ>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
+  if (rc) return rc;
+  rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
+  if (rc) return rc;
+  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+//                      pre-packed operands (gemm_prepacked.nim:63-292)
+// ---------------------------------------------------------------------------------------
+// Layout of a packed operand seen as [mn][k] (A: mn = M, B: mn = N), a pure function of (mn, k):
+//   [hi : mn x ld  fp32][xb : mn x ld_b bf16][lb : mn x ld_b bf16], sections 256-byte aligned,
+//   ld = round_up(k, 4), ld_b = round_up(k, 8): compact K-major arrays of the mixed mode.
+int finish(Ctx &c, cudaStream_t user, cudaStream_t s);
+
+struct PackedLayout {
+  int64_t ld, ld_b;
+  size_t off_hi, off_xb, off_lb, bytes;
+};
+inline PackedLayout packed_layout(int64_t mn, int64_t k) {
+  PackedLayout L;
+  L.ld = round_up(k, 4);
+  L.ld_b = round_up(k, 8);
+  auto al = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+  L.off_hi = 0;
+  L.off_xb = al(static_cast<size_t>(mn) * L.ld * 4);
+  L.off_lb = L.off_xb + al(static_cast<size_t>(mn) * L.ld_b * 2);
+  L.bytes = L.off_lb + al(static_cast<size_t>(mn) * L.ld_b * 2);
+  return L;
+}
+
+int prepack_dev(void *dst, int64_t mn, int64_t k, const float *src, int64_t s_mn, int64_t s_k,
+                void *stream) {
+  if (mn < 0 || k < 0) return set_error(LASER_B200_EINVAL, "negative extent");
+  if (mn == 0 || k == 0) return LASER_B200_OK;
+  if (!dst || !src) return set_error(LASER_B200_EINVAL, "null pointer");
+  if (reinterpret_cast<uintptr_t>(dst) & 255) return set_error(LASER_B200_EINVAL, "packed buffer must be 256-byte aligned");
+  Ctx *c;
+  int rc = get_ctx(&c);
+  if (rc) return rc;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const PackedLayout L = packed_layout(mn, k);
+  uint8_t *base = static_cast<uint8_t *>(dst);
+  const int64_t tiles = ((mn + 31) / 32) * ((k + 31) / 32);
+  const int read_along_r = (llabs(s_mn) < llabs(s_k)) ? 1 : 0;
+  pack_general_kernel<float, 2><<<grid_for(*c, tiles, 8), 256, 0, s>>>(
+      src, mn, k, s_mn, s_k, reinterpret_cast<float *>(base + L.off_hi), nullptr, L.ld, read_along_r,
+      reinterpret_cast<uint16_t *>(base + L.off_xb), reinterpret_cast<uint16_t *>(base + L.off_lb), L.ld_b);
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return finish(*c, static_cast<cudaStream_t>(stream), s);
+}
+
+int packed_maps(Ctx &c, const void *packed, int64_t mn, int64_t k, int block_mn, OperandMaps *m) {
+  const PackedLayout L = packed_layout(mn, k);
+  const uint8_t *base = static_cast<const uint8_t *>(packed);
+  int rc;
+  m->mn_major = false;
+  if ((rc = operand_map(c, &m->hi, 4, base + L.off_hi, K_MAJOR, mn, k, L.ld, block_mn))) return rc;
+  m->lo = m->hi;
+  if ((rc = operand_map(c, &m->xb, 2, base + L.off_xb, K_MAJOR, mn, k, L.ld_b, block_mn))) return rc;
+  return operand_map(c, &m->lb, 2, base + L.off_lb, K_MAJOR, mn, k, L.ld_b, block_mn);
+}
+
+// A: either raw (A != nullptr) or packed (packedA != nullptr); B always packed
+int gemm_packed_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA,
+                    int64_t csA, const void *packedA, const void *packedB, float beta, float *C,
+                    int64_t rsC, int64_t csC, void *stream) {
+  if (M < 0 || N < 0 || K < 0) return set_error(LASER_B200_EINVAL, "negative extent");
+  if (M == 0 || N == 0 || K == 0) return LASER_B200_OK;
+  if ((!A && !packedA) || !packedB || !C) return set_error(LASER_B200_EINVAL, "null pointer");
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
+    return set_error(LASER_B200_EUNSUPPORTED, "extents must fit in int32");
+  Ctx *cp;
+  int rc = get_ctx(&cp);
+  if (rc) return rc;
+  Ctx &c = *cp;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    const bool pair = c.cta_pair && M > TC_BLOCK_M;
+    OperandMaps ma, mb;
+    bool used_ws = false;
+    if (packedA) {
+      if ((rc = packed_maps(c, packedA, M, K, TC_BLOCK_M, &ma))) return rc;
+    } else {
+      CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
+      Operand oa{A, M, K, rsA, csA};
+      EventPair ep;
+      const int64_t before = g_launches.load();
+      if ((rc = prof_open(c, s, &ep, 1))) return rc;
+      if ((rc = prepare_operand<4>(c, oa, SPLIT_MIXED, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s))) return rc;
+      if ((rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - before)))) return rc;
+    }
+    if ((rc = packed_maps(c, packedB, N, K, pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb))) return rc;
+    if ((rc = tc_run<4, float>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, 2, pair, s))) return rc;
+    if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
+  }
+  g_last_path = LASER_B200_PATH_TF32_BF16C;
+  return finish(c, static_cast<cudaStream_t>(stream), s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -570,6 +682,90 @@ Span span_of(int64_t rows, int64_t cols, int64_t rs, int64_t cs) {
   return sp;
 }
 
+// Host-pointer fp32 GEMM, pipelined over row panels (the drop-in call's fast path).
+// PCIe is the bound of a host-resident GEMM (805 MB cross the bus for 1.1 TFLOP at 8192^3), so
+// the three phases run on three streams: B is uploaded and prepared once; then row panel p+1 of
+// A is in flight H2D while panel p is split + multiplied and panel p-1 of C returns D2H.
+// Preconditions (checked by the caller): tensor-core path, row panels of A and of C are
+// (nearly) disjoint address ranges, beta == 0 and C dense inside each panel span.
+struct PanelPlan {
+  int64_t rows;   // rows per panel
+  int panels;
+};
+inline bool panel_separable(int64_t rows, int64_t cols, int64_t rs, int64_t cs) {
+  // a panel of `rows` consecutive rows must cover an address span not much larger than its data
+  const Span sp = span_of(rows, cols, rs, cs);
+  const double span = static_cast<double>(sp.hi - sp.lo + 1);
+  return llabs(rs) >= llabs(cs) && span <= 1.25 * static_cast<double>(rows) * static_cast<double>(cols);
+}
+
+int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                            int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
+                            float beta, float *C, int64_t rsC, int64_t csC, int npass) {
+  std::lock_guard<std::mutex> host_lk(c.host_mu);
+  std::lock_guard<std::mutex> lk(c.mu);
+  int rc;
+  const int64_t panel_rows = 1024;
+  const int panels = static_cast<int>((M + panel_rows - 1) / panel_rows);
+  const Span sa = span_of(M, K, rsA, csA), sb = span_of(K, N, rsB, csB), sc = span_of(M, N, rsC, csC);
+  const size_t na = static_cast<size_t>(sa.hi - sa.lo + 1) * 4, nb = static_cast<size_t>(sb.hi - sb.lo + 1) * 4;
+  const size_t nc = static_cast<size_t>(sc.hi - sc.lo + 1) * 4;
+  if ((rc = ensure(c.stage[0], na + 256))) return rc;
+  if ((rc = ensure(c.stage[1], nb + 256))) return rc;
+  if ((rc = ensure(c.stage[2], nc + 256))) return rc;
+  float *dA = static_cast<float *>(c.stage[0].ptr) - sa.lo;   // device address of element A[0,0]
+  float *dB = static_cast<float *>(c.stage[1].ptr) - sb.lo;
+  float *dC = static_cast<float *>(c.stage[2].ptr) - sc.lo;
+  if (static_cast<int>(c.panel_ev.size()) < 2 * panels + 1) {
+    const size_t old = c.panel_ev.size();
+    c.panel_ev.resize(2 * panels + 1);
+    for (size_t i = old; i < c.panel_ev.size(); ++i)
+      CUDA_TRY(cudaEventCreateWithFlags(&c.panel_ev[i], cudaEventDisableTiming));
+  }
+  cudaStream_t up = c.up, cmp = c.stream, down = c.down;
+  const SplitMode mode = split_mode(npass);
+  const bool pair = c.cta_pair && panel_rows > TC_BLOCK_M && M > TC_BLOCK_M;
+  // staging buffers / workspace may still be in use by an earlier call
+  CUDA_TRY(cudaStreamWaitEvent(up, c.ws_free, 0));
+  CUDA_TRY(cudaStreamWaitEvent(cmp, c.ws_free, 0));
+  // ---- B: upload once, prepare once ----
+  CUDA_TRY(cudaMemcpyAsync(dB + sb.lo, B + sb.lo, nb, cudaMemcpyHostToDevice, up));
+  CUDA_TRY(cudaEventRecord(c.panel_ev[2 * panels], up));
+  CUDA_TRY(cudaStreamWaitEvent(cmp, c.panel_ev[2 * panels], 0));
+  OperandMaps mb;
+  bool used_ws = false;
+  Operand ob{dB, N, K, csB, rsB};
+  if ((rc = prepare_operand<4>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, cmp)))
+    return rc;
+  // ---- row panels ----
+  for (int pnl = 0; pnl < panels; ++pnl) {
+    const int64_t m0 = pnl * panel_rows;
+    const int64_t mp = (M - m0 < panel_rows) ? (M - m0) : panel_rows;
+    const float *Ap = A + m0 * rsA;
+    float *Cp = C + m0 * rsC;
+    const Span pa = span_of(mp, K, rsA, csA), pc = span_of(mp, N, rsC, csC);
+    CUDA_TRY(cudaMemcpyAsync(dA + m0 * rsA + pa.lo, Ap + pa.lo, static_cast<size_t>(pa.hi - pa.lo + 1) * 4,
+                             cudaMemcpyHostToDevice, up));
+    CUDA_TRY(cudaEventRecord(c.panel_ev[pnl], up));
+    CUDA_TRY(cudaStreamWaitEvent(cmp, c.panel_ev[pnl], 0));
+    OperandMaps ma;
+    Operand oa{dA + m0 * rsA, mp, K, rsA, csA};
+    if ((rc = prepare_operand<4>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, cmp))) return rc;
+    if ((rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass,
+                               pair && mp > TC_BLOCK_M, cmp)))
+      return rc;
+    CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));
+    CUDA_TRY(cudaStreamWaitEvent(down, c.panel_ev[panels + pnl], 0));
+    CUDA_TRY(cudaMemcpyAsync(Cp + pc.lo, dC + m0 * rsC + pc.lo, static_cast<size_t>(pc.hi - pc.lo + 1) * 4,
+                             cudaMemcpyDeviceToHost, down));
+  }
+  CUDA_TRY(cudaEventRecord(c.ws_free, cmp));
+  CUDA_TRY(cudaStreamSynchronize(down));
+  CUDA_TRY(cudaStreamSynchronize(cmp));
+  g_last_path = (npass == 3) ? LASER_B200_PATH_TF32X3 : (npass == 2 ? LASER_B200_PATH_TF32_BF16C : LASER_B200_PATH_TF32X1);
+  return LASER_B200_OK;
+}
+
 template <typename T, typename Fn>
 int host_gemm(int64_t M, int64_t N, int64_t K, const T *A, int64_t rsA, int64_t csA, const T *B,
               int64_t rsB, int64_t csB, bool beta_zero, T *C, int64_t rsC, int64_t csC, Fn run) {
@@ -627,7 +823,11 @@ void laser_b200_shutdown(void) {
     for (auto &b : c.ws) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     cudaEventDestroy(c.ws_free);
+    for (auto e : c.panel_ev) cudaEventDestroy(e);
+    c.panel_ev.clear();
     cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.up);
+    cudaStreamDestroy(c.down);
     c.ready = false;
   }
   cudaSetDevice(cur);
@@ -723,6 +923,20 @@ int laser_b200_gemm_strided_bf16_dev(int64_t M, int64_t N, int64_t K, float alph
 int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                                 int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
                                 float beta, float *C, int64_t rsC, int64_t csC) {
+  // large tensor-core problems whose row panels are separate address ranges: overlap the
+  // PCIe transfers with the compute, panel by panel
+  if (M >= 2048 && N > 4 && K > 0 && A && B && C && beta == 0.0f &&
+      M <= 0x7fffffffLL && N <= 0x7fffffffLL && K <= 0x7fffffffLL) {
+    Ctx *c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    const int mode = g_f32_mode.load();
+    const int npass = mode == LASER_B200_PATH_TF32X3 ? 3 : mode == LASER_B200_PATH_TF32_BF16C ? 2
+                      : mode == LASER_B200_PATH_TF32X1 ? 1 : 0;
+    if (npass && panel_separable(1024, K, rsA, csA) && panel_separable(1024, N, rsC, csC) &&
+        span_of(1024, N, rsC, csC).dense && rsA > 0 && rsC > 0)
+      return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, npass);
+  }
   return host_gemm<float>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0f, C, rsC, csC,
                           [&](const float *a, const float *b, float *c, void *s) {
                             return f32_dev(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c, rsC, csC,
@@ -764,6 +978,37 @@ int laser_b200_gemm_strided_bf16(int64_t M, int64_t N, int64_t K, float alpha, c
                                return bf16_dev(M, N, K, alpha, a, rsA, csA, b, rsB, csB, beta, c, rsC,
                                                csC, s);
                              });
+}
+
+// ---- pre-packed operands (gemm_prepacked.nim:63-292) --------------------------------------
+size_t laser_b200_gemm_prepackA_mem_required_f32(int64_t M, int64_t N, int64_t K) {
+  (void)N;
+  return (M > 0 && K > 0) ? packed_layout(M, K).bytes : 0;
+}
+size_t laser_b200_gemm_prepackB_mem_required_f32(int64_t M, int64_t N, int64_t K) {
+  (void)M;
+  return (N > 0 && K > 0) ? packed_layout(N, K).bytes : 0;
+}
+int laser_b200_gemm_prepackA_f32_dev(void *dst, int64_t M, int64_t N, int64_t K, const float *A,
+                                     int64_t rsA, int64_t csA, void *stream) {
+  (void)N;
+  return prepack_dev(dst, M, K, A, rsA, csA, stream);
+}
+int laser_b200_gemm_prepackB_f32_dev(void *dst, int64_t M, int64_t N, int64_t K, const float *B,
+                                     int64_t rsB, int64_t csB, void *stream) {
+  (void)M;
+  return prepack_dev(dst, N, K, B, csB, rsB, stream);   // B seen as [n][k]
+}
+int laser_b200_gemm_packed_f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const void *packedA,
+                                   const void *packedB, float beta, float *C, int64_t rsC, int64_t csC,
+                                   void *stream) {
+  return gemm_packed_dev(M, N, K, alpha, nullptr, 0, 0, packedA, packedB, beta, C, rsC, csC, stream);
+}
+int laser_b200_gemm_packedB_f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                    int64_t rsA, int64_t csA, const void *packedB, float beta, float *C,
+                                    int64_t rsC, int64_t csC, void *stream) {
+  if (!A) return set_error(LASER_B200_EINVAL, "null pointer");
+  return gemm_packed_dev(M, N, K, alpha, A, rsA, csA, nullptr, packedB, beta, C, rsC, csC, stream);
 }
 
 // ---- storage -----------------------------------------------------------------------------

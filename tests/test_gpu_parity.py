@@ -202,6 +202,22 @@ def test_host_pointer_entry_strided(la, lb, lc):
         assert np.array_equal(bc[mask], before[mask])
 
 
+@pytest.mark.parametrize("la,lc", [("row", "row"), ("padded", "padded"), ("col", "row")])
+def test_host_pointer_entry_pipelined(la, lc):
+    """M >= 2048 with separable row panels takes the 3-stream pipelined host path (H2D of panel
+    p+1 | split+GEMM of panel p | D2H of panel p-1); 'col' A is not separable -> plain path."""
+    M, N, K = 2500, 520, 300
+    A = O.fill_uniform_f32(M * K, 81, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 82, 0, 1).reshape(K, N)
+    want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 0.5, A, K, 1, B, N, 1, 0.0, want, N, 1)
+    ba, oa, rsa, csa = embed(A, la); bc, oc, rsc, csc = embed(np.full((M, N), np.nan, np.float32), lc)
+    before = bc.copy()
+    L.gemm_strided(M, N, K, 0.5, ba[oa:], rsa, csa, B, N, 1, 0.0, bc[oc:], rsc, csc)
+    got = extract(bc, oc, rsc, csc, M, N)
+    assert O.max_relative_error(got, want) < 1e-4
+    mask = np.ones(bc.size, bool); mask[(oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc).ravel()] = False
+    assert np.array_equal(bc[mask], before[mask], equal_nan=True)
+
+
 def test_auto_path_selection():
     a = dev(np.ones(128 * 128, np.float32)); c = dev(np.zeros(128 * 128, np.float32))
     L.gemm_strided(128, 128, 128, 1.0, a, 128, 1, a, 128, 1, 0.0, c, 128, 1)

@@ -59,6 +59,19 @@ def perf():
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/perf_probe.json", "w"))
 
+def perf_packed():
+    n = 8192
+    a = torch.rand(n, n, device="cuda"); b = torch.rand(n, n, device="cuda"); c = torch.empty(n, n, device="cuda")
+    pa = L.alloc_packed(L.gemm_prepackA_mem_required(n, n, n)); pb = L.alloc_packed(L.gemm_prepackB_mem_required(n, n, n))
+    mn, _ = timeit(lambda: L.gemm_prepackB(pb, n, n, n, b, n, 1)); print("prepackB 8192^2 (transposing gather) best %.3f ms" % mn)
+    mn, _ = timeit(lambda: L.gemm_prepackA(pa, n, n, n, a, n, 1)); print("prepackA 8192^2 best %.3f ms" % mn)
+    for name, fn in (("default (split every call)", lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1)),
+                     ("packedB (A split per call)", lambda: L.gemm_packedB(n, n, n, 1.0, a, n, 1, pb, 0.0, c, n, 1)),
+                     ("packed A and B", lambda: L.gemm_packed(n, n, n, 1.0, pa, pb, 0.0, c, n, 1))):
+        mn, av = timeit(fn, iters=8)
+        print("n=8192 %-28s best %.3f ms  %.1f TFLOP/s (avg %.3f)" % (name, mn, 2 * n**3 / mn / 1e9, av))
+
 if __name__ == "__main__":
     probe_rounding()
+    perf_packed()
     perf()
