@@ -68,6 +68,7 @@ struct EventPair {
 };
 
 struct Ctx {
+  int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
@@ -125,6 +126,7 @@ int get_ctx(Ctx **out) {
         if (v >= 32) c.kc_faithful = v;
       }
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
+      if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32_BF16C;
@@ -428,6 +430,7 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
     if (p.kb_per_block < 1) p.kb_per_block = 1;
     if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
   }
+  p.raster_g = c.raster_g > 0 ? c.raster_g : (pair ? 8 : 16);
   const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
   p.num_m_blocks = static_cast<int>((M + tile_m - 1) / tile_m);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);

@@ -66,13 +66,14 @@ struct TcParams {
   int npass;          // 1 single pass | 3 tf32 hi/lo split | 2 mixed: tf32 hi*hi + bf16 cross terms
   int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
+  int raster_g;       // m-blocks per raster group (see tile_coords)
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int &mb, int &nb) {
-  // groups of 16 m-blocks sweep n together: the ~148 concurrently resident tiles then cover
-  // a near-square 16 x 9 patch, which minimises the A + B panels one wave pulls through L2
-  constexpr int G = 16;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int G, int &mb, int &nb) {
+  // groups of G m-blocks sweep n together: the concurrently resident tiles (148 of 128 x 256, or
+  // 74 pairs of 256 x 256) then cover a near-square patch, which minimises the A + B panels one
+  // wave pulls through L2 (G = 16 single-CTA tiles / 8 pair tiles = 2048 rows)
   const int per_group = G * num_n;
   const int g = t / per_group;
   const int first_m = g * G;
@@ -224,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       using E_bf = std::integral_constant<int, 2>;
       for (int t = sched_id; t < num_tiles; t += sched_stride) {
         int mb, nb;
-        tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
+        tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
         // pair: this CTA's 128 rows of A and its half of the B columns
         const int m0 = mb * TILE_M + static_cast<int>(cta_rank) * TC_BLOCK_M;
         const int n0 = nb * TC_BLOCK_N + static_cast<int>(cta_rank) * (TC_BLOCK_N - Cfg::B_COLS);
@@ -345,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     for (int t = sched_id; t < num_tiles; t += sched_stride) {
       int mb, nb;
-      tile_coords(t, p.num_m_blocks, p.num_n_blocks, mb, nb);
+      tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
       const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
       float run[TC_EPI_COLS];  // running sums of this thread's row segment (registers)
