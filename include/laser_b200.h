@@ -143,6 +143,27 @@ int laser_b200_gemm_strided_bf16_dev(int64_t M, int64_t N, int64_t K, float alph
                                      float beta, uint16_t *C, int64_t rowStrideC, int64_t colStrideC,
                                      void *stream);
 
+/* ---- fused epilogue ------------------------------------------------------
+ * C <- act(alpha * A*B + beta * C + bias).  The reference lists this as the intended next step
+ * of exactly the epilogue replaced here ("TODO: elementwise epilogue fusion like
+ * relu/tanh/sigmoid", gemm.nim:196; gemm_ukernel_generic.nim:50-51,78-79,128-129).
+ * bias: NULL, or a device vector added per column (length N, bias_per_row = 0) or per row
+ * (length M, bias_per_row = 1).  epi == NULL behaves like laser_b200_gemm_strided_f32_dev. */
+#define LASER_B200_ACT_NONE 0
+#define LASER_B200_ACT_RELU 1
+#define LASER_B200_ACT_TANH 2
+#define LASER_B200_ACT_SIGMOID 3
+typedef struct {
+  const float *bias;
+  int32_t bias_per_row;
+  int32_t activation;
+} laser_b200_epilogue;
+int laser_b200_gemm_strided_f32_epi_dev(int64_t M, int64_t N, int64_t K, float alpha,
+                                        const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                        const float *B, int64_t rowStrideB, int64_t colStrideB,
+                                        float beta, float *C, int64_t rowStrideC, int64_t colStrideC,
+                                        const laser_b200_epilogue *epi, int path, void *stream);
+
 /* ---- pre-packed operands (device) -----------------------------------------
  * Replaces  gemm_prepackA_mem_required / gemm_prepackB_mem_required, gemm_prepackA / gemm_prepackB
  * and gemm_packed   (laser/primitives/matrix_multiplication/gemm_prepacked.nim:63-292).

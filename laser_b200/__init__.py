@@ -6,7 +6,7 @@ host-side mirror of the reference interface on top of it.  See DESIGN.md / INTEG
 """
 from ._capi import (PATH_AUTO, PATH_BF16, PATH_NAMES, PATH_SIMT, PATH_TF32_BF16C, PATH_TF32X1,
                     PATH_TF32X3, LaserB200Error, lib, lib_path)
-from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, get_f32_mode, init, last_path,
+from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, gemm_strided_fused, get_f32_mode, init, last_path,
                    launch_count, profile_begin, profile_end, set_f32_mode, shutdown,
                    synchronize)
 from .prepacked import (alloc_packed, gemm_packed, gemm_packedB, gemm_prepackA, gemm_prepackA_mem_required,

@@ -22,6 +22,13 @@ class LaserB200Error(RuntimeError):
         self.code = code
 
 
+class Epilogue(ctypes.Structure):
+    _fields_ = [("bias", vp), ("bias_per_row", i32), ("activation", i32)]
+
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+
 class TensorView(ctypes.Structure):
     _fields_ = [("rank", i32), ("dtype", i32), ("shape", i64 * MAXRANK), ("strides", i64 * MAXRANK),
                 ("offset", i64), ("storage", vp)]
@@ -50,6 +57,7 @@ SIGNATURES = {
     "laser_b200_gemm_strided_i64": (ctypes.c_int, _gemm_sig(i64)),
     "laser_b200_gemm_strided_bf16": (ctypes.c_int, _gemm_sig(f32)),
     "laser_b200_gemm_strided_f32_dev": (ctypes.c_int, _gemm_sig(f32) + [ctypes.c_int, vp]),
+    "laser_b200_gemm_strided_f32_epi_dev": (ctypes.c_int, _gemm_sig(f32) + [ctypes.POINTER(Epilogue), ctypes.c_int, vp]),
     "laser_b200_gemm_strided_f64_dev": (ctypes.c_int, _gemm_sig(f64) + [vp]),
     "laser_b200_gemm_strided_i32_dev": (ctypes.c_int, _gemm_sig(i32) + [vp]),
     "laser_b200_gemm_strided_i64_dev": (ctypes.c_int, _gemm_sig(i64) + [vp]),

@@ -32,6 +32,7 @@ using namespace lb200;
 
 thread_local std::string g_last_error;
 thread_local int g_last_path = 0;
+thread_local Epilogue g_epi;   // fused epilogue of the call in flight on this thread (default: none)
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_f32_mode{-1};
 
@@ -195,6 +196,7 @@ int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, in
   p.A = A; p.rsA = rsA; p.csA = csA;
   p.B = B; p.rsB = rsB; p.csB = csB;
   p.C = C; p.rsC = rsC; p.csC = csC;
+  if constexpr (std::is_same<T, float>::value) { p.bias = g_epi.bias; p.bias_per_row = g_epi.bias_per_row; p.act = g_epi.act; }
   p.a_along_m = (llabs(rsA) < llabs(csA)) ? 1 : 0;
   p.b_along_k = (llabs(rsB) < llabs(csB)) ? 1 : 0;
   constexpr int BM = 16 * TM, BN = 16 * TN;
@@ -418,7 +420,7 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
            cudaStream_t s) {
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
-  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0;
+  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
   {
     // K extent accumulated inside the tensor core before the epilogue warps add the block
     // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
@@ -601,7 +603,7 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
     // a 128x256 tensor-core tile is mostly padding and the exact kernel is used
     const double work = static_cast<double>(M) * N * K;
     if (work <= 128.0 * 128.0 * 128.0) path = LASER_B200_PATH_SIMT;
-    else if (N <= 4 && M >= 1024) path = -1;  // skinny: warp-shuffle GEMV
+    else if (N <= 4 && M >= 1024 && !g_epi.bias && !g_epi.act) path = -1;  // skinny: warp-shuffle GEMV
     else path = g_f32_mode.load();
   }
   switch (path) {
@@ -896,6 +898,20 @@ int laser_b200_gemm_strided_f32_dev(int64_t M, int64_t N, int64_t K, float alpha
                                     int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
                                     int path, void *stream) {
   return f32_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, path, stream);
+}
+int laser_b200_gemm_strided_f32_epi_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                        int64_t rsA, int64_t csA, const float *B, int64_t rsB,
+                                        int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
+                                        const laser_b200_epilogue *epi, int path, void *stream) {
+  if (epi) {
+    if (epi->activation < 0 || epi->activation > 3) return set_error(LASER_B200_EINVAL, "unknown activation %d", epi->activation);
+    g_epi.bias = epi->bias;
+    g_epi.bias_per_row = epi->bias_per_row ? 1 : 0;
+    g_epi.act = epi->activation;
+  }
+  const int rc = f32_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, path, stream);
+  g_epi = Epilogue();
+  return rc;
 }
 int laser_b200_gemm_strided_f64_dev(int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                                     int64_t rsA, int64_t csA, const double *B, int64_t rsB,

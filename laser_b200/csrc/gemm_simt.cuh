@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace lb200 {
 
 template <typename T> struct SimtOps;
@@ -67,10 +69,14 @@ struct SimtParams {
   int a_along_m;  // 1: consecutive loader threads walk m (|rsA| < |csA|), 0: walk k
   int b_along_k;  // 1: consecutive loader threads walk k (|rsB| < |csB|), 0: walk n
   int num_m_blocks, num_n_blocks;
+  // fused epilogue (float only), applied after the LAST kc block: v -> act(v + bias)
+  const float *bias = nullptr;
+  int bias_per_row = 0;
+  int act = 0;
 };
 
 template <typename T, int TM, int TN, int BK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // <= 128 registers: two CTAs (16 warps) per SM
 gemm_simt_kernel(const SimtParams<T> p) {
   constexpr int BM = 16 * TM, BN = 16 * TN;
   constexpr int HM = TM / 2, HN = TN / 2;       // the two halves of the micro-tile
@@ -179,6 +185,16 @@ gemm_simt_kernel(const SimtParams<T> p) {
           else v = *c;
           if (p.alpha == T(1)) v = Op::add(v, acc[i][j]);
           else v = Op::add(v, Op::mul(p.alpha, acc[i][j]));
+          if constexpr (sizeof(T) == 4 && !std::is_integral<T>::value) {
+            if (kend == p.K && (p.bias != nullptr || p.act != 0)) {
+              float f = static_cast<float>(v);
+              if (p.bias) f += p.bias_per_row ? p.bias[gm] : p.bias[gn];
+              if (p.act == 1) f = fmaxf(f, 0.0f);
+              else if (p.act == 2) f = tanhf(f);
+              else if (p.act == 3) f = 1.0f / (1.0f + expf(-f));
+              v = static_cast<T>(f);
+            }
+          }
           *c = v;
         }
       }

@@ -58,6 +58,19 @@ constexpr int TC_EPI_COLS = TC_BLOCK_N / 2;  // columns owned by one epilogue th
 constexpr int TC_REGS_CTRL = 56;   // setmaxnreg for the producer/MMA warpgroup
 constexpr int TC_REGS_EPI = 216;   // ... and for the epilogue warpgroups (running sums)
 
+// fused epilogue: v -> act(v + bias)   (gemm.nim:196 "elementwise epilogue fusion")
+struct Epilogue {
+  const float *bias = nullptr;
+  int bias_per_row = 0;
+  int act = 0;  // 0 none, 1 relu, 2 tanh, 3 sigmoid
+};
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.0f);
+  if (act == 2) return tanhf(v);
+  if (act == 3) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
 struct TcParams {
   int64_t M, N, K;
   float alpha, beta;
@@ -67,6 +80,7 @@ struct TcParams {
   int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
   int raster_g;       // m-blocks per raster group (see tile_coords)
+  Epilogue epi;
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
 
@@ -378,6 +392,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       // ---- C <- alpha * sum + beta * C  (gemm_ukernel_generic.nim:53-76 semantics) ----
       if (row < p.M && col0 < p.N) {
         OutT *crow = C + row * p.rsC;
+        const bool has_epi = (p.epi.bias != nullptr) || (p.epi.act != 0);
+        const float row_bias = (p.epi.bias && p.epi.bias_per_row) ? p.epi.bias[row] : 0.0f;
         if (vec_ok && col0 + TC_EPI_COLS <= p.N) {
           if constexpr (sizeof(OutT) == 4) {
             float4 *dst = reinterpret_cast<float4 *>(crow + col0);
@@ -394,6 +410,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 v.y = fmaf(p.beta, o.y, v.y);
                 v.z = fmaf(p.beta, o.z, v.z);
                 v.w = fmaf(p.beta, o.w, v.w);
+              }
+              if (has_epi) {
+                float4 bv = make_float4(row_bias, row_bias, row_bias, row_bias);
+                if (p.epi.bias && !p.epi.bias_per_row) {
+                  const float *bp = p.epi.bias + col0 + 4 * v4;
+                  if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) bv = *reinterpret_cast<const float4 *>(bp);
+                  else bv = make_float4(bp[0], bp[1], bp[2], bp[3]);
+                }
+                v.x = epi_act(v.x + bv.x, p.epi.act);
+                v.y = epi_act(v.y + bv.y, p.epi.act);
+                v.z = epi_act(v.z + bv.z, p.epi.act);
+                v.w = epi_act(v.w + bv.w, p.epi.act);
               }
               dst[v4] = v;
             }
@@ -413,6 +441,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   f[2 * e + 1] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
                 }
               }
+              if (has_epi) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float bv = (p.epi.bias && !p.epi.bias_per_row) ? p.epi.bias[col0 + 8 * v8 + e] : row_bias;
+                  f[e] = epi_act(f[e] + bv, p.epi.act);
+                }
+              }
               uint4 w;
               w.x = f32_to_bf16_bits(f[0]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[1])) << 16);
               w.y = f32_to_bf16_bits(f[2]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[3])) << 16);
@@ -430,13 +465,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < TC_EPI_COLS; ++j) {
             if (j < ncols) {
               float v = p.alpha * run[j];
-              if constexpr (sizeof(OutT) == 4) {
-                if (p.beta != 0.0f) v = fmaf(p.beta, *dst, v);
-                *dst = v;
-              } else {
-                if (p.beta != 0.0f) v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
-                *dst = f32_to_bf16_bits(v);
+              if (p.beta != 0.0f) {
+                if constexpr (sizeof(OutT) == 4) v = fmaf(p.beta, *dst, v);
+                else v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
               }
+              if (has_epi) {
+                const float bv = (p.epi.bias && !p.epi.bias_per_row) ? p.epi.bias[col0 + j] : row_bias;
+                v = epi_act(v + bv, p.epi.act);
+              }
+              if constexpr (sizeof(OutT) == 4) *dst = v;
+              else *dst = f32_to_bf16_bits(v);
             }
             dst += p.csC;
           }

@@ -21,7 +21,7 @@ from . import _capi
 from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32_BF16C, PATH_TF32X1, PATH_TF32X3,
                     LaserB200Error, check, lib)
 
-__all__ = ["gemm_strided", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",
+__all__ = ["gemm_strided", "gemm_strided_fused", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",
            "fill_uniform_f32", "init", "shutdown", "synchronize", "profile_begin", "profile_end"]
 
 _NP_DTYPES = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.int32): "i32",
@@ -112,6 +112,29 @@ def gemm_strided(M, N, K, alpha, A, rowStrideA, colStrideA, B, rowStrideB, colSt
         if path not in (PATH_AUTO, PATH_SIMT if ta != "bf16" else PATH_BF16):
             raise ValueError("path %d is not available for %s" % (path, ta))
         check(getattr(L, "laser_b200_gemm_strided_%s_dev" % ta)(*args, stream))
+
+
+def gemm_strided_fused(M, N, K, alpha, A, rowStrideA, colStrideA, B, rowStrideB, colStrideB, beta, C,
+                       rowStrideC, colStrideC, bias=None, bias_per_row=False, activation="none",
+                       path=PATH_AUTO, stream=None):
+    """C <- act(alpha*A*B + beta*C + bias) on float32 DEVICE buffers: the epilogue fusion the
+    reference lists as its next step (gemm.nim:196).  activation: none | relu | tanh | sigmoid."""
+    pa, ta, da = _resolve(A); pb, tb, db = _resolve(B); pc, tc, dc = _resolve(C)
+    if not (ta == tb == tc == "f32") or not (da and db and dc):
+        raise TypeError("gemm_strided_fused takes float32 device buffers")
+    epi = _capi.Epilogue()
+    if bias is not None:
+        pbias, tbias, dbias = _resolve(bias)
+        if not dbias or tbias != "f32":
+            raise TypeError("bias must be a float32 device vector")
+        epi.bias = pbias
+    epi.bias_per_row = 1 if bias_per_row else 0
+    epi.activation = {"none": 0, "relu": 1, "tanh": 2, "sigmoid": 3}[activation]
+    if stream is None:
+        stream = _current_stream()
+    check(lib().laser_b200_gemm_strided_f32_epi_dev(M, N, K, float(alpha), pa, rowStrideA, colStrideA, pb, rowStrideB,
+                                                    colStrideB, float(beta), pc, rowStrideC, colStrideC,
+                                                    ctypes.byref(epi), path, stream))
 
 
 def last_path():
