@@ -76,7 +76,7 @@ struct SimtParams {
 };
 
 template <typename T, int TM, int TN, int BK>
-__global__ void __launch_bounds__(256, 2)   // <= 128 registers: two CTAs (16 warps) per SM
+__global__ void __launch_bounds__(256)
 gemm_simt_kernel(const SimtParams<T> p) {
   constexpr int BM = 16 * TM, BN = 16 * TN;
   constexpr int HM = TM / 2, HN = TN / 2;       // the two halves of the micro-tile

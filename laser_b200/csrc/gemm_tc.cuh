@@ -363,6 +363,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
       const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
+      if (p.beta != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {
+        // beta != 0: pull this thread's 512 bytes of old C into L2 now; they are needed only
+        // after the whole K loop of the tile, so the latency is free
+        const OutT *cp = C + row * p.rsC + col0;
+#pragma unroll
+        for (int l = 0; l < TC_EPI_COLS * static_cast<int>(sizeof(OutT)) / 128; ++l) {
+          if (col0 + l * (128 / static_cast<int>(sizeof(OutT))) < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + l * (128 / sizeof(OutT))));
+        }
+      }
       float run[TC_EPI_COLS];  // running sums of this thread's row segment (registers)
 #pragma unroll
       for (int j = 0; j < TC_EPI_COLS; ++j) run[j] = 0.0f;
@@ -397,33 +407,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (vec_ok && col0 + TC_EPI_COLS <= p.N) {
           if constexpr (sizeof(OutT) == 4) {
             float4 *dst = reinterpret_cast<float4 *>(crow + col0);
+            // batches of 4 x 16 B: with beta != 0 the four loads of a batch are in flight
+            // together (the old C lines were prefetched into L2 when the tile started)
 #pragma unroll
-            for (int v4 = 0; v4 < TC_EPI_COLS / 4; ++v4) {
-              float4 v;
-              v.x = p.alpha * run[4 * v4 + 0];
-              v.y = p.alpha * run[4 * v4 + 1];
-              v.z = p.alpha * run[4 * v4 + 2];
-              v.w = p.alpha * run[4 * v4 + 3];
+            for (int b8 = 0; b8 < TC_EPI_COLS / 16; ++b8) {
+              float4 o[4];
               if (p.beta != 0.0f) {
-                const float4 o = dst[v4];
-                v.x = fmaf(p.beta, o.x, v.x);
-                v.y = fmaf(p.beta, o.y, v.y);
-                v.z = fmaf(p.beta, o.z, v.z);
-                v.w = fmaf(p.beta, o.w, v.w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = dst[b8 * 4 + e];
               }
-              if (has_epi) {
-                float4 bv = make_float4(row_bias, row_bias, row_bias, row_bias);
-                if (p.epi.bias && !p.epi.bias_per_row) {
-                  const float *bp = p.epi.bias + col0 + 4 * v4;
-                  if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) bv = *reinterpret_cast<const float4 *>(bp);
-                  else bv = make_float4(bp[0], bp[1], bp[2], bp[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int v4 = b8 * 4 + e;
+                float4 v;
+                v.x = p.alpha * run[4 * v4 + 0];
+                v.y = p.alpha * run[4 * v4 + 1];
+                v.z = p.alpha * run[4 * v4 + 2];
+                v.w = p.alpha * run[4 * v4 + 3];
+                if (p.beta != 0.0f) {
+                  v.x = fmaf(p.beta, o[e].x, v.x);
+                  v.y = fmaf(p.beta, o[e].y, v.y);
+                  v.z = fmaf(p.beta, o[e].z, v.z);
+                  v.w = fmaf(p.beta, o[e].w, v.w);
                 }
-                v.x = epi_act(v.x + bv.x, p.epi.act);
-                v.y = epi_act(v.y + bv.y, p.epi.act);
-                v.z = epi_act(v.z + bv.z, p.epi.act);
-                v.w = epi_act(v.w + bv.w, p.epi.act);
+                if (has_epi) {
+                  float4 bv = make_float4(row_bias, row_bias, row_bias, row_bias);
+                  if (p.epi.bias && !p.epi.bias_per_row) {
+                    const float *bp = p.epi.bias + col0 + 4 * v4;
+                    if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) bv = *reinterpret_cast<const float4 *>(bp);
+                    else bv = make_float4(bp[0], bp[1], bp[2], bp[3]);
+                  }
+                  v.x = epi_act(v.x + bv.x, p.epi.act);
+                  v.y = epi_act(v.y + bv.y, p.epi.act);
+                  v.z = epi_act(v.z + bv.z, p.epi.act);
+                  v.w = epi_act(v.w + bv.w, p.epi.act);
+                }
+                dst[v4] = v;
               }
-              dst[v4] = v;
             }
           } else {
             uint4 *dst = reinterpret_cast<uint4 *>(crow + col0);
