@@ -9,7 +9,7 @@ the reference's bench makes, benchmarks/gemm/gemm_bench_float32.nim:184-189), th
 C ABI of liblaser_b200.so in its DEFAULT fp32-faithful mode (tcgen05: one tf32 hi*hi pass + two
 bf16 passes for the hi*lo / lo*hi correction terms, parity-gated at 1e-4).  At N GPUs the problem is row-sharded (weak scaling: every rank owns 8192 rows of A
 and C, so N=4 is BASELINE.json's "M=32768, N=K=8192" case) and each step includes the
-K-panelled NCCL broadcast of B from rank 0.
+NCCL broadcast of B from rank 0.
 
 One JSON line on stdout (rank 0).  Extra keys beyond the driver's contract:
   roofline      dominant kernel (gemm_tc_kernel) against the tensor roofline
@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch at 8192^3 in the default
 # mode, from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc_8192.md); None until measured
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 7.99e9
 METRIC = "sgemm_tflops_m8192_n8192_k8192"
 UNIT = "TFLOP/s"
 MNK = 8192
@@ -223,7 +223,7 @@ def run_ours(args):
         if world == 1:
             L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1)
         else:
-            gemm_rowsharded(M, N, K, 1.0, A2, B2, 0.0, C2, src=0, n_panels=8)
+            gemm_rowsharded(M, N, K, 1.0, A2, B2, 0.0, C2, src=0, n_panels=1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -336,7 +336,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic U(-0.1,0.1), counter-based generator, seed 42 (device-generated)",
             "config": {"workload": "SGEMM fp32 C=A*B, per-GPU M=8192 N=K=8192 row-major, alpha=1 beta=0"
-                                   + ("" if world == 1 else "; row-sharded: total M=%d, B broadcast from rank 0 over NCCL in 8 K-panels every step" % (M * world)),
+                                   + ("" if world == 1 else "; row-sharded: total M=%d, one NCCL broadcast of B from rank 0 every step" % (M * world)),
                        "global_M": M * world, "N": N, "K": K, "parallelism": "rowshard%d" % world,
                        "f32_mode": "tf32_bf16c (fp32-faithful, default)", "l2": "inputs larger than L2 (A+B+C = 805 MB vs 126 MB)",
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks"},

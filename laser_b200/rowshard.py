@@ -4,9 +4,13 @@ The reference parallelises exactly this way on a CPU: its `ic` loop hands each w
 row block of A and C while all workers share one packed panel of B per `pc` iteration, and
 beta is applied on the first K-panel only (gemm.nim:150-176).  Here:
   * rank r owns rows [start_r, stop_r) of A and C (never moved);
-  * B lives on `src` and is broadcast once, as K-panels, over NCCL/NVLink
-    (torch.distributed); panel i+1 is in flight while the GEMM consumes panel i with
-    beta' = beta (i == 0) or 1 (i > 0) -- no collective inside the MMA loop, no reduction.
+  * B lives on `src` and is broadcast once over NCCL/NVLink (torch.distributed) -- no
+    collective inside the MMA loop, no reduction.  With n_panels > 1 the broadcast is cut in
+    K-panels and panel i+1 is in flight while the GEMM consumes panel i with beta' = beta
+    (i == 0) or 1 (i > 0), the reference's own rule for its K blocks.  Measured on 2 and 4
+    B200s (tools/rowshard_probe.py): one panel is fastest -- a 256 MB broadcast costs 0.45 ms
+    against a 3.6 ms GEMM, while every extra K-panel costs a C read-modify-write pass and a
+    kernel ramp -- so n_panels defaults to 1.
 The host logic is backend-agnostic (tested on CPU with gloo + the oracle as gemm_fn).
 """
 import torch
@@ -41,7 +45,7 @@ def k_panels(K, n_panels, align=32):
 
 
 def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, group=None,
-                    n_panels=8, gemm_fn=None, broadcast=True):
+                    n_panels=1, gemm_fn=None, broadcast=True):
     """C_local <- alpha * A_local @ B + beta * C_local on every rank.
 
     A_local: (M_local, K) tensor view (any strides), C_local: (M_local, N) view,
