@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -6
+echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -5
+echo "=== bench"; timeout 900 python bench.py --steps 20 --warmup 3 2> gpurun_out/bench_err.log | tee gpurun_out/bench_n1.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for k in ('value','ms_per_step','clocks','e2e','gpu_launches','cpu_baseline'): print(k, d.get(k))
+print({k:d['roofline'][k] for k in ('achieved','frac','tensor_pipe_frac','kernel_ms','prep_ms_per_step','traffic')}); print(d['modes'])"
+echo "=== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> gpurun_out/bench_err.log | tee gpurun_out/bench_ref.json | cut -c1-250
+echo "=== ncu launch list (bench.py)"; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1; wc -l gpurun_out/launches_bench.csv
+echo "=== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 6 -o gpurun_out/prof_tc python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
