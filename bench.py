@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch at 8192^3 in the default
 # mode, from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc_8192.md); None until measured
-TRAFFIC_BYTES_PER_LAUNCH = 7.99e9
+TRAFFIC_BYTES_PER_LAUNCH = 10.08e9
 METRIC = "sgemm_tflops_m8192_n8192_k8192"
 UNIT = "TFLOP/s"
 MNK = 8192

@@ -210,7 +210,7 @@ gemm_simt_kernel(const SimtParams<T> p) {
 // reduction tree differs) - used only when the caller asks for PATH_AUTO on a
 // skinny problem; PATH_SIMT always takes the exact kernel above.
 // ---------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool VEC>
 __global__ void __launch_bounds__(256)
 gemv_warp_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A, int64_t rsA,
                  int64_t csA, const float *__restrict__ B, int64_t rsB, int64_t csB, float beta,
@@ -223,10 +223,30 @@ gemv_warp_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A,
 #pragma unroll
     for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
     const float *a = A + row * rsA;
-    for (int64_t k = lane; k < K; k += 32) {
-      const float av = a[k * csA];
+    if constexpr (VEC) {
+      // A rows contiguous and 16-byte aligned, K % 4 == 0: each lane streams float4s, four
+      // independent 16-byte loads in flight per lane (the kernel is pure HBM streaming of A)
+      const float4 *a4 = reinterpret_cast<const float4 *>(a);
+      const int64_t K4 = K >> 2;
+#pragma unroll 4
+      for (int64_t q = lane; q < K4; q += 32) {
+        const float4 av = __ldg(a4 + q);
+        const int64_t k = q << 2;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) acc[j] = fmaf(av, B[k * rsB + j * csB], acc[j]);
+        for (int j = 0; j < NV; ++j) {
+          acc[j] = fmaf(av.x, __ldg(B + (k + 0) * rsB + j * csB), acc[j]);
+          acc[j] = fmaf(av.y, __ldg(B + (k + 1) * rsB + j * csB), acc[j]);
+          acc[j] = fmaf(av.z, __ldg(B + (k + 2) * rsB + j * csB), acc[j]);
+          acc[j] = fmaf(av.w, __ldg(B + (k + 3) * rsB + j * csB), acc[j]);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int64_t k = lane; k < K; k += 32) {
+        const float av = a[k * csA];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[j] = fmaf(av, B[k * rsB + j * csB], acc[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < NV; ++j) {

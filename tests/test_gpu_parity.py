@@ -229,8 +229,9 @@ def test_auto_path_selection():
     assert np.all(c.cpu().numpy() == 256.0)
 
 
-def test_skinny_gemv_path():
-    M, N, K = 5000, 3, 777
+@pytest.mark.parametrize("K", [777, 776])      # 776: the 16-byte vectorised variant
+def test_skinny_gemv_path(K):
+    M, N = 5000, 3
     A = O.fill_uniform_f32(M * K, 61, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 62, 0, 1).reshape(K, N)
     want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, want, N, 1)
     got, *_ = run_dev("f32", M, N, K, 1.0, A, "row", B, "row", 0.0, np.zeros((M, N), np.float32), "row")
