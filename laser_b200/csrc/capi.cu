@@ -610,9 +610,18 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
     case -1: {
       const int grid = grid_for(*c, (M + 7) / 8, 8);
 const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+      const size_t bsmem = static_cast<size_t>(N) * K * sizeof(float);
+      const bool use_smem = vec && bsmem <= 96 * 1024;
 #define LB200_GEMV(NV)                                                                                         \
   do {                                                                                                         \
-    if (vec) gemv_warp_kernel<NV, true><<<grid, 256, 0, s>>>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);  \
+    if (use_smem) {                                                                                            \
+      static bool attr_set = false;                                                                            \
+      if (!attr_set) {                                                                                         \
+        CUDA_TRY(cudaFuncSetAttribute(gemv_warp_smem_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+        attr_set = true;                                                                                       \
+      }                                                                                                        \
+      gemv_warp_smem_kernel<NV><<<grid_for(*c, (M + 7) / 8, 2), 256, bsmem, s>>>(M, K, alpha, A, rsA, B, rsB, csB, beta, C, rsC, csC); \
+    } else if (vec) gemv_warp_kernel<NV, true><<<grid, 256, 0, s>>>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);  \
     else gemv_warp_kernel<NV, false><<<grid, 256, 0, s>>>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);     \
   } while (0)
       if (N == 1) LB200_GEMV(1); else if (N == 2) LB200_GEMV(2); else if (N == 3) LB200_GEMV(3); else LB200_GEMV(4);

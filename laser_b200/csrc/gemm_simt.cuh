@@ -264,4 +264,57 @@ gemv_warp_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A,
   }
 }
 
+// Same contract, B (K x NV) staged once per CTA in shared memory, transposed to Bs[j][k] so
+// that each 16-byte load of A is matched by NV 16-byte shared loads instead of 4*NV global
+// ones.  Needs A rows contiguous + 16-byte aligned, K % 4 == 0 and NV*K*4 bytes of smem.
+template <int NV>
+__global__ void __launch_bounds__(256)
+gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A, int64_t rsA,
+                      const float *__restrict__ B, int64_t rsB, int64_t csB, float beta,
+                      float *__restrict__ C, int64_t rsC, int64_t csC) {
+  extern __shared__ float4 gemv_smem4[];
+  float *Bs = reinterpret_cast<float *>(gemv_smem4);
+  for (int64_t i = threadIdx.x; i < K * NV; i += blockDim.x) {
+    const int64_t k = i / NV;
+    const int j = static_cast<int>(i - k * NV);
+    Bs[j * K + k] = B[k * rsB + j * csB];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t K4 = K >> 2;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M;
+       row += warps_total) {
+    float acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = 0.0f;
+    const float4 *a4 = reinterpret_cast<const float4 *>(A + row * rsA);
+#pragma unroll 8
+    for (int64_t q = lane; q < K4; q += 32) {
+      const float4 av = __ldg(a4 + q);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 bv = *reinterpret_cast<const float4 *>(Bs + j * K + (q << 2));
+        acc[j] = fmaf(av.x, bv.x, acc[j]);
+        acc[j] = fmaf(av.y, bv.y, acc[j]);
+        acc[j] = fmaf(av.z, bv.z, acc[j]);
+        acc[j] = fmaf(av.w, bv.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float *c = C + row * rsC + j * csC;
+        const float v = alpha * acc[j];
+        *c = (beta == 0.0f) ? v : fmaf(beta, *c, v);
+      }
+    }
+  }
+}
+
 }  // namespace lb200
