@@ -87,7 +87,7 @@ def lib():
     cannot be built or loaded: there is no Python/CPU fallback for any compute entry."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("LASER_B200_LIB") or _build.build()   # override: A/B builds in tools/
         L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the header and the library disagree

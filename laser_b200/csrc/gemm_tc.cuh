@@ -38,6 +38,9 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_N = 256;
 constexpr int TC_ROW_BYTES = 128;  // one swizzle row; BLOCK_K = 128 / sizeof(element)
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_ROW_BYTES;  // 16 KB
+#ifndef TC_PAIR_STAGES
+#define TC_PAIR_STAGES 6
+#endif
 // Single-CTA kernel: the CTA stages all 256 B columns (32 KB) -> 48 KB stages, 4 of them.
 // CTA-pair kernel (cta_group::2, 256 x 256 tile per pair): each CTA stages its own 128 rows
 // of A and HALF of the B columns (16 KB) -> 32 KB stages, 6 of them; the tensor cores of both
@@ -46,7 +49,7 @@ template <bool PAIR> struct TcCfg {
   static constexpr int B_COLS = PAIR ? TC_BLOCK_N / 2 : TC_BLOCK_N;
   static constexpr int B_STAGE_BYTES = B_COLS * TC_ROW_BYTES;
   static constexpr int STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = PAIR ? TC_PAIR_STAGES : 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 constexpr int TC_ACC_STAGES = 2;
