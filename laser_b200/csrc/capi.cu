@@ -215,8 +215,11 @@ template <typename T>
 int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
               int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
               int64_t csC, cudaStream_t s) {
+#ifndef LB200_SIMT_BK
+#define LB200_SIMT_BK 16
+#endif
   if constexpr (sizeof(T) == 4)
-    return launch_simt<T, 8, 8, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+    return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
   else
     return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
 }

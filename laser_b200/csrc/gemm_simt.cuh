@@ -75,8 +75,11 @@ struct SimtParams {
   int act = 0;
 };
 
+#ifndef LB200_SIMT_MINB
+#define LB200_SIMT_MINB 1
+#endif
 template <typename T, int TM, int TN, int BK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LB200_SIMT_MINB)
 gemm_simt_kernel(const SimtParams<T> p) {
   constexpr int BM = 16 * TM, BN = 16 * TN;
   constexpr int HM = TM / 2, HN = TN / 2;       // the two halves of the micro-tile
