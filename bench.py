@@ -178,7 +178,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = 2 * n**3 / dt / 1e12
     cb = dict(base); cb.pop("ms"); cb.pop("n"); cb["value"] = v
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic U(-0.1,0.1), counter-based, seed 42",
@@ -186,7 +186,7 @@ def run_reference(args):
                    "impl": "C restatement of laser gemm_strided (oracle/), OpenMP, all host threads"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------- our arm
@@ -344,13 +344,40 @@ def run_ours(args):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class StdoutGuard:
+    """Only the result line may reach stdout: native libraries (NCCL prints its version banner
+    to stdout) get fd 1 redirected to stderr for the duration of the run."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
