@@ -85,7 +85,7 @@ struct Ctx {
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
-  bool ready = false;
+  std::atomic<bool> ready{false};
 };
 
 constexpr int kMaxDevices = 32;
