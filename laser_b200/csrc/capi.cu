@@ -70,6 +70,7 @@ struct EventPair {
 
 struct Ctx {
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
+  bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
@@ -82,6 +83,7 @@ struct Ctx {
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   Buffer ws[8];      // per operand: hi, lo (fp32) and xb, lb (bf16) -- A then B
   Buffer stage[3];   // device staging of host A, B, C spans
+  Buffer splitk;     // split-K partial-sum planes
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
@@ -128,6 +130,7 @@ int get_ctx(Ctx **out) {
       }
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
+      if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32_BF16C;
@@ -290,8 +293,8 @@ enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2 };
 template <int ESZ, typename OutT, bool PAIR>
 int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, cudaStream_t s) {
   const bool a_mn = A.mn_major, b_mn = B.mn_major;
-  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
-  // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than tiles
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;  // work units
+  // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than units
   const int units = PAIR ? c.sm_count / 2 : c.sm_count;
   const int sched = static_cast<int>(tiles < units ? tiles : units);
   cudaLaunchConfig_t cfg{};
@@ -439,9 +442,52 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
   const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
   p.num_m_blocks = static_cast<int>((M + tile_m - 1) / tile_m);
   p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
+  // ---- split-K: too few output tiles to fill the machine and a long K (fp32 output only) ----
+  p.k_splits = 1;
+  p.split_plane = 0;
+  {
+    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;
+    const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
+    p.kb_per_split = num_kb;
+    const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+    const int units = pair ? c.sm_count / 2 : c.sm_count;
+    if constexpr (std::is_same<OutT, float>::value) {
+      const int blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;   // accumulation blocks along K
+      int S = static_cast<int>(units / (tiles > 0 ? tiles : 1));
+      if (S > blocks / 4) S = blocks / 4;     // every split keeps >= 4 accumulation blocks (>= 512 K-elements)
+      if (S > 16) S = 16;
+      if (c.splitk_enabled && S >= 2) {
+        const int blocks_per_split = (blocks + S - 1) / S;
+        p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;
+        p.kb_per_split = blocks_per_split * p.kb_per_block;
+      }
+    }
+  }
   EventPair ep;
   int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;
+  if (p.k_splits > 1) {
+    if constexpr (std::is_same<OutT, float>::value) {
+      // partial sums of split s go to plane s of the workspace; a second kernel reduces
+      const int64_t ld = round_up(N, 4);
+      const int64_t plane = M * ld;
+      if ((rc = ensure(c.splitk, static_cast<size_t>(p.k_splits) * plane * sizeof(float)))) return rc;
+      TcParams q = p;
+      q.C = c.splitk.ptr; q.rsC = ld; q.csC = 1; q.alpha = 1.0f; q.beta = 0.0f; q.epi = Epilogue();
+      q.split_plane = plane;
+      if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, q, s);
+      else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, q, s);
+      if (rc) return rc;
+      const int64_t items = (M * N + 255) / 256;
+      splitk_reduce_kernel<<<grid_for(c, items, 8), 256, 0, s>>>(
+          static_cast<const float *>(c.splitk.ptr), p.k_splits, M, N, ld, plane, alpha, beta, C, rsC, csC,
+          p.epi.bias, p.epi.bias_per_row, p.epi.act);
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      CUDA_TRY(cudaEventRecord(c.ws_free, s));  // the planes are workspace too
+      return prof_close(c, s, &ep, 2);
+    }
+  }
   if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, p, s);
   else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, p, s);
   if (rc) return rc;
@@ -556,10 +602,10 @@ int gemm_packed_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A
     const bool pair = c.cta_pair && M > TC_BLOCK_M;
     OperandMaps ma, mb;
     bool used_ws = false;
+    CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
     if (packedA) {
       if ((rc = packed_maps(c, packedA, M, K, TC_BLOCK_M, &ma))) return rc;
     } else {
-      CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
       Operand oa{A, M, K, rsA, csA};
       EventPair ep;
       const int64_t before = g_launches.load();
@@ -844,6 +890,7 @@ void laser_b200_shutdown(void) {
     cudaStreamSynchronize(c.stream);
     for (auto &b : c.ws) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
+    if (c.splitk.ptr) { cudaFree(c.splitk.ptr); c.splitk = Buffer(); }
     cudaEventDestroy(c.ws_free);
     for (auto e : c.panel_ev) cudaEventDestroy(e);
     c.panel_ev.clear();

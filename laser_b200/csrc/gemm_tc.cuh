@@ -84,6 +84,12 @@ struct TcParams {
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
   int raster_g;       // m-blocks per raster group (see tile_coords)
   Epilogue epi;
+  // split-K (few output tiles, long K): unit u = (tile, split) covers the K range of one split
+  // and writes its raw partial sums to plane `split` of a workspace (C points at it, alpha = 1,
+  // beta = 0); splitk_reduce_kernel then adds the planes in order and applies alpha/beta/epilogue
+  int k_splits;          // >= 1
+  int kb_per_split;      // scheduling units (k-tiles / 64-groups) per split
+  int64_t split_plane;   // elements between consecutive planes
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
 
@@ -158,7 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_kb = static_cast<int>((p.K + unit_k - 1) / unit_k);       // scheduling units along K
-  const int num_blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
+  const int num_units = num_tiles * p.k_splits;  // work units of the persistent scheduler
+  // K range [kb_lo, kb_hi) of split sp, in scheduling units
+  auto split_range = [&](int sp, int &kb_lo, int &kb_hi) {
+    kb_lo = min(num_kb, sp * p.kb_per_split);
+    kb_hi = min(num_kb, kb_lo + p.kb_per_split);
+  };
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&mapA0);
@@ -240,14 +251,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       };
       using E_in = std::integral_constant<int, ESZ>;
       using E_bf = std::integral_constant<int, 2>;
-      for (int t = sched_id; t < num_tiles; t += sched_stride) {
-        int mb, nb;
+      for (int u = sched_id; u < num_units; u += sched_stride) {
+        const int t = u / p.k_splits;
+        int mb, nb, kb_lo, kb_hi;
         tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
+        split_range(u - t * p.k_splits, kb_lo, kb_hi);
         // pair: this CTA's 128 rows of A and its half of the B columns
         const int m0 = mb * TILE_M + static_cast<int>(cta_rank) * TC_BLOCK_M;
         const int n0 = nb * TC_BLOCK_N + static_cast<int>(cta_rank) * (TC_BLOCK_N - Cfg::B_COLS);
-        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
-          const int kb1 = min(num_kb, kb0 + p.kb_per_block);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += p.kb_per_block) {
+          const int kb1 = min(kb_hi, kb0 + p.kb_per_block);
           // the small cross terms first (the accumulator is still small, so its truncation
           // does not touch them), then the hi*hi chain
           if (p.npass == 3) {
@@ -322,9 +335,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       };
       using E_in = std::integral_constant<int, ESZ>;
       using E_bf = std::integral_constant<int, 2>;
-      for (int t = sched_id; t < num_tiles; t += sched_stride) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += p.kb_per_block) {
-          const int kb1 = min(num_kb, kb0 + p.kb_per_block);
+      for (int u = sched_id; u < num_units; u += sched_stride) {
+        int kb_lo, kb_hi;
+        split_range(u % p.k_splits, kb_lo, kb_hi);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += p.kb_per_block) {
+          const int kb1 = min(kb_hi, kb0 + p.kb_per_block);
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           ptx::tc_fence_after_sync();
           d_tmem = tmem_base + acc * TC_BLOCK_N;
@@ -358,12 +373,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int h = (warp_idx - 4) >> 2;   // column half
     int acc = 0;
     uint32_t acc_phase = 0;
-    OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C);
     const bool vec_ok = (p.csC == 1) && ((p.rsC * sizeof(OutT)) % 16 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int t = sched_id; t < num_tiles; t += sched_stride) {
-      int mb, nb;
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        ((p.split_plane * sizeof(OutT)) % 16 == 0);
+    for (int u = sched_id; u < num_units; u += sched_stride) {
+      const int t = u / p.k_splits;
+      int mb, nb, kb_lo, kb_hi;
       tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
+      split_range(u - t * p.k_splits, kb_lo, kb_hi);
+      const int num_blocks = (kb_hi - kb_lo + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
+      OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C) + (u - t * p.k_splits) * p.split_plane;
       const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
       if (p.beta != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {

@@ -151,6 +151,31 @@ pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr
   }
 }
 
+// Second half of a split-K GEMM: C <- act(alpha * sum_s ws[s] + beta * C + bias), planes added in
+// the fixed order s = 0 .. S-1 (deterministic).  ws: S planes of M x ld (row-major, fp32).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float *__restrict__ ws, int S, int64_t M, int64_t N, int64_t ld,
+                     int64_t plane, float alpha, float beta, float *__restrict__ C, int64_t rsC,
+                     int64_t csC, const float *__restrict__ bias, int bias_per_row, int act) {
+  const int64_t total = M * N;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / N, c = i - r * N;
+    float sum = ws[r * ld + c];
+    for (int s = 1; s < S; ++s) sum = __fadd_rn(sum, ws[s * plane + r * ld + c]);
+    float *dst = C + r * rsC + c * csC;
+    float v = alpha * sum;
+    if (beta != 0.0f) v = fmaf(beta, *dst, v);
+    if (bias != nullptr || act != 0) {
+      if (bias) v += bias_per_row ? bias[r] : bias[c];
+      if (act == 1) v = fmaxf(v, 0.0f);
+      else if (act == 2) v = tanhf(v);
+      else if (act == 3) v = 1.0f / (1.0f + expf(-v));
+    }
+    *dst = v;
+  }
+}
+
 // counter-based uniform fill, bit-identical to oracle_fill_uniform_f32
 __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

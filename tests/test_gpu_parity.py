@@ -164,6 +164,25 @@ def test_bf16(shape, lay):
         assert O.normwise_relative_error(g, w) < 4e-3
 
 
+@pytest.mark.parametrize("shape", [(256, 256, 8192), (300, 520, 4096), (128, 2048, 16384), (1000, 1000, 3000)])
+@pytest.mark.parametrize("path", FAITHFUL)
+def test_split_k_small_mn_long_k(shape, path):
+    """few output tiles + long K: the K range is split over idle SMs, partial planes are reduced in
+    a fixed order by a second kernel (deterministic), alpha/beta/strided C applied there."""
+    M, N, K = shape
+    A = O.fill_uniform_f32(M * K, 5, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 6, 0, 1).reshape(K, N)
+    C0 = O.fill_uniform_f32(M * N, 7, 0, 1).reshape(M, N)
+    want = C0.copy(); O.gemm_strided(M, N, K, 0.5, A, K, 1, B, N, 1, -1.25, want, N, 1)
+    n0 = L.launch_count()
+    got, *_ = run_dev("f32", M, N, K, 0.5, A, "row", B, "row", -1.25, C0, "padded", path)
+    launches = L.launch_count() - n0
+    assert O.max_relative_error(got, want) < 1e-4 and O.normwise_relative_error(got, want) < 2e-6
+    again, *_ = run_dev("f32", M, N, K, 0.5, A, "row", B, "row", -1.25, C0, "padded", path)
+    assert np.array_equal(got, again)                      # deterministic reduction order
+    if shape != (1000, 1000, 3000):
+        assert launches == 4                               # 2 splits + GEMM + reduce
+
+
 def test_beta_zero_never_reads_c():
     M, N, K = 130, 260, 600
     A = O.fill_uniform_f32(M * K, 4, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 5, 0, 1).reshape(K, N)

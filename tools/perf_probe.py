@@ -71,7 +71,21 @@ def perf_packed():
         mn, av = timeit(fn, iters=8)
         print("n=8192 %-28s best %.3f ms  %.1f TFLOP/s (avg %.3f)" % (name, mn, 2 * n**3 / mn / 1e9, av))
 
+def perf_midsize():
+    for (M, N, K) in ((512, 512, 512), (1024, 1024, 1024), (1920, 1920, 1920), (1024, 1024, 8192), (256, 256, 65536), (2048, 2048, 2048), (4096, 4096, 4096)):
+        a = torch.rand(M, K, device="cuda"); b = torch.rand(K, N, device="cuda"); c = torch.empty(M, N, device="cuda")
+        mn, av = timeit(lambda: L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1), iters=10)
+        print("midsize %dx%dx%d default best %.1f us  %.1f TFLOP/s" % (M, N, K, mn * 1e3, 2.0 * M * N * K / mn / 1e9))
+
+def perf_pcie():
+    n = 8192
+    h = torch.empty(n * n, dtype=torch.float32).pin_memory(); d = torch.empty(n * n, device="cuda")
+    mn, _ = timeit(lambda: d.copy_(h, non_blocking=True)); print("pinned H2D 268 MB: %.2f ms  %.1f GB/s" % (mn, 0.268435 / mn * 1e3))
+    mn, _ = timeit(lambda: h.copy_(d, non_blocking=True)); print("pinned D2H 268 MB: %.2f ms  %.1f GB/s" % (mn, 0.268435 / mn * 1e3))
+
 if __name__ == "__main__":
     probe_rounding()
+    perf_pcie()
+    perf_midsize()
     perf_packed()
     perf()
