@@ -68,7 +68,27 @@ struct EventPair {
   int launches;
 };
 
+// cache of encoded tensor maps (cuTensorMapEncodeTiled costs microseconds; the reference's
+// analogue is re-using its Tiles object): keyed by everything the encoding depends on
+struct MapKey {
+  const void *base;
+  int64_t inner, outer, stride;
+  int esz, box_inner, box_outer, swz;
+  bool operator==(const MapKey &o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride && esz == o.esz &&
+           box_inner == o.box_inner && box_outer == o.box_outer && swz == o.swz;
+  }
+};
+struct MapCacheEntry {
+  MapKey key;
+  CUtensorMap map;
+  bool valid = false;
+};
+constexpr int kMapCacheSize = 64;
+
 struct Ctx {
+  MapCacheEntry map_cache[kMapCacheSize];
+  int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
@@ -249,6 +269,12 @@ Major classify(const Operand &o, int esz) {
 
 int encode_map(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer,
                int64_t outer_stride_elems, int box_inner, int box_outer, CUtensorMapSwizzle swz) {
+  const MapKey key{base, inner, outer, outer_stride_elems, esz, box_inner, box_outer, static_cast<int>(swz)};
+  for (int i = 0; i < kMapCacheSize; ++i)
+    if (c.map_cache[i].valid && c.map_cache[i].key == key) {
+      *map = c.map_cache[i].map;
+      return LASER_B200_OK;
+    }
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(outer_stride_elems) * esz};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
@@ -262,6 +288,11 @@ int encode_map(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inne
                      "cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld stride=%lld box=%dx%d",
                      static_cast<int>(r), base, (long long)inner, (long long)outer,
                      (long long)outer_stride_elems, box_inner, box_outer);
+  MapCacheEntry &e = c.map_cache[c.map_cache_next];
+  c.map_cache_next = (c.map_cache_next + 1) % kMapCacheSize;
+  e.key = key;
+  e.map = *map;
+  e.valid = true;
   return LASER_B200_OK;
 }
 
