@@ -203,8 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     else ptx::tmem_alloc<TC_TMEM_COLS>(tmem_base_smem);
   }
   ptx::tc_fence_before_sync();
+  __syncthreads();                          // CTA-level: barrier inits + TMEM base visible to all warps
   if constexpr (PAIR) ptx::cluster_sync();  // peer barriers must exist before any remote arrive
-  else __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
 
