@@ -850,8 +850,9 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     OperandMaps ma;
     Operand oa{dA + m0 * rsA, mp, K, rsA, csA};
     if ((rc = prepare_operand<4>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, cmp))) return rc;
-    if ((rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass,
-                               pair && mp > TC_BLOCK_M, cmp)))
+    // B's tensor maps were built for `pair` (128- vs 256-column boxes): every panel, however
+    // short, must run the same kernel variant
+    if ((rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp)))
       return rc;
     CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));
     CUDA_TRY(cudaStreamWaitEvent(down, c.panel_ev[panels + pnl], 0));

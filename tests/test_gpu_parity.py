@@ -221,11 +221,13 @@ def test_host_pointer_entry_strided(la, lb, lc):
         assert np.array_equal(bc[mask], before[mask])
 
 
-@pytest.mark.parametrize("la,lc", [("row", "row"), ("padded", "padded"), ("col", "row")])
-def test_host_pointer_entry_pipelined(la, lc):
+@pytest.mark.parametrize("la,lc,M", [("row", "row", 2500), ("padded", "padded", 2500), ("col", "row", 2500),
+                                     ("row", "row", 2100), ("row", "row", 2049)])
+def test_host_pointer_entry_pipelined(la, lc, M):
     """M >= 2048 with separable row panels takes the 3-stream pipelined host path (H2D of panel
-    p+1 | split+GEMM of panel p | D2H of panel p-1); 'col' A is not separable -> plain path."""
-    M, N, K = 2500, 520, 300
+    p+1 | split+GEMM of panel p | D2H of panel p-1); 'col' A is not separable -> plain path.
+    2100 / 2049: the last panel is shorter than one 128-row tile."""
+    N, K = 520, 300
     A = O.fill_uniform_f32(M * K, 81, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 82, 0, 1).reshape(K, N)
     want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 0.5, A, K, 1, B, N, 1, 0.0, want, N, 1)
     ba, oa, rsa, csa = embed(A, la); bc, oc, rsc, csc = embed(np.full((M, N), np.nan, np.float32), lc)
