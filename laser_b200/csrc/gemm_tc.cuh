@@ -14,18 +14,22 @@
 //       it and add it (IEEE round-to-nearest FADD) to running sums held in registers
 //       while the tensor core is already working on the next block in the other TMEM
 //       stage.  This matters numerically: the tensor core's own accumulator truncates
-//       (measured on B200: ~0.5 ulp of bias per MMA instruction, i.e. 8.6e-5 relative at
+//       (measured on B200: ~0.3 ulp of bias per MMA instruction, i.e. 5.5e-5 relative at
 //       K = 8192 for positive inputs), so long chains must not live in TMEM.
 //   gebp_mkernel loops jr/ir + loop ic (gemm.nim:48-176)
-//       -> persistent CTAs walking 128 x 256 output tiles; the k loop is a 4-deep
-//       mbarrier ring between the TMA producer thread and the MMA thread.
+//       -> persistent CTAs (or CTA pairs, cta_group::2) walking 128 x 256 (256 x 256) output
+//       tiles; the k loop is a 4- (6-) deep mbarrier ring between the TMA producer thread
+//       and the MMA thread; few-tile / long-K problems split K across the idle SMs.
 //   epilogues (gemm_ukernel_generic.nim:53-126)
-//       -> alpha/beta in fp32 from the running sums; beta == 0 never reads C.
+//       -> alpha/beta in fp32 from the running sums; beta == 0 never reads C; optional fused
+//       bias + activation (the reference's TODO at gemm.nim:196).
 //
 // Operand "major-ness" (which of the two strides is 1) is a template parameter:
 // UMMA reads K-major and MN-major tiles natively, so A^T*B, A*B^T ... need no
-// data movement.  fp32-faithful mode runs three tf32 passes per k-tile
-// (hi*lo, lo*hi, then hi*hi) over hi/lo arrays produced by split.cuh.
+// data movement.  The fp32-faithful modes run, per k-tile, the small cross terms first and
+// the hi*hi product last over arrays produced by split.cuh: either three tf32 passes
+// (hi*lo, lo*hi, hi*hi) or -- the default -- two bf16 passes for the cross terms at twice
+// the rate plus one tf32 pass (npass = 2).
 #pragma once
 
 #include <type_traits>
