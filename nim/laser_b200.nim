@@ -48,6 +48,18 @@ proc laser_b200_gemm_strided_f32_dev*(M, N, K: int64, alpha: float32,
     B: ptr float32, rowStrideB, colStrideB: int64,
     beta: float32, C: ptr float32, rowStrideC, colStrideC: int64,
     path: cint, stream: pointer): cint
+# pre-packed operands (gemm_prepacked.nim:63-292) and fused epilogue (gemm.nim:196 TODO)
+proc laser_b200_gemm_prepackA_mem_required_f32*(M, N, K: int64): csize_t
+proc laser_b200_gemm_prepackB_mem_required_f32*(M, N, K: int64): csize_t
+proc laser_b200_gemm_prepackA_f32_dev*(dst: pointer, M, N, K: int64, A: ptr float32,
+    rowStrideA, colStrideA: int64, stream: pointer): cint
+proc laser_b200_gemm_prepackB_f32_dev*(dst: pointer, M, N, K: int64, B: ptr float32,
+    rowStrideB, colStrideB: int64, stream: pointer): cint
+proc laser_b200_gemm_packed_f32_dev*(M, N, K: int64, alpha: float32, packedA, packedB: pointer,
+    beta: float32, C: ptr float32, rowStrideC, colStrideC: int64, stream: pointer): cint
+proc laser_b200_gemm_packedB_f32_dev*(M, N, K: int64, alpha: float32, A: ptr float32,
+    rowStrideA, colStrideA: int64, packedB: pointer, beta: float32, C: ptr float32,
+    rowStrideC, colStrideC: int64, stream: pointer): cint
 proc laser_b200_malloc*(devPtr: ptr pointer, bytes: csize_t): cint
 proc laser_b200_free*(devPtr: pointer): cint
 proc laser_b200_memcpy_h2d*(dst, src: pointer, bytes: csize_t): cint
@@ -141,6 +153,23 @@ proc newCudaTensor*[T](shape: varargs[int]): CudaTensor[T] =
   check laser_b200_memset_zero(p, csize_t(acc * sizeof(T)))
   result.storage.raw_buffer = cast[ptr UncheckedArray[T]](p)
   result.storage.memowner = true
+
+# ---- pre-packed API with the reference's names (gemm_prepacked.nim) on device tensors ----
+proc gemm_prepackB_mem_required*(M, N, K: int): int =
+  int laser_b200_gemm_prepackB_mem_required_f32(M, N, K)
+proc gemm_prepackA_mem_required*(M, N, K: int): int =
+  int laser_b200_gemm_prepackA_mem_required_f32(M, N, K)
+proc gemm_prepackB*(dst_packedB: pointer, M, N, K: int, src_B: ptr float32,
+                    rowStrideB, colStrideB: int) =
+  ## dst_packedB, src_B: device pointers (gemm_prepacked.nim:111-135)
+  check laser_b200_gemm_prepackB_f32_dev(dst_packedB, M, N, K, src_B, rowStrideB, colStrideB, nil)
+proc gemm_prepackA*(dst_packedA: pointer, M, N, K: int, src_A: ptr float32,
+                    rowStrideA, colStrideA: int) =
+  check laser_b200_gemm_prepackA_f32_dev(dst_packedA, M, N, K, src_A, rowStrideA, colStrideA, nil)
+proc gemm_packed*(M, N, K: int, alpha: float32, packedA, packedB: pointer, beta: float32,
+                  C: ptr float32, rowStrideC, colStrideC: int) =
+  ## gemm_prepacked.nim:275-292
+  check laser_b200_gemm_packed_f32_dev(M, N, K, alpha, packedA, packedB, beta, C, rowStrideC, colStrideC, nil)
 
 proc matmul*(a, b: CudaTensor[float32], c: var CudaTensor[float32],
              alpha = 1'f32, beta = 0'f32, path = pathAuto) =
