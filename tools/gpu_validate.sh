@@ -10,3 +10,4 @@ print({k:d['roofline'][k] for k in ('achieved','frac','tensor_pipe_frac','kernel
 echo "=== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> gpurun_out/bench_err.log | tee gpurun_out/bench_ref.json | cut -c1-250
 echo "=== ncu launch list (bench.py)"; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1; wc -l gpurun_out/launches_bench.csv
 echo "=== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 6 -o gpurun_out/prof_tc python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
+echo "=== ncu full (split pre-pass)"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:split_rows -c 2 -o gpurun_out/prof_split python tools/ncu_target.py > gpurun_out/ncu_split.log 2>&1; tail -1 gpurun_out/ncu_split.log
