@@ -357,3 +357,27 @@ def test_full_size_bf16_8192():
     O.gemm_strided(len(rows), N, K, 1.0, a, K, 1, b, N, 1, 0.0, want, N, 1, bf16=True)
     got = tC[rows].view(torch.int16).cpu().numpy().view(np.uint16)
     assert O.max_relative_error(bf16_bits_to_f32(got), bf16_bits_to_f32(want)) <= 2.0 ** -7
+
+
+@pytest.mark.parametrize("mode,want_path,tol", [("simt", "PATH_SIMT", 0.0), ("tf32x3", "PATH_TF32X3", 1e-4),
+                                                 ("tf32x1", "PATH_TF32X1", 5e-3), ("tf32_bf16c", "PATH_TF32_BF16C", 1e-4)])
+def test_env_selects_f32_mode(mode, want_path, tol):
+    """LASER_B200_F32_MODE picks the kernel family of the drop-in (host-pointer) call; 'simt' makes
+    it bit-identical to the CPU reference order."""
+    import os, subprocess, sys
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import laser_b200 as L, oracle as O
+M, N, K = 300, 280, 520
+A = O.fill_uniform_f32(M * K, 1, 0, 1).reshape(M, K); B = O.fill_uniform_f32(K * N, 2, 0, 1).reshape(K, N)
+want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, want, N, 1)
+C = np.zeros((M, N), np.float32); L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1)
+assert L.last_path() == L.{want_path}, L.last_path()
+err = O.max_relative_error(C, want)
+assert err <= {tol}, err
+print("ok", err)
+"""
+    env = dict(os.environ, LASER_B200_F32_MODE=mode)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
