@@ -166,7 +166,7 @@ def run_reference(args):
         return
     import numpy as np
     import oracle as O
-    base = cpu_reference_sample(budget_s=20.0)
+    base = cpu_reference_sample(budget_s=float(os.environ.get("LASER_B200_REF_BUDGET_S", "20")))
     n = base["n"]
     a = O.fill_uniform_f32(n * n, 42, -0.1, 0.1); b = O.fill_uniform_f32(n * n, 43, -0.1, 0.1)
     c = np.zeros(n * n, np.float32)
