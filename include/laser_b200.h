@@ -115,7 +115,8 @@ int laser_b200_gemm_strided_bf16(int64_t M, int64_t N, int64_t K, float alpha,
 /* ---- device-resident variants (what the metric is measured on) ---------
  * Same contract as above (gemm.nim:184-193) with DEVICE pointers on the
  * current device, asynchronous on `stream` (a cudaStream_t passed as void*;
- * NULL = the library's own stream, synchronised before return).
+ * NULL = the library's own stream, synchronised before return; to run on the legacy default
+ * stream pass cudaStreamLegacy, i.e. (void*)0x1).
  * `path` is a LASER_B200_PATH_* value. */
 int laser_b200_gemm_strided_f32_dev(int64_t M, int64_t N, int64_t K, float alpha,
                                     const float *A, int64_t rowStrideA, int64_t colStrideA,

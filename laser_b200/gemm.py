@@ -36,15 +36,30 @@ class DevPtr:
         self.dtype = dtype
 
 
+_torch = None          # the torch module, once a torch tensor has been seen
+_TORCH_DTYPES = None   # torch dtype -> element-type name (built once: this sits on the call path)
+
+
 def _torch_dtype_name(t):
-    import torch
-    return {torch.float32: "f32", torch.float64: "f64", torch.int32: "i32", torch.int64: "i64",
-            torch.bfloat16: "bf16"}.get(t.dtype)
+    global _torch, _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        import torch
+        _torch = torch
+        _TORCH_DTYPES = {torch.float32: "f32", torch.float64: "f64", torch.int32: "i32", torch.int64: "i64",
+                         torch.bfloat16: "bf16"}
+    return _TORCH_DTYPES.get(t.dtype)
+
+
+_Tensor = None
 
 
 def _resolve(x):
     """-> (address, dtype name, is_device)"""
-    from .tensor import Tensor
+    global _Tensor
+    if _Tensor is None:
+        from .tensor import Tensor as _T
+        _Tensor = _T
+    Tensor = _Tensor
     if isinstance(x, np.ndarray):
         name = _NP_DTYPES.get(x.dtype)
         if name is None:
@@ -66,13 +81,21 @@ def _resolve(x):
 
 
 def _current_stream():
+    """torch's current CUDA stream if torch is in use in this process, else 0 (library stream)."""
+    global _torch
+    if _torch is None:
+        import sys
+        _torch = sys.modules.get("torch")
+        if _torch is None:
+            return 0
     try:
-        import torch
-        if torch.cuda.is_available():
-            return int(torch.cuda.current_stream().cuda_stream)
-    except Exception:  # torch absent: the library's own stream is used
-        pass
-    return 0
+        h = int(_torch.cuda.current_stream().cuda_stream)
+    except Exception:  # no CUDA in this torch build / no device: the library reports the error
+        return 0
+    # torch reports its default stream as handle 0, which the C ABI reserves for "the library's
+    # own stream, synchronous".  The legacy default stream has the explicit handle
+    # cudaStreamLegacy == (cudaStream_t)0x1: work is then ordered with everything torch queued.
+    return h if h != 0 else 1
 
 
 def _scalar(name, v):
