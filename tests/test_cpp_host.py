@@ -1,0 +1,31 @@
+"""The compiled-language host mirror (include/laser_b200.hpp): the reference's own GEMM self-tests
+re-stated in C++ (tests/cpp_host/reference_selftests.cpp) compile and link on CPU and pass on the GPU."""
+import os
+import subprocess
+
+import pytest
+
+import laser_b200 as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp_host", "reference_selftests.cpp")
+
+
+def build(tmp_path):
+    exe = str(tmp_path / "reference_selftests")
+    libdir = os.path.dirname(L.lib_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), SRC,
+                           "-o", exe, "-L", libdir, "-llaser_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    out = subprocess.run([build(tmp_path), "--link-only"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("laser_b200")
+
+
+@pytest.mark.gpu
+def test_reference_selftests_in_cpp(tmp_path):
+    out = subprocess.run([build(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("SUCCESS") == 12
