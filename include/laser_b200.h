@@ -226,6 +226,15 @@ int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_te
                             laser_b200_tensor_view *C, double alpha, double beta, int path,
                             void *stream);
 
+/* ---- host-logic introspection (pure functions, no GPU needed; used by the CPU tests) --------
+ * classify: how the tensor-core path would feed an operand seen as [mn][k] with element strides
+ * (s_mn, s_k): 0 = K-major TMA, 1 = MN-major TMA, 2 = general (gathered by pack_general_kernel).
+ * span: lowest/highest element offset touched by a rows x cols view and whether the view is dense
+ * in that span (decides what the host-pointer entry has to copy). */
+int laser_b200_debug_classify(int elem_size, const void *base, int64_t s_mn, int64_t s_k);
+int laser_b200_debug_span(int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+                          int64_t *lo, int64_t *hi, int *dense);
+
 /* ---- synthetic inputs ---------------------------------------------------
  * Counter-based uniform generator, bit-identical to the CPU oracle's
  * (oracle_fill_uniform_f32); stands in for the reference bench's

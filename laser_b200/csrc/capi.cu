@@ -1197,6 +1197,19 @@ int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_te
 #undef LB200_RAW
 }
 
+int laser_b200_debug_classify(int elem_size, const void *base, int64_t s_mn, int64_t s_k) {
+  if (elem_size != 2 && elem_size != 4) return -1;
+  Operand o{base, 1, 1, s_mn, s_k};
+  return static_cast<int>(classify(o, elem_size));
+}
+int laser_b200_debug_span(int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride, int64_t *lo,
+                          int64_t *hi, int *dense) {
+  if (rows <= 0 || cols <= 0 || !lo || !hi || !dense) return LASER_B200_EINVAL;
+  const Span sp = span_of(rows, cols, row_stride, col_stride);
+  *lo = sp.lo; *hi = sp.hi; *dense = sp.dense ? 1 : 0;
+  return LASER_B200_OK;
+}
+
 int laser_b200_fill_uniform_f32_dev(float *dst_dev, int64_t n, uint64_t seed, float lo, float hi,
                                     void *stream) {
   if (n <= 0) return LASER_B200_OK;
