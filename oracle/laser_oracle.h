@@ -93,6 +93,27 @@ double oracle_normwise_relative_error_f32(const float *y, const float *y_true, i
  * (laser_b200_fill_uniform_f32): value(seed, idx) in [lo, hi). */
 void oracle_fill_uniform_f32(float *dst, int64_t n, uint64_t seed, float lo, float hi);
 
+/* ---- the steps either side of the GEMM (laser_layers.c) ---- */
+void oracle_transpose2d_copy(void *dst, const void *src, int64_t NR, int64_t NC, int elem_size);
+void oracle_transpose2d_batched(void *dst, const void *src, int64_t N, int64_t NR, int64_t NC, int elem_size);
+void oracle_nchw2nhwc(void *dst, const void *src, int64_t N, int64_t C, int64_t H, int64_t W, int elem_size);
+void oracle_nhwc2nchw(void *dst, const void *src, int64_t N, int64_t C, int64_t H, int64_t W, int elem_size);
+int oracle_conv2d_out_shape(const int64_t ishape[4], const int64_t kshape[4], const int64_t padding[2],
+                            const int64_t strides[2], int64_t out[4]);
+int64_t oracle_im2col_workspace_size(const int64_t ishape[4], const int64_t kshape[4], const int64_t padding[2],
+                                     const int64_t strides[2]);
+void oracle_im2col_f32(float *workspace, int64_t outH, int64_t outW, const float *input, int64_t C, int64_t H,
+                       int64_t W, int64_t kH, int64_t kW, int64_t pH, int64_t pW, int64_t sH, int64_t sW);
+int oracle_conv2d_im2col_f32(float *output, const float *input, const int64_t ishape[4], const float *kernel,
+                             const int64_t kshape[4], const int64_t padding[2], const int64_t strides[2],
+                             float *workspace);
+int oracle_conv2d_direct_f32(float *output, const float *input, const int64_t ishape[4], const float *kernel,
+                             const int64_t kshape[4], const int64_t padding[2], const int64_t strides[2]);
+void oracle_gemm_strided_batched_f32(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                                     int64_t rsA, int64_t csA, int64_t bsA, const float *B, int64_t rsB,
+                                     int64_t csB, int64_t bsB, float beta, float *C, int64_t rsC, int64_t csC,
+                                     int64_t bsC);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,8 @@ __all__ = [
     "build", "lib", "gemm_strided", "cpu_gemm_strided_f32", "gemm_f32_in_f64",
     "fill_uniform_f32", "mean_relative_error", "max_relative_error",
     "normwise_relative_error", "detect_isa", "num_threads", "set_num_threads", "ISA_NAMES",
+    "transpose2D_copy", "transpose2D_batched", "nchw2nhwc", "nhwc2nchw", "conv2d_out_shape",
+    "im2col_workspace_size", "im2col", "conv2d_im2col", "conv2d_direct", "gemm_strided_batched",
 ]
 
 ISA_NAMES = {1: "generic 2x1", 2: "avx+fma 6x16", 3: "avx512 14x32"}
@@ -57,6 +59,27 @@ def lib():
         L.laser_cpu_num_threads.restype = ctypes.c_int
         L.laser_cpu_set_num_threads.restype = None
         L.laser_cpu_set_num_threads.argtypes = [ctypes.c_int]
+        I4, I2 = i64 * 4, i64 * 2
+        L.oracle_transpose2d_copy.restype = None
+        L.oracle_transpose2d_copy.argtypes = [vp, vp, i64, i64, ctypes.c_int]
+        L.oracle_transpose2d_batched.restype = None
+        L.oracle_transpose2d_batched.argtypes = [vp, vp, i64, i64, i64, ctypes.c_int]
+        for n in ("oracle_nchw2nhwc", "oracle_nhwc2nchw"):
+            getattr(L, n).restype = None
+            getattr(L, n).argtypes = [vp, vp, i64, i64, i64, i64, ctypes.c_int]
+        L.oracle_conv2d_out_shape.restype = ctypes.c_int
+        L.oracle_conv2d_out_shape.argtypes = [I4, I4, I2, I2, I4]
+        L.oracle_im2col_workspace_size.restype = i64
+        L.oracle_im2col_workspace_size.argtypes = [I4, I4, I2, I2]
+        L.oracle_im2col_f32.restype = None
+        L.oracle_im2col_f32.argtypes = [vp, i64, i64, vp] + [i64] * 9
+        L.oracle_conv2d_im2col_f32.restype = ctypes.c_int
+        L.oracle_conv2d_im2col_f32.argtypes = [vp, vp, I4, vp, I4, I2, I2, vp]
+        L.oracle_conv2d_direct_f32.restype = ctypes.c_int
+        L.oracle_conv2d_direct_f32.argtypes = [vp, vp, I4, vp, I4, I2, I2]
+        L.oracle_gemm_strided_batched_f32.restype = None
+        L.oracle_gemm_strided_batched_f32.argtypes = [i64, i64, i64, i64, f32, vp, i64, i64, i64, vp, i64, i64, i64,
+                                                      f32, vp, i64, i64, i64]
         _lib = L
     return _lib
 
@@ -133,3 +156,99 @@ def num_threads():
 
 def set_num_threads(n):
     lib().laser_cpu_set_num_threads(int(n))
+
+
+# ---- the steps either side of the GEMM (laser_layers.c) --------------------------------------
+def _i4(t):
+    return (ctypes.c_int64 * 4)(*[int(v) for v in t])
+
+
+def _i2(t):
+    return (ctypes.c_int64 * 2)(*[int(v) for v in t])
+
+
+def transpose2D_batched(src, N, NR, NC):
+    """swapaxes.nim:56-81 on a contiguous buffer of N matrices [NR, NC]; returns [N, NC, NR]."""
+    src = np.ascontiguousarray(src)
+    dst = np.empty(N * NR * NC, dtype=src.dtype)
+    lib().oracle_transpose2d_batched(_ptr(dst), _ptr(src), N, NR, NC, src.dtype.itemsize)
+    return dst.reshape(N, NC, NR)
+
+
+def transpose2D_copy(src, NR, NC):
+    """swapaxes.nim:16-54."""
+    src = np.ascontiguousarray(src)
+    dst = np.empty(NR * NC, dtype=src.dtype)
+    lib().oracle_transpose2d_copy(_ptr(dst), _ptr(src), NR, NC, src.dtype.itemsize)
+    return dst.reshape(NC, NR)
+
+
+def nchw2nhwc(src, N, C, H, W):
+    src = np.ascontiguousarray(src)
+    dst = np.empty(N * C * H * W, dtype=src.dtype)
+    lib().oracle_nchw2nhwc(_ptr(dst), _ptr(src), N, C, H, W, src.dtype.itemsize)
+    return dst.reshape(N, H, W, C)
+
+
+def nhwc2nchw(src, N, C, H, W):
+    src = np.ascontiguousarray(src)
+    dst = np.empty(N * C * H * W, dtype=src.dtype)
+    lib().oracle_nhwc2nchw(_ptr(dst), _ptr(src), N, C, H, W, src.dtype.itemsize)
+    return dst.reshape(N, C, H, W)
+
+
+def conv2d_out_shape(ishape, kshape, padding, strides):
+    """conv2d_common.nim:15-45; (n, c, h, w) of the output."""
+    out = (ctypes.c_int64 * 4)()
+    if lib().oracle_conv2d_out_shape(_i4(ishape), _i4(kshape), _i2(padding), _i2(strides), out):
+        raise ValueError("strides must satisfy 0 < s < extent (conv2d_common.nim:35-36)")
+    return tuple(out)
+
+
+def im2col_workspace_size(ishape, kshape, padding, strides):
+    return int(lib().oracle_im2col_workspace_size(_i4(ishape), _i4(kshape), _i2(padding), _i2(strides)))
+
+
+def im2col(image, ishape, kshape, padding, strides):
+    """One image [C, H, W] -> [C*kH*kW, outH*outW] (conv2d_im2col.nim:44-93)."""
+    o = conv2d_out_shape(ishape, kshape, padding, strides)
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    K = ishape[1] * kshape[2] * kshape[3]
+    ws = np.empty(K * o[2] * o[3], dtype=np.float32)
+    lib().oracle_im2col_f32(_ptr(ws), o[2], o[3], _ptr(image), ishape[1], ishape[2], ishape[3], kshape[2],
+                            kshape[3], padding[0], padding[1], strides[0], strides[1])
+    return ws.reshape(K, o[2] * o[3])
+
+
+def conv2d_im2col(inp, ishape, kernel, kshape, padding, strides):
+    """conv2d_im2col.nim:95-166; NCHW in, NCHW out."""
+    o = conv2d_out_shape(ishape, kshape, padding, strides)
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    out = np.zeros(int(np.prod(o)), dtype=np.float32)
+    ws = np.empty(max(1, im2col_workspace_size(ishape, kshape, padding, strides)), dtype=np.float32)
+    rc = lib().oracle_conv2d_im2col_f32(_ptr(out), _ptr(inp), _i4(ishape), _ptr(kernel), _i4(kshape), _i2(padding),
+                                        _i2(strides), _ptr(ws))
+    if rc:
+        raise ValueError("oracle_conv2d_im2col_f32 -> %d" % rc)
+    return out.reshape(o)
+
+
+def conv2d_direct(inp, ishape, kernel, kshape, padding, strides):
+    """conv2d_direct_convolution.nim:8-76 (cross-check)."""
+    o = conv2d_out_shape(ishape, kshape, padding, strides)
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    out = np.zeros(int(np.prod(o)), dtype=np.float32)
+    rc = lib().oracle_conv2d_direct_f32(_ptr(out), _ptr(inp), _i4(ishape), _ptr(kernel), _i4(kshape), _i2(padding),
+                                        _i2(strides))
+    if rc:
+        raise ValueError("oracle_conv2d_direct_f32 -> %d" % rc)
+    return out.reshape(o)
+
+
+def gemm_strided_batched(batch, M, N, K, alpha, A, rsA, csA, bsA, B, rsB, csB, bsB, beta, C, rsC, csC, bsC):
+    assert A.dtype == B.dtype == C.dtype == np.float32
+    lib().oracle_gemm_strided_batched_f32(batch, M, N, K, alpha, _ptr(A), rsA, csA, bsA, _ptr(B), rsB, csB, bsB,
+                                          beta, _ptr(C), rsC, csC, bsC)
+    return C
