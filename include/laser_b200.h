@@ -226,6 +226,76 @@ int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_te
                             laser_b200_tensor_view *C, double alpha, double beta, int path,
                             void *stream);
 
+/* ---- the steps either side of the GEMM -------------------------------
+ * Batched GEMM: problem b reads A + b*batchStrideA, B + b*batchStrideB and writes
+ * C + b*batchStrideC (strides in elements; a batch stride of 0 shares that operand, e.g. one
+ * filter matrix against many images).  The reference has no batched entry -- its README lists it
+ * as roadmap (README.md:253-263); each problem follows gemm_strided (gemm.nim:184-193). */
+int laser_b200_gemm_strided_batched_f32_dev(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha,
+                                            const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                            int64_t batchStrideA, const float *B, int64_t rowStrideB,
+                                            int64_t colStrideB, int64_t batchStrideB, float beta, float *C,
+                                            int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC,
+                                            int path, void *stream);
+
+/* Physical transposition of contiguous matrices, elem_size in {1, 2, 4, 8} bytes
+ * (generic T in the reference):
+ *   transpose2D_copy(dst, src, NR, NC)         laser/primitives/swapaxes.nim:16-54
+ *   transpose2D_batched(dst, src, N, NR, NC)   swapaxes.nim:56-81
+ *   nchw2nhwc / nhwc2nchw(dst, src, N,C,H,W)   swapaxes.nim:83-112
+ * dst is overwritten and must not alias src.  Plain names take host pointers and are
+ * synchronous (the reference's contract); _dev names take device pointers + stream. */
+int laser_b200_transpose2D_copy(void *dst, const void *src, int64_t NR, int64_t NC, int elem_size);
+int laser_b200_transpose2D_batched(void *dst, const void *src, int64_t N, int64_t NR, int64_t NC,
+                                   int elem_size);
+int laser_b200_nchw2nhwc(void *dst_nhwc, const void *src_nchw, int64_t N, int64_t C, int64_t H, int64_t W,
+                         int elem_size);
+int laser_b200_nhwc2nchw(void *dst_nchw, const void *src_nhwc, int64_t N, int64_t C, int64_t H, int64_t W,
+                         int elem_size);
+int laser_b200_transpose2D_copy_dev(void *dst, const void *src, int64_t NR, int64_t NC, int elem_size,
+                                    void *stream);
+int laser_b200_transpose2D_batched_dev(void *dst, const void *src, int64_t N, int64_t NR, int64_t NC,
+                                       int elem_size, void *stream);
+int laser_b200_nchw2nhwc_dev(void *dst_nhwc, const void *src_nchw, int64_t N, int64_t C, int64_t H,
+                             int64_t W, int elem_size, void *stream);
+int laser_b200_nhwc2nchw_dev(void *dst_nchw, const void *src_nhwc, int64_t N, int64_t C, int64_t H,
+                             int64_t W, int elem_size, void *stream);
+
+/* im2col convolution (benchmarks/convolution/conv2d_im2col.nim, shapes as in conv2d_common.nim:6-10):
+ *   ishape = (n, c, h, w)  kshape = (c_out, c_in, kH, kW)  padding = (h, w)  strides = (h, w)
+ *   conv2d_out_shape        conv2d_common.nim:15-45 (EINVAL unless 0 < stride < extent, :35-36)
+ *   im2col_workspace_size   conv2d_im2col.nim:8-18: ELEMENTS for one image, c*kH*kW*outH*outW
+ *   im2col                  conv2d_im2col.nim:44-93: `images` images [c][h][w] (image stride
+ *                           c*h*w) -> `images` matrices [c*kH*kW][outH*outW], zero padding
+ *   conv2d_im2col           conv2d_im2col.nim:95-166: NCHW in, NCHW out (fully overwritten,
+ *                           alpha 1 / beta 0), per image O[c_out x outHW] = F[c_out x K] * W[K x outHW]
+ *                           through gemm_strided; `workspace` holds workspace_images >= 1 images
+ *                           (the reference's buffer holds one and is reused between images; a
+ *                           larger one lets several images share one im2col launch and one batched
+ *                           GEMM).  1x1 kernels with unit stride and no padding skip im2col (:121).
+ *                           Divergence: the reference takes that shortcut for every 1x1 kernel, which
+ *                           is wrong for strided/padded ones; those go through im2col here. */
+int laser_b200_conv2d_out_shape(const int64_t ishape[4], const int64_t kshape[4], const int64_t padding[2],
+                                const int64_t strides[2], int64_t oshape[4]);
+int64_t laser_b200_im2col_workspace_size(const int64_t ishape[4], const int64_t kshape[4],
+                                         const int64_t padding[2], const int64_t strides[2]);
+int laser_b200_im2col_f32_dev(float *workspace, const float *input, int64_t images, const int64_t ishape[4],
+                              const int64_t kshape[4], const int64_t padding[2], const int64_t strides[2],
+                              void *stream);
+int laser_b200_conv2d_im2col_f32_dev(float *output, const float *input, const int64_t ishape[4],
+                                     const float *kernel, const int64_t kshape[4], const int64_t padding[2],
+                                     const int64_t strides[2], float *workspace, int64_t workspace_images,
+                                     int path, void *stream);
+/* host pointers, synchronous, library-owned workspace */
+int laser_b200_conv2d_im2col_f32(float *output, const float *input, const int64_t ishape[4],
+                                 const float *kernel, const int64_t kshape[4], const int64_t padding[2],
+                                 const int64_t strides[2]);
+
+/* dst <- src over a common shape, any strides (device tensor views of the same dtype and shape):
+ * copyFrom of laser/tensor/initialization.nim:80-112 (contiguous pairs take a plain device copy,
+ * the rest the strided kernel -- the reference's forEachStrided d in dst, s in src: d = s). */
+int laser_b200_copy_views(laser_b200_tensor_view *dst, const laser_b200_tensor_view *src, void *stream);
+
 /* ---- host-logic introspection (pure functions, no GPU needed; used by the CPU tests) --------
  * classify: how the tensor-core path would feed an operand seen as [mn][k] with element strides
  * (s_mn, s_k): 0 = K-major TMA, 1 = MN-major TMA, 2 = general (gathered by pack_general_kernel).

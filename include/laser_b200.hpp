@@ -12,6 +12,11 @@
 //   laser::newTensor<T>, toTensor<T>, toHost          laser/tensor/initialization.nim:156-202
 //   laser::gemm_prepackA/B_mem_required, gemm_prepackA/B, gemm_packed
 //                                                     .../gemm_prepacked.nim:63-292
+//   laser::transpose2D_copy, transpose2D_batched, nchw2nhwc, nhwc2nchw
+//                                                     laser/primitives/swapaxes.nim:16-112
+//   laser::TensorShape/KernelShape/Padding/Strides, conv2d_out_shape, im2col_workspace_size,
+//   conv2d_im2col                                     benchmarks/convolution/conv2d_common.nim:6-45,
+//                                                     conv2d_im2col.nim:8-166
 #pragma once
 
 #include <cstdint>
@@ -173,6 +178,53 @@ inline void gemm_prepackB(void *dst_packedB, int64_t M, int64_t N, int64_t K, co
 inline void gemm_packed(int64_t M, int64_t N, int64_t K, float alpha, const void *packedA, const void *packedB, float beta,
                         float *C, int64_t rowStrideC, int64_t colStrideC) {
   check(laser_b200_gemm_packed_f32_dev(M, N, K, alpha, packedA, packedB, beta, C, rowStrideC, colStrideC, nullptr));
+}
+
+// ---- physical transposition (swapaxes.nim:16-112); host pointers, synchronous ---------------
+template <typename T>
+void transpose2D_copy(T *dst, const T *src, int64_t NR, int64_t NC) {
+  check(laser_b200_transpose2D_copy(dst, src, NR, NC, static_cast<int>(sizeof(T))));
+}
+template <typename T>
+void transpose2D_batched(T *dst, const T *src, int64_t N, int64_t NR, int64_t NC) {
+  check(laser_b200_transpose2D_batched(dst, src, N, NR, NC, static_cast<int>(sizeof(T))));
+}
+template <typename T>
+void nchw2nhwc(T *dst_nhwc, const T *src_nchw, int64_t N, int64_t C, int64_t H, int64_t W) {
+  check(laser_b200_nchw2nhwc(dst_nhwc, src_nchw, N, C, H, W, static_cast<int>(sizeof(T))));
+}
+template <typename T>
+void nhwc2nchw(T *dst_nchw, const T *src_nhwc, int64_t N, int64_t C, int64_t H, int64_t W) {
+  check(laser_b200_nhwc2nchw(dst_nchw, src_nhwc, N, C, H, W, static_cast<int>(sizeof(T))));
+}
+
+// ---- im2col convolution (conv2d_common.nim:6-45, conv2d_im2col.nim:8-166) ---------------------
+struct TensorShape { int64_t n, c, h, w; };          // batch, channels, height, width
+struct KernelShape { int64_t c_out, c_in, kH, kW; };
+struct Padding { int64_t h, w; };
+struct Strides { int64_t h, w; };
+
+inline TensorShape conv2d_out_shape(TensorShape input, KernelShape kernel, Padding padding, Strides strides) {
+  const int64_t is[4] = {input.n, input.c, input.h, input.w}, ks[4] = {kernel.c_out, kernel.c_in, kernel.kH, kernel.kW};
+  const int64_t pd[2] = {padding.h, padding.w}, st[2] = {strides.h, strides.w};
+  int64_t o[4];
+  check(laser_b200_conv2d_out_shape(is, ks, pd, st, o));
+  return TensorShape{o[0], o[1], o[2], o[3]};
+}
+inline int64_t im2col_workspace_size(TensorShape ishape, KernelShape kshape, Padding padding, Strides strides) {
+  const TensorShape o = conv2d_out_shape(ishape, kshape, padding, strides);
+  return ishape.c * kshape.kH * kshape.kW * o.h * o.w;
+}
+// output / input NCHW, kernel (c_out, c_in, kH, kW); host pointers; output fully overwritten.
+// The reference's caller-provided one-image workspace is owned by the library here.
+inline void conv2d_im2col(float *output, TensorShape oshape, const float *input, TensorShape ishape,
+                          const float *kernel, KernelShape kshape, Padding padding, Strides strides) {
+  const TensorShape expect = conv2d_out_shape(ishape, kshape, padding, strides);
+  if (expect.n != oshape.n || expect.c != oshape.c || expect.h != oshape.h || expect.w != oshape.w)
+    throw std::invalid_argument("conv2d_im2col: oshape does not match conv2d_out_shape");
+  const int64_t is[4] = {ishape.n, ishape.c, ishape.h, ishape.w}, ks[4] = {kshape.c_out, kshape.c_in, kshape.kH, kshape.kW};
+  const int64_t pd[2] = {padding.h, padding.w}, st[2] = {strides.h, strides.w};
+  check(laser_b200_conv2d_im2col_f32(output, input, is, kernel, ks, pd, st));
 }
 
 }  // namespace laser

@@ -76,6 +76,23 @@ SIGNATURES = {
     "laser_b200_synchronize": (ctypes.c_int, []),
     "laser_b200_matmul_views": (ctypes.c_int, [ctypes.POINTER(TensorView), ctypes.POINTER(TensorView),
                                                ctypes.POINTER(TensorView), f64, f64, ctypes.c_int, vp]),
+    "laser_b200_gemm_strided_batched_f32_dev": (ctypes.c_int, [i64, i64, i64, i64, f32, vp, i64, i64, i64, vp, i64, i64, i64,
+                                                               f32, vp, i64, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_transpose2D_copy": (ctypes.c_int, [vp, vp, i64, i64, ctypes.c_int]),
+    "laser_b200_transpose2D_batched": (ctypes.c_int, [vp, vp, i64, i64, i64, ctypes.c_int]),
+    "laser_b200_nchw2nhwc": (ctypes.c_int, [vp, vp, i64, i64, i64, i64, ctypes.c_int]),
+    "laser_b200_nhwc2nchw": (ctypes.c_int, [vp, vp, i64, i64, i64, i64, ctypes.c_int]),
+    "laser_b200_transpose2D_copy_dev": (ctypes.c_int, [vp, vp, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_transpose2D_batched_dev": (ctypes.c_int, [vp, vp, i64, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_nchw2nhwc_dev": (ctypes.c_int, [vp, vp, i64, i64, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_nhwc2nchw_dev": (ctypes.c_int, [vp, vp, i64, i64, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_conv2d_out_shape": (ctypes.c_int, [i64 * 4, i64 * 4, i64 * 2, i64 * 2, i64 * 4]),
+    "laser_b200_im2col_workspace_size": (i64, [i64 * 4, i64 * 4, i64 * 2, i64 * 2]),
+    "laser_b200_im2col_f32_dev": (ctypes.c_int, [vp, vp, i64, i64 * 4, i64 * 4, i64 * 2, i64 * 2, vp]),
+    "laser_b200_conv2d_im2col_f32_dev": (ctypes.c_int, [vp, vp, i64 * 4, vp, i64 * 4, i64 * 2, i64 * 2, vp, i64,
+                                                        ctypes.c_int, vp]),
+    "laser_b200_conv2d_im2col_f32": (ctypes.c_int, [vp, vp, i64 * 4, vp, i64 * 4, i64 * 2, i64 * 2]),
+    "laser_b200_copy_views": (ctypes.c_int, [ctypes.POINTER(TensorView), ctypes.POINTER(TensorView), vp]),
     "laser_b200_debug_classify": (ctypes.c_int, [ctypes.c_int, vp, i64, i64]),
     "laser_b200_debug_span": (ctypes.c_int, [i64, i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64),
                                              ctypes.POINTER(ctypes.c_int)]),

@@ -24,6 +24,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "layers.cuh"
 #include "split.cuh"
 
 namespace {
@@ -104,6 +105,7 @@ struct Ctx {
   Buffer ws[8];      // per operand: hi, lo (fp32) and xb, lb (bf16) -- A then B
   Buffer stage[3];   // device staging of host A, B, C spans
   Buffer splitk;     // split-K partial-sum planes
+  Buffer layer_ws;   // im2col workspace of the host-pointer convolution
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
@@ -923,6 +925,7 @@ void laser_b200_shutdown(void) {
     for (auto &b : c.ws) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     if (c.splitk.ptr) { cudaFree(c.splitk.ptr); c.splitk = Buffer(); }
+    if (c.layer_ws.ptr) { cudaFree(c.layer_ws.ptr); c.layer_ws = Buffer(); }
     cudaEventDestroy(c.ws_free);
     for (auto e : c.panel_ev) cudaEventDestroy(e);
     c.panel_ev.clear();
@@ -1225,3 +1228,5 @@ int laser_b200_fill_uniform_f32_dev(float *dst_dev, int64_t n, uint64_t seed, fl
 }
 
 }  // extern "C"
+
+#include "capi_layers.inc"

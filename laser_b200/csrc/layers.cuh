@@ -1,0 +1,206 @@
+// layers.cuh -- the HBM-bound steps either side of the GEMM in the reference's intended use
+// (SURVEY.md section 8f, rank 4): physical transposition / NCHW<->NHWC
+// (laser/primitives/swapaxes.nim:16-112), im2col (benchmarks/convolution/conv2d_im2col.nim:44-93)
+// and the strided N-d copy behind copyFrom (laser/tensor/initialization.nim:80-112).
+// All of them move each byte once: coalesced 16-byte global accesses where the shapes allow,
+// shared-memory tiles for the transposition, grids sized from the SM count by the host.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb200 {
+
+// ---- batched 2-d transposition: dst[n][j][i] = src[n][i][j], src = N x [NR][NC] contiguous ----
+// 64 x 64 element tiles through shared memory (row pitch 65 elements: the transposed read hits
+// 2-way bank conflicts at worst, far from limiting an HBM-bound kernel).  V = elements per
+// global access (4 when NR, NC are multiples of 4 and both bases are aligned to 4 elements,
+// else 1).  256 threads: 16 accesses of V=4 per tile row, 16 rows per pass.
+template <typename T>
+struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) Vec4 {
+  T v[4];
+};
+
+// host side: may the 4-element accesses be used?
+template <typename T>
+inline bool transpose_can_vec(const void *dst, const void *src, int64_t NR, int64_t NC) {
+  const uintptr_t align = sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4;
+  return (NR % 4 == 0) && (NC % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % align == 0) &&
+         (reinterpret_cast<uintptr_t>(src) % align == 0);
+}
+inline int64_t transpose_tiles(int64_t N, int64_t NR, int64_t NC) { return N * ((NR + 63) / 64) * ((NC + 63) / 64); }
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+transpose_batched_kernel(T *__restrict__ dst, const T *__restrict__ src, int64_t N, int64_t NR, int64_t NC) {
+  constexpr int TILE = 64;
+  __shared__ T tile[TILE][TILE + 1];
+  const int64_t tiles_r = (NR + TILE - 1) / TILE, tiles_c = (NC + TILE - 1) / TILE;
+  const int64_t per_mat = tiles_r * tiles_c, total = per_mat * N;
+  const int tid = threadIdx.x;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t n = t / per_mat, rem = t - n * per_mat;
+    const int64_t r0 = (rem / tiles_c) * TILE, c0 = (rem % tiles_c) * TILE;
+    const T *s = src + n * NR * NC;
+    T *d = dst + n * NR * NC;
+    if constexpr (V == 4) {
+      const int q = tid & 15, rr = tid >> 4;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int r = p * 16 + rr;
+        if (r0 + r < NR && c0 + 4 * q < NC) {
+          const Vec4<T> v = *reinterpret_cast<const Vec4<T> *>(s + (r0 + r) * NC + c0 + 4 * q);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tile[r][4 * q + e] = v.v[e];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int j = p * 16 + rr;  // row of dst inside the tile = column of src
+        if (c0 + j < NC && r0 + 4 * q < NR) {
+          Vec4<T> v;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v.v[e] = tile[4 * q + e][j];
+          *reinterpret_cast<Vec4<T> *>(d + (c0 + j) * NR + r0 + 4 * q) = v;
+        }
+      }
+    } else {
+      const int x = tid & 63, y = tid >> 6;  // 64 x 4
+#pragma unroll 4
+      for (int p = 0; p < 16; ++p) {
+        const int r = p * 4 + y;
+        if (r0 + r < NR && c0 + x < NC) tile[r][x] = s[(r0 + r) * NC + c0 + x];
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int p = 0; p < 16; ++p) {
+        const int j = p * 4 + y;
+        if (c0 + j < NC && r0 + x < NR) d[(c0 + j) * NR + r0 + x] = tile[x][j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- im2col: images x [C][H][W] -> images x [C*kH*kW][outH*outW], zero outside the image ----
+struct Im2colParams {
+  int C, H, W, kH, kW, pH, pW, sH, sW, outH, outW;
+  int K;         // C * kH * kW  (rows of the workspace matrix)
+  int outHW;     // columns
+  int64_t rows;  // K * images
+  int64_t in_image_stride, ws_image_stride;  // elements
+  int tx_log2;   // threads along the columns = 1 << tx_log2 (each owns 4 consecutive columns)
+  int chunks;    // column chunks of (4 << tx_log2) per row
+};
+
+// host side: launch geometry.  geom = {C, H, W, kH, kW, pH, pW, sH, sW, outH, outW} (all < 2^31).
+// Returns the number of blocks of 256 threads; *vec4 says whether the float4 store variant applies.
+inline int64_t im2col_plan(const int64_t geom[11], int64_t images, const void *workspace, Im2colParams *p,
+                           bool *vec4) {
+  p->C = (int)geom[0]; p->H = (int)geom[1]; p->W = (int)geom[2]; p->kH = (int)geom[3]; p->kW = (int)geom[4];
+  p->pH = (int)geom[5]; p->pW = (int)geom[6]; p->sH = (int)geom[7]; p->sW = (int)geom[8];
+  p->outH = (int)geom[9]; p->outW = (int)geom[10];
+  p->K = p->C * p->kH * p->kW;
+  p->outHW = p->outH * p->outW;
+  p->rows = static_cast<int64_t>(p->K) * images;
+  p->in_image_stride = geom[0] * geom[1] * geom[2];
+  p->ws_image_stride = static_cast<int64_t>(p->K) * p->outHW;
+  const int quads = (p->outHW + 3) / 4;
+  int tx_log2 = 0;
+  while ((1 << tx_log2) < quads && tx_log2 < 8) ++tx_log2;
+  p->tx_log2 = tx_log2;
+  p->chunks = (quads + (1 << tx_log2) - 1) >> tx_log2;
+  const int rows_per_block = 256 >> tx_log2;
+  *vec4 = (p->outHW % 4 == 0) && (reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
+  return ((p->rows + rows_per_block - 1) / rows_per_block) * p->chunks;
+}
+
+// thread (tx, ty): row = block_row_group * rows_per_block + ty, columns 4*(chunk*TX + tx) .. +3.
+// The row is decoded once per thread (kk -> c, krow, kcol), the column once per 4 outputs.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+im2col_kernel(float *__restrict__ ws, const float *__restrict__ in, Im2colParams p) {
+  const int tx = threadIdx.x & ((1 << p.tx_log2) - 1), ty = threadIdx.x >> p.tx_log2;
+  const int rows_per_block = 256 >> p.tx_log2;
+  const int64_t blk = blockIdx.x;
+  const int chunk = static_cast<int>(blk % p.chunks);
+  const int64_t row = (blk / p.chunks) * rows_per_block + ty;
+  if (row >= p.rows) return;
+  const int64_t img = row / p.K;
+  const int kk = static_cast<int>(row - img * p.K);
+  const int khw = p.kH * p.kW;
+  const int c = kk / khw, r2 = kk - c * khw;
+  const int krow = r2 / p.kW, kcol = r2 - krow * p.kW;
+  const int p0 = ((chunk << p.tx_log2) + tx) * 4;
+  if (p0 >= p.outHW) return;
+  int oh = p0 / p.outW, ow = p0 - oh * p.outW;
+  const float *src = in + img * p.in_image_stride + static_cast<int64_t>(c) * p.H * p.W;
+  float *dst = ws + img * p.ws_image_stride + static_cast<int64_t>(kk) * p.outHW + p0;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = oh * p.sH - p.pH + krow, cc = ow * p.sW - p.pW + kcol;
+    const bool inside = (p0 + e < p.outHW) && static_cast<unsigned>(r) < static_cast<unsigned>(p.H) &&
+                        static_cast<unsigned>(cc) < static_cast<unsigned>(p.W);
+    v[e] = inside ? src[static_cast<int64_t>(r) * p.W + cc] : 0.0f;
+    if (++ow == p.outW) { ow = 0; ++oh; }
+  }
+  if constexpr (VEC4) {
+    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (p0 + e < p.outHW) dst[e] = v[e];
+  }
+}
+
+// ---- strided N-d copy (copyFrom): dst[idx] = src[idx] over a common shape, rank <= 6 ----
+struct CopyParams {
+  int rank;
+  int64_t shape[6], dst_strides[6], src_strides[6];  // elements; innermost dimension last
+  int64_t total;
+};
+// host side: merge neighbouring dimensions that are contiguous in both views, drop extents of 1
+inline void copy_plan(int rank, const int64_t *shape, const int64_t *dst_strides, const int64_t *src_strides,
+                      CopyParams *p) {
+  p->rank = 0;
+  p->total = 1;
+  for (int d = 0; d < rank; ++d) {
+    p->total *= shape[d];
+    if (shape[d] == 1) continue;
+    if (p->rank > 0 && p->dst_strides[p->rank - 1] == dst_strides[d] * shape[d] &&
+        p->src_strides[p->rank - 1] == src_strides[d] * shape[d]) {
+      p->shape[p->rank - 1] *= shape[d];
+      p->dst_strides[p->rank - 1] = dst_strides[d];
+      p->src_strides[p->rank - 1] = src_strides[d];
+    } else {
+      p->shape[p->rank] = shape[d];
+      p->dst_strides[p->rank] = dst_strides[d];
+      p->src_strides[p->rank] = src_strides[d];
+      ++p->rank;
+    }
+  }
+  for (int d = p->rank; d < 6; ++d) { p->shape[d] = 1; p->dst_strides[d] = 0; p->src_strides[d] = 0; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_strided_kernel(T *__restrict__ dst, const T *__restrict__ src, CopyParams p) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < p.total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t rem = i, od = 0, os = 0;
+#pragma unroll
+    for (int d = 5; d >= 0; --d) {
+      if (d < p.rank) {
+        const int64_t q = rem / p.shape[d], x = rem - q * p.shape[d];
+        od += x * p.dst_strides[d];
+        os += x * p.src_strides[d];
+        rem = q;
+      }
+    }
+    dst[od] = src[os];
+  }
+}
+
+}  // namespace lb200

@@ -181,3 +181,43 @@ proc matmul*(a, b: CudaTensor[float32], c: var CudaTensor[float32],
     a.unsafe_raw_data, a.strides.data[0], a.strides.data[1],
     b.unsafe_raw_data, b.strides.data[0], b.strides.data[1],
     beta, c.unsafe_raw_data, c.strides.data[0], c.strides.data[1], path.cint, nil)
+
+# ---- the steps either side of the GEMM: transposes (laser/primitives/swapaxes.nim:16-112) and
+# ---- im2col convolution (benchmarks/convolution/conv2d_common.nim:6-45, conv2d_im2col.nim:8-166)
+{.push importc, cdecl, dynlib: laserB200Lib.}
+proc laser_b200_transpose2D_copy*(dst, src: pointer, NR, NC: int64, elemSize: cint): cint
+proc laser_b200_transpose2D_batched*(dst, src: pointer, N, NR, NC: int64, elemSize: cint): cint
+proc laser_b200_nchw2nhwc*(dst, src: pointer, N, C, H, W: int64, elemSize: cint): cint
+proc laser_b200_nhwc2nchw*(dst, src: pointer, N, C, H, W: int64, elemSize: cint): cint
+proc laser_b200_conv2d_out_shape*(ishape, kshape: ptr array[4, int64], padding, strides: ptr array[2, int64],
+                                  oshape: ptr array[4, int64]): cint
+proc laser_b200_conv2d_im2col_f32*(output, input: ptr float32, ishape: ptr array[4, int64], kernel: ptr float32,
+                                   kshape: ptr array[4, int64], padding, strides: ptr array[2, int64]): cint
+{.pop.}
+
+proc transpose2D_copy*[T](dst, src: ptr (T or UncheckedArray[T]), NR, NC: Natural) =
+  ## swapaxes.nim:16-54 (host pointers, synchronous)
+  check laser_b200_transpose2D_copy(dst, src, NR, NC, sizeof(T).cint)
+proc transpose2D_batched*[T](dst, src: ptr (T or UncheckedArray[T]), N, NR, NC: Natural) =
+  ## swapaxes.nim:56-81
+  check laser_b200_transpose2D_batched(dst, src, N, NR, NC, sizeof(T).cint)
+proc nchw2nhwc*[T](dst_hwnc, src_nchw: ptr (T or UncheckedArray[T]), N, C, H, W: Natural) =
+  check laser_b200_nchw2nhwc(dst_hwnc, src_nchw, N, C, H, W, sizeof(T).cint)
+proc nhwc2nchw*[T](dst_nchw, src_nhwc: ptr (T or UncheckedArray[T]), N, C, H, W: Natural) =
+  check laser_b200_nhwc2nchw(dst_nchw, src_nhwc, N, C, H, W, sizeof(T).cint)
+
+type
+  TensorShape* = tuple[n, c, h, w: int]
+  KernelShape* = tuple[c_out, c_in, kH, kW: int]
+  Padding* = tuple[h, w: int]
+  Strides* = tuple[h, w: int]
+
+proc conv2d_im2col*(output: ptr float32, oshape: TensorShape, input: ptr float32, ishape: TensorShape,
+                    kernel: ptr float32, kshape: KernelShape, padding: Padding, strides: Strides) =
+  ## conv2d_im2col.nim:95-166 without the caller-provided workspace (owned by the library)
+  var
+    ish = [ishape.n.int64, ishape.c, ishape.h, ishape.w]
+    ksh = [kshape.c_out.int64, kshape.c_in, kshape.kH, kshape.kW]
+    pad = [padding.h.int64, padding.w]
+    st = [strides.h.int64, strides.w]
+  check laser_b200_conv2d_im2col_f32(output, input, ish.addr, kernel, ksh.addr, pad.addr, st.addr)

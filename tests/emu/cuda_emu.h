@@ -1,0 +1,64 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE: runs a __global__ function of the product on host threads so
+// that the CPU test suite can execute the kernels' index arithmetic, bounds handling and
+// shared-memory choreography without a GPU (one std::thread per CUDA thread of a block, a pthread
+// barrier for __syncthreads, blocks one after the other).  Only kernels written in plain CUDA C++
+// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh.
+// It is a test of the product's source, not a fallback: nothing under laser_b200/ includes it.
+#pragma once
+
+#include <cuda_runtime.h>  // host-side definitions of float4 / make_float4
+#include <pthread.h>
+#include <stdint.h>
+
+#include <thread>
+#include <vector>
+
+#undef __global__
+#define __global__
+#undef __device__
+#define __device__
+#undef __host__
+#define __host__
+#undef __forceinline__
+#define __forceinline__ inline
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __shared__
+#define __shared__ static  // one block at a time: a function-local static is the block's shared memory
+
+namespace emu {
+struct Idx {
+  unsigned x, y, z;
+};
+inline thread_local Idx t_idx{0, 0, 0};
+inline thread_local Idx b_idx{0, 0, 0};
+inline Idx b_dim{1, 1, 1}, g_dim{1, 1, 1};
+inline pthread_barrier_t barrier;
+
+// kernels whose threads all reach every __syncthreads (or that have none) only
+template <typename Body>
+void launch(unsigned grid, unsigned block, Body body) {
+  g_dim = Idx{grid, 1, 1};
+  b_dim = Idx{block, 1, 1};
+  pthread_barrier_init(&barrier, nullptr, block);
+  std::vector<std::thread> threads;
+  threads.reserve(block);
+  for (unsigned t = 0; t < block; ++t)
+    threads.emplace_back([=]() {
+      t_idx = Idx{t, 0, 0};
+      for (unsigned b = 0; b < grid; ++b) {
+        b_idx = Idx{b, 0, 0};
+        body();
+        pthread_barrier_wait(&barrier);  // next block only when this one is done (shared memory reuse)
+      }
+    });
+  for (auto &th : threads) th.join();
+  pthread_barrier_destroy(&barrier);
+}
+}  // namespace emu
+
+#define threadIdx (emu::t_idx)
+#define blockIdx (emu::b_idx)
+#define blockDim (emu::b_dim)
+#define gridDim (emu::g_dim)
+inline void __syncthreads() { pthread_barrier_wait(&emu::barrier); }

@@ -11,10 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp_host", "reference_selftests.cpp")
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "reference_selftests")
+CONV_SRC = os.path.join(ROOT, "tests", "cpp_host", "conv_selftests.cpp")
+
+
+def build(tmp_path, src=SRC):
+    exe = str(tmp_path / os.path.splitext(os.path.basename(src))[0])
     libdir = os.path.dirname(L.lib_path())
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), SRC,
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
                            "-o", exe, "-L", libdir, "-llaser_b200", "-Wl,-rpath," + libdir])
     return exe
 
@@ -29,3 +32,17 @@ def test_reference_selftests_in_cpp(tmp_path):
     out = subprocess.run([build(tmp_path)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("SUCCESS") == 12
+
+
+def test_cpp_layers_mirror_compiles_and_links(tmp_path):
+    out = subprocess.run([build(tmp_path, CONV_SRC), "--link-only"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip().endswith("workspace 243"), out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("LASER_B200_UNVALIDATED", "0") != "1",
+                    reason="layer kernels not yet validated on a B200 (set LASER_B200_UNVALIDATED=1)")
+def test_conv_selftests_in_cpp(tmp_path):
+    out = subprocess.run([build(tmp_path, CONV_SRC)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("SUCCESS") == 3

@@ -1,0 +1,136 @@
+"""CPU-only: the kernels of laser_b200/csrc/layers.cuh (transposition, im2col, strided copy) run on
+host threads (tests/emu/cuda_emu.h: one thread per CUDA thread, a barrier for __syncthreads) and are
+compared with the oracle bit for bit.  This executes the product's kernel source -- index
+arithmetic, bounds, shared-memory choreography, launch planning -- without a GPU; the GPU tests
+(test_gpu_layers.py) then only have to confirm the same on the device."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not installed")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    out_dir = os.path.join(EMU_DIR, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "liblayers_emu.so")
+    srcs = [os.path.join(EMU_DIR, "layers_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(HERE, "..", "laser_b200", "csrc", "layers.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.check_call([gxx, "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-I", CUDA_INC,
+                               "-Wno-attributes", "-Wno-unknown-pragmas", srcs[0], "-o", so], env=env)
+    L = ctypes.CDLL(so)
+    i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+    L.emu_transpose_batched.restype = ci
+    L.emu_transpose_batched.argtypes = [ci, vp, vp, i64, i64, i64, ci, ci]
+    L.emu_im2col.restype = ci
+    L.emu_im2col.argtypes = [vp, vp, i64, i64 * 11, ci]
+    L.emu_copy_strided.restype = ci
+    L.emu_copy_strided.argtypes = [ci, vp, vp, ci, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
+    return L
+
+
+def ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.float32, np.float64])
+@pytest.mark.parametrize("N,NR,NC,grid", [
+    (1, 64, 64, 0), (1, 128, 192, 3), (2, 68, 132, 2),      # multiples of 4: vector path, ragged tiles
+    (1, 1, 1, 0), (1, 65, 63, 0), (3, 33, 70, 4), (1, 5, 257, 2),   # scalar path
+    (1, 4, 1000, 0), (1, 1000, 4, 5),
+])
+def test_transpose_kernel(emu, dt, N, NR, NC, grid):
+    src = (np.arange(N * NR * NC, dtype=np.int64) * 2654435761 % 65521).astype(dt)
+    dst = np.full(N * NR * NC, 77, dt)
+    v = emu.emu_transpose_batched(np.dtype(dt).itemsize, ptr(dst), ptr(src), N, NR, NC, grid, 0)
+    assert v == (4 if NR % 4 == 0 and NC % 4 == 0 else 1)
+    assert np.array_equal(dst.reshape(N, NC, NR), O.transpose2D_batched(src, N, NR, NC))
+    if v == 4:   # the scalar kernel must agree on the same shape
+        dst2 = np.zeros_like(dst)
+        assert emu.emu_transpose_batched(np.dtype(dt).itemsize, ptr(dst2), ptr(src), N, NR, NC, grid, 1) == 1
+        assert np.array_equal(dst2, dst)
+
+
+def test_transpose_misaligned_base_takes_scalar_path(emu):
+    N, NR, NC = 1, 64, 64
+    buf = np.arange(NR * NC + 1, dtype=np.float32)
+    src = buf[1:]                                   # 4 bytes off a 16-byte boundary
+    dst = np.zeros(NR * NC, np.float32)
+    assert emu.emu_transpose_batched(4, ptr(dst), ptr(src), N, NR, NC, 0, 0) == 1
+    assert np.array_equal(dst.reshape(NC, NR), src.reshape(NR, NC).T)
+
+
+IM2COL_CASES = [
+    # ishape (images, C, H, W), kshape (c_out, c_in, kH, kW), padding, strides
+    ((1, 1, 4, 4), (1, 1, 3, 3), (1, 1), (1, 1)),          # the reference's first known-answer geometry
+    ((1, 3, 5, 5), (2, 3, 3, 3), (1, 1), (2, 2)),          # the second
+    ((2, 3, 9, 11), (4, 3, 3, 3), (0, 0), (1, 1)),
+    ((3, 2, 8, 8), (5, 2, 3, 3), (1, 1), (2, 2)),          # outHW = 16: float4 stores
+    ((2, 1, 12, 6), (2, 1, 5, 2), (2, 1), (3, 3)),
+    ((1, 2, 40, 36), (1, 2, 3, 3), (1, 1), (1, 1)),        # outHW = 1440 > 1024: several column chunks
+    ((2, 5, 7, 7), (1, 5, 7, 7), (3, 3), (1, 1)),          # kernel as large as the image
+    ((1, 1, 3, 70), (1, 1, 1, 3), (0, 2), (1, 2)),
+]
+
+
+@pytest.mark.parametrize("ishape,kshape,padding,strides", IM2COL_CASES)
+def test_im2col_kernel(emu, ishape, kshape, padding, strides):
+    B, C, H, W = ishape
+    o = O.conv2d_out_shape(ishape, kshape, padding, strides)
+    K, outHW = C * kshape[2] * kshape[3], o[2] * o[3]
+    rng = np.random.default_rng(11)
+    inp = rng.random(ishape, dtype=np.float32) + 1.0       # strictly positive: zero means padding
+    geom = (ctypes.c_int64 * 11)(C, H, W, kshape[2], kshape[3], padding[0], padding[1], strides[0], strides[1], o[2], o[3])
+    exp = np.stack([O.im2col(inp[b], ishape, kshape, padding, strides) for b in range(B)])
+    for force_scalar in (0, 1):
+        ws = np.full(B * K * outHW + 8, -5.0, np.float32)   # 8 guard elements
+        v = emu.emu_im2col(ptr(ws), ptr(inp), B, geom, force_scalar)
+        assert v == (4 if (outHW % 4 == 0 and not force_scalar) else 1)
+        assert np.array_equal(ws[:B * K * outHW].reshape(B, K, outHW), exp)
+        assert np.all(ws[B * K * outHW:] == -5.0)
+
+
+def as_strided_idx(shape, strides, offset):
+    idx = np.full(shape, offset, dtype=np.int64)
+    for d, (n, s) in enumerate(zip(shape, strides)):
+        sh = [1] * len(shape); sh[d] = n
+        idx = idx + (np.arange(n, dtype=np.int64) * s).reshape(sh)
+    return idx
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.uint16])
+@pytest.mark.parametrize("shape,dst_strides,src_strides,merged", [
+    ((6, 10), (10, 1), (1, 6), 2),                 # transposed source
+    ((4, 5, 6), (30, 6, 1), (60, 12, 2), 1),       # every other element of the source: all dims merge
+    ((3, 1, 7), (7, 7, 1), (14, 99, 2), 1),        # extent-1 dimension dropped, the rest merges
+    ((2, 3, 4, 5), (60, 20, 5, 1), (1, 2, 6, 24), 4),
+    ((8, 16), (16, 1), (32, 1), 2),                # padded rows
+    ((5, 4, 3, 2, 2, 2), (96, 24, 8, 4, 2, 1), (1, 5, 20, 60, 120, 240), 6),
+])
+def test_copy_strided_kernel(emu, dt, shape, dst_strides, src_strides, merged):
+    n_src = 1 + sum((n - 1) * abs(s) for n, s in zip(shape, src_strides))
+    n_dst = 1 + sum((n - 1) * abs(s) for n, s in zip(shape, dst_strides))
+    src = (np.arange(n_src) % 60000 + 1).astype(dt)
+    dst = np.zeros(n_dst, dt)
+    i64 = ctypes.c_int64
+    arr = lambda t: (i64 * len(t))(*t)
+    rank = emu.emu_copy_strided(np.dtype(dt).itemsize, ptr(dst), ptr(src), len(shape), arr(shape), arr(dst_strides),
+                                arr(src_strides), 3)
+    assert rank == merged
+    exp = np.zeros(n_dst, dt)
+    exp[as_strided_idx(shape, dst_strides, 0)] = src[as_strided_idx(shape, src_strides, 0)]
+    assert np.array_equal(dst, exp)
