@@ -217,17 +217,8 @@ int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, in
                 int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
                 int64_t csC, cudaStream_t s) {
   SimtParams<T> p;
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
-  p.A = A; p.rsA = rsA; p.csA = csA;
-  p.B = B; p.rsB = rsB; p.csB = csB;
-  p.C = C; p.rsC = rsC; p.csC = csC;
+  const int64_t tiles = simt_plan<T, TM, TN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   if constexpr (std::is_same<T, float>::value) { p.bias = g_epi.bias; p.bias_per_row = g_epi.bias_per_row; p.act = g_epi.act; }
-  p.a_along_m = (llabs(rsA) < llabs(csA)) ? 1 : 0;
-  p.b_along_k = (llabs(rsB) < llabs(csB)) ? 1 : 0;
-  constexpr int BM = 16 * TM, BN = 16 * TN;
-  p.num_m_blocks = static_cast<int>((M + BM - 1) / BM);
-  p.num_n_blocks = static_cast<int>((N + BN - 1) / BN);
-  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   if (tiles > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
   const int grid = grid_for(c, tiles, 2);
   gemm_simt_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);

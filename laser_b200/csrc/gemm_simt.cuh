@@ -75,6 +75,24 @@ struct SimtParams {
   int act = 0;
 };
 
+// host side: everything but the fused epilogue; returns the number of output tiles
+template <typename T, int TM, int TN>
+inline int64_t simt_plan(SimtParams<T> &p, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
+                         int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
+                         int64_t csC) {
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
+  p.A = A; p.rsA = rsA; p.csA = csA;
+  p.B = B; p.rsB = rsB; p.csB = csB;
+  p.C = C; p.rsC = rsC; p.csC = csC;
+  p.a_along_m = ((rsA < 0 ? -rsA : rsA) < (csA < 0 ? -csA : csA)) ? 1 : 0;
+  p.b_along_k = ((rsB < 0 ? -rsB : rsB) < (csB < 0 ? -csB : csB)) ? 1 : 0;
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  const int64_t mblocks = (M + BM - 1) / BM, nblocks = (N + BN - 1) / BN;
+  p.num_m_blocks = static_cast<int>(mblocks);
+  p.num_n_blocks = static_cast<int>(nblocks);
+  return mblocks * nblocks;
+}
+
 #ifndef LB200_SIMT_MINB
 #define LB200_SIMT_MINB 1
 #endif
@@ -206,6 +224,7 @@ gemm_simt_kernel(const SimtParams<T> p) {
   }
 }
 
+#ifndef LB200_HOST_EMULATION  // warp-shuffle kernels cannot run in tests/emu (one host thread per CUDA thread)
 // ---------------------------------------------------------------------------
 // Skinny GEMM: N <= 4 (matrix x few vectors).  One warp per output row: lanes stride
 // over K with coalesced loads of A's row, partial dot products are combined with
@@ -319,5 +338,7 @@ gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict
     }
   }
 }
+
+#endif  // LB200_HOST_EMULATION
 
 }  // namespace lb200

@@ -2,7 +2,7 @@
 // that the CPU test suite can execute the kernels' index arithmetic, bounds handling and
 // shared-memory choreography without a GPU (one std::thread per CUDA thread of a block, a pthread
 // barrier for __syncthreads, blocks one after the other).  Only kernels written in plain CUDA C++
-// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh.
+// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh and gemm_simt_kernel.
 // It is a test of the product's source, not a fallback: nothing under laser_b200/ includes it.
 #pragma once
 
@@ -56,6 +56,17 @@ void launch(unsigned grid, unsigned block, Body body) {
   pthread_barrier_destroy(&barrier);
 }
 }  // namespace emu
+
+// correctly rounded single operations (compile with -ffp-contract=off so that a * b + c stays unfused)
+#include <cmath>
+inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+template <typename T>
+inline T __ldg(const T *p) { return *p; }
 
 #define threadIdx (emu::t_idx)
 #define blockIdx (emu::b_idx)

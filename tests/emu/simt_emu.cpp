@@ -1,0 +1,46 @@
+// simt_emu.cpp -- TEST INFRASTRUCTURE: the exact CUDA-core GEMM kernel of
+// laser_b200/csrc/gemm_simt.cuh (gemm_simt_kernel, the path that must be bit-identical to the CPU
+// reference) compiled for the host (cuda_emu.h) with the library's own launch planning
+// (simt_plan) and the library's tile configurations (8x8x16 for 4-byte, 4x4x16 for 8-byte types).
+#define LB200_HOST_EMULATION 1
+#include "cuda_emu.h"
+
+#include "../../laser_b200/csrc/gemm_simt.cuh"
+
+using namespace lb200;
+
+template <typename T, int TM, int TN, int BK>
+static int run(int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA, int64_t csA, const T *B, int64_t rsB,
+               int64_t csB, T beta, T *C, int64_t rsC, int64_t csC, int grid, const float *bias, int bias_per_row,
+               int act) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;   // gemm.nim:150: nothing to do, C untouched
+  SimtParams<T> p;
+  const int64_t tiles = simt_plan<T, TM, TN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  p.bias = bias; p.bias_per_row = bias_per_row; p.act = act;
+  if (grid <= 0 || grid > tiles) grid = static_cast<int>(tiles);
+  emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_simt_kernel<T, TM, TN, BK>(p); });
+  return static_cast<int>(tiles);
+}
+
+extern "C" {
+int emu_gemm_simt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
+                      const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
+                      int grid, const float *bias, int bias_per_row, int act) {
+  return run<float, 8, 8, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, bias, bias_per_row, act);
+}
+int emu_gemm_simt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t rsA, int64_t csA,
+                      const double *B, int64_t rsB, int64_t csB, double beta, double *C, int64_t rsC, int64_t csC,
+                      int grid) {
+  return run<double, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0);
+}
+int emu_gemm_simt_i32(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t *A, int64_t rsA, int64_t csA,
+                      const int32_t *B, int64_t rsB, int64_t csB, int32_t beta, int32_t *C, int64_t rsC, int64_t csC,
+                      int grid) {
+  return run<int32_t, 8, 8, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0);
+}
+int emu_gemm_simt_i64(int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t *A, int64_t rsA, int64_t csA,
+                      const int64_t *B, int64_t rsB, int64_t csB, int64_t beta, int64_t *C, int64_t rsC, int64_t csC,
+                      int grid) {
+  return run<int64_t, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0);
+}
+}  // extern "C"

@@ -4,34 +4,18 @@ compared with the oracle bit for bit.  This executes the product's kernel source
 arithmetic, bounds, shared-memory choreography, launch planning -- without a GPU; the GPU tests
 (test_gpu_layers.py) then only have to confirm the same on the device."""
 import ctypes
-import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
 
 import oracle as O
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-EMU_DIR = os.path.join(HERE, "emu")
-CUDA_INC = "/usr/local/cuda/include"
+from emu_build import build_emu
 
 
 @pytest.fixture(scope="module")
 def emu():
-    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
-        pytest.skip("CUDA headers not installed")
-    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
-    out_dir = os.path.join(EMU_DIR, "_build")
-    os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "liblayers_emu.so")
-    srcs = [os.path.join(EMU_DIR, "layers_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
-            os.path.join(HERE, "..", "laser_b200", "csrc", "layers.cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call([gxx, "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-I", CUDA_INC,
-                               "-Wno-attributes", "-Wno-unknown-pragmas", srcs[0], "-o", so], env=env)
+    so = build_emu("layers_emu", ["layers.cuh"])
     L = ctypes.CDLL(so)
     i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
     L.emu_transpose_batched.restype = ci

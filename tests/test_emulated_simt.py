@@ -1,0 +1,111 @@
+"""CPU-only: the exact CUDA-core GEMM kernel (laser_b200/csrc/gemm_simt.cuh: gemm_simt_kernel, the
+path that has to be bit-identical to the reference's CPU order of operations) executed on host
+threads (tests/emu/) with the library's own launch planning, against the oracle: the reference's
+known-answer vectors for every dtype, strided layouts, alpha/beta, kc-block boundaries, wrapping
+integer arithmetic, the fused epilogue."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle as O
+from emu_build import build_emu
+from util import LAYOUTS, embed, extract, golden_cases
+
+i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+SCALAR = {"f32": ctypes.c_float, "f64": ctypes.c_double, "i32": ctypes.c_int32, "i64": ctypes.c_int64}
+NP = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = ctypes.CDLL(build_emu("simt_emu", ["gemm_simt.cuh"]))
+    for name, sc in SCALAR.items():
+        fn = getattr(L, "emu_gemm_simt_" + name)
+        fn.restype = ci
+        fn.argtypes = [i64, i64, i64, sc, vp, i64, i64, vp, i64, i64, sc, vp, i64, i64, ci] + \
+                      ([vp, ci, ci] if name == "f32" else [])
+    return L
+
+
+def at(buf, off):
+    return ctypes.c_void_p(buf.ctypes.data + off * buf.itemsize)
+
+
+def run(emu, name, M, N, K, alpha, A, oa, rsa, csa, B, ob, rsb, csb, beta, C, oc, rsc, csc, grid=0, epi=None):
+    extra = []
+    if name == "f32":
+        bias, per_row, act = epi if epi else (None, 0, 0)
+        extra = [ctypes.c_void_p(bias.ctypes.data) if bias is not None else None, per_row, act]
+    return getattr(emu, "emu_gemm_simt_" + name)(M, N, K, alpha, at(A, oa), rsa, csa, at(B, ob), rsb, csb, beta,
+                                                 at(C, oc), rsc, csc, grid, *extra)
+
+
+@pytest.mark.parametrize("name", ["f32", "f64", "i32", "i64"])
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["src"])
+def test_known_answer_vectors(emu, name, case):
+    dt = NP[name]
+    M, N, K = case["M"], case["N"], case["K"]
+    a = np.array(case["a"], dt); b = np.array(case["b"], dt)
+    c = np.full((M, N), 99, dt)
+    run(emu, name, M, N, K, 1, a, 0, K, 1, b, 0, N, 1, 0, c, 0, N, 1)
+    assert np.array_equal(c, np.array(case["c"], dt))
+
+
+@pytest.mark.parametrize("la,lb,lc", [(a, b, c) for a in LAYOUTS for b, c in (("row", "row"), ("col", "both2"))] +
+                         [("row", b, "negrow") for b in LAYOUTS] + [("colslice", "padded", c) for c in LAYOUTS])
+def test_strided_layouts_bit_exact(emu, la, lb, lc):
+    M, N, K = 70, 45, 90
+    rng = np.random.default_rng(1)
+    a = rng.random((M, K), dtype=np.float32); b = rng.random((K, N), dtype=np.float32)
+    c0 = rng.random((M, N), dtype=np.float32)
+    A, oa, rsa, csa = embed(a, la); B, ob, rsb, csb = embed(b, lb); C, oc, rsc, csc = embed(c0, lc)
+    Cref = C.copy()
+    O.gemm_strided(M, N, K, 1.0, A[oa:] if oa >= 0 else A, rsa, csa, B[ob:], rsb, csb, 2.0, Cref[oc:], rsc, csc)
+    run(emu, "f32", M, N, K, 1.0, A, oa, rsa, csa, B, ob, rsb, csb, 2.0, C, oc, rsc, csc, grid=2)
+    assert np.array_equal(C, Cref)          # the whole buffer: nothing outside the view is touched
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (128, 128, 128), (129, 127, 513), (5, 300, 1030), (257, 3, 17)])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.0, 1.0), (0.5, -1.25)])
+def test_shapes_and_scalars(emu, M, N, K, alpha, beta):
+    a = O.fill_uniform_f32(M * K, 5, -0.1, 0.1).reshape(M, K); b = O.fill_uniform_f32(K * N, 6, -0.1, 0.1).reshape(K, N)
+    c = O.fill_uniform_f32(M * N, 7, -1, 1).reshape(M, N)
+    if beta == 0.0:
+        c[:] = np.nan                        # beta == 0: C is not read (gemm_ukernel_generic.nim:60-62)
+    ref = c.copy()
+    O.gemm_strided(M, N, K, alpha, a, K, 1, b, N, 1, beta, ref, N, 1)
+    run(emu, "f32", M, N, K, alpha, a, 0, K, 1, b, 0, N, 1, beta, c, 0, N, 1, grid=3)
+    if alpha == 1.0:
+        assert np.array_equal(c, ref)        # bit-identical, across kc = 512 block boundaries too
+    else:                                    # alpha != 1: the oracle's compiler may contract C += alpha*AB (1 ulp)
+        assert np.abs(c - ref).max() <= 2e-7 * np.abs(ref).max()
+
+
+def test_f64_and_integers(emu):
+    M, N, K = 40, 50, 300                    # kc = 256 for 8-byte types
+    rng = np.random.default_rng(2)
+    a = rng.random((M, K)); b = rng.random((K, N)); c = rng.random((M, N)); ref = c.copy()
+    O.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 1.0, ref, N, 1)
+    run(emu, "f64", M, N, K, 1.0, a, 0, K, 1, b, 0, N, 1, 1.0, c, 0, N, 1)
+    assert np.array_equal(c, ref)
+    for name, big in (("i32", 2**31 - 5), ("i64", 2**63 - 5)):
+        dt = NP[name]
+        ai = rng.integers(-big, big, size=(M, K), dtype=dt); bi = rng.integers(-big, big, size=(K, N), dtype=dt)
+        ci_ = rng.integers(-9, 9, size=(M, N), dtype=dt); refi = ci_.copy()
+        O.gemm_strided(M, N, K, 3, ai, K, 1, bi, N, 1, -2, refi, N, 1)
+        run(emu, name, M, N, K, 3, ai, 0, K, 1, bi, 0, N, 1, -2, ci_, 0, N, 1, grid=1)
+        assert np.array_equal(ci_, refi)     # wrapping arithmetic, as the reference's mullo + add
+
+
+@pytest.mark.parametrize("per_row,act", [(0, 0), (1, 1), (0, 2), (1, 3)])
+def test_fused_epilogue_applies_once_after_the_last_k_block(emu, per_row, act):
+    M, N, K = 33, 20, 700                    # two kc blocks: the epilogue must run on the second only
+    a = O.fill_uniform_f32(M * K, 8, -0.1, 0.1).reshape(M, K); b = O.fill_uniform_f32(K * N, 9, -0.1, 0.1).reshape(K, N)
+    bias = O.fill_uniform_f32(M if per_row else N, 10, -1, 1)
+    c = np.zeros((M, N), np.float32); ref = c.copy()
+    O.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, ref, N, 1)
+    run(emu, "f32", M, N, K, 1.0, a, 0, K, 1, b, 0, N, 1, 0.0, c, 0, N, 1, epi=(bias, per_row, act))
+    v = ref + (bias[:, None] if per_row else bias[None, :])
+    exp = {0: v, 1: np.maximum(v, 0), 2: np.tanh(v), 3: 1 / (1 + np.exp(-v))}[act]
+    assert np.allclose(c, exp, rtol=2e-6, atol=2e-7)
