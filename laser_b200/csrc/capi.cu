@@ -215,12 +215,14 @@ inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
 template <typename T, int TM, int TN, int BK>
 int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
                 int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
-                int64_t csC, cudaStream_t s) {
+                int64_t csC, cudaStream_t s, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0,
+                int64_t bsC = 0) {
   SimtParams<T> p;
   const int64_t tiles = simt_plan<T, TM, TN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   if constexpr (std::is_same<T, float>::value) { p.bias = g_epi.bias; p.bias_per_row = g_epi.bias_per_row; p.act = g_epi.act; }
   if (tiles > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
-  const int grid = grid_for(c, tiles, 2);
+  p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+  const int grid = grid_for(c, tiles * batch, 2);
   gemm_simt_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);
   COUNT_LAUNCH();
   CHECK_LAUNCH();
@@ -230,14 +232,17 @@ int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, in
 template <typename T>
 int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
               int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
-              int64_t csC, cudaStream_t s) {
+              int64_t csC, cudaStream_t s, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0,
+              int64_t bsC = 0) {
 #ifndef LB200_SIMT_BK
 #define LB200_SIMT_BK 16
 #endif
   if constexpr (sizeof(T) == 4)
-    return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+    return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, batch,
+                                               bsA, bsB, bsC);
   else
-    return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+    return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, batch, bsA, bsB,
+                                    bsC);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -73,6 +73,9 @@ struct SimtParams {
   const float *bias = nullptr;
   int bias_per_row = 0;
   int act = 0;
+  // batch of independent problems in one launch: problem b reads A + b*bsA, B + b*bsB and
+  // writes C + b*bsC (a stride of 0 shares the operand; outputs must not overlap)
+  int64_t batch = 1, bsA = 0, bsB = 0, bsC = 0;
 };
 
 // host side: everything but the fused epilogue; returns the number of output tiles
@@ -114,7 +117,14 @@ gemm_simt_kernel(const SimtParams<T> p) {
   const int tx = tid & 15, ty = tid >> 4;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  const int64_t total_tiles = static_cast<int64_t>(num_tiles) * p.batch;
+
+  for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int64_t bi = t / num_tiles;
+    const int tile = static_cast<int>(t - bi * num_tiles);
+    const T *Ab = p.A + bi * p.bsA;
+    const T *Bb = p.B + bi * p.bsB;
+    T *Cb = p.C + bi * p.bsC;
     const int mb = tile % p.num_m_blocks, nb = tile / p.num_m_blocks;
     const int64_t m0 = static_cast<int64_t>(mb) * BM, n0 = static_cast<int64_t>(nb) * BN;
 
@@ -126,7 +136,7 @@ gemm_simt_kernel(const SimtParams<T> p) {
         const int m = p.a_along_m ? (idx % BM) : (idx / BK);
         const int k = p.a_along_m ? (idx / BM) : (idx % BK);
         const int64_t gm = m0 + m, gk = k0 + k;
-        ra[i] = (gm < p.M && gk < kend) ? p.A[gm * p.rsA + gk * p.csA] : T(0);
+        ra[i] = (gm < p.M && gk < kend) ? Ab[gm * p.rsA + gk * p.csA] : T(0);
       }
 #pragma unroll
       for (int i = 0; i < B_PER_T; ++i) {
@@ -134,7 +144,7 @@ gemm_simt_kernel(const SimtParams<T> p) {
         const int n = p.b_along_k ? (idx / BK) : (idx % BN);
         const int k = p.b_along_k ? (idx % BK) : (idx / BN);
         const int64_t gn = n0 + n, gk = k0 + k;
-        rb[i] = (gn < p.N && gk < kend) ? p.B[gk * p.rsB + gn * p.csB] : T(0);
+        rb[i] = (gn < p.N && gk < kend) ? Bb[gk * p.rsB + gn * p.csB] : T(0);
       }
     };
     auto store_tiles = [&]() {
@@ -199,7 +209,7 @@ gemm_simt_kernel(const SimtParams<T> p) {
         for (int j = 0; j < TN; ++j) {
           const int64_t gn = n0 + ((j < HN) ? (tx * HN + j) : (BN / 2 + tx * HN + (j - HN)));
           if (gn >= p.N) continue;
-          T *c = p.C + gm * p.rsC + gn * p.csC;
+          T *c = Cb + gm * p.rsC + gn * p.csC;
           T v;
           if (beta1 == T(0)) v = T(0);
           else if (beta1 != T(1)) v = Op::mul(*c, beta1);

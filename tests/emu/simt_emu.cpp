@@ -12,12 +12,14 @@ using namespace lb200;
 template <typename T, int TM, int TN, int BK>
 static int run(int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA, int64_t csA, const T *B, int64_t rsB,
                int64_t csB, T beta, T *C, int64_t rsC, int64_t csC, int grid, const float *bias, int bias_per_row,
-               int act) {
+               int act, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0, int64_t bsC = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;   // gemm.nim:150: nothing to do, C untouched
   SimtParams<T> p;
   const int64_t tiles = simt_plan<T, TM, TN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   p.bias = bias; p.bias_per_row = bias_per_row; p.act = act;
-  if (grid <= 0 || grid > tiles) grid = static_cast<int>(tiles);
+  p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+  if (batch <= 0) return 0;
+  if (grid <= 0 || grid > tiles * batch) grid = static_cast<int>(tiles * batch);
   emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_simt_kernel<T, TM, TN, BK>(p); });
   return static_cast<int>(tiles);
 }
@@ -27,6 +29,12 @@ int emu_gemm_simt_f32(int64_t M, int64_t N, int64_t K, float alpha, const float 
                       const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
                       int grid, const float *bias, int bias_per_row, int act) {
   return run<float, 8, 8, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, bias, bias_per_row, act);
+}
+int emu_gemm_simt_batched_f32(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA,
+                              int64_t csA, int64_t bsA, const float *B, int64_t rsB, int64_t csB, int64_t bsB, float beta,
+                              float *C, int64_t rsC, int64_t csC, int64_t bsC, int grid) {
+  return run<float, 8, 8, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0, batch, bsA,
+                              bsB, bsC);
 }
 int emu_gemm_simt_f64(int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t rsA, int64_t csA,
                       const double *B, int64_t rsB, int64_t csB, double beta, double *C, int64_t rsC, int64_t csC,

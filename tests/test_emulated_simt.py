@@ -25,6 +25,10 @@ def emu():
         fn.restype = ci
         fn.argtypes = [i64, i64, i64, sc, vp, i64, i64, vp, i64, i64, sc, vp, i64, i64, ci] + \
                       ([vp, ci, ci] if name == "f32" else [])
+    f32 = ctypes.c_float
+    L.emu_gemm_simt_batched_f32.restype = ci
+    L.emu_gemm_simt_batched_f32.argtypes = [i64, i64, i64, i64, f32, vp, i64, i64, i64, vp, i64, i64, i64, f32, vp, i64, i64,
+                                            i64, ci]
     return L
 
 
@@ -109,3 +113,17 @@ def test_fused_epilogue_applies_once_after_the_last_k_block(emu, per_row, act):
     v = ref + (bias[:, None] if per_row else bias[None, :])
     exp = {0: v, 1: np.maximum(v, 0), 2: np.tanh(v), 3: 1 / (1 + np.exp(-v))}[act]
     assert np.allclose(c, exp, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("batch,M,N,K,grid", [(1, 20, 30, 40, 0), (7, 64, 64, 64, 3), (5, 130, 129, 20, 4), (3, 17, 9, 600, 0)])
+@pytest.mark.parametrize("shared_b", [False, True])
+def test_batched_launch_equals_a_loop_of_gemm_strided(emu, batch, M, N, K, grid, shared_b):
+    A = O.fill_uniform_f32(batch * M * K, 11, -1, 1); C = O.fill_uniform_f32(batch * M * N, 13, -1, 1)
+    B = O.fill_uniform_f32((1 if shared_b else batch) * K * N, 12, -1, 1)
+    bsB = 0 if shared_b else K * N
+    ref = C.copy()
+    O.gemm_strided_batched(batch, M, N, K, 1.0, A, K, 1, M * K, B, N, 1, bsB, 1.0, ref, N, 1, M * N)
+    tiles = emu.emu_gemm_simt_batched_f32(batch, M, N, K, 1.0, at(A, 0), K, 1, M * K, at(B, 0), N, 1, bsB, 1.0, at(C, 0), N, 1,
+                                          M * N, grid)
+    assert tiles == -(-M // 128) * -(-N // 128)
+    assert np.array_equal(C, ref)

@@ -195,6 +195,19 @@ def test_batched_gemm(path):
         assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
 
 
+def test_batched_small_problems_single_launch_is_bit_exact():
+    batch, M, N, K = 64, 32, 48, 40          # below the 128^3 threshold: exact kernel, one launch
+    A = O.fill_uniform_f32(batch * M * K, 51, -1, 1); B = O.fill_uniform_f32(batch * K * N, 52, -1, 1)
+    ref = np.zeros(batch * M * N, np.float32)
+    O.gemm_strided_batched(batch, M, N, K, 1.0, A, K, 1, M * K, B, N, 1, K * N, 0.0, ref, N, 1, M * N)
+    tC = torch.full((batch * M * N,), float("nan"), device="cuda")
+    before = L.launch_count()
+    L.gemm_strided_batched(batch, M, N, K, 1.0, dev(A), K, 1, M * K, dev(B), N, 1, K * N, 0.0, tC, N, 1, M * N)
+    torch.cuda.synchronize()
+    assert L.launch_count() - before == 1
+    assert np.array_equal(tC.cpu().numpy(), ref)
+
+
 # ---- copyFrom on strided views ------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", ["f32", "f64", "i32", "i64", "bf16"])
 def test_copyFrom_views(dtype):
