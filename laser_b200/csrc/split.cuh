@@ -19,11 +19,19 @@
 
 namespace lb200 {
 
+#ifndef LB200_HOST_EMULATION
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+#else   // tests/emu: round to nearest, ties away from zero, onto 10 mantissa bits (finite inputs)
+inline float tf32_rna(float x) {
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+  return __uint_as_float(u);
+}
+#endif
 
 // src: R rows of Cc contiguous floats, leading dimension src_ld (16-byte aligned rows).
 // hi/lo: compact, leading dimension dst_ld (multiple of 4).

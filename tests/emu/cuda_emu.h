@@ -2,7 +2,7 @@
 // that the CPU test suite can execute the kernels' index arithmetic, bounds handling and
 // shared-memory choreography without a GPU (one std::thread per CUDA thread of a block, a pthread
 // barrier for __syncthreads, blocks one after the other).  Only kernels written in plain CUDA C++
-// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh and gemm_simt_kernel.
+// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh, gemm_simt_kernel, split.cuh (with a software tf32 rounding).
 // It is a test of the product's source, not a fallback: nothing under laser_b200/ includes it.
 #pragma once
 
@@ -67,6 +67,10 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
+#include <cstring>
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __fsub_rn(float a, float b) { return a - b; }
 
 #define threadIdx (emu::t_idx)
 #define blockIdx (emu::b_idx)

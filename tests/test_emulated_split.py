@@ -1,0 +1,132 @@
+"""CPU-only: the operand-preparation kernels of laser_b200/csrc/split.cuh (hi/lo split of
+TMA-addressable operands, gather of general-stride operands -- the descendant of the reference's
+pack_A_mc_kc / pack_B_kc_nc, gemm_packing.nim:24-94 --, the deterministic split-K reduction and the
+synthetic-input generator) executed on host threads (tests/emu/) against numpy restatements."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle as O
+from emu_build import build_emu
+from util import f32_to_bf16_bits
+
+i64, vp, ci, f32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = ctypes.CDLL(build_emu("split_emu", ["split.cuh"]))
+    L.emu_split_rows_tf32.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
+    L.emu_split_rows_mixed.argtypes = [vp, i64, i64, i64, vp, i64, vp, vp, i64, ci]
+    L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, vp, vp, i64, ci]
+    L.emu_pack_general_u16.argtypes = [vp, i64, i64, i64, i64, vp, i64, ci, ci]
+    L.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
+    L.emu_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, ci]
+    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_pack_general_f32", "emu_pack_general_u16",
+              "emu_splitk_reduce", "emu_fill_uniform_f32"):
+        getattr(L, n).restype = None
+    return L
+
+
+def p(a, off=0):
+    return ctypes.c_void_p(a.ctypes.data + off * a.itemsize)
+
+
+def tf32_rna(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_fill_uniform_matches_the_oracle_generator(emu):
+    n = 10007
+    out = np.zeros(n, np.float32)
+    emu.emu_fill_uniform_f32(p(out), n, 42, -0.1, 0.1, 5)
+    assert np.array_equal(out, O.fill_uniform_f32(n, 42, -0.1, 0.1))
+
+
+@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (7, 1, 4), (130, 257, 260)])
+def test_split_rows(emu, R, Cc, src_ld):
+    rng = np.random.default_rng(0)
+    src = (rng.standard_normal((R, src_ld)) * 3).astype(np.float32)
+    ld = -(-Cc // 4) * 4; ldb = -(-Cc // 8) * 8
+    x = src[:, :Cc]
+    h = tf32_rna(x)
+    hi = np.full((R, ld), 9, np.float32); lo = np.full((R, ld), 9, np.float32)
+    emu.emu_split_rows_tf32(p(src), R, Cc, src_ld, p(hi), p(lo), ld, 3)
+    assert np.array_equal(hi[:, :Cc], h) and np.array_equal(lo[:, :Cc], tf32_rna(x - h))
+    assert np.all(hi[:, Cc:] == 0) and np.all(lo[:, Cc:] == 0)        # k padding is zero (it feeds the MMA)
+    assert np.abs((hi[:, :Cc].astype(np.float64) + lo[:, :Cc]) - x).max() <= 2.0 ** -21 * np.abs(x).max()
+    hi2 = np.full((R, ld), 9, np.float32); xb = np.full((R, ldb), 9, np.uint16); lb = np.full((R, ldb), 9, np.uint16)
+    emu.emu_split_rows_mixed(p(src), R, Cc, src_ld, p(hi2), ld, p(xb), p(lb), ldb, 2)
+    assert np.array_equal(hi2[:, :Cc], h)
+    assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
+    assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - h).reshape(R, Cc))
+    assert np.all(hi2[:, Cc:] == 0) and np.all(xb[:, Cc:ld] == 0) and np.all(lb[:, Cc:ld] == 0)
+
+
+@pytest.mark.parametrize("R,Cc,sr,sc,along_r", [
+    (40, 50, 50, 1, 0),       # plain row-major (copy)
+    (40, 50, 1, 40, 1),       # column-major source: transposing gather
+    (33, 65, 130, 2, 0),      # every other column
+    (20, 31, -31, 1, 0),      # rows bottom-up
+    (20, 31, 31, -1, 0),      # columns right-to-left
+    (70, 3, 2, 140, 1),
+])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pack_general(emu, R, Cc, sr, sc, along_r, mode):
+    lo_off = min(0, (R - 1) * sr) + min(0, (Cc - 1) * sc)
+    hi_off = max(0, (R - 1) * sr) + max(0, (Cc - 1) * sc)
+    rng = np.random.default_rng(1)
+    buf = (rng.standard_normal(hi_off - lo_off + 1) * 2).astype(np.float32)
+    idx = -lo_off + np.arange(R)[:, None] * sr + np.arange(Cc)[None, :] * sc
+    x = buf[idx]
+    ld = -(-Cc // 4) * 4; ldb = -(-Cc // 8) * 8
+    dst = np.full((R, ld), 7, np.float32); dlo = np.full((R, ld), 7, np.float32)
+    xb = np.full((R, ldb), 7, np.uint16); lb = np.full((R, ldb), 7, np.uint16)
+    emu.emu_pack_general_f32(mode, p(buf, -lo_off), R, Cc, sr, sc, p(dst), p(dlo), ld, along_r, p(xb), p(lb), ldb, 4)
+    h = tf32_rna(x)
+    if mode == 0:
+        assert np.array_equal(dst[:, :Cc], x)
+    elif mode == 1:
+        assert np.array_equal(dst[:, :Cc], h) and np.array_equal(dlo[:, :Cc], tf32_rna(x - h))
+    else:
+        assert np.array_equal(dst[:, :Cc], h)
+        assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
+        assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - h).reshape(R, Cc))
+    assert np.all(dst[:, Cc:] == 7)      # the gather never writes the padding (the host zeroes it once)
+
+
+def test_pack_general_bf16(emu):
+    R, Cc, sr, sc = 37, 29, 1, 37
+    buf = np.arange(R * Cc, dtype=np.uint16)
+    dst = np.zeros((R, 32), np.uint16)
+    emu.emu_pack_general_u16(p(buf), R, Cc, sr, sc, p(dst), 32, 1, 2)
+    assert np.array_equal(dst[:, :Cc], buf.reshape(Cc, R).T)
+
+
+@pytest.mark.parametrize("S,alpha,beta,per_row,act", [(1, 1.0, 0.0, 0, 0), (4, 0.5, -1.25, 0, 0), (3, 1.0, 0.0, 1, 1),
+                                                      (5, 2.0, 1.0, 0, 2)])
+def test_splitk_reduce_is_a_fixed_order_sum(emu, S, alpha, beta, per_row, act):
+    M, N, ld = 23, 37, 40
+    rng = np.random.default_rng(2)
+    ws = rng.standard_normal((S, M, ld)).astype(np.float32)
+    C = rng.standard_normal((N, M)).astype(np.float32)            # column-major C: rsC = 1, csC = M
+    bias = rng.standard_normal(M if per_row else N).astype(np.float32) if act else None
+    c0 = C.copy()
+    if beta == 0.0:
+        C[:] = np.nan
+    emu.emu_splitk_reduce(p(ws), S, M, N, ld, M * ld, alpha, beta, p(C), 1, M, p(bias) if bias is not None else None,
+                          per_row, act, 3)
+    s = ws[0, :, :N].copy()
+    for k in range(1, S):
+        s = s + ws[k, :, :N]                                        # planes in order 0..S-1, fp32
+    v = np.float32(alpha) * s
+    if beta != 0.0:
+        v = (np.float64(beta) * c0.T.astype(np.float64) + v.astype(np.float64)).astype(np.float32)   # fmaf
+    if act:
+        v = v + (bias[:, None] if per_row else bias[None, :])
+        v = np.maximum(v, 0) if act == 1 else np.tanh(v)
+    assert np.allclose(C.T, v, rtol=1e-6, atol=1e-6)
+    if S > 1 and beta == 0.0 and not act:
+        assert np.array_equal(C.T, v)
