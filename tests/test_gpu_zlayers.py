@@ -22,7 +22,7 @@ torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NP_OF = {1: np.uint8, 2: np.uint16, 4: np.float32, 8: np.float64}
+NP_OF = {2: np.int16, 4: np.float32, 8: np.float64}   # int16: torch has no full uint16 support
 
 
 def dev(a):
