@@ -341,11 +341,11 @@ int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams
 #define LB200_LAUNCH(AMN, BMN)                                                                   \
   do {                                                                                           \
     auto kfn = gemm_tc_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                        \
-    static bool attr_set = false;                                                                \
-    if (!attr_set) {                                                                             \
+    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
+    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
       CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                     TcCfg<PAIR>::SMEM_BYTES));                                   \
-      attr_set = true;                                                                           \
+      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
     }                                                                                            \
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
   } while (0)
@@ -693,10 +693,10 @@ const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_c
 #define LB200_GEMV(NV)                                                                                         \
   do {                                                                                                         \
     if (use_smem) {                                                                                            \
-      static bool attr_set = false;                                                                            \
-      if (!attr_set) {                                                                                         \
+      static std::atomic<uint32_t> attr_set{0};                                                                \
+      if (!(attr_set.load(std::memory_order_acquire) & (1u << c->dev))) {                                      \
         CUDA_TRY(cudaFuncSetAttribute(gemv_warp_smem_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-        attr_set = true;                                                                                       \
+        attr_set.fetch_or(1u << c->dev, std::memory_order_release);                                            \
       }                                                                                                        \
       gemv_warp_smem_kernel<NV><<<grid_for(*c, (M + 7) / 8, 2), 256, bsmem, s>>>(M, K, alpha, A, rsA, B, rsB, csB, beta, C, rsC, csC); \
     } else if (vec) gemv_warp_kernel<NV, true><<<grid, 256, 0, s>>>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);  \

@@ -50,3 +50,34 @@ def test_rowsharded_overlap_prepack_single_gpu():
         scale = np.abs(ref).max()
         assert np.abs(got2 - ref).max() / scale < 1e-4
         assert np.abs(got2 - got1).max() / scale < 2e-6
+
+
+def test_one_process_two_devices():
+    """A single process driving two GPUs through the C ABI (per-device context, tensor-map cache,
+    function attributes): the second device must behave like the first."""
+    import numpy as np
+    import oracle as O
+    import laser_b200 as L
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    M, N, K = 300, 260, 520
+    a = O.fill_uniform_f32(M * K, 1, 0, 1).reshape(M, K); b = O.fill_uniform_f32(K * N, 2, 0, 1).reshape(K, N)
+    ref = np.zeros((M, N), np.float32)
+    O.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, ref, N, 1)
+    try:
+        for d in (0, 1, 0):
+            torch.cuda.set_device(d)
+            A, B = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+            C = torch.full((M, N), float("nan"), device="cuda")
+            L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1)                       # tensor cores
+            E = torch.empty((M, N), device="cuda")
+            L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, E, N, 1, path=L.PATH_SIMT)      # exact kernel
+            v = torch.empty((M, 1), device="cuda")
+            L.gemm_strided(M, 1, K, 1.0, A, K, 1, B, N, 1, 0.0, v, 1, 1)                       # column of B (small: exact)
+            torch.cuda.synchronize()
+            assert C.device.index == d
+            assert np.abs(C.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4
+            assert np.array_equal(E.cpu().numpy(), ref)
+    finally:
+        torch.cuda.set_device(0)
