@@ -229,7 +229,9 @@ int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_te
 /* ---- the steps either side of the GEMM -------------------------------
  * Batched GEMM: problem b reads A + b*batchStrideA, B + b*batchStrideB and writes
  * C + b*batchStrideC (strides in elements; a batch stride of 0 shares that operand, e.g. one
- * filter matrix against many images).  The reference has no batched entry -- its README lists it
+ * filter matrix against many images; the outputs of different problems must not overlap).
+ * Problems the dispatch sends to the exact kernel (path SIMT, or AUTO with M*N*K <= 128^3) run as
+ * ONE launch; tensor-core problems take one launch sequence each.  The reference has no batched entry -- its README lists it
  * as roadmap (README.md:253-263); each problem follows gemm_strided (gemm.nim:184-193). */
 int laser_b200_gemm_strided_batched_f32_dev(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha,
                                             const float *A, int64_t rowStrideA, int64_t colStrideA,
@@ -237,6 +239,26 @@ int laser_b200_gemm_strided_batched_f32_dev(int64_t batch, int64_t M, int64_t N,
                                             int64_t colStrideB, int64_t batchStrideB, float beta, float *C,
                                             int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC,
                                             int path, void *stream);
+
+/* f64 / i32 / i64 batches: the exact kernel, always one launch */
+int laser_b200_gemm_strided_batched_f64_dev(int64_t batch, int64_t M, int64_t N, int64_t K, double alpha,
+                                            const double *A, int64_t rowStrideA, int64_t colStrideA,
+                                            int64_t batchStrideA, const double *B, int64_t rowStrideB,
+                                            int64_t colStrideB, int64_t batchStrideB, double beta, double *C,
+                                            int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC,
+                                            void *stream);
+int laser_b200_gemm_strided_batched_i32_dev(int64_t batch, int64_t M, int64_t N, int64_t K, int32_t alpha,
+                                            const int32_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                            int64_t batchStrideA, const int32_t *B, int64_t rowStrideB,
+                                            int64_t colStrideB, int64_t batchStrideB, int32_t beta, int32_t *C,
+                                            int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC,
+                                            void *stream);
+int laser_b200_gemm_strided_batched_i64_dev(int64_t batch, int64_t M, int64_t N, int64_t K, int64_t alpha,
+                                            const int64_t *A, int64_t rowStrideA, int64_t colStrideA,
+                                            int64_t batchStrideA, const int64_t *B, int64_t rowStrideB,
+                                            int64_t colStrideB, int64_t batchStrideB, int64_t beta, int64_t *C,
+                                            int64_t rowStrideC, int64_t colStrideC, int64_t batchStrideC,
+                                            void *stream);
 
 /* Physical transposition of contiguous matrices, elem_size in {1, 2, 4, 8} bytes
  * (generic T in the reference):

@@ -78,6 +78,12 @@ SIGNATURES = {
                                                ctypes.POINTER(TensorView), f64, f64, ctypes.c_int, vp]),
     "laser_b200_gemm_strided_batched_f32_dev": (ctypes.c_int, [i64, i64, i64, i64, f32, vp, i64, i64, i64, vp, i64, i64, i64,
                                                                f32, vp, i64, i64, i64, ctypes.c_int, vp]),
+    "laser_b200_gemm_strided_batched_f64_dev": (ctypes.c_int, [i64, i64, i64, i64, f64, vp, i64, i64, i64, vp, i64, i64, i64,
+                                                               f64, vp, i64, i64, i64, vp]),
+    "laser_b200_gemm_strided_batched_i32_dev": (ctypes.c_int, [i64, i64, i64, i64, i32, vp, i64, i64, i64, vp, i64, i64, i64,
+                                                               i32, vp, i64, i64, i64, vp]),
+    "laser_b200_gemm_strided_batched_i64_dev": (ctypes.c_int, [i64, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
+                                                               i64, vp, i64, i64, i64, vp]),
     "laser_b200_transpose2D_copy": (ctypes.c_int, [vp, vp, i64, i64, ctypes.c_int]),
     "laser_b200_transpose2D_batched": (ctypes.c_int, [vp, vp, i64, i64, i64, ctypes.c_int]),
     "laser_b200_nchw2nhwc": (ctypes.c_int, [vp, vp, i64, i64, i64, i64, ctypes.c_int]),

@@ -18,7 +18,7 @@ import ctypes
 import numpy as np
 
 from ._capi import PATH_AUTO, check, lib
-from .gemm import _current_stream, _resolve
+from .gemm import _current_stream, _resolve, _scalar
 from .tensor import _ITEMSIZE, Tensor
 
 __all__ = ["transpose2D_copy", "transpose2D_batched", "nchw2nhwc", "nhwc2nchw", "conv2d_out_shape",
@@ -128,12 +128,24 @@ def conv2d_im2col(output, input, ishape, kernel, kshape, padding, strides, works
 
 def gemm_strided_batched(batch, M, N, K, alpha, A, rowStrideA, colStrideA, batchStrideA, B, rowStrideB, colStrideB,
                          batchStrideB, beta, C, rowStrideC, colStrideC, batchStrideC, path=PATH_AUTO, stream=None):
-    """`batch` float32 problems C_b <- alpha * A_b * B_b + beta * C_b on device pointers; a batch
-    stride of 0 shares that operand."""
+    """`batch` problems C_b <- alpha * A_b * B_b + beta * C_b on device pointers (f32, f64, i32,
+    i64); a batch stride of 0 shares that operand; outputs must not overlap."""
+    pa, ta, da = _resolve(A)
+    pb, tb, db = _resolve(B)
+    pc, tc, dc = _resolve(C)
+    if not (ta == tb == tc) or ta == "bf16":
+        raise TypeError("batched GEMM needs A, B, C of one type among f32, f64, i32, i64 (got %s, %s, %s)" % (ta, tb, tc))
+    if not (da and db and dc):
+        raise TypeError("batched GEMM takes device pointers")
     stream = _current_stream() if stream is None else stream
-    check(lib().laser_b200_gemm_strided_batched_f32_dev(
-        batch, M, N, K, float(alpha), _dev_f32(A), rowStrideA, colStrideA, batchStrideA, _dev_f32(B), rowStrideB,
-        colStrideB, batchStrideB, float(beta), _dev_f32(C), rowStrideC, colStrideC, batchStrideC, int(path), stream))
+    args = [batch, M, N, K, _scalar(ta, alpha), pa, rowStrideA, colStrideA, batchStrideA, pb, rowStrideB, colStrideB,
+            batchStrideB, _scalar(ta, beta), pc, rowStrideC, colStrideC, batchStrideC]
+    if ta == "f32":
+        check(lib().laser_b200_gemm_strided_batched_f32_dev(*args, int(path), stream))
+    else:
+        if path not in (PATH_AUTO, 1):
+            raise ValueError("path %d is not available for %s" % (path, ta))
+        check(getattr(lib(), "laser_b200_gemm_strided_batched_%s_dev" % ta)(*args, stream))
 
 
 def copyFrom(dst, src, stream=None):

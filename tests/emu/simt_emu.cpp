@@ -51,4 +51,16 @@ int emu_gemm_simt_i64(int64_t M, int64_t N, int64_t K, int64_t alpha, const int6
                       int grid) {
   return run<int64_t, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0);
 }
+int emu_gemm_simt_batched_f64(int64_t batch, int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t rsA,
+                              int64_t csA, int64_t bsA, const double *B, int64_t rsB, int64_t csB, int64_t bsB,
+                              double beta, double *C, int64_t rsC, int64_t csC, int64_t bsC, int grid) {
+  return run<double, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0, batch, bsA,
+                               bsB, bsC);
+}
+int emu_gemm_simt_batched_i64(int64_t batch, int64_t M, int64_t N, int64_t K, int64_t alpha, const int64_t *A, int64_t rsA,
+                              int64_t csA, int64_t bsA, const int64_t *B, int64_t rsB, int64_t csB, int64_t bsB,
+                              int64_t beta, int64_t *C, int64_t rsC, int64_t csC, int64_t bsC, int grid) {
+  return run<int64_t, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0, batch,
+                                bsA, bsB, bsC);
+}
 }  // extern "C"

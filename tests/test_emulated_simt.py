@@ -29,6 +29,10 @@ def emu():
     L.emu_gemm_simt_batched_f32.restype = ci
     L.emu_gemm_simt_batched_f32.argtypes = [i64, i64, i64, i64, f32, vp, i64, i64, i64, vp, i64, i64, i64, f32, vp, i64, i64,
                                             i64, ci]
+    for name, sc in (("f64", ctypes.c_double), ("i64", i64)):
+        fn = getattr(L, "emu_gemm_simt_batched_" + name)
+        fn.restype = ci
+        fn.argtypes = [i64, i64, i64, i64, sc, vp, i64, i64, i64, vp, i64, i64, i64, sc, vp, i64, i64, i64, ci]
     return L
 
 
@@ -127,3 +131,38 @@ def test_batched_launch_equals_a_loop_of_gemm_strided(emu, batch, M, N, K, grid,
                                           M * N, grid)
     assert tiles == -(-M // 128) * -(-N // 128)
     assert np.array_equal(C, ref)
+
+
+def test_batched_f64_and_i64(emu):
+    batch, M, N, K = 4, 70, 33, 300
+    rng = np.random.default_rng(4)
+    A = rng.random(batch * M * K); B = rng.random(batch * K * N); C = rng.random(batch * M * N); ref = C.copy()
+    for b in range(batch):
+        r = ref[b * M * N:(b + 1) * M * N]
+        O.gemm_strided(M, N, K, 1.0, A[b * M * K:], K, 1, B[b * K * N:], N, 1, 1.0, r, N, 1)
+    emu.emu_gemm_simt_batched_f64(batch, M, N, K, 1.0, at(A, 0), K, 1, M * K, at(B, 0), N, 1, K * N, 1.0, at(C, 0), N, 1, M * N, 3)
+    assert np.array_equal(C, ref)
+    Ai = rng.integers(-2**62, 2**62, size=batch * M * K, dtype=np.int64); Bi = rng.integers(-2**62, 2**62, size=K * N, dtype=np.int64)
+    Ci = np.zeros(batch * M * N, np.int64); refi = Ci.copy()
+    for b in range(batch):
+        O.gemm_strided(M, N, K, 1, Ai[b * M * K:], K, 1, Bi, N, 1, 0, refi[b * M * N:(b + 1) * M * N], N, 1)
+    emu.emu_gemm_simt_batched_i64(batch, M, N, K, 1, at(Ai, 0), K, 1, M * K, at(Bi, 0), N, 1, 0, 0, at(Ci, 0), N, 1, M * N, 0)
+    assert np.array_equal(Ci, refi)
+
+
+# ---- property-based: random shapes, strides and scalars against the oracle ------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(M=st.integers(1, 140), N=st.integers(1, 140), K=st.integers(1, 560), la=st.sampled_from(LAYOUTS),
+       lb=st.sampled_from(LAYOUTS), lc=st.sampled_from(LAYOUTS), beta=st.sampled_from([0.0, 1.0, -0.5]),
+       grid=st.integers(0, 4), seed=st.integers(0, 2**31))
+def test_property_random_problems_bit_exact(emu, M, N, K, la, lb, lc, beta, grid, seed):
+    a = O.fill_uniform_f32(M * K, seed, -1, 1).reshape(M, K); b = O.fill_uniform_f32(K * N, seed + 1, -1, 1).reshape(K, N)
+    c0 = O.fill_uniform_f32(M * N, seed + 2, -1, 1).reshape(M, N)
+    A, oa, rsa, csa = embed(a, la); B, ob, rsb, csb = embed(b, lb); C, oc, rsc, csc = embed(c0, lc)
+    Cref = C.copy()
+    O.gemm_strided(M, N, K, 1.0, A[oa:], rsa, csa, B[ob:], rsb, csb, beta, Cref[oc:], rsc, csc)
+    run(emu, "f32", M, N, K, 1.0, A, oa, rsa, csa, B, ob, rsb, csb, beta, C, oc, rsc, csc, grid=grid)
+    assert np.array_equal(C, Cref)

@@ -208,6 +208,26 @@ def test_batched_small_problems_single_launch_is_bit_exact():
     assert np.array_equal(tC.cpu().numpy(), ref)
 
 
+def test_batched_f64_and_i64():
+    batch, M, N, K = 6, 40, 50, 300
+    rng = np.random.default_rng(4)
+    A = rng.random(batch * M * K); B = rng.random(batch * K * N); C0 = rng.random(batch * M * N); ref = C0.copy()
+    for b in range(batch):
+        O.gemm_strided(M, N, K, 1.0, A[b * M * K:], K, 1, B[b * K * N:], N, 1, 1.0, ref[b * M * N:(b + 1) * M * N], N, 1)
+    tC = dev(C0)
+    L.gemm_strided_batched(batch, M, N, K, 1.0, dev(A), K, 1, M * K, dev(B), N, 1, K * N, 1.0, tC, N, 1, M * N)
+    torch.cuda.synchronize()
+    assert np.array_equal(tC.cpu().numpy(), ref)
+    Ai = rng.integers(-2**62, 2**62, size=batch * M * K, dtype=np.int64); Bi = rng.integers(-2**62, 2**62, size=K * N, dtype=np.int64)
+    refi = np.zeros(batch * M * N, np.int64)
+    for b in range(batch):
+        O.gemm_strided(M, N, K, 1, Ai[b * M * K:], K, 1, Bi, N, 1, 0, refi[b * M * N:(b + 1) * M * N], N, 1)
+    tCi = torch.zeros(batch * M * N, dtype=torch.int64, device="cuda")
+    L.gemm_strided_batched(batch, M, N, K, 1, dev(Ai), K, 1, M * K, dev(Bi), N, 1, 0, 0, tCi, N, 1, M * N)
+    torch.cuda.synchronize()
+    assert np.array_equal(tCi.cpu().numpy(), refi)
+
+
 # ---- copyFrom on strided views ------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", ["f32", "f64", "i32", "i64", "bf16"])
 def test_copyFrom_views(dtype):
