@@ -234,7 +234,13 @@ gemm_simt_kernel(const SimtParams<T> p) {
   }
 }
 
-#ifndef LB200_HOST_EMULATION  // warp-shuffle kernels cannot run in tests/emu (one host thread per CUDA thread)
+// dynamic shared memory (tests/emu runs this header on host threads, where it is a plain buffer)
+#ifdef LB200_HOST_EMULATION
+#define LB200_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
+#else
+#define LB200_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 // ---------------------------------------------------------------------------
 // Skinny GEMM: N <= 4 (matrix x few vectors).  One warp per output row: lanes stride
 // over K with coalesced loads of A's row, partial dot products are combined with
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(256)
 gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict__ A, int64_t rsA,
                       const float *__restrict__ B, int64_t rsB, int64_t csB, float beta,
                       float *__restrict__ C, int64_t rsC, int64_t csC) {
-  extern __shared__ float4 gemv_smem4[];
+  LB200_DYN_SMEM(float4, gemv_smem4);
   float *Bs = reinterpret_cast<float *>(gemv_smem4);
   for (int64_t i = threadIdx.x; i < K * NV; i += blockDim.x) {
     const int64_t k = i / NV;
@@ -348,7 +354,5 @@ gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict
     }
   }
 }
-
-#endif  // LB200_HOST_EMULATION
 
 }  // namespace lb200

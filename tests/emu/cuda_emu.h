@@ -2,7 +2,7 @@
 // that the CPU test suite can execute the kernels' index arithmetic, bounds handling and
 // shared-memory choreography without a GPU (one std::thread per CUDA thread of a block, a pthread
 // barrier for __syncthreads, blocks one after the other).  Only kernels written in plain CUDA C++
-// (no inline PTX, no warp intrinsics) can be run this way: layers.cuh, gemm_simt_kernel, split.cuh (with a software tf32 rounding).
+// (no inline PTX; of the warp intrinsics only full-mask __shfl_xor_sync) can be run this way: layers.cuh, gemm_simt_kernel, split.cuh (with a software tf32 rounding).
 // It is a test of the product's source, not a fallback: nothing under laser_b200/ includes it.
 #pragma once
 
@@ -34,6 +34,9 @@ inline thread_local Idx t_idx{0, 0, 0};
 inline thread_local Idx b_idx{0, 0, 0};
 inline Idx b_dim{1, 1, 1}, g_dim{1, 1, 1};
 inline pthread_barrier_t barrier;
+inline pthread_barrier_t warp_barrier[32];     // one per warp of the block (warp shuffles)
+inline float warp_scratch[1024];
+alignas(16) inline unsigned char dyn_smem[96 * 1024];   // dynamic shared memory of the block
 
 // kernels whose threads all reach every __syncthreads (or that have none) only
 template <typename Body>
@@ -41,6 +44,7 @@ void launch(unsigned grid, unsigned block, Body body) {
   g_dim = Idx{grid, 1, 1};
   b_dim = Idx{block, 1, 1};
   pthread_barrier_init(&barrier, nullptr, block);
+  for (unsigned w = 0; w < block / 32; ++w) pthread_barrier_init(&warp_barrier[w], nullptr, 32);
   std::vector<std::thread> threads;
   threads.reserve(block);
   for (unsigned t = 0; t < block; ++t)
@@ -54,6 +58,7 @@ void launch(unsigned grid, unsigned block, Body body) {
     });
   for (auto &th : threads) th.join();
   pthread_barrier_destroy(&barrier);
+  for (unsigned w = 0; w < block / 32; ++w) pthread_barrier_destroy(&warp_barrier[w]);
 }
 }  // namespace emu
 
@@ -77,3 +82,12 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 #define blockDim (emu::b_dim)
 #define gridDim (emu::g_dim)
 inline void __syncthreads() { pthread_barrier_wait(&emu::barrier); }
+// full-mask butterfly shuffle: every lane of the warp must call it (true for the reductions it is used in)
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  const unsigned t = emu::t_idx.x, w = t >> 5;
+  emu::warp_scratch[t] = v;
+  pthread_barrier_wait(&emu::warp_barrier[w]);
+  const float r = emu::warp_scratch[t ^ static_cast<unsigned>(lane_mask)];
+  pthread_barrier_wait(&emu::warp_barrier[w]);
+  return r;
+}

@@ -63,4 +63,18 @@ int emu_gemm_simt_batched_i64(int64_t batch, int64_t M, int64_t N, int64_t K, in
   return run<int64_t, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0, batch,
                                 bsA, bsB, bsC);
 }
+// skinny GEMM (N <= 4): variant 0 = scalar loads, 1 = float4 loads of A, 2 = B staged in shared memory
+int emu_gemv(int variant, int NV, int64_t M, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
+             const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC, int grid) {
+#define GEMV(NVC)                                                                                                  \
+  do {                                                                                                             \
+    if (variant == 2) emu::launch(grid, 256, [=]() { gemv_warp_smem_kernel<NVC>(M, K, alpha, A, rsA, B, rsB, csB, beta, C, rsC, csC); }); \
+    else if (variant == 1) emu::launch(grid, 256, [=]() { gemv_warp_kernel<NVC, true>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC); }); \
+    else emu::launch(grid, 256, [=]() { gemv_warp_kernel<NVC, false>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC); }); \
+  } while (0)
+  if (variant == 2 && static_cast<size_t>(NV) * K * 4 > sizeof(emu::dyn_smem)) return -1;
+  if (NV == 1) GEMV(1); else if (NV == 2) GEMV(2); else if (NV == 3) GEMV(3); else if (NV == 4) GEMV(4); else return -1;
+#undef GEMV
+  return 0;
+}
 }  // extern "C"

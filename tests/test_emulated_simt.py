@@ -33,6 +33,8 @@ def emu():
         fn = getattr(L, "emu_gemm_simt_batched_" + name)
         fn.restype = ci
         fn.argtypes = [i64, i64, i64, i64, sc, vp, i64, i64, i64, vp, i64, i64, i64, sc, vp, i64, i64, i64, ci]
+    L.emu_gemv.restype = ci
+    L.emu_gemv.argtypes = [ci, ci, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64, ci]
     return L
 
 
@@ -166,3 +168,21 @@ def test_property_random_problems_bit_exact(emu, M, N, K, la, lb, lc, beta, grid
     O.gemm_strided(M, N, K, 1.0, A[oa:], rsa, csa, B[ob:], rsb, csb, beta, Cref[oc:], rsc, csc)
     run(emu, "f32", M, N, K, 1.0, A, oa, rsa, csa, B, ob, rsb, csb, beta, C, oc, rsc, csc, grid=grid)
     assert np.array_equal(C, Cref)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("NV", [1, 2, 3, 4])
+@pytest.mark.parametrize("M,K,grid", [(1, 4, 1), (37, 1000, 2), (300, 4096, 3)])
+def test_skinny_gemm_warp_kernels(emu, variant, NV, M, K, grid):
+    """N <= 4: one warp per row, shuffle reduction (a different summation tree from the reference's
+    k-sequential chain, hence a tolerance; PATH_SIMT never takes these kernels)."""
+    a = O.fill_uniform_f32(M * K, 3, -1, 1).reshape(M, K); b = O.fill_uniform_f32(K * NV, 4, -1, 1).reshape(K, NV)
+    c = O.fill_uniform_f32(M * NV, 5, -1, 1).reshape(M, NV); ref = c.copy()
+    O.gemm_strided(M, NV, K, 0.5, a, K, 1, b, NV, 1, -1.25, ref, NV, 1)
+    assert emu.emu_gemv(variant, NV, M, K, 0.5, at(a, 0), K, 1, at(b, 0), NV, 1, -1.25, at(c, 0), NV, 1, grid) == 0
+    assert np.abs(c - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()) * np.sqrt(K)
+    if variant == 0:      # the scalar variant also takes arbitrary strides: A transposed, C column-major
+        at_ = np.ascontiguousarray(a.T); c2 = np.full((NV, M), np.nan, np.float32); ref2 = np.zeros((M, NV), np.float32)
+        O.gemm_strided(M, NV, K, 1.0, a, K, 1, b, NV, 1, 0.0, ref2, NV, 1)
+        assert emu.emu_gemv(0, NV, M, K, 1.0, at(at_, 0), 1, M, at(b, 0), NV, 1, 0.0, at(c2, 0), 1, M, grid) == 0
+        assert np.abs(c2.T - ref2).max() <= 2e-6 * max(1.0, np.abs(ref2).max()) * np.sqrt(K)
