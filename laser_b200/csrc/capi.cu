@@ -456,42 +456,7 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
-  {
-    // K extent accumulated inside the tensor core before the epilogue warps add the block
-    // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
-    // Only the fp32-faithful modes need short chains; see gemm_tc.cuh.
-    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;  // scheduling unit along K
-    const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
-    int kc = (npass == 3 || npass == 2) ? c.kc_faithful : 0;
-    p.kb_per_block = (kc > 0) ? (kc + block_k - 1) / block_k : num_kb;
-    if (p.kb_per_block < 1) p.kb_per_block = 1;
-    if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
-  }
-  p.raster_g = c.raster_g > 0 ? c.raster_g : (pair ? 8 : 16);
-  const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
-  p.num_m_blocks = static_cast<int>((M + tile_m - 1) / tile_m);
-  p.num_n_blocks = static_cast<int>((N + TC_BLOCK_N - 1) / TC_BLOCK_N);
-  // ---- split-K: too few output tiles to fill the machine and a long K (fp32 output only) ----
-  p.k_splits = 1;
-  p.split_plane = 0;
-  {
-    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;
-    const int num_kb = static_cast<int>((K + block_k - 1) / block_k);
-    p.kb_per_split = num_kb;
-    const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
-    const int units = pair ? c.sm_count / 2 : c.sm_count;
-    if constexpr (std::is_same<OutT, float>::value) {
-      const int blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;   // accumulation blocks along K
-      int S = static_cast<int>(units / (tiles > 0 ? tiles : 1));
-      if (S > blocks / 4) S = blocks / 4;     // every split keeps >= 4 accumulation blocks (>= 512 K-elements)
-      if (S > 16) S = 16;
-      if (c.splitk_enabled && S >= 2) {
-        const int blocks_per_split = (blocks + S - 1) / S;
-        p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;
-        p.kb_per_split = blocks_per_split * p.kb_per_block;
-      }
-    }
-  }
+  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count});
   EventPair ep;
   int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;

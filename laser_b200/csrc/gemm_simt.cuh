@@ -235,10 +235,12 @@ gemm_simt_kernel(const SimtParams<T> p) {
 }
 
 // dynamic shared memory (tests/emu runs this header on host threads, where it is a plain buffer)
+#ifndef LB200_DYN_SMEM
 #ifdef LB200_HOST_EMULATION
-#define LB200_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
+#define LB200_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem_ptr())
 #else
 #define LB200_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
 #endif
 
 // ---------------------------------------------------------------------------

@@ -97,6 +97,54 @@ struct TcParams {
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
 
+// host side: the part of TcParams that depends only on the problem (p.M, p.N, p.K set by the
+// caller) and on the configuration
+struct TcPlanCfg {
+  int kc_faithful;      // K extent per TMEM accumulation block in the fp32-faithful modes
+  int raster_g;         // 0 = default
+  bool splitk_enabled;
+  int sm_count;
+};
+template <int ESZ, bool OUT_F32>
+inline void tc_plan(TcParams &p, int npass, bool pair, const TcPlanCfg &cfg) {
+  {
+    // K extent accumulated inside the tensor core before the epilogue warps add the block
+    // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
+    // Only the fp32-faithful modes need short chains.
+    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;  // scheduling unit along K
+    const int num_kb = static_cast<int>((p.K + block_k - 1) / block_k);
+    int kc = (npass == 3 || npass == 2) ? cfg.kc_faithful : 0;
+    p.kb_per_block = (kc > 0) ? (kc + block_k - 1) / block_k : num_kb;
+    if (p.kb_per_block < 1) p.kb_per_block = 1;
+    if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
+  }
+  p.raster_g = cfg.raster_g > 0 ? cfg.raster_g : (pair ? 8 : 16);
+  const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+  p.num_m_blocks = static_cast<int>((p.M + tile_m - 1) / tile_m);
+  p.num_n_blocks = static_cast<int>((p.N + TC_BLOCK_N - 1) / TC_BLOCK_N);
+  // ---- split-K: too few output tiles to fill the machine and a long K (fp32 output only) ----
+  p.k_splits = 1;
+  p.split_plane = 0;
+  {
+    const int block_k = (npass == 2) ? 64 : TC_ROW_BYTES / ESZ;
+    const int num_kb = static_cast<int>((p.K + block_k - 1) / block_k);
+    p.kb_per_split = num_kb;
+    const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+    const int units = pair ? cfg.sm_count / 2 : cfg.sm_count;
+    if constexpr (OUT_F32) {
+      const int blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;   // accumulation blocks along K
+      int S = static_cast<int>(units / (tiles > 0 ? tiles : 1));
+      if (S > blocks / 4) S = blocks / 4;     // every split keeps >= 4 accumulation blocks (>= 512 K-elements)
+      if (S > 16) S = 16;
+      if (cfg.splitk_enabled && S >= 2) {
+        const int blocks_per_split = (blocks + S - 1) / S;
+        p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;
+        p.kb_per_split = blocks_per_split * p.kb_per_block;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int G, int &mb, int &nb) {
   // groups of G m-blocks sweep n together: the concurrently resident tiles (148 of 128 x 256, or
   // 74 pairs of 256 x 256) then cover a near-square patch, which minimises the A + B panels one
@@ -118,15 +166,6 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
   if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return static_cast<uint16_t>(u >> 16);
-}
-
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ESZ: element size of A/B in bytes (4 = tf32 containers, 2 = bf16).
@@ -152,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int sched_id = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int sched_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  extern __shared__ uint8_t smem_raw[];
+  LB200_DYN_SMEM(uint8_t, smem_raw);
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
   uint8_t *smem_a = smem;
@@ -213,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp_idx < 4) {
-    setmaxnreg_dec<TC_REGS_CTRL>();  // hand registers to the epilogue warpgroups
+    ptx::setmaxnreg_dec<TC_REGS_CTRL>();  // hand registers to the epilogue warpgroups
     if (warp_idx == 0 && lane == 0) {
       // ===================== TMA producer (one thread) =====================
       int stage = 0;
@@ -372,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else {
     // ============ epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and 128 columns ============
-    setmaxnreg_inc<TC_REGS_EPI>();
+    ptx::setmaxnreg_inc<TC_REGS_EPI>();
     const int q = warp_idx & 3;          // TMEM lane quarter this warp may read
     const int h = (warp_idx - 4) >> 2;   // column half
     int acc = 0;
@@ -396,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
         for (int l = 0; l < TC_EPI_COLS * static_cast<int>(sizeof(OutT)) / 128; ++l) {
           if (col0 + l * (128 / static_cast<int>(sizeof(OutT))) < p.N)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + l * (128 / sizeof(OutT))));
+            ptx::prefetch_l2(cp + l * (128 / sizeof(OutT)));
         }
       }
       float run[TC_EPI_COLS];  // running sums of this thread's row segment (registers)

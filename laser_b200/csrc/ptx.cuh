@@ -8,6 +8,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifdef LB200_HOST_EMULATION
+// tests/emu: the same names backed by a functional model of mbarrier / TMA / tcgen05 / TMEM on
+// host threads (test infrastructure; see tests/emu/ptx_emu.h)
+#include "ptx_emu.h"
+#else
+
+// dynamic shared memory of the kernel
+#define LB200_DYN_SMEM(T, name) extern __shared__ T name[]
+
 namespace lb200 {
 namespace ptx {
 
@@ -94,6 +103,18 @@ __device__ __forceinline__ void tma_store_wait_read() {
 template <int N>
 __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ------------------------------------------------------------------- tcgen05
@@ -302,3 +323,5 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_mn_ma
 
 }  // namespace ptx
 }  // namespace lb200
+
+#endif  // LB200_HOST_EMULATION

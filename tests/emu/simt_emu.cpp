@@ -72,7 +72,7 @@ int emu_gemv(int variant, int NV, int64_t M, int64_t K, float alpha, const float
     else if (variant == 1) emu::launch(grid, 256, [=]() { gemv_warp_kernel<NVC, true>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC); }); \
     else emu::launch(grid, 256, [=]() { gemv_warp_kernel<NVC, false>(M, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC); }); \
   } while (0)
-  if (variant == 2 && static_cast<size_t>(NV) * K * 4 > sizeof(emu::dyn_smem)) return -1;
+  if (variant == 2 && static_cast<size_t>(NV) * K * 4 > 96 * 1024) return -1;
   if (NV == 1) GEMV(1); else if (NV == 2) GEMV(2); else if (NV == 3) GEMV(3); else if (NV == 4) GEMV(4); else return -1;
 #undef GEMV
   return 0;

@@ -21,10 +21,10 @@ def build_emu(name, product_headers):
     out_dir = os.path.join(EMU_DIR, "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "lib%s.so" % name)
-    srcs = [os.path.join(EMU_DIR, name + ".cpp"), os.path.join(EMU_DIR, "cuda_emu.h")] + \
+    srcs = [os.path.join(EMU_DIR, name + ".cpp"), os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "ptx_emu.h")] + \
            [os.path.join(CSRC, h) for h in product_headers]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call([gxx, "-O1", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-I", CUDA_INC, "-Wno-attributes", "-Wno-unknown-pragmas", srcs[0], "-o", so], env=env)
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", srcs[0], "-o", so], env=env)
     return so
