@@ -212,3 +212,36 @@ def test_bf16(emu, pair, a_mn, b_mn):
     want = exact + 0.5 * bf16_bits_to_f32(c0)
     got = bf16_bits_to_f32(c.reshape(M, N))
     assert np.abs(got - want).max() <= 2.0 ** -8 * max(1.0, np.abs(want).max())
+
+
+# ---- property-based: random problems / configurations against the mode's operand model -------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(mode=st.sampled_from(["tf32x1", "tf32x3", "mixed", "bf16"]), M=st.integers(1, 300), N=st.integers(1, 300),
+       K=st.integers(1, 400), a_mn=st.booleans(), b_mn=st.booleans(), pair=st.booleans(),
+       kc=st.sampled_from([32, 64, 128, 512]), raster=st.sampled_from([0, 1, 3]), sms=st.sampled_from([2, 4, 10]),
+       splitk=st.booleans(), ccol=st.booleans(), beta=st.sampled_from([0.0, 1.0, -0.75]), seed=st.integers(0, 2**30))
+def test_property_random_configurations(emu, mode, M, N, K, a_mn, b_mn, pair, kc, raster, sms, splitk, ccol, beta, seed):
+    if pair and M <= 128:
+        pair = False                              # capi.cu: pairs only when there are at least two 128-row blocks
+    a, b = rnd((M, K), seed), rnd((K, N), seed + 1)
+    c0 = rnd((M, N), seed + 2)
+    rs, cs = (1, M) if ccol else (N, 1)
+    idx = np.arange(M)[:, None] * rs + np.arange(N)[None, :] * cs
+    if mode == "bf16":
+        c0b = f32_to_bf16_bits(c0).reshape(M, N)
+        buf = np.zeros(M * N, np.uint16); buf[idx] = c0b
+        exact, _, _ = run_tc(emu, mode, a, b, buf, rs, cs, beta=beta, a_mn=a_mn, b_mn=b_mn, pair=pair, kc=kc, raster=raster,
+                             splitk=int(splitk), sms=sms)
+        want = exact + beta * bf16_bits_to_f32(c0b)
+        assert np.abs(bf16_bits_to_f32(buf[idx]) - want).max() <= 2.0 ** -8 * max(1.0, np.abs(want).max())
+        return
+    buf = np.full(M * N, np.nan, np.float32)
+    if beta != 0.0:
+        buf[idx] = c0
+    exact, ks, _ = run_tc(emu, mode, a, b, buf, rs, cs, beta=beta, a_mn=a_mn, b_mn=b_mn, pair=pair, kc=kc, raster=raster,
+                          splitk=int(splitk), sms=sms)
+    want = exact + (beta * c0 if beta != 0.0 else 0.0)
+    assert np.abs(buf[idx] - want).max() <= 4e-6 * max(1.0, np.abs(want).max()), (ks,)
