@@ -223,7 +223,7 @@ def run_ours(args):
         if world == 1:
             L.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, C, N, 1)
         else:
-            gemm_rowsharded(M, N, K, 1.0, A2, B2, 0.0, C2, src=0, n_panels=1)
+            gemm_rowsharded(M, N, K, 1.0, A2, B2, 0.0, C2, src=0)
 
     def barrier():
         torch.cuda.synchronize()

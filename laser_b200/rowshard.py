@@ -70,12 +70,14 @@ def _overlap_applicable(A_local, B, C_local, n_panels, M_local):
 
 
 def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, group=None,
-                    n_panels=1, gemm_fn=None, broadcast=True, overlap_prepack=None):
+                    n_panels=None, gemm_fn=None, broadcast=True, overlap_prepack=None):
     """C_local <- alpha * A_local @ B + beta * C_local on every rank.
 
     A_local: (M_local, K) tensor view (any strides), C_local: (M_local, N) view,
     B: (K, N) row-major contiguous tensor on every rank, valid on `src` only (unless
     broadcast=False).  gemm_fn has the gemm_strided signature (default: the CUDA library)."""
+    if n_panels is None:     # default 1 (measured best in round 1); env override for A/B runs of bench.py
+        n_panels = int(os.environ.get("LASER_B200_ROWSHARD_PANELS", "1"))
     if overlap_prepack is None:
         overlap_prepack = os.environ.get("LASER_B200_ROWSHARD_OVERLAP", "0") == "1"
     overlap = bool(overlap_prepack) and gemm_fn is None and _overlap_applicable(A_local, B, C_local, n_panels, M_local)
