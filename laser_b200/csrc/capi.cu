@@ -92,6 +92,7 @@ struct Ctx {
   int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
+  int l2_hint = 0;        // env LASER_B200_L2HINT: 0 plain loads (default), 1 A evict_last / B evict_first, 2 the reverse
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
@@ -153,6 +154,7 @@ int get_ctx(Ctx **out) {
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
+      if (const char *lh = getenv("LASER_B200_L2HINT")) c.l2_hint = atoi(lh);
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32_BF16C;
@@ -457,6 +459,8 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
   tc_plan<ESZ, std::is_same<OutT, float>::value>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count});
+  if (c.l2_hint == 1) { p.hint_a = ptx::kEvictLast; p.hint_b = ptx::kEvictFirst; }
+  else if (c.l2_hint == 2) { p.hint_a = ptx::kEvictFirst; p.hint_b = ptx::kEvictLast; }
   EventPair ep;
   int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;

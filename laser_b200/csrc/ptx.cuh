@@ -86,6 +86,18 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "r"(c0), "r"(c1)
       : "memory");
 }
+// The same with an L2 eviction-priority hint (64-bit cache policy, see kEvict*).
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull,
+                   kEvictLast = 0x14F0000000000000ull;   // createpolicy.fractional.L2::evict_* 1.0
+__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                                 int32_t c0, int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src,
                                              int32_t c0, int32_t c1) {
@@ -237,6 +249,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                                      int32_t c0, int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 template <uint32_t NCOLS>

@@ -150,6 +150,11 @@ inline void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, i
   emu::mb_complete_tx(bar, bytes);
 }
 
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
+inline void tma_load_2d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, uint64_t) {
+  tma_load_2d(smem_dst, map, bar, c0, c1);   // cache policies have no functional effect
+}
+
 // ------------------------------------------------------------------- tcgen05
 inline void tc_fence_before_sync() {}
 inline void tc_fence_after_sync() {}
@@ -266,6 +271,9 @@ inline void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *b
   long bytes;
   tma_copy_box(smem_dst, map, c0, c1, &bytes);               // into THIS CTA's shared memory
   emu::mb_complete_tx(emu::peer_ptr(bar, 0), bytes);        // bytes credited to the LEADER's barrier
+}
+inline void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, uint64_t) {
+  tma_load_2d_pair(smem_dst, map, bar, c0, c1);
 }
 template <uint32_t NCOLS> inline void tmem_alloc_pair(uint32_t *smem_dst) { *smem_dst = 0; }
 template <uint32_t NCOLS> inline void tmem_dealloc_pair(uint32_t) {}
