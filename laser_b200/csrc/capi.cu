@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "gemm_simt.cuh"
@@ -92,6 +93,8 @@ struct Ctx {
   int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
+  int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
+  bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   int l2_hint = 0;        // env LASER_B200_L2HINT: 0 plain loads (default), 1 A evict_last / B evict_first, 2 the reverse
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
@@ -155,6 +158,11 @@ int get_ctx(Ctx **out) {
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       if (const char *lh = getenv("LASER_B200_L2HINT")) c.l2_hint = atoi(lh);
+      if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
+      if (const char *pr = getenv("LASER_B200_PANEL_ROWS")) {
+        const int64_t v = atoll(pr) / 256 * 256;   // whole CTA-pair tiles
+        if (v >= 256) c.panel_rows = v;
+      }
       const char *mode = getenv("LASER_B200_F32_MODE");
       if (g_f32_mode.load() < 0) {
         int m = LASER_B200_PATH_TF32_BF16C;
@@ -771,8 +779,24 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
   std::lock_guard<std::mutex> host_lk(c.host_mu);
   std::lock_guard<std::mutex> lk(c.mu);
   int rc;
-  const int64_t panel_rows = 1024;
-  const int panels = static_cast<int>((M + panel_rows - 1) / panel_rows);
+  const int64_t panel_rows = c.panel_rows;
+  // row panels (first row, rows).  The time after the last byte of A has crossed the bus is one
+  // panel's split + GEMM + D2H: optionally the last panel is cut finer (halves down to 256 rows).
+  std::vector<std::pair<int64_t, int64_t>> plist;
+  for (int64_t m0 = 0; m0 < M; m0 += panel_rows) plist.emplace_back(m0, (M - m0 < panel_rows) ? (M - m0) : panel_rows);
+  if (c.panel_taper && plist.size() >= 2) {
+    int64_t m0 = plist.back().first, rows = plist.back().second;
+    plist.pop_back();
+    while (rows > 256) {
+      const int64_t h = (rows / 2 + 255) / 256 * 256;
+      if (h >= rows) break;
+      plist.emplace_back(m0, h);
+      m0 += h;
+      rows -= h;
+    }
+    plist.emplace_back(m0, rows);
+  }
+  const int panels = static_cast<int>(plist.size());
   const Span sa = span_of(M, K, rsA, csA), sb = span_of(K, N, rsB, csB), sc = span_of(M, N, rsC, csC);
   const size_t na = static_cast<size_t>(sa.hi - sa.lo + 1) * 4, nb = static_cast<size_t>(sb.hi - sb.lo + 1) * 4;
   const size_t nc = static_cast<size_t>(sc.hi - sc.lo + 1) * 4;
@@ -805,8 +829,8 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     return rc;
   // ---- row panels ----
   for (int pnl = 0; pnl < panels; ++pnl) {
-    const int64_t m0 = pnl * panel_rows;
-    const int64_t mp = (M - m0 < panel_rows) ? (M - m0) : panel_rows;
+    const int64_t m0 = plist[pnl].first;
+    const int64_t mp = plist[pnl].second;
     const float *Ap = A + m0 * rsA;
     float *Cp = C + m0 * rsC;
     const Span pa = span_of(mp, K, rsA, csA), pc = span_of(mp, N, rsC, csC);
@@ -1016,8 +1040,8 @@ int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, co
     const int mode = g_f32_mode.load();
     const int npass = mode == LASER_B200_PATH_TF32X3 ? 3 : mode == LASER_B200_PATH_TF32_BF16C ? 2
                       : mode == LASER_B200_PATH_TF32X1 ? 1 : 0;
-    if (npass && panel_separable(1024, K, rsA, csA) && panel_separable(1024, N, rsC, csC) &&
-        span_of(1024, N, rsC, csC).dense && rsA > 0 && rsC > 0)
+    if (npass && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
+        span_of(c->panel_rows, N, rsC, csC).dense && rsA > 0 && rsC > 0)
       return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, npass);
   }
   return host_gemm<float>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0f, C, rsC, csC,
