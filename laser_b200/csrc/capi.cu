@@ -638,7 +638,7 @@ int check_args(int64_t M, int64_t N, int64_t K, const void *A, const void *B, co
   return LASER_B200_OK;
 }
 
-int finish(Ctx &c, cudaStream_t user, cudaStream_t s) {
+int finish(Ctx &, cudaStream_t user, cudaStream_t s) {
   if (!user) CUDA_TRY(cudaStreamSynchronize(s));
   return LASER_B200_OK;
 }
