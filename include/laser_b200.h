@@ -318,6 +318,24 @@ int laser_b200_conv2d_im2col_f32(float *output, const float *input, const int64_
  * the rest the strided kernel -- the reference's forEachStrided d in dst, s in src: d = s). */
 int laser_b200_copy_views(laser_b200_tensor_view *dst, const laser_b200_tensor_view *src, void *stream);
 
+/* forEach over up to four equal-shape device tensor views of any strides (float32 / float64):
+ *   forEach o in out, x in a, y in b, z in c: <body>     laser/strided_iteration/foreach.nim:229-251
+ * An arbitrary body cannot cross a C ABI; the bodies the reference's own code, documentation and
+ * iteration benchmark use are opcodes.  Operands an opcode does not read may be NULL; `out` may
+ * alias an input element for element (in-place updates). */
+#define LASER_B200_FOREACH_COPY 0   /* o = x                 (initialization.nim:68,104) */
+#define LASER_B200_FOREACH_FILL 1   /* o = alpha */
+#define LASER_B200_FOREACH_SCALE 2  /* o = alpha * x */
+#define LASER_B200_FOREACH_ADD 3    /* o = x + y */
+#define LASER_B200_FOREACH_SUB 4    /* o = x - y */
+#define LASER_B200_FOREACH_MUL 5    /* o = x * y */
+#define LASER_B200_FOREACH_FMA 6    /* o = x + y * z         (`x += y * z`, foreach.nim:231-232) */
+#define LASER_B200_FOREACH_AXPY 7   /* o = alpha * x + y */
+#define LASER_B200_FOREACH_BENCH 8  /* o = x + y - sin(z)    (benchmarks/loop_iteration/iter_bench_prod.nim:88-90) */
+int laser_b200_foreach_views(int op, laser_b200_tensor_view *out, const laser_b200_tensor_view *x,
+                             const laser_b200_tensor_view *y, const laser_b200_tensor_view *z, double alpha,
+                             void *stream);
+
 /* ---- host-logic introspection (pure functions, no GPU needed; used by the CPU tests) --------
  * classify: how the tensor-core path would feed an operand seen as [mn][k] with element strides
  * (s_mn, s_k): 0 = K-major TMA, 1 = MN-major TMA, 2 = general (gathered by pack_general_kernel).

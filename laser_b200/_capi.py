@@ -99,6 +99,8 @@ SIGNATURES = {
                                                         ctypes.c_int, vp]),
     "laser_b200_conv2d_im2col_f32": (ctypes.c_int, [vp, vp, i64 * 4, vp, i64 * 4, i64 * 2, i64 * 2]),
     "laser_b200_copy_views": (ctypes.c_int, [ctypes.POINTER(TensorView), ctypes.POINTER(TensorView), vp]),
+    "laser_b200_foreach_views": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(TensorView), ctypes.POINTER(TensorView),
+                                                ctypes.POINTER(TensorView), ctypes.POINTER(TensorView), f64, vp]),
     "laser_b200_debug_classify": (ctypes.c_int, [ctypes.c_int, vp, i64, i64]),
     "laser_b200_debug_span": (ctypes.c_int, [i64, i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64),
                                              ctypes.POINTER(ctypes.c_int)]),

@@ -203,4 +203,93 @@ copy_strided_kernel(T *__restrict__ dst, const T *__restrict__ src, CopyParams p
   }
 }
 
+
+// ---- forEach over up to four equal-shape strided views (laser/strided_iteration/foreach.nim:229-251) ----
+// `forEach o in out, x in a, y in b, z in c: <body>` -- the body cannot cross a C ABI, so the bodies
+// the reference's own code, docs and iteration benchmark use are provided as opcodes.
+enum ForeachOp : int {
+  FE_COPY = 0,    // o = x                      (copyFrom / deepCopy, initialization.nim:68,104)
+  FE_FILL = 1,    // o = alpha
+  FE_SCALE = 2,   // o = alpha * x
+  FE_ADD = 3,     // o = x + y
+  FE_SUB = 4,     // o = x - y
+  FE_MUL = 5,     // o = x * y
+  FE_FMA = 6,     // o = x + y * z               (`x += y * z`, foreach.nim:231-232, with o aliasing x)
+  FE_AXPY = 7,    // o = alpha * x + y
+  FE_BENCH = 8,   // o = x + y - sin(z)          (benchmarks/loop_iteration/iter_bench_prod.nim:88-90)
+  FE_NUM_OPS = 9
+};
+struct ForeachParams {
+  int rank;
+  int64_t shape[6];
+  int64_t strides[4][6];   // o, x, y, z (elements; 0 for unused operands)
+  int64_t total;
+};
+// host side: merge neighbouring dimensions contiguous in every operand, drop extents of 1
+inline void foreach_plan(int rank, const int64_t *shape, const int64_t *const strides[4], ForeachParams *p) {
+  p->rank = 0;
+  p->total = 1;
+  for (int d = 0; d < rank; ++d) {
+    p->total *= shape[d];
+    if (shape[d] == 1) continue;
+    bool merge = p->rank > 0;
+    for (int t = 0; t < 4 && merge; ++t)
+      merge = p->strides[t][p->rank - 1] == (strides[t] ? strides[t][d] : 0) * shape[d];
+    if (merge) {
+      p->shape[p->rank - 1] *= shape[d];
+      for (int t = 0; t < 4; ++t) p->strides[t][p->rank - 1] = strides[t] ? strides[t][d] : 0;
+    } else {
+      p->shape[p->rank] = shape[d];
+      for (int t = 0; t < 4; ++t) p->strides[t][p->rank] = strides[t] ? strides[t][d] : 0;
+      ++p->rank;
+    }
+  }
+  for (int d = p->rank; d < 6; ++d) {
+    p->shape[d] = 1;
+    for (int t = 0; t < 4; ++t) p->strides[t][d] = 0;
+  }
+}
+template <typename T> __device__ __forceinline__ T fe_sin(T v);
+template <> __device__ __forceinline__ float fe_sin<float>(float v) { return sinf(v); }
+template <> __device__ __forceinline__ double fe_sin<double>(double v) { return sin(v); }
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+foreach_strided_kernel(T *o, const T *x, const T *y, const T *z, ForeachParams p, T alpha) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < p.total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t rem = i, off[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int d = 5; d >= 0; --d) {
+      if (d < p.rank) {
+        const int64_t q = rem / p.shape[d], c = rem - q * p.shape[d];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) off[t] += c * p.strides[t][d];
+        rem = q;
+      }
+    }
+    T v;
+    if constexpr (OP == FE_COPY) v = x[off[1]];
+    else if constexpr (OP == FE_FILL) v = alpha;
+    else if constexpr (OP == FE_SCALE) v = alpha * x[off[1]];
+    else if constexpr (OP == FE_ADD) v = x[off[1]] + y[off[2]];
+    else if constexpr (OP == FE_SUB) v = x[off[1]] - y[off[2]];
+    else if constexpr (OP == FE_MUL) v = x[off[1]] * y[off[2]];
+    else if constexpr (OP == FE_FMA) v = x[off[1]] + y[off[2]] * z[off[3]];
+    else if constexpr (OP == FE_AXPY) v = alpha * x[off[1]] + y[off[2]];
+    else v = x[off[1]] + y[off[2]] - fe_sin<T>(z[off[3]]);
+    o[off[0]] = v;
+  }
+}
+// operands an opcode reads (bit 0: x, bit 1: y, bit 2: z)
+inline int foreach_operands(int op) {
+  switch (op) {
+    case FE_COPY: case FE_SCALE: return 1;
+    case FE_FILL: return 0;
+    case FE_ADD: case FE_SUB: case FE_MUL: case FE_AXPY: return 3;
+    case FE_FMA: case FE_BENCH: return 7;
+    default: return -1;
+  }
+}
+
 }  // namespace lb200

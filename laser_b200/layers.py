@@ -21,7 +21,9 @@ from ._capi import PATH_AUTO, check, lib
 from .gemm import _current_stream, _resolve, _scalar
 from .tensor import _ITEMSIZE, Tensor
 
-__all__ = ["transpose2D_copy", "transpose2D_batched", "nchw2nhwc", "nhwc2nchw", "conv2d_out_shape",
+FOREACH_OPS = {"copy": 0, "fill": 1, "scale": 2, "add": 3, "sub": 4, "mul": 5, "fma": 6, "axpy": 7, "bench": 8}
+
+__all__ = ["forEach", "FOREACH_OPS", "transpose2D_copy", "transpose2D_batched", "nchw2nhwc", "nhwc2nchw", "conv2d_out_shape",
            "im2col_workspace_size", "im2col", "conv2d_im2col", "gemm_strided_batched", "copyFrom"]
 
 _i64 = ctypes.c_int64
@@ -157,3 +159,16 @@ def copyFrom(dst, src, stream=None):
     stream = _current_stream() if stream is None else stream
     check(lib().laser_b200_copy_views(ctypes.byref(vd), ctypes.byref(vs), stream))
     return dst
+
+
+def forEach(op, out, x=None, y=None, z=None, alpha=0.0, stream=None):
+    """forEach o in out, x in a, y in b, z in c: <body> on device Tensors of one shape, any strides
+    (laser/strided_iteration/foreach.nim:229-251).  `op` names the body:
+      copy o = x | fill o = alpha | scale o = alpha*x | add o = x+y | sub o = x-y | mul o = x*y |
+      fma o = x + y*z | axpy o = alpha*x + y | bench o = x + y - sin(z) (the reference's iteration benchmark)"""
+    code = FOREACH_OPS[op] if isinstance(op, str) else int(op)
+    views = [t.view_struct() if t is not None else None for t in (out, x, y, z)]
+    refs = [ctypes.byref(v) if v is not None else None for v in views]
+    stream = _current_stream() if stream is None else stream
+    check(lib().laser_b200_foreach_views(code, refs[0], refs[1], refs[2], refs[3], float(alpha), stream))
+    return out

@@ -17,6 +17,24 @@ static int run_transpose(T *dst, const T *src, int64_t N, int64_t NR, int64_t NC
   return vec ? 4 : 1;
 }
 
+// forEach opcodes: strides[t] may be NULL for operands the opcode does not read; returns the merged rank
+template <typename T>
+static int run_foreach(int op, T *o, const T *x, const T *y, const T *z, int rank, const int64_t *shape,
+                       const int64_t *so, const int64_t *sx, const int64_t *sy, const int64_t *sz, double alpha, int grid) {
+  const int64_t *strides[4] = {so, sx, sy, sz};
+  ForeachParams p;
+  foreach_plan(rank, shape, strides, &p);
+  if (p.total == 0) return p.rank;
+  const T a = static_cast<T>(alpha);
+#define FE(OP) case OP: emu::launch(grid, 256, [=]() { foreach_strided_kernel<T, OP>(o, x, y, z, p, a); }); break
+  switch (op) {
+    FE(FE_COPY); FE(FE_FILL); FE(FE_SCALE); FE(FE_ADD); FE(FE_SUB); FE(FE_MUL); FE(FE_FMA); FE(FE_AXPY); FE(FE_BENCH);
+    default: return -1;
+  }
+#undef FE
+  return p.rank;
+}
+
 extern "C" {
 
 // returns the vector width used (4 or 1), -1 on a bad element size
@@ -56,6 +74,18 @@ int emu_copy_strided(int elem_size, void *dst, const void *src, int rank, const 
     emu::launch(grid, 256, [=]() { copy_strided_kernel<uint16_t>(static_cast<uint16_t *>(dst), static_cast<const uint16_t *>(src), p); });
   else return -1;
   return p.rank;
+}
+
+int emu_foreach(int elem_size, int op, void *o, const void *x, const void *y, const void *z, int rank, const int64_t *shape,
+                const int64_t *so, const int64_t *sx, const int64_t *sy, const int64_t *sz, double alpha, int grid) {
+  if (foreach_operands(op) < 0) return -1;
+  if (elem_size == 4)
+    return run_foreach(op, static_cast<float *>(o), static_cast<const float *>(x), static_cast<const float *>(y),
+                       static_cast<const float *>(z), rank, shape, so, sx, sy, sz, alpha, grid);
+  if (elem_size == 8)
+    return run_foreach(op, static_cast<double *>(o), static_cast<const double *>(x), static_cast<const double *>(y),
+                       static_cast<const double *>(z), rank, shape, so, sx, sy, sz, alpha, grid);
+  return -1;
 }
 
 }  // extern "C"

@@ -12,6 +12,8 @@ import oracle as O
 
 from emu_build import build_emu
 
+i64 = ctypes.c_int64
+
 
 @pytest.fixture(scope="module")
 def emu():
@@ -24,6 +26,9 @@ def emu():
     L.emu_im2col.argtypes = [vp, vp, i64, i64 * 11, ci]
     L.emu_copy_strided.restype = ci
     L.emu_copy_strided.argtypes = [ci, vp, vp, ci, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
+    P = ctypes.POINTER(i64)
+    L.emu_foreach.restype = ci
+    L.emu_foreach.argtypes = [ci, ci, vp, vp, vp, vp, ci, P, P, P, P, P, ctypes.c_double, ci]
     return L
 
 
@@ -118,3 +123,56 @@ def test_copy_strided_kernel(emu, dt, shape, dst_strides, src_strides, merged):
     exp = np.zeros(n_dst, dt)
     exp[as_strided_idx(shape, dst_strides, 0)] = src[as_strided_idx(shape, src_strides, 0)]
     assert np.array_equal(dst, exp)
+
+
+FOREACH = {0: lambda x, y, z, a: x, 1: lambda x, y, z, a: np.full_like(x, a), 2: lambda x, y, z, a: a * x,
+           3: lambda x, y, z, a: x + y, 4: lambda x, y, z, a: x - y, 5: lambda x, y, z, a: x * y,
+           6: lambda x, y, z, a: x + y * z, 7: lambda x, y, z, a: a * x + y, 8: lambda x, y, z, a: x + y - np.sin(z)}
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("op", sorted(FOREACH))
+@pytest.mark.parametrize("shape,layouts", [
+    ((100, 70), ("c", "c", "c", "c")),                       # all contiguous: one merged dimension
+    ((100, 70), ("c", "t", "c", "t")),                       # the reference's non-contiguous bench case (transposed inputs)
+    ((6, 5, 4), ("s2", "c", "t", "s2")),                     # sliced output
+])
+def test_foreach_kernel(emu, dt, op, shape, layouts):
+    rng = np.random.default_rng(op)
+    n = int(np.prod(shape))
+
+    def make(kind):
+        if kind == "c":
+            st = [int(np.prod(shape[i + 1:])) for i in range(len(shape))]; size = n
+        elif kind == "t":                                  # dimensions stored in reverse order
+            st = [int(np.prod(shape[:i])) for i in range(len(shape))]; size = n
+        else:                                              # every other element of a contiguous parent
+            st = [2 * int(np.prod(shape[i + 1:])) for i in range(len(shape))]; size = 2 * n
+        return rng.standard_normal(size).astype(dt), st
+    bufs = [make(k) for k in layouts]
+    idx = [as_strided_idx(shape, st, 0) for _, st in bufs]
+    o0 = bufs[0][0].copy()
+    alpha = 0.75
+    want = FOREACH[op](bufs[1][0][idx[1]], bufs[2][0][idx[2]], bufs[3][0][idx[3]], dt(alpha))
+    arr = lambda t: (i64 * len(t))(*t)
+    rank = emu.emu_foreach(np.dtype(dt).itemsize, op, ptr(bufs[0][0]), ptr(bufs[1][0]), ptr(bufs[2][0]), ptr(bufs[3][0]),
+                           len(shape), arr(shape), arr(bufs[0][1]), arr(bufs[1][1]), arr(bufs[2][1]), arr(bufs[3][1]), alpha, 3)
+    assert rank == (1 if set(layouts) == {"c"} else len(shape))
+    got = bufs[0][0]
+    tol = 0 if op != 8 else (1e-6 if dt == np.float32 else 1e-15)
+    assert np.abs(got[idx[0]] - want).max() <= tol * 4
+    mask = np.ones(got.size, bool); mask[idx[0].reshape(-1)] = False
+    assert np.array_equal(got[mask], o0[mask])              # only the elements the output view exposes are written
+
+
+def test_foreach_in_place_update(emu):
+    # `forEach x in a, y in b, z in c: x += y * z` (foreach.nim:231-232): the output aliases the first input
+    shape = (33, 17)
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(shape).astype(np.float32); y = rng.standard_normal(shape).astype(np.float32)
+    z = rng.standard_normal(shape).astype(np.float32)
+    want = x + y * z
+    arr = lambda t: (i64 * len(t))(*t)
+    st = (17, 1)
+    emu.emu_foreach(4, 6, ptr(x), ptr(x), ptr(y), ptr(z), 2, arr(shape), arr(st), arr(st), arr(st), arr(st), 0.0, 2)
+    assert np.array_equal(x, want)

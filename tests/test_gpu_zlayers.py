@@ -246,3 +246,38 @@ def test_copyFrom_views(dtype):
     assert np.array_equal(dst3.to_numpy(), src_host)
     with pytest.raises(L.LaserB200Error):
         L.copyFrom(L.newTensor([40, 61], dtype), src)             # shape mismatch (initialization.nim:96)
+
+
+# ---- forEach opcodes on strided device views (foreach.nim:229-251) ---------------------------------
+FOREACH = {"copy": lambda x, y, z, a: x, "fill": lambda x, y, z, a: np.full_like(x, a), "scale": lambda x, y, z, a: a * x,
+           "add": lambda x, y, z, a: x + y, "sub": lambda x, y, z, a: x - y, "mul": lambda x, y, z, a: x * y,
+           "fma": lambda x, y, z, a: x + y * z, "axpy": lambda x, y, z, a: a * x + y,
+           "bench": lambda x, y, z, a: x + y - np.sin(z)}
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("op", sorted(FOREACH))
+def test_forEach_ops(dtype, op):
+    npdt = np.float32 if dtype == "f32" else np.float64
+    rng = np.random.default_rng(3)
+    hx, hy, hz = (rng.standard_normal((100, 10000)).astype(npdt), rng.standard_normal((10000, 100)).astype(npdt),
+                  rng.standard_normal((10000, 100)).astype(npdt))          # the reference's non-contiguous bench shapes
+    x, y, z = L.toTensor(hx, dtype), L.toTensor(hy, dtype).transpose(), L.toTensor(hz, dtype).transpose()
+    out = L.newTensor([100, 10000], dtype)
+    L.forEach(op, out, x, y, z, alpha=0.75)
+    want = FOREACH[op](hx, hy.T, hz.T, npdt(0.75))
+    tol = 4e-6 if dtype == "f32" else 1e-14                               # mul+add may be contracted to an FMA
+    assert np.abs(out.to_numpy() - want).max() <= tol * max(1.0, np.abs(want).max())
+
+
+def test_forEach_in_place_and_errors():
+    hx, hy, hz = (np.arange(12, dtype=np.float32).reshape(3, 4), np.ones((3, 4), np.float32) * 2, np.ones((3, 4), np.float32) * 3)
+    x, y, z = L.toTensor(hx), L.toTensor(hy), L.toTensor(hz)
+    L.forEach("fma", x, x, y, z)                                          # x += y * z
+    assert np.array_equal(x.to_numpy(), hx + 6)
+    with pytest.raises(L.LaserB200Error):
+        L.forEach("add", x, y)                                            # missing operand
+    with pytest.raises(L.LaserB200Error):
+        L.forEach("add", x, y, L.newTensor([4, 3]))                       # shape mismatch
+    with pytest.raises(L.LaserB200Error):
+        L.forEach("add", L.newTensor([3, 4], "i32"), L.newTensor([3, 4], "i32"), L.newTensor([3, 4], "i32"))
