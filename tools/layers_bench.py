@@ -68,6 +68,17 @@ def main():
         report("conv2d_im2col 16x3x224x224 -> 20 k3, workspace_images=%d" % wi, ms,
                4 * (inp.numel() + ker.numel() + out.numel()), gflops=round(flops / ms / 1e6, 1),
                reference_cpu_note="reference bench prints GFLOP/s for the same shape (conv2d_bench.nim)")
+    # forEach o in output, x in a, y in b, z in c: o = x + y - sin z   (iter_bench_prod.nim:86-107, float64)
+    for name, shape, transposed in (("contiguous", (1000, 1000), False), ("transposed inputs", (100, 10000), True),
+                                    ("contiguous 8192^2", (8192, 8192), False)):
+        hx = np.random.rand(*shape)
+        x = L.toTensor(hx, "f64"); out = L.newTensor(list(shape), "f64")
+        if transposed:
+            y = L.toTensor(np.random.rand(shape[1], shape[0]), "f64").transpose(); z = L.toTensor(np.random.rand(shape[1], shape[0]), "f64").transpose()
+        else:
+            y = L.toTensor(np.random.rand(*shape), "f64"); z = L.toTensor(np.random.rand(*shape), "f64")
+        ms = timeit(lambda: L.forEach("bench", out, x, y, z))
+        report("forEach o = x + y - sin z, f64 %s %s" % (shape, name), ms, 4 * 8 * shape[0] * shape[1])
     ref = torch.nn.functional.conv2d(inp, ker)
     print(json.dumps(dict(check="conv2d vs torch", max_rel=float(((out - ref).abs().max() / ref.abs().max()).item()))))
 
