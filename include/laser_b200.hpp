@@ -164,6 +164,25 @@ void matmul(const CudaTensor<T> &A, const CudaTensor<T> &B, CudaTensor<T> &C, do
   check(laser_b200_matmul_views(&va, &vb, &vc, alpha, beta, path, nullptr));
 }
 
+// dst <- src over a common shape, any strides (copyFrom, initialization.nim:80-112)
+template <typename T>
+void copyFrom(CudaTensor<T> &dst, const CudaTensor<T> &src) {
+  laser_b200_tensor_view vd = dst.view();
+  const laser_b200_tensor_view vs = src.view();
+  check(laser_b200_copy_views(&vd, &vs, nullptr));
+}
+// forEach o in out, x in a, y in b, z in c: <body named by op> (foreach.nim:229-251); op = LASER_B200_FOREACH_*
+template <typename T>
+void forEach(int op, CudaTensor<T> &out, const CudaTensor<T> *x = nullptr, const CudaTensor<T> *y = nullptr,
+             const CudaTensor<T> *z = nullptr, double alpha = 0.0) {
+  static_assert(std::is_floating_point<T>::value, "forEach opcodes are float32 / float64 only");
+  laser_b200_tensor_view vo = out.view(), vx{}, vy{}, vz{};
+  if (x) vx = x->view();
+  if (y) vy = y->view();
+  if (z) vz = z->view();
+  check(laser_b200_foreach_views(op, &vo, x ? &vx : nullptr, y ? &vy : nullptr, z ? &vz : nullptr, alpha, nullptr));
+}
+
 // ---- pre-packed API (gemm_prepacked.nim:63-292); device pointers --------------------------
 inline size_t gemm_prepackA_mem_required(int64_t M, int64_t N, int64_t K) { return laser_b200_gemm_prepackA_mem_required_f32(M, N, K); }
 inline size_t gemm_prepackB_mem_required(int64_t M, int64_t N, int64_t K) { return laser_b200_gemm_prepackB_mem_required_f32(M, N, K); }

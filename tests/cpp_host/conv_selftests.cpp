@@ -21,6 +21,12 @@ static int conv_case(const char *src, TensorShape ishape, KernelShape kshape, Pa
 }
 
 int main(int argc, char **argv) {
+  if (argc > 1 && std::strcmp(argv[1], "--instantiate") == 0) {   // never run: instantiates the tensor-level templates
+    CudaTensor<float> a = newTensor<float>({2, 3}), b = newTensor<float>({2, 3}), o = newTensor<float>({2, 3});
+    forEach(LASER_B200_FOREACH_FMA, o, &o, &a, &b);
+    copyFrom(o, a);
+    return 0;
+  }
   if (argc > 1 && std::strcmp(argv[1], "--link-only") == 0) {
     std::printf("laser_b200 %d workspace %lld\n", laser_b200_version(),
                 (long long)im2col_workspace_size({1, 3, 5, 5}, {2, 3, 3, 3}, {1, 1}, {2, 2}));
