@@ -1,0 +1,124 @@
+// capi_layers_emu.cpp -- TEST INFRASTRUCTURE: the HOST side of the layer entry points
+// (laser_b200/csrc/capi_layers.inc: argument checks, convolution geometry, the im2col + batched-GEMM
+// loop, host-pointer staging, view handling of copyFrom / forEach) compiled by g++ and run on the CPU.
+// capi_layers.inc is included verbatim; what it needs from capi.cu (context, error reporting, the
+// float32 GEMM entry, the exact-kernel launcher) and from the CUDA runtime (copies, stream
+// synchronisation) is replaced by the stand-ins below: "device" memory is host memory, kernels run on
+// host threads (cuda_emu.h), every GEMM goes through the emulated EXACT kernel, so convolution
+// results can be compared with the oracle bit for bit.
+#define LB200_HOST_EMULATION 1
+#include "cuda_emu.h"
+
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+
+#include "../../include/laser_b200.h"
+#include "../../laser_b200/csrc/gemm_simt.cuh"
+#include "../../laser_b200/csrc/layers.cuh"
+
+// ---- CUDA runtime stand-ins (declared by cuda_runtime_api.h) -----------------------------------
+extern "C" {
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memmove(dst, src, n);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+}
+
+namespace {
+using namespace lb200;
+
+thread_local std::string g_last_error;
+thread_local int g_last_path = 0;
+struct Epilogue { const float *bias = nullptr; int bias_per_row = 0; int act = 0; };
+thread_local Epilogue g_epi;
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr) do { if ((expr) != cudaSuccess) return set_error(LASER_B200_ECUDA, "%s failed", #expr); } while (0)
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+#define CHECK_LAUNCH() do { } while (0)
+
+struct Buffer { void *ptr = nullptr; size_t bytes = 0; };
+struct Ctx {
+  int sm_count = 4;   // few "SMs": grid-stride loops iterate
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(0x10);
+  std::mutex host_mu;
+  Buffer stage[3], layer_ws;
+};
+Ctx g_ctx;
+int get_ctx(Ctx **out) { *out = &g_ctx; return LASER_B200_OK; }
+int ensure(Buffer &b, size_t bytes) {
+  if (b.bytes >= bytes) return LASER_B200_OK;
+  std::free(b.ptr);
+  b.ptr = std::aligned_alloc(256, (bytes + 255) / 256 * 256);
+  b.bytes = bytes;
+  return b.ptr ? LASER_B200_OK : set_error(LASER_B200_ENOMEM, "out of memory");
+}
+inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
+  int64_t g = static_cast<int64_t>(c.sm_count) * per_sm;
+  if (work_items < g) g = work_items > 0 ? work_items : 1;
+  return static_cast<int>(g);
+}
+int check_args(int64_t M, int64_t N, int64_t K, const void *A, const void *B, const void *C) {
+  if (M < 0 || N < 0 || K < 0) return set_error(LASER_B200_EINVAL, "negative extent");
+  if (M == 0 || N == 0 || K == 0) return -1;
+  if (!A || !B || !C) return set_error(LASER_B200_EINVAL, "null matrix pointer");
+  return LASER_B200_OK;
+}
+int finish(Ctx &, cudaStream_t, cudaStream_t) { return LASER_B200_OK; }
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t, Args &&...args) {
+  emu::launch(grid, block, [=]() { kernel(static_cast<KArgs>(args)...); });
+}
+
+// capi.cu: gemm_simt -- the exact kernel with the library's tile configurations
+template <typename T>
+int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA, int64_t csA, const T *B, int64_t rsB,
+              int64_t csB, T beta, T *C, int64_t rsC, int64_t csC, cudaStream_t, int64_t batch = 1, int64_t bsA = 0,
+              int64_t bsB = 0, int64_t bsC = 0) {
+  constexpr int TMN = sizeof(T) == 4 ? 8 : 4;
+  SimtParams<T> p;
+  const int64_t tiles = simt_plan<T, TMN, TMN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+  const int grid = grid_for(c, tiles * batch, 2);
+  emu::launch(grid, 256, [=]() { gemm_simt_kernel<T, TMN, TMN, 16>(p); });
+  COUNT_LAUNCH();
+  return LASER_B200_OK;
+}
+// capi.cu: f32_dev -- here every problem takes the exact kernel (the tensor-core paths are
+// covered by test_emulated_tc.py); the path argument is recorded for the dispatch checks
+int g_last_requested_path = -1;
+int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA, const float *B,
+            int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC, int path, void *) {
+  int rc = check_args(M, N, K, A, B, C);
+  if (rc == -1) return LASER_B200_OK;
+  if (rc) return rc;
+  g_last_requested_path = path;
+  return gemm_simt<float>(g_ctx, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, nullptr);
+}
+}  // namespace
+
+#include "../../laser_b200/csrc/capi_layers.inc"
+
+extern "C" {
+const char *emu_last_error(void) { return g_last_error.c_str(); }
+int64_t emu_launch_count(void) { return g_launches.load(); }
+int emu_last_requested_path(void) { return g_last_requested_path; }
+}

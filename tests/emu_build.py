@@ -26,5 +26,6 @@ def build_emu(name, product_headers):
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", srcs[0], "-o", so], env=env)
+                               "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic"   # stand-ins of CUDA runtime calls must win over a loaded libcudart
+                              , srcs[0], "-o", so], env=env)
     return so

@@ -34,6 +34,22 @@ def raw(t, esz):
     return L.DevPtr(t.data_ptr(), {2: "bf16", 4: "f32", 8: "f64"}[esz])
 
 
+def conv_ref(inp, ishape, ker, kshape, padding, strides):
+    """Oracle convolution.  For 1x1 kernels with a stride or padding the reference's im2col shortcut
+    (conv2d_im2col.nim:121,145-149) reads the image in place and is wrong; the product deliberately
+    goes through im2col there (include/laser_b200.h), so the expectation is im2col + the GEMM oracle."""
+    if kshape[2] * kshape[3] != 1 or (tuple(strides) == (1, 1) and tuple(padding) == (0, 0)):
+        return O.conv2d_im2col(inp, ishape, ker, kshape, padding, strides)
+    o = O.conv2d_out_shape(ishape, kshape, padding, strides)
+    M, K, N = kshape[0], ishape[1], o[2] * o[3]
+    out = np.zeros((ishape[0], M, N), np.float32)
+    kmat = np.ascontiguousarray(ker, np.float32).reshape(M, K)
+    for n in range(ishape[0]):
+        ws = np.ascontiguousarray(O.im2col(np.ascontiguousarray(inp[n]), ishape, kshape, padding, strides))
+        O.gemm_strided(M, N, K, 1.0, kmat, K, 1, ws, N, 1, 0.0, out[n], N, 1)
+    return out.reshape(o)
+
+
 # ---- transposes ------------------------------------------------------------------------------
 @pytest.mark.parametrize("esz", [2, 4, 8])
 @pytest.mark.parametrize("N,NR,NC", [(1, 1, 1), (1, 64, 64), (1, 4000, 2000), (3, 33, 70), (2, 68, 132),
@@ -150,7 +166,7 @@ def test_im2col_matches_oracle(ishape, kshape, padding, strides):
 def test_conv2d_matches_oracle(ishape, kshape, padding, strides, ws_images):
     inp = O.fill_uniform_f32(int(np.prod(ishape)), 31, 0, 1).reshape(ishape)
     ker = O.fill_uniform_f32(int(np.prod(kshape)), 32, 0, 1).reshape(kshape)
-    ref = O.conv2d_im2col(inp, ishape, ker, kshape, padding, strides)
+    ref = conv_ref(inp, ishape, ker, kshape, padding, strides)
     oshape = L.conv2d_out_shape(ishape, kshape, padding, strides)
     tout = torch.full(oshape, float("nan"), device="cuda")      # beta = 0: NaN must not survive
     per = L.im2col_workspace_size(ishape, kshape, padding, strides)

@@ -90,3 +90,20 @@ def test_batched_gemm_is_a_loop_of_gemm_strided():
         ref = C0[b].copy()
         O.gemm_strided(M, N, K, 0.5, A[b].copy(), K, 1, B, N, 1, 2.0, ref, N, 1)
         assert np.array_equal(C[b], ref)
+
+
+def test_reference_1x1_shortcut_is_only_valid_for_unit_stride_without_padding():
+    """conv2d_im2col.nim:121 skips im2col for every 1x1 kernel and reads the image in place; with a
+    stride or padding that is a different (wrong) result than the reference's own direct convolution.
+    The oracle restates the shortcut faithfully; the product goes through im2col for those cases
+    (documented divergence, include/laser_b200.h) and is tested against im2col + GEMM instead."""
+    ishape, kshape = (2, 4, 9, 9), (3, 4, 1, 1)
+    rng = np.random.default_rng(0)
+    inp = rng.integers(-3, 4, size=ishape).astype(np.float32); ker = rng.integers(-2, 3, size=kshape).astype(np.float32)
+    assert np.array_equal(O.conv2d_im2col(inp, ishape, ker, kshape, (0, 0), (1, 1)), O.conv2d_direct(inp, ishape, ker, kshape, (0, 0), (1, 1)))
+    direct = O.conv2d_direct(inp, ishape, ker, kshape, (1, 1), (2, 2))
+    assert not np.array_equal(O.conv2d_im2col(inp, ishape, ker, kshape, (1, 1), (2, 2)), direct)
+    M, K = kshape[0], ishape[1]
+    o = O.conv2d_out_shape(ishape, kshape, (1, 1), (2, 2))
+    via_im2col = np.stack([ker.reshape(M, K) @ O.im2col(inp[n], ishape, kshape, (1, 1), (2, 2)) for n in range(ishape[0])]).reshape(o)
+    assert np.array_equal(via_im2col, direct)
