@@ -1,12 +1,15 @@
 """GPU: the steps either side of the GEMM through the C ABI against the
 oracle: transposes / NCHW<->NHWC (swapaxes.nim:16-112), im2col convolution
 (conv2d_im2col.nim:44-166, the reference's conv known-answer vectors conv2d_common.nim:128-283),
-batched GEMM, copyFrom on strided views (initialization.nim:80-112).
+batched GEMM, copyFrom and forEach on strided views (initialization.nim:80-112, foreach.nim:229-251).
 
-These kernels were written after the round's GPU budget was spent: their source is executed on
-CPU threads by tests/test_emulated_kernels.py, but they have NOT yet run on a B200.  Until they
-have, this file only runs with LASER_B200_UNVALIDATED=1 (first thing to do next round:
-`LASER_B200_UNVALIDATED=1 python -m pytest tests/test_gpu_zlayers.py -m gpu`, then drop the gate)."""
+These kernels were written after the round's GPU budget was spent, so their first run on a B200 is the
+round-end run of this file (kept last among the GPU test files for that reason).  Before that they were
+checked as far as a machine without a GPU allows: the kernel source runs on CPU threads against the
+oracle (tests/test_emulated_kernels.py), the host side of the entry points too
+(tests/test_emulated_layers_host.py), and this very file runs on the CPU against a stand-in library
+(LASER_B200_EMU=1, tests/test_emulated_python_mirror.py), which checks the Python mirror and the
+expectations below."""
 import json
 import os
 
@@ -15,23 +18,55 @@ import pytest
 
 import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LASER_B200_UNVALIDATED", "0") != "1",
-                                 reason="layer kernels not yet validated on a B200 (set LASER_B200_UNVALIDATED=1)")]
-torch = pytest.importorskip("torch")
+EMU = os.environ.get("LASER_B200_EMU", "0") == "1"       # CPU stand-in library: "device" memory is host memory
+pytestmark = pytest.mark.gpu
+if not EMU:
+    torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 NP_OF = {2: np.int16, 4: np.float32, 8: np.float64}   # int16: torch has no full uint16 support
+NAME_OF = {np.dtype(np.int16): "bf16", np.dtype(np.uint16): "bf16", np.dtype(np.float32): "f32", np.dtype(np.float64): "f64",
+           np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}
+
+
+class HostDev(L.DevPtr):
+    """EMU backend: a numpy array posing as device memory."""
+
+    def __init__(self, arr):
+        self.arr = np.ascontiguousarray(arr)
+        super().__init__(self.arr.ctypes.data, NAME_OF[self.arr.dtype])
 
 
 def dev(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    """host array -> device array"""
+    a = np.ascontiguousarray(a)
+    return HostDev(a.copy()) if EMU else torch.from_numpy(a).cuda()
+
+
+def full(shape, value, dt=np.float32):
+    return dev(np.full(shape, value, dt))
+
+
+def to_np(t):
+    if EMU:
+        return t.arr
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def addr(t):
+    return t.ptr if EMU else t.data_ptr()
 
 
 def raw(t, esz):
     """DevPtr of the right element width for byte-level transposes."""
-    return L.DevPtr(t.data_ptr(), {2: "bf16", 4: "f32", 8: "f64"}[esz])
+    return L.DevPtr(addr(t), {2: "bf16", 4: "f32", 8: "f64"}[esz])
+
+
+def cpu_budget(elements):
+    if EMU and elements > 400_000:
+        pytest.skip("too large for the CPU stand-in")
 
 
 def conv_ref(inp, ishape, ker, kshape, padding, strides):
@@ -57,55 +92,52 @@ def conv_ref(inp, ishape, ker, kshape, padding, strides):
 def test_transpose_dev(esz, N, NR, NC):
     if esz == 8 and NR * NC > 4000 * 2000:
         pytest.skip("large case covered at 4 bytes")
+    cpu_budget(N * NR * NC)
     dt = NP_OF[esz]
     src = (np.arange(N * NR * NC, dtype=np.int64) * 2654435761 % 65521).astype(dt)
-    tsrc = dev(src); tdst = torch.zeros_like(tsrc)
+    tsrc = dev(src); tdst = full(src.shape, 0, dt)
     L.transpose2D_batched(raw(tdst, esz), raw(tsrc, esz), N, NR, NC)
-    torch.cuda.synchronize()
-    assert np.array_equal(tdst.cpu().numpy().reshape(N, NC, NR), src.reshape(N, NR, NC).transpose(0, 2, 1))
+    assert np.array_equal(to_np(tdst).reshape(N, NC, NR), src.reshape(N, NR, NC).transpose(0, 2, 1))
 
 
 def test_transpose_matches_oracle_and_round_trips():
-    NR, NC = 4000, 2000          # the reference transpose bench shape (transpose_bench.nim:54-55)
+    NR, NC = (400, 200) if EMU else (4000, 2000)   # the reference transpose bench shape (transpose_bench.nim:54-55)
     src = O.fill_uniform_f32(NR * NC, 7, 0, 1)
-    tsrc = dev(src); t1 = torch.empty_like(tsrc); t2 = torch.empty_like(tsrc)
+    tsrc = dev(src); t1 = full(src.shape, 0); t2 = full(src.shape, 0)
     L.transpose2D_copy(t1, tsrc, NR, NC)
     L.transpose2D_copy(t2, t1, NC, NR)
-    torch.cuda.synchronize()
-    assert np.array_equal(t1.cpu().numpy().reshape(NC, NR), O.transpose2D_copy(src, NR, NC))
-    assert torch.equal(t2, tsrc)
+    assert np.array_equal(to_np(t1).reshape(NC, NR), O.transpose2D_copy(src, NR, NC))
+    assert np.array_equal(to_np(t2), src)
 
 
 def test_misaligned_pointers_take_the_scalar_kernel():
     NR, NC = 128, 256
     buf = dev(np.arange(NR * NC + 1, dtype=np.float32))
-    out = torch.zeros(NR * NC + 1, device="cuda")
-    L.transpose2D_copy(L.DevPtr(out.data_ptr() + 4, "f32"), L.DevPtr(buf.data_ptr() + 4, "f32"), NR, NC)
-    torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy()[1:].reshape(NC, NR), buf.cpu().numpy()[1:].reshape(NR, NC).T)
-    assert out[0].item() == 0.0
+    out = full((NR * NC + 1,), 0)
+    L.transpose2D_copy(L.DevPtr(addr(out) + 4, "f32"), L.DevPtr(addr(buf) + 4, "f32"), NR, NC)
+    assert np.array_equal(to_np(out)[1:].reshape(NC, NR), to_np(buf)[1:].reshape(NR, NC).T)
+    assert to_np(out)[0] == 0.0
 
 
 def test_nchw_nhwc_device_and_host():
     N, C, H, W = 4, 3, 17, 20
     x = O.fill_uniform_f32(N * C * H * W, 3, -1, 1).reshape(N, C, H, W)
-    tx = dev(x); ty = torch.empty(N * H * W * C, device="cuda"); tz = torch.empty_like(tx)
+    tx = dev(x); ty = full((N * H * W * C,), 0); tz = full(x.shape, 0)
     L.nchw2nhwc(ty, tx, N, C, H, W)
     L.nhwc2nchw(tz, ty, N, C, H, W)
-    torch.cuda.synchronize()
-    assert np.array_equal(ty.cpu().numpy().reshape(N, H, W, C), x.transpose(0, 2, 3, 1))
-    assert torch.equal(tz, tx)
+    assert np.array_equal(to_np(ty).reshape(N, H, W, C), x.transpose(0, 2, 3, 1))
+    assert np.array_equal(to_np(tz), x)
     hy = np.empty(N * H * W * C, np.float32)
     L.nchw2nhwc(hy, x.reshape(-1).copy(), N, C, H, W)          # host-pointer entry, synchronous
     assert np.array_equal(hy.reshape(N, H, W, C), x.transpose(0, 2, 3, 1))
 
 
 def test_transpose_rejects_bad_arguments():
-    a = torch.zeros(16, device="cuda")
+    a = full((16,), 0)
     with pytest.raises(L.LaserB200Error):
         L.transpose2D_copy(a, a, 4, 4)                          # aliasing
     with pytest.raises(L.LaserB200Error):
-        L.transpose2D_copy(a, torch.zeros(16, device="cuda"), -1, 4)
+        L.transpose2D_copy(a, full((16,), 0), -1, 4)
 
 
 # ---- convolution ------------------------------------------------------------------------------
@@ -123,11 +155,10 @@ def test_conv2d_known_answer(case):
     out = np.full(tgt.shape, 99.0, np.float32)
     L.conv2d_im2col(out, inp, ish, ker, ksh, pad, st)           # host entry
     assert np.array_equal(out, tgt)
-    tout = torch.full(tgt.shape, 99.0, device="cuda")
-    ws = torch.empty(L.im2col_workspace_size(ish, ksh, pad, st), device="cuda")
+    tout = full(tgt.shape, 99.0)
+    ws = full((L.im2col_workspace_size(ish, ksh, pad, st),), 0)
     L.conv2d_im2col(tout, dev(inp), ish, dev(ker), ksh, pad, st, workspace=ws)
-    torch.cuda.synchronize()
-    assert np.array_equal(tout.cpu().numpy(), tgt)
+    assert np.array_equal(to_np(tout), tgt)
 
 
 IM2COL_CASES = [
@@ -143,13 +174,13 @@ IM2COL_CASES = [
 @pytest.mark.parametrize("ishape,kshape,padding,strides", IM2COL_CASES)
 def test_im2col_matches_oracle(ishape, kshape, padding, strides):
     B = ishape[0]
-    inp = O.fill_uniform_f32(int(np.prod(ishape)), 21, 1, 2).reshape(ishape)
     per = L.im2col_workspace_size(ishape, kshape, padding, strides)
+    cpu_budget(B * per)
+    inp = O.fill_uniform_f32(int(np.prod(ishape)), 21, 1, 2).reshape(ishape)
     assert per == O.im2col_workspace_size(ishape, kshape, padding, strides)
-    ws = torch.full((B * per + 8,), -5.0, device="cuda")
+    ws = full((B * per + 8,), -5.0)
     L.im2col(ws, dev(inp), ishape, kshape, padding, strides, images=B)
-    torch.cuda.synchronize()
-    got = ws.cpu().numpy()
+    got = to_np(ws)
     for b in range(B):
         assert np.array_equal(got[b * per:(b + 1) * per], O.im2col(inp[b], ishape, kshape, padding, strides).reshape(-1))
     assert np.all(got[B * per:] == -5.0)
@@ -164,29 +195,28 @@ def test_im2col_matches_oracle(ishape, kshape, padding, strides):
     ((2, 3, 224, 224), (20, 3, 3, 3), (0, 0), (1, 1), 2),
 ])
 def test_conv2d_matches_oracle(ishape, kshape, padding, strides, ws_images):
+    per = L.im2col_workspace_size(ishape, kshape, padding, strides)
+    cpu_budget(ishape[0] * per)
     inp = O.fill_uniform_f32(int(np.prod(ishape)), 31, 0, 1).reshape(ishape)
     ker = O.fill_uniform_f32(int(np.prod(kshape)), 32, 0, 1).reshape(kshape)
     ref = conv_ref(inp, ishape, ker, kshape, padding, strides)
     oshape = L.conv2d_out_shape(ishape, kshape, padding, strides)
-    tout = torch.full(oshape, float("nan"), device="cuda")      # beta = 0: NaN must not survive
-    per = L.im2col_workspace_size(ishape, kshape, padding, strides)
-    ws = torch.empty(ws_images * per, device="cuda")
+    tout = full(oshape, np.nan)                                 # beta = 0: NaN must not survive
+    ws = full((max(1, ws_images * per),), 0)
     L.conv2d_im2col(tout, dev(inp), ishape, dev(ker), kshape, padding, strides, workspace=ws, workspace_images=ws_images)
-    torch.cuda.synchronize()
-    got = tout.cpu().numpy()
+    got = to_np(tout)
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-4   # BASELINE gate for fp32 (positive data)
-    exact = torch.empty(oshape, device="cuda")
+    exact = full(oshape, 0)
     L.conv2d_im2col(exact, dev(inp), ishape, dev(ker), kshape, padding, strides, workspace=ws,
                     workspace_images=ws_images, path=L.PATH_SIMT)
-    torch.cuda.synchronize()
-    assert np.array_equal(exact.cpu().numpy(), ref)             # exact kernel: bit-identical to the CPU order
+    assert np.array_equal(to_np(exact), ref)                    # exact kernel: bit-identical to the CPU order
     hout = np.empty(oshape, np.float32)
     L.conv2d_im2col(hout, inp, ishape, ker, kshape, padding, strides)
     assert np.abs(hout - ref).max() / np.abs(ref).max() < 1e-4
 
 
 def test_conv2d_rejects_bad_shapes():
-    x = torch.zeros(16, device="cuda")
+    x = full((16,), 0)
     with pytest.raises(L.LaserB200Error):
         L.conv2d_out_shape((1, 1, 4, 4), (1, 1, 3, 3), (0, 0), (4, 1))
     with pytest.raises(L.LaserB200Error):   # c_in mismatch (conv2d_direct_convolution.nim:20)
@@ -203,8 +233,7 @@ def test_batched_gemm(path):
     O.gemm_strided_batched(batch, M, N, K, 0.5, A, K, 1, M * K, B, N, 1, 0, -1.25, ref, N, 1, M * N)
     tC = dev(C0)
     L.gemm_strided_batched(batch, M, N, K, 0.5, dev(A), K, 1, M * K, dev(B), N, 1, 0, -1.25, tC, N, 1, M * N, path=path)
-    torch.cuda.synchronize()
-    got = tC.cpu().numpy()
+    got = to_np(tC)
     if path == L.PATH_SIMT:
         assert np.abs(got - ref).max() <= 1e-6 * np.abs(ref).max()   # alpha != 1: contraction may differ by 1 ulp
     else:
@@ -216,12 +245,11 @@ def test_batched_small_problems_single_launch_is_bit_exact():
     A = O.fill_uniform_f32(batch * M * K, 51, -1, 1); B = O.fill_uniform_f32(batch * K * N, 52, -1, 1)
     ref = np.zeros(batch * M * N, np.float32)
     O.gemm_strided_batched(batch, M, N, K, 1.0, A, K, 1, M * K, B, N, 1, K * N, 0.0, ref, N, 1, M * N)
-    tC = torch.full((batch * M * N,), float("nan"), device="cuda")
+    tC = full((batch * M * N,), np.nan)
     before = L.launch_count()
     L.gemm_strided_batched(batch, M, N, K, 1.0, dev(A), K, 1, M * K, dev(B), N, 1, K * N, 0.0, tC, N, 1, M * N)
-    torch.cuda.synchronize()
     assert L.launch_count() - before == 1
-    assert np.array_equal(tC.cpu().numpy(), ref)
+    assert np.array_equal(to_np(tC), ref)
 
 
 def test_batched_f64_and_i64():
@@ -232,16 +260,14 @@ def test_batched_f64_and_i64():
         O.gemm_strided(M, N, K, 1.0, A[b * M * K:], K, 1, B[b * K * N:], N, 1, 1.0, ref[b * M * N:(b + 1) * M * N], N, 1)
     tC = dev(C0)
     L.gemm_strided_batched(batch, M, N, K, 1.0, dev(A), K, 1, M * K, dev(B), N, 1, K * N, 1.0, tC, N, 1, M * N)
-    torch.cuda.synchronize()
-    assert np.array_equal(tC.cpu().numpy(), ref)
+    assert np.array_equal(to_np(tC), ref)
     Ai = rng.integers(-2**62, 2**62, size=batch * M * K, dtype=np.int64); Bi = rng.integers(-2**62, 2**62, size=K * N, dtype=np.int64)
     refi = np.zeros(batch * M * N, np.int64)
     for b in range(batch):
         O.gemm_strided(M, N, K, 1, Ai[b * M * K:], K, 1, Bi, N, 1, 0, refi[b * M * N:(b + 1) * M * N], N, 1)
-    tCi = torch.zeros(batch * M * N, dtype=torch.int64, device="cuda")
+    tCi = full((batch * M * N,), 0, np.int64)
     L.gemm_strided_batched(batch, M, N, K, 1, dev(Ai), K, 1, M * K, dev(Bi), N, 1, 0, 0, tCi, N, 1, M * N)
-    torch.cuda.synchronize()
-    assert np.array_equal(tCi.cpu().numpy(), refi)
+    assert np.array_equal(to_np(tCi), refi)
 
 
 # ---- copyFrom on strided views ------------------------------------------------------------------
@@ -276,10 +302,11 @@ FOREACH = {"copy": lambda x, y, z, a: x, "fill": lambda x, y, z, a: np.full_like
 def test_forEach_ops(dtype, op):
     npdt = np.float32 if dtype == "f32" else np.float64
     rng = np.random.default_rng(3)
-    hx, hy, hz = (rng.standard_normal((100, 10000)).astype(npdt), rng.standard_normal((10000, 100)).astype(npdt),
-                  rng.standard_normal((10000, 100)).astype(npdt))          # the reference's non-contiguous bench shapes
+    R, Cc = (100, 1000) if EMU else (100, 10000)                           # the reference's non-contiguous bench shapes
+    hx, hy, hz = (rng.standard_normal((R, Cc)).astype(npdt), rng.standard_normal((Cc, R)).astype(npdt),
+                  rng.standard_normal((Cc, R)).astype(npdt))
     x, y, z = L.toTensor(hx, dtype), L.toTensor(hy, dtype).transpose(), L.toTensor(hz, dtype).transpose()
-    out = L.newTensor([100, 10000], dtype)
+    out = L.newTensor([R, Cc], dtype)
     L.forEach(op, out, x, y, z, alpha=0.75)
     want = FOREACH[op](hx, hy.T, hz.T, npdt(0.75))
     tol = 4e-6 if dtype == "f32" else 1e-14                               # mul+add may be contracted to an FMA

@@ -11,10 +11,10 @@ echo "=== bench reference"; timeout 600 python bench.py --impl reference --steps
 echo "=== ncu launch list (bench.py)"; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1; wc -l gpurun_out/launches_bench.csv
 echo "=== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 6 -o gpurun_out/prof_tc python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
 echo "=== ncu full (split pre-pass)"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:split_rows -c 2 -o gpurun_out/prof_split python tools/ncu_target.py > gpurun_out/ncu_split.log 2>&1; tail -1 gpurun_out/ncu_split.log
-echo "=== layers (first run on a B200: gated tests + HBM timings + sanitizer)"
-LASER_B200_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_zlayers.py tests/test_cpp_host.py -m gpu -q 2>&1 | tee gpurun_out/pytest_layers.log | tail -8
+echo "=== layers (C++ self-check + HBM timings + sanitizer)"
+LASER_B200_UNVALIDATED=1 timeout 900 python -m pytest tests/test_cpp_host.py -m gpu -q 2>&1 | tee gpurun_out/pytest_layers.log | tail -8
 timeout 300 python tools/layers_bench.py > gpurun_out/layers_bench.jsonl 2> gpurun_out/layers_bench_err.log; cat gpurun_out/layers_bench.jsonl; tail -3 gpurun_out/layers_bench_err.log
-LASER_B200_UNVALIDATED=1 timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zlayers.py -m gpu -q -k "not 8192 and not 224" > gpurun_out/sanitizer_layers.log 2>&1; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_layers.log | tail -3
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zlayers.py -m gpu -q -k "not 8192 and not 224" > gpurun_out/sanitizer_layers.log 2>&1; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_layers.log | tail -3
 echo "=== host-pointer entry: panel geometry variants"
 for v in "" "LASER_B200_PANEL_ROWS=512" "LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=512 LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=2048 LASER_B200_PANEL_TAPER=1"; do env $v timeout 200 python tools/e2e_probe.py 2>> gpurun_out/e2e_probe_err.log | tee -a gpurun_out/e2e_probe.jsonl; done
 echo "=== L2 hints / raster on the default kernel"
