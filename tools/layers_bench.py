@@ -63,11 +63,15 @@ def main():
     ms = timeit(lambda: L.im2col(ws, inp, ish, ksh, pad, st, images=ish[0]))
     report("im2col 16x3x224x224 k3", ms, 4 * (ish[0] * per + inp.numel()))
     flops = 2 * ish[0] * ksh[0] * ksh[1] * 9 * osh[2] * osh[3]      # conv2d_common.nim:47-78
-    for wi in (1, 16):
-        ms = timeit(lambda: L.conv2d_im2col(out, inp, ish, ker, ksh, pad, st, workspace=ws, workspace_images=wi))
-        report("conv2d_im2col 16x3x224x224 -> 20 k3, workspace_images=%d" % wi, ms,
-               4 * (inp.numel() + ker.numel() + out.numel()), gflops=round(flops / ms / 1e6, 1),
-               reference_cpu_note="reference bench prints GFLOP/s for the same shape (conv2d_bench.nim)")
+    # AUTO sends each image's 20 x 49284 x 27 product to the tensor cores (one launch sequence per image);
+    # PATH_SIMT runs all images of a workspace chunk as ONE launch of the exact kernel -- for so small an M
+    # and K the latter may well win: measure both before choosing a dispatch rule for convolutions
+    for path, pname in ((L.PATH_AUTO, "auto"), (L.PATH_SIMT, "exact")):
+        for wi in (1, 16):
+            ms = timeit(lambda: L.conv2d_im2col(out, inp, ish, ker, ksh, pad, st, workspace=ws, workspace_images=wi, path=path))
+            report("conv2d_im2col 16x3x224x224 -> 20 k3, path=%s, workspace_images=%d" % (pname, wi), ms,
+                   4 * (inp.numel() + ker.numel() + out.numel()), gflops=round(flops / ms / 1e6, 1),
+                   reference_cpu_note="reference bench prints GFLOP/s for the same shape (conv2d_bench.nim)")
     # forEach o in output, x in a, y in b, z in c: o = x + y - sin z   (iter_bench_prod.nim:86-107, float64)
     for name, shape, transposed in (("contiguous", (1000, 1000), False), ("transposed inputs", (100, 10000), True),
                                     ("contiguous 8192^2", (8192, 8192), False)):
