@@ -107,8 +107,8 @@ inline int max(int a, int b) { return a > b ? a : b; }
 
 #define threadIdx (emu::t_idx)
 #define blockIdx (emu::b_idx)
-#define blockDim (emu::b_dim)
-#define gridDim (emu::g_dim)
+inline emu::Idx &blockDim = emu::b_dim;   // plain references, not macros: `cfg.gridDim` must stay a member access
+inline emu::Idx &gridDim = emu::g_dim;
 inline void __syncthreads() { pthread_barrier_wait(&emu::cta_barrier[emu::cta_rank]); }
 inline void __syncwarp() { pthread_barrier_wait(&emu::warp_barrier[emu::cta_rank][emu::t_idx.x >> 5]); }
 // full-mask butterfly shuffle: every lane of the warp must call it (true for the reductions it is used in)

@@ -1,0 +1,212 @@
+"""Scenarios run by tests/test_emulated_library.py in a subprocess whose LASER_B200_LIB points at the
+host-emulated build of the WHOLE library (tests/emu_build.py: build_capi_host_emu).  "Device" memory is
+host memory (numpy arrays wrapped in DevPtr); everything else is the ordinary Python mirror.  Each
+scenario asserts and prints `OK <name> <count>`."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import laser_b200 as L  # noqa: E402
+import oracle as O  # noqa: E402
+from util import LAYOUTS, embed, f32_to_bf16_bits, bf16_bits_to_f32  # noqa: E402
+
+NAME = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64",
+        np.dtype(np.uint16): "bf16"}
+
+
+def D(arr, off=0):
+    """numpy array (kept alive by the caller) -> device pointer at element `off`"""
+    return L.DevPtr(arr.ctypes.data + off * arr.itemsize, NAME[arr.dtype])
+
+
+def rnd(shape, seed, lo=0.0, hi=1.0):
+    return O.fill_uniform_f32(int(np.prod(shape)), seed, lo, hi).reshape(shape)
+
+
+def ref_gemm(M, N, K, alpha, a, b, beta, c0):
+    ref = c0.copy()
+    O.gemm_strided(M, N, K, alpha, a, K, 1, b, N, 1, beta, ref, N, 1)
+    return ref
+
+
+TOL = {L.PATH_AUTO: 1e-5, L.PATH_TF32_BF16C: 1e-5, L.PATH_TF32X3: 1e-5, L.PATH_TF32X1: 3e-3, L.PATH_SIMT: 0.0}
+
+
+def dispatch_and_modes():
+    n = 0
+    for (M, N, K) in ((64, 64, 64), (200, 300, 150), (130, 40, 70), (300, 9, 33)):
+        a, b, c0 = rnd((M, K), 1), rnd((K, N), 2), rnd((M, N), 3)
+        for path in (L.PATH_AUTO, L.PATH_TF32X3, L.PATH_TF32X1, L.PATH_SIMT):
+            for alpha, beta in ((1.0, 0.0), (0.5, -1.25)):
+                c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
+                L.gemm_strided(M, N, K, alpha, D(a), K, 1, D(b), N, 1, beta, D(c), N, 1, path=path)
+                ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
+                small = M * N * K <= 128 ** 3
+                want_path = L.PATH_SIMT if (path == L.PATH_SIMT or (path == L.PATH_AUTO and small)) else \
+                    (L.PATH_TF32_BF16C if path == L.PATH_AUTO else path)
+                assert L.last_path() == want_path, (L.last_path(), want_path, M, N, K, path)
+                tol = 0.0 if want_path == L.PATH_SIMT and alpha == 1.0 else max(TOL[path], 3e-7)
+                err = np.abs(c - ref).max() / np.abs(ref).max()
+                assert err <= tol, (err, tol, M, N, K, path, alpha, beta)
+                n += 1
+    print("OK dispatch_and_modes", n)
+
+
+def strided_operands():
+    """every operand class: K-major / MN-major TMA, general (gathered) -- and C of any strides"""
+    M, N, K = 150, 140, 100
+    a, b, c0 = rnd((M, K), 4), rnd((K, N), 5), rnd((M, N), 6)
+    n = 0
+    for la, lb, lc in [(x, "row", "row") for x in LAYOUTS] + [("row", x, "row") for x in LAYOUTS] + [("col", "col", x) for x in LAYOUTS]:
+        A, oa, rsa, csa = embed(a, la); B, ob, rsb, csb = embed(b, lb); C, oc, rsc, csc = embed(c0, lc)
+        Cref = C.copy()
+        O.gemm_strided(M, N, K, 1.0, A[oa:], rsa, csa, B[ob:], rsb, csb, 2.0, Cref[oc:], rsc, csc)
+        L.gemm_strided(M, N, K, 1.0, D(A, oa), rsa, csa, D(B, ob), rsb, csb, 2.0, D(C, oc), rsc, csc)   # AUTO -> tensor cores
+        assert L.last_path() == L.PATH_TF32_BF16C
+        idx = oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc
+        assert np.abs(C[idx] - Cref[idx]).max() <= 1e-5 * np.abs(Cref[idx]).max(), (la, lb, lc)
+        mask = np.ones(C.size, bool); mask[idx.reshape(-1)] = False
+        assert np.array_equal(C[mask], Cref[mask]), (la, lb, lc)       # nothing outside the view is touched
+        n += 1
+    print("OK strided_operands", n)
+
+
+def host_entry():
+    """host-pointer (drop-in) entry: the staged path and, for M >= 2048, the pipelined row-panel path
+    (panel geometry from LASER_B200_PANEL_ROWS / LASER_B200_PANEL_TAPER)"""
+    n = 0
+    for (M, N, K) in ((300, 70, 90), (2048, 24, 64), (2600, 16, 40)):
+        a, b = rnd((M, K), 7), rnd((K, N), 8)
+        c = np.full((M, N), np.nan, np.float32)
+        L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1)
+        ref = ref_gemm(M, N, K, 1.0, a, b, 0.0, np.zeros((M, N), np.float32))
+        assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max(), (M, N, K)
+        n += 1
+    # padded C rows (span not dense) and beta != 0 take the staged path even for large M
+    M, N, K = 2100, 12, 40
+    a, b = rnd((M, K), 9), rnd((K, N), 10)
+    cbuf = np.full((M, N + 3), -7.0, np.float32); c0 = rnd((M, N), 11); cbuf[:, :N] = c0
+    L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 1.0, cbuf, N + 3, 1)
+    ref = ref_gemm(M, N, K, 1.0, a, b, 1.0, c0)
+    assert np.abs(cbuf[:, :N] - ref).max() <= 1e-5 * np.abs(ref).max() and np.all(cbuf[:, N:] == -7.0)
+    print("OK host_entry", n + 1)
+
+
+def prepacked():
+    n = 0
+    for (M, N, K) in ((300, 520, 200), (100, 36, 77)):
+        a, b, c0 = rnd((M, K), 12), rnd((K, N), 13), rnd((M, N), 14)
+        pa = L.alloc_packed(L.gemm_prepackA_mem_required(M, N, K)); pb = L.alloc_packed(L.gemm_prepackB_mem_required(M, N, K))
+        at = np.ascontiguousarray(a.T)                                  # A given transposed: rowStride 1, colStride M
+        L.gemm_prepackA(pa, M, N, K, D(at), 1, M)
+        L.gemm_prepackB(pb, M, N, K, D(b), N, 1)
+        ref = ref_gemm(M, N, K, 0.5, a, b, 2.0, c0)
+        c = c0.copy()
+        L.gemm_packed(M, N, K, 0.5, pa, pb, 2.0, D(c), N, 1)
+        assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max()
+        c2 = c0.copy()
+        L.gemm_packedB(M, N, K, 0.5, D(a), K, 1, pb, 2.0, D(c2), N, 1)
+        assert np.array_equal(c2, c)                                      # same prepared operands, same kernel
+        c3 = c0.copy()
+        L.gemm_strided(M, N, K, 0.5, D(a), K, 1, D(b), N, 1, 2.0, D(c3), N, 1, path=L.PATH_TF32_BF16C)
+        assert np.array_equal(c3, c)                                      # and the unpacked call agrees bit for bit
+        n += 1
+    print("OK prepacked", n)
+
+
+def split_k():
+    """few output tiles, long K (run with a many-SM device model): (tile, K-split) units + the reduce kernel"""
+    M, N, K = 120, 200, 1100
+    a, b, c0 = rnd((M, K), 15, -1, 1), rnd((K, N), 16, -1, 1), rnd((M, N), 17)
+    n0 = L.launch_count()
+    c = c0.copy()
+    L.gemm_strided(M, N, K, 0.5, D(a), K, 1, D(b), N, 1, -1.0, D(c), N, 1, path=L.PATH_TF32_BF16C)
+    launches = L.launch_count() - n0
+    ref = ref_gemm(M, N, K, 0.5, a, b, -1.0, c0)
+    assert np.abs(c - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert launches == 4, launches                                        # split A, split B, GEMM, reduce
+    os.environ  # (LASER_B200_SPLITK=0 variant is a separate process)
+    print("OK split_k", launches)
+
+
+def no_split_k():
+    M, N, K = 120, 200, 1100
+    a, b = rnd((M, K), 15, -1, 1), rnd((K, N), 16, -1, 1)
+    n0 = L.launch_count()
+    c = np.zeros((M, N), np.float32)
+    L.gemm_strided(M, N, K, 1.0, D(a), K, 1, D(b), N, 1, 0.0, D(c), N, 1, path=L.PATH_TF32_BF16C)
+    assert L.launch_count() - n0 == 3
+    ref = ref_gemm(M, N, K, 1.0, a, b, 0.0, c * 0)
+    assert np.abs(c - ref).max() <= 2e-5 * np.abs(ref).max()
+    print("OK no_split_k 3")
+
+
+def other_types():
+    n = 0
+    M, N, K = 70, 50, 300
+    rng = np.random.default_rng(0)
+    for dt, big in ((np.float64, None), (np.int32, 2 ** 31 - 5), (np.int64, 2 ** 62)):
+        if big is None:
+            a, b, c0 = rng.random((M, K)), rng.random((K, N)), rng.random((M, N))
+            al, be = 1.0, 1.0
+        else:
+            a = rng.integers(-big, big, (M, K), dtype=dt); b = rng.integers(-big, big, (K, N), dtype=dt); c0 = rng.integers(-9, 9, (M, N), dtype=dt)
+            al, be = 3, -2
+        ref = c0.copy(); O.gemm_strided(M, N, K, al, a, K, 1, b, N, 1, be, ref, N, 1)
+        c = c0.copy(); L.gemm_strided(M, N, K, al, D(a), K, 1, D(b), N, 1, be, D(c), N, 1)
+        assert np.array_equal(c, ref), dt
+        ch = c0.copy(); L.gemm_strided(M, N, K, al, a, K, 1, b, N, 1, be, ch, N, 1)       # host entry
+        assert np.array_equal(ch, ref), dt
+        n += 2
+    # bf16 (tensor cores, fp32 accumulate, bf16 out)
+    M, N, K = 200, 264, 100
+    a, b, c0 = rnd((M, K), 18, -1, 1), rnd((K, N), 19, -1, 1), rnd((M, N), 20)
+    ab, bb, cb = f32_to_bf16_bits(a).reshape(M, K), f32_to_bf16_bits(b).reshape(K, N), f32_to_bf16_bits(c0).reshape(M, N)
+    ref = cb.copy(); O.gemm_strided(M, N, K, 1.0, ab, K, 1, bb, N, 1, 0.5, ref, N, 1, bf16=True)
+    c = cb.copy(); L.gemm_strided(M, N, K, 1.0, D(ab), K, 1, D(bb), N, 1, 0.5, D(c), N, 1)
+    assert L.last_path() == L.PATH_BF16
+    assert np.abs(bf16_bits_to_f32(c) - bf16_bits_to_f32(ref)).max() <= 2.0 ** -7 * np.abs(bf16_bits_to_f32(ref)).max()
+    print("OK other_types", n + 1)
+
+
+def fused_and_skinny():
+    M, N, K = 140, 270, 90
+    a, b = rnd((M, K), 21, -1, 1), rnd((K, N), 22, -1, 1)
+    bias = rnd((N,), 23, -1, 1)
+    for path in (L.PATH_AUTO, L.PATH_SIMT):
+        c = np.zeros((M, N), np.float32)
+        L.gemm_strided_fused(M, N, K, 1.0, D(a), K, 1, D(b), N, 1, 0.0, D(c), N, 1, bias=D(bias), activation="relu", path=path)
+        ref = np.maximum(ref_gemm(M, N, K, 1.0, a, b, 0.0, c * 0) + bias[None, :], 0)
+        assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max(), path
+    # skinny: N <= 4 and M >= 1024 -> warp-shuffle GEMV (three variants by alignment / size)
+    n = 0
+    for (M, K, NV, lda) in ((1024, 256, 1, 256), (1100, 300, 3, 301), (1024, 8192, 4, 8192)):
+        A = rnd((M, lda), 24, -1, 1); b = rnd((K, NV), 25, -1, 1); c = np.zeros((M, NV), np.float32)
+        L.gemm_strided(M, NV, K, 1.0, D(A), lda, 1, D(b), NV, 1, 0.0, D(c), NV, 1)
+        ref = np.zeros((M, NV), np.float32); O.gemm_strided(M, NV, K, 1.0, A, lda, 1, b, NV, 1, 0.0, ref, NV, 1)
+        assert np.abs(c - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), (M, K, NV)
+        n += 1
+    print("OK fused_and_skinny", n + 2)
+
+
+def tensors():
+    a = rnd((90, 40), 26); b = rnd((40, 60), 27)
+    A, B = L.toTensor(a), L.toTensor(b)
+    C = L.matmul(A, B)
+    ref = ref_gemm(90, 60, 40, 1.0, a, b, 0.0, np.zeros((90, 60), np.float32))
+    assert np.array_equal(C.to_numpy(), ref)                              # 90*60*40 <= 128^3: exact kernel
+    Ct = L.newTensor([60, 90])
+    L.matmul(B.transpose(), A.transpose(), Ct)                            # (AB)^T = B^T A^T on transposed views
+    assert np.array_equal(Ct.to_numpy(), ref.T)
+    buf = np.zeros(1000, np.float32)
+    L.fill_uniform_f32(D(buf), 1000, 42, -0.1, 0.1)
+    assert np.array_equal(buf, O.fill_uniform_f32(1000, 42, -0.1, 0.1))
+    print("OK tensors 3")
+
+
+if __name__ == "__main__":
+    globals()[sys.argv[1]]()

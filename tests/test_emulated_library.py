@@ -1,0 +1,53 @@
+"""CPU-only: the WHOLE library on the CPU.  tests/emu_build.py compiles laser_b200/csrc/capi.cu -- the
+complete host side: dispatch, operand classification, tensor-map construction, workspaces, the pipelined
+host-pointer entry, the pre-packed API, split-K planning -- with g++ (kernel launches rewritten
+textually, CUDA runtime and cuTensorMapEncodeTiled replaced by stand-ins, tests/emu/capi_host_prelude.h)
+on top of the host-thread execution of every kernel, the tcgen05 one included (ptx_emu.h).  The ordinary
+Python mirror is then loaded against that build in a subprocess (LASER_B200_LIB) and driven through the
+scenarios of tests/emu_driver.py with numpy arrays as "device" memory, each checked against the oracle.
+What this cannot show is listed in tests/emu/ptx_emu.h (silicon properties) -- and timing, of course."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from emu_build import build_capi_host_emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(1200)
+
+
+@pytest.fixture(scope="module")
+def emulated_lib():
+    return build_capi_host_emu()
+
+
+def run(lib, scenario, **env):
+    e = dict(os.environ, LASER_B200_LIB=lib, PYTHONPATH=ROOT, **{k: str(v) for k, v in env.items()})
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_driver.py"), scenario], cwd=ROOT, env=e,
+                         capture_output=True, text=True, timeout=1100)
+    assert out.returncode == 0 and out.stdout.strip().startswith("OK " + scenario), out.stdout[-1500:] + out.stderr[-3000:]
+    return out.stdout.strip()
+
+
+@pytest.mark.parametrize("scenario", ["dispatch_and_modes", "strided_operands", "host_entry", "prepacked", "other_types",
+                                      "fused_and_skinny", "tensors"])
+def test_scenario(emulated_lib, scenario):
+    run(emulated_lib, scenario)
+
+
+def test_split_k_planning_and_reduce(emulated_lib):
+    assert run(emulated_lib, "split_k", LASER_B200_EMU_SMS=32).endswith("4")        # split A, split B, GEMM, reduce
+    assert run(emulated_lib, "no_split_k", LASER_B200_EMU_SMS=32, LASER_B200_SPLITK=0).endswith("3")
+
+
+@pytest.mark.parametrize("env", [dict(LASER_B200_PANEL_ROWS=512), dict(LASER_B200_PANEL_TAPER=1),
+                                 dict(LASER_B200_PANEL_ROWS=512, LASER_B200_PANEL_TAPER=1), dict(LASER_B200_CTA_PAIR=0),
+                                 dict(LASER_B200_F32_MODE="tf32x3"), dict(LASER_B200_L2HINT=1),
+                                 dict(LASER_B200_KC=64, LASER_B200_RASTER=2)],
+                         ids=lambda e: ",".join("%s=%s" % (k.replace("LASER_B200_", ""), v) for k, v in e.items()))
+def test_host_entry_under_configuration(emulated_lib, env):
+    """the panel geometry of the pipelined host-pointer entry and the kernel configuration knobs are read
+    from the environment when the library initialises: one process per configuration"""
+    run(emulated_lib, "host_entry", **env)

@@ -1,22 +1,20 @@
-"""CPU-only: the Python mirror of the layer entry points (laser_b200/layers.py, tensor.py) and the
-layer tests themselves (tests/test_gpu_zlayers.py) run against a CPU stand-in of the C-ABI library
-(tests/emu/capi_python_emu.cpp: capi_layers.inc compiled for the host, kernels on host threads, every
-GEMM through the emulated exact kernel).  This checks the ctypes marshalling, the view handling and
-the tests' own expectations without a GPU; sizes that would take too long on host threads are skipped
-there.  The stand-in is loaded only in the subprocess below (LASER_B200_LIB); the product never sees it."""
+"""CPU-only: the layer tests themselves (tests/test_gpu_zlayers.py) and with them the Python mirror of the
+layer entry points (laser_b200/layers.py, tensor.py) run against the host-emulated build of the whole
+library (tests/emu_build.py: build_capi_host_emu -- capi.cu compiled by g++ over stand-ins for the CUDA
+runtime, kernels on host threads).  Sizes that would take too long on host threads are skipped there.
+The emulated build is loaded only in the subprocess below (LASER_B200_LIB); the product never sees it."""
 import os
 import re
 import subprocess
 import sys
 
-from emu_build import build_emu
+from emu_build import build_capi_host_emu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_layer_tests_pass_against_the_cpu_stand_in():
-    so = build_emu("capi_python_emu", ["capi_layers.inc", "layers.cuh", "gemm_simt.cuh", "split.cuh",
-                                        "../../include/laser_b200.h", "../../tests/emu/capi_layers_emu.cpp"])
+def test_layer_tests_pass_against_the_host_emulated_library():
+    so = build_capi_host_emu()
     env = dict(os.environ, LASER_B200_LIB=so, LASER_B200_EMU="1", PYTHONPATH=ROOT)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zlayers.py"), "-m", "gpu", "-q",
                           "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
