@@ -761,7 +761,8 @@ Span span_of(int64_t rows, int64_t cols, int64_t rs, int64_t cs) {
 // the three phases run on three streams: B is uploaded and prepared once; then row panel p+1 of
 // A is in flight H2D while panel p is split + multiplied and panel p-1 of C returns D2H.
 // Preconditions (checked by the caller): tensor-core path, row panels of A and of C are
-// (nearly) disjoint address ranges, beta == 0 and C dense inside each panel span.
+// (nearly) disjoint address ranges, C dense inside each panel span (with beta != 0 the old panel of
+// C travels to the device next to its panel of A).
 struct PanelPlan {
   int64_t rows;   // rows per panel
   int panels;
@@ -836,6 +837,9 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     const Span pa = span_of(mp, K, rsA, csA), pc = span_of(mp, N, rsC, csC);
     CUDA_TRY(cudaMemcpyAsync(dA + m0 * rsA + pa.lo, Ap + pa.lo, static_cast<size_t>(pa.hi - pa.lo + 1) * 4,
                              cudaMemcpyHostToDevice, up));
+    if (beta != 0.0f)   // the old values of this panel of C are read by the epilogue
+      CUDA_TRY(cudaMemcpyAsync(dC + m0 * rsC + pc.lo, Cp + pc.lo, static_cast<size_t>(pc.hi - pc.lo + 1) * 4,
+                               cudaMemcpyHostToDevice, up));
     CUDA_TRY(cudaEventRecord(c.panel_ev[pnl], up));
     CUDA_TRY(cudaStreamWaitEvent(cmp, c.panel_ev[pnl], 0));
     OperandMaps ma;
@@ -1032,7 +1036,7 @@ int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, co
                                 float beta, float *C, int64_t rsC, int64_t csC) {
   // large tensor-core problems whose row panels are separate address ranges: overlap the
   // PCIe transfers with the compute, panel by panel
-  if (M >= 2048 && N > 4 && K > 0 && A && B && C && beta == 0.0f &&
+  if (M >= 2048 && N > 4 && K > 0 && A && B && C &&
       M <= 0x7fffffffLL && N <= 0x7fffffffLL && K <= 0x7fffffffLL) {
     Ctx *c;
     int rc = get_ctx(&c);

@@ -86,7 +86,17 @@ def host_entry():
         ref = ref_gemm(M, N, K, 1.0, a, b, 0.0, np.zeros((M, N), np.float32))
         assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max(), (M, N, K)
         n += 1
-    # padded C rows (span not dense) and beta != 0 take the staged path even for large M
+    # beta != 0 on dense C: still the pipelined path, the old panel of C is uploaded next to its panel of A
+    M, N, K = 2304, 20, 48
+    a, b, c0 = rnd((M, K), 30), rnd((K, N), 31), rnd((M, N), 32)
+    c = c0.copy()
+    n0 = L.launch_count()
+    L.gemm_strided(M, N, K, 0.5, a, K, 1, b, N, 1, -1.25, c, N, 1)
+    assert L.launch_count() - n0 >= 1 + 2 * 2, L.launch_count() - n0     # prepare B once, then (prepare A, GEMM) per row panel
+    ref = ref_gemm(M, N, K, 0.5, a, b, -1.25, c0)
+    assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max()
+    n += 1
+    # padded C rows (span not dense) take the staged path even for large M
     M, N, K = 2100, 12, 40
     a, b = rnd((M, K), 9), rnd((K, N), 10)
     cbuf = np.full((M, N + 3), -7.0, np.float32); c0 = rnd((M, N), 11); cbuf[:, :N] = c0
