@@ -5,10 +5,10 @@ import numpy as np
 import pytest
 
 import oracle as O
+from backend import dev, sync
 from util import LAYOUTS, embed, extract
 
 pytestmark = pytest.mark.gpu
-torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
 
 PATHS = [L.PATH_SIMT, L.PATH_TF32_BF16C, L.PATH_TF32X3, L.PATH_AUTO]
@@ -35,10 +35,10 @@ def test_random_cases(seed):
             C0 = np.full((M, N), np.nan, np.float32)
         want = C0.copy(); O.gemm_strided(M, N, K, alpha, A, K, 1, B, N, 1, beta, want, N, 1)
         ba, oa, rsa, csa = embed(A, la); bb, ob, rsb, csb = embed(B, lb); bc, oc, rsc, csc = embed(C0, lc)
-        ta, tb, tc = (torch.from_numpy(x).cuda() for x in (ba, bb, bc))
+        ta, tb, tc = (dev(x) for x in (ba, bb, bc))
         L.gemm_strided(M, N, K, alpha, L.DevPtr(ta.data_ptr() + 4 * oa, "f32"), rsa, csa, L.DevPtr(tb.data_ptr() + 4 * ob, "f32"),
                        rsb, csb, beta, L.DevPtr(tc.data_ptr() + 4 * oc, "f32"), rsc, csc, path=path)
-        torch.cuda.synchronize()
+        sync()
         after = tc.cpu().numpy()
         got = extract(after, oc, rsc, csc, M, N)
         tag = (M, N, K, la, lb, lc, alpha, beta, path)

@@ -12,20 +12,18 @@ import numpy as np
 import pytest
 
 import oracle as O
+from backend import EMU, dev, emu_budget, needs_gpu, sync
 from util import LAYOUTS, bf16_bits_to_f32, embed, extract, f32_to_bf16_bits, golden_cases
 
 pytestmark = pytest.mark.gpu
 
-torch = pytest.importorskip("torch")
+if not EMU:
+    import torch
 import laser_b200 as L  # noqa: E402
 
 NP = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
 F32_PATHS = [L.PATH_SIMT, L.PATH_TF32X1, L.PATH_TF32X3, L.PATH_TF32_BF16C]
 FAITHFUL = (L.PATH_TF32X3, L.PATH_TF32_BF16C)   # fp32-faithful tensor-core modes (same gates)
-
-
-def dev(buf):
-    return torch.from_numpy(np.ascontiguousarray(buf)).cuda()
 
 
 def dptr(t, off, name):
@@ -38,9 +36,10 @@ def run_dev(name, M, N, K, alpha, A, la, B, lb, beta, C0, lc, path=L.PATH_AUTO):
     ba, oa, rsa, csa = embed(A, la); bb, ob, rsb, csb = embed(B, lb); bc, oc, rsc, csc = embed(C0, lc)
     view = lambda b: b.view(np.int16) if name == "bf16" else b  # torch has no uint16 math; bits only
     ta, tb, tc = dev(view(ba)), dev(view(bb)), dev(view(bc))
+    emu_budget(float(M) * N * K)
     L.gemm_strided(M, N, K, alpha, dptr(ta, oa, name), rsa, csa, dptr(tb, ob, name), rsb, csb, beta,
                    dptr(tc, oc, name), rsc, csc, path=path)
-    torch.cuda.synchronize()
+    sync()
     after = tc.cpu().numpy().view(bc.dtype)
     return extract(after, oc, rsc, csc, M, N), after, bc, (oc, rsc, csc)
 
@@ -195,12 +194,13 @@ def test_beta_zero_never_reads_c():
 
 def test_degenerate_extents_and_errors():
     c = dev(np.arange(6, dtype=np.float32)); a = dev(np.zeros(8, np.float32))
-    L.gemm_strided(2, 3, 0, 1.0, a, 0, 1, a, 3, 1, 0.5, c, 3, 1)     # K == 0: C untouched (gemm.nim:150)
-    L.gemm_strided(0, 3, 2, 1.0, a, 2, 1, a, 3, 1, 0.5, c, 3, 1)
-    torch.cuda.synchronize()
+    pa, pc = dptr(a, 0, "f32"), dptr(c, 0, "f32")
+    L.gemm_strided(2, 3, 0, 1.0, pa, 0, 1, pa, 3, 1, 0.5, pc, 3, 1)     # K == 0: C untouched (gemm.nim:150)
+    L.gemm_strided(0, 3, 2, 1.0, pa, 2, 1, pa, 3, 1, 0.5, pc, 3, 1)
+    sync()
     assert np.array_equal(c.cpu().numpy(), np.arange(6, dtype=np.float32))
     with pytest.raises(L.LaserB200Error):
-        L.gemm_strided(-1, 3, 2, 1.0, a, 2, 1, a, 3, 1, 0.5, c, 3, 1)
+        L.gemm_strided(-1, 3, 2, 1.0, pa, 2, 1, pa, 3, 1, 0.5, pc, 3, 1)
 
 
 # ------------------------------------------------------------------- host-pointer drop-in
@@ -241,12 +241,12 @@ def test_host_pointer_entry_pipelined(la, lc, M):
 
 def test_auto_path_selection():
     a = dev(np.ones(128 * 128, np.float32)); c = dev(np.zeros(128 * 128, np.float32))
-    L.gemm_strided(128, 128, 128, 1.0, a, 128, 1, a, 128, 1, 0.0, c, 128, 1)
+    L.gemm_strided(128, 128, 128, 1.0, dptr(a, 0, "f32"), 128, 1, dptr(a, 0, "f32"), 128, 1, 0.0, dptr(c, 0, "f32"), 128, 1)
     assert L.last_path() == L.PATH_SIMT            # M*N*K <= 128^3: exact kernel (gemm.nim:140-141 threshold)
     a = dev(np.ones(256 * 256, np.float32)); c = dev(np.zeros(256 * 256, np.float32))
-    L.gemm_strided(256, 256, 256, 1.0, a, 256, 1, a, 256, 1, 0.0, c, 256, 1)
+    L.gemm_strided(256, 256, 256, 1.0, dptr(a, 0, "f32"), 256, 1, dptr(a, 0, "f32"), 256, 1, 0.0, dptr(c, 0, "f32"), 256, 1)
     assert L.last_path() == L.PATH_TF32_BF16C
-    torch.cuda.synchronize()
+    sync()
     assert np.all(c.cpu().numpy() == 256.0)
 
 
@@ -279,11 +279,13 @@ def test_tensor_contract_and_matmul():
     want2 = np.zeros((100, N), np.float32); Asub = np.ascontiguousarray(A[10:110, ::2]); Bsub = B[::2].copy()
     O.gemm_strided(100, N, Asub.shape[1], 1.0, Asub, Asub.shape[1], 1, Bsub, N, 1, 0.0, want2, N, 1)
     assert np.array_equal(tC2.to_numpy(), want2)
-    tt = L.Tensor.from_torch(torch.arange(12, dtype=torch.float32, device="cuda").reshape(3, 4)[:, 1:])
-    assert tt.shape == [3, 3] and tt.strides == [4, 1] and tt.offset == 1
-    assert np.array_equal(tt.to_numpy(), np.arange(12, dtype=np.float32).reshape(3, 4)[:, 1:])
+    if not EMU:
+        tt = L.Tensor.from_torch(torch.arange(12, dtype=torch.float32, device="cuda").reshape(3, 4)[:, 1:])
+        assert tt.shape == [3, 3] and tt.strides == [4, 1] and tt.offset == 1
+        assert np.array_equal(tt.to_numpy(), np.arange(12, dtype=np.float32).reshape(3, 4)[:, 1:])
 
 
+@needs_gpu
 def test_device_fill_matches_oracle_bit_for_bit():
     n = 100003
     t = torch.empty(n, dtype=torch.float32, device="cuda")
@@ -301,6 +303,7 @@ def _rows_check(M, N, K, tA, tB, tC, rows, tol):
     assert O.max_relative_error(got, want) < tol, O.max_relative_error(got, want)
 
 
+@needs_gpu
 @pytest.mark.parametrize("n", [4096, 8192])
 def test_full_size_sgemm_sampled_rows(n):
     """configs[1] (4096^3) and the metric shape (8192^3): device-generated U(0,1) inputs; 48
@@ -330,6 +333,7 @@ def test_full_size_sgemm_sampled_rows(n):
         assert np.array_equal(panel.cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
+@needs_gpu
 def test_full_size_transposed_a_4096():
     """configs[2]: A given transposed (storage K x M, rowStrideA = 1, colStrideA = M)."""
     M = N = K = 4096
@@ -344,6 +348,7 @@ def test_full_size_transposed_a_4096():
         _rows_check(M, N, K, A_logical, tB.view(K, N), tC, rows, 1e-4 if path in FAITHFUL else 5e-3)
 
 
+@needs_gpu
 def test_full_size_bf16_8192():
     """configs[3]: bf16 8192^3, sampled rows vs the bf16 oracle."""
     M = N = K = 8192
