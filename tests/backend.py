@@ -13,11 +13,19 @@ if not EMU:
 needs_gpu = pytest.mark.skipif(EMU, reason="uses torch CUDA tensors directly / too large for the CPU build")
 
 
-class HostTensor:
-    """the few torch.Tensor methods the tests use, on a numpy array"""
+import laser_b200 as L  # noqa: E402
+
+_NAME = {np.dtype(np.int16): "bf16", np.dtype(np.uint16): "bf16", np.dtype(np.float32): "f32", np.dtype(np.float64): "f64",
+         np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}
+
+
+class HostTensor(L.DevPtr):
+    """EMU backend: a numpy array posing as device memory.  It is a DevPtr, so it can be handed to the
+    Python mirror like a torch CUDA tensor, and it has the few torch.Tensor methods the tests use."""
 
     def __init__(self, arr):
         self.arr = np.ascontiguousarray(arr)
+        super().__init__(self.arr.ctypes.data, _NAME.get(self.arr.dtype, "f32"))
 
     def data_ptr(self):
         return self.arr.ctypes.data

@@ -47,11 +47,12 @@ def test_parity_file_subset_against_the_host_emulated_library():
     """tests/test_gpu_parity.py is backend-neutral (tests/backend.py): the same assertions the B200 has to
     meet -- known-answer vectors on every path and dtype, bit-exactness of the exact kernel, bf16, the
     host-pointer entry, dispatch, the Tensor contract -- are checked here on the CPU build.  A fast
-    subset by default; LASER_B200_EMU_FULL=1 runs the whole parity and fuzz files (about 11 minutes:
-    656 cases passed when last run, 34 skipped for size)."""
+    subset by default; LASER_B200_EMU_FULL=1 runs the whole parity, fuzz, pre-packed and fused-epilogue
+    files (about 18 minutes: 718 cases passed when last run, 34 skipped for size)."""
     assert _run_gpu_files(["test_gpu_parity.py"], ["-k", FAST], 1500) >= 50
 
 
-@pytest.mark.skipif(os.environ.get("LASER_B200_EMU_FULL", "0") != "1", reason="about 11 minutes; set LASER_B200_EMU_FULL=1")
+@pytest.mark.skipif(os.environ.get("LASER_B200_EMU_FULL", "0") != "1", reason="about 18 minutes; set LASER_B200_EMU_FULL=1")
 def test_whole_parity_and_fuzz_files_against_the_host_emulated_library():
-    assert _run_gpu_files(["test_gpu_parity.py", "test_gpu_fuzz.py"], [], 3000) >= 600
+    assert _run_gpu_files(["test_gpu_parity.py", "test_gpu_fuzz.py", "test_gpu_prepacked.py", "test_gpu_fused_epilogue.py"], [],
+                          5000) >= 700

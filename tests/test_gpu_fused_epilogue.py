@@ -4,9 +4,9 @@ import numpy as np
 import pytest
 
 import oracle as O
+from backend import dev, sync
 
 pytestmark = pytest.mark.gpu
-torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
 
 ACTS = {"none": lambda x: x, "relu": lambda x: np.maximum(x, 0), "tanh": np.tanh,
@@ -24,15 +24,17 @@ def test_fused_bias_activation(act, per_row, path, ldc):
     bias = O.fill_uniform_f32(M if per_row else N, 4, -1, 1)
     base = C0.copy(); O.gemm_strided(M, N, K, 0.5, A, K, 1, B, N, 1, -1.25, base, N, 1)
     want = ACTS[act]((base.astype(np.float64) + (bias[:, None] if per_row else bias[None, :]))).astype(np.float32)
-    tA, tB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
-    buf = torch.full((M, ldc), -7.0, device="cuda"); buf[:, :N] = torch.from_numpy(C0).cuda()
-    L.gemm_strided_fused(M, N, K, 0.5, tA, K, 1, tB, N, 1, -1.25, buf, ldc, 1, bias=torch.from_numpy(bias).cuda(),
+    tA, tB = dev(A), dev(B)
+    hbuf = np.full((M, ldc), -7.0, np.float32); hbuf[:, :N] = C0
+    buf = dev(hbuf)
+    L.gemm_strided_fused(M, N, K, 0.5, tA, K, 1, tB, N, 1, -1.25, buf, ldc, 1, bias=dev(bias),
                          bias_per_row=per_row, activation=act, path=path)
-    torch.cuda.synchronize()
-    got = buf[:, :N].cpu().numpy()
+    sync()
+    after = buf.cpu().numpy()
+    got = after[:, :N]
     assert np.allclose(got, want, rtol=2e-5, atol=2e-6), np.abs(got - want).max()
-    assert torch.all(buf[:, N:] == -7.0)
+    assert np.all(after[:, N:] == -7.0)
     # the thread-local epilogue must not leak into the next plain call
-    tC = torch.from_numpy(C0).cuda(); L.gemm_strided(M, N, K, 0.5, tA, K, 1, tB, N, 1, -1.25, tC, N, 1, path=path)
-    torch.cuda.synchronize()
+    tC = dev(C0); L.gemm_strided(M, N, K, 0.5, tA, K, 1, tB, N, 1, -1.25, tC, N, 1, path=path)
+    sync()
     assert np.allclose(tC.cpu().numpy(), base, rtol=2e-5, atol=2e-6)

@@ -5,15 +5,11 @@ import numpy as np
 import pytest
 
 import oracle as O
+from backend import dev, sync
 from util import embed, golden_cases
 
 pytestmark = pytest.mark.gpu
-torch = pytest.importorskip("torch")
 import laser_b200 as L  # noqa: E402
-
-
-def dev(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
 def pack_both(M, N, K, tA, oa, rsa, csa, tB, ob, rsb, csb):
@@ -27,10 +23,10 @@ def pack_both(M, N, K, tA, oa, rsa, csa, tB, ob, rsb, csb):
 def test_golden_through_prepack(case):
     M, N, K = case["M"], case["N"], case["K"]
     a = np.array(case["a"], np.float32); b = np.array(case["b"], np.float32)
-    tA, tB = dev(a), dev(b); tC = torch.full((M, N), 99.0, device="cuda")
+    tA, tB = dev(a), dev(b); tC = dev(np.full((M, N), 99.0, np.float32))
     pa, pb = pack_both(M, N, K, tA, 0, K, 1, tB, 0, N, 1)
     L.gemm_packed(M, N, K, 1.0, pa, pb, 0.0, tC, N, 1)
-    torch.cuda.synchronize()
+    sync()
     assert np.array_equal(tC.cpu().numpy(), np.array(case["c"], np.float32))
 
 
@@ -48,7 +44,7 @@ def test_packed_matches_oracle_and_unpacked(la, lb):
     tC3 = dev(C0)
     L.gemm_strided(M, N, K, 0.5, L.DevPtr(tA.data_ptr() + 4 * oa, "f32"), rsa, csa, L.DevPtr(tB.data_ptr() + 4 * ob, "f32"), rsb, csb,
                    -1.25, tC3, N, 1, path=L.PATH_TF32_BF16C)
-    torch.cuda.synchronize()
+    sync()
     got = tC.cpu().numpy()
     assert O.max_relative_error(got, want) < 1e-4
     # same tiles, same order of accumulation: packing changes nothing numerically
@@ -65,7 +61,7 @@ def test_mem_required_and_reuse():
     for seed in (1, 2, 3):       # fixed B, fresh A: one split (A only) + one GEMM launch per product
         A = O.fill_uniform_f32(M * K, seed, 0, 1).reshape(M, K)
         want = np.zeros((M, N), np.float32); O.gemm_strided(M, N, K, 1.0, A, K, 1, B, N, 1, 0.0, want, N, 1)
-        tC = torch.empty((M, N), device="cuda"); L.gemm_packedB(M, N, K, 1.0, dev(A), K, 1, pb, 0.0, tC, N, 1)
-        torch.cuda.synchronize()
+        tC = dev(np.empty((M, N), np.float32)); L.gemm_packedB(M, N, K, 1.0, dev(A), K, 1, pb, 0.0, tC, N, 1)
+        sync()
         assert O.max_relative_error(tC.cpu().numpy(), want) < 1e-4
     assert L.launch_count() - n0 == 6

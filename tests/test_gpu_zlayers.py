@@ -30,7 +30,7 @@ NAME_OF = {np.dtype(np.int16): "bf16", np.dtype(np.uint16): "bf16", np.dtype(np.
            np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}
 
 
-class HostDev(L.DevPtr):
+class HostDev(L.DevPtr):  # (same idea as backend.HostTensor)
     """EMU backend: a numpy array posing as device memory."""
 
     def __init__(self, arr):
