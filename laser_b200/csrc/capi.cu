@@ -95,7 +95,6 @@ struct Ctx {
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
-  int l2_hint = 0;        // env LASER_B200_L2HINT: 0 plain loads (default), 1 A evict_last / B evict_first, 2 the reverse
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
   bool profiling = false;
@@ -157,7 +156,6 @@ int get_ctx(Ctx **out) {
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
-      if (const char *lh = getenv("LASER_B200_L2HINT")) c.l2_hint = atoi(lh);
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
       if (const char *pr = getenv("LASER_B200_PANEL_ROWS")) {
         const int64_t v = atoll(pr) / 256 * 256;   // whole CTA-pair tiles
@@ -467,8 +465,6 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
   tc_plan<ESZ, std::is_same<OutT, float>::value>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count});
-  if (c.l2_hint == 1) { p.hint_a = ptx::kEvictLast; p.hint_b = ptx::kEvictFirst; }
-  else if (c.l2_hint == 2) { p.hint_a = ptx::kEvictFirst; p.hint_b = ptx::kEvictLast; }
   EventPair ep;
   int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;

@@ -95,8 +95,6 @@ struct TcParams {
   int kb_per_split;      // scheduling units (k-tiles / 64-groups) per split
   int64_t split_plane;   // elements between consecutive planes
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
-  // optional L2 eviction-priority hints of the A / B tile loads (ptx::kEvict*; 0 = plain loads)
-  uint64_t hint_a = 0, hint_b = 0;
 };
 
 // host side: the part of TcParams that depends only on the problem (p.M, p.N, p.K set by the
@@ -259,14 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       // ===================== TMA producer (one thread) =====================
       int stage = 0;
       uint32_t phase = 0;
-      auto tma = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint64_t hint) {
-        if (hint != 0) {
-          if constexpr (PAIR) ptx::tma_load_2d_pair_hint(dst, m, bar, c0, c1, hint);
-          else ptx::tma_load_2d_hint(dst, m, bar, c0, c1, hint);
-        } else {
-          if constexpr (PAIR) ptx::tma_load_2d_pair(dst, m, bar, c0, c1);  // bytes -> leader's barrier
-          else ptx::tma_load_2d(dst, m, bar, c0, c1);
-        }
+      auto tma = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+        if constexpr (PAIR) ptx::tma_load_2d_pair(dst, m, bar, c0, c1);  // bytes -> leader's barrier
+        else ptx::tma_load_2d(dst, m, bar, c0, c1);
       };
       // E = element size of the tiles of THIS stage (4: fp32/tf32, 2: bf16)
       auto load_stage = [&](auto esz_tag, const CUtensorMap *ma, const CUtensorMap *mbp, int m0, int n0, int k0) {
@@ -284,18 +277,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint8_t *sa = smem_a + stage * TC_A_STAGE_BYTES;
         uint8_t *sb = smem_b + stage * TC_B_STAGE_BYTES;
         if constexpr (!A_MN) {
-          tma(sa, ma, &full_bar[stage], k0, m0, p.hint_a);  // box {BLOCK_K, 128}
+          tma(sa, ma, &full_bar[stage], k0, m0);  // box {BLOCK_K, 128}
         } else {
 #pragma unroll
           for (int c = 0; c < TC_BLOCK_M / MN_ATOM; ++c)  // boxes {MN_ATOM, BLOCK_K}
-            tma(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0, p.hint_a);
+            tma(sa + c * MN_BOX_BYTES, ma, &full_bar[stage], m0 + c * MN_ATOM, k0);
         }
         if constexpr (!B_MN) {
-          tma(sb, mbp, &full_bar[stage], k0, n0, p.hint_b);  // box {BLOCK_K, B_COLS}
+          tma(sb, mbp, &full_bar[stage], k0, n0);  // box {BLOCK_K, B_COLS}
         } else {
 #pragma unroll
           for (int c = 0; c < Cfg::B_COLS / MN_ATOM; ++c)
-            tma(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0, p.hint_b);
+            tma(sb + c * MN_BOX_BYTES, mbp, &full_bar[stage], n0 + c * MN_ATOM, k0);
         }
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       };

@@ -17,5 +17,3 @@ timeout 300 python tools/layers_bench.py > gpurun_out/layers_bench.jsonl 2> gpur
 timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zlayers.py -m gpu -q -k "not 8192 and not 224" > gpurun_out/sanitizer_layers.log 2>&1; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_layers.log | tail -3
 echo "=== host-pointer entry: panel geometry variants"
 for v in "" "LASER_B200_PANEL_ROWS=512" "LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=512 LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=2048 LASER_B200_PANEL_TAPER=1"; do env $v timeout 200 python tools/e2e_probe.py 2>> gpurun_out/e2e_probe_err.log | tee -a gpurun_out/e2e_probe.jsonl; done
-echo "=== L2 hints / raster on the default kernel"
-for v in "" "LASER_B200_L2HINT=1" "LASER_B200_L2HINT=2" "LASER_B200_L2HINT=1 LASER_B200_RASTER=6" "LASER_B200_L2HINT=1 LASER_B200_RASTER=4"; do echo "$v"; env $v timeout 300 python tools/perf_probe.py 2>> gpurun_out/perf_hint_err.log | tail -4 | tee -a gpurun_out/perf_hint.log; done
