@@ -231,7 +231,8 @@ int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, in
   if (tiles > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
   p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   const int grid = grid_for(c, tiles * batch, 2);
-  gemm_simt_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);
+  if (batch > 1) gemm_simt_batched_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);
+  else gemm_simt_kernel<T, TM, TN, BK><<<grid, 256, 0, s>>>(p);
   COUNT_LAUNCH();
   CHECK_LAUNCH();
   return LASER_B200_OK;

@@ -99,140 +99,16 @@ inline int64_t simt_plan(SimtParams<T> &p, int64_t M, int64_t N, int64_t K, T al
 #ifndef LB200_SIMT_MINB
 #define LB200_SIMT_MINB 1
 #endif
-template <typename T, int TM, int TN, int BK>
-__global__ void __launch_bounds__(256, LB200_SIMT_MINB)
-gemm_simt_kernel(const SimtParams<T> p) {
-  constexpr int BM = 16 * TM, BN = 16 * TN;
-  constexpr int HM = TM / 2, HN = TN / 2;       // the two halves of the micro-tile
-  constexpr int A_PER_T = BM * BK / 256, B_PER_T = BN * BK / 256;
-  static_assert(TM % 2 == 0 && TN % 2 == 0, "micro tile halves");
-  static_assert((BM * BK) % 256 == 0 && (BN * BK) % 256 == 0, "loader mapping");
-  using Op = SimtOps<T>;
-  constexpr int64_t KC = 2048 / static_cast<int64_t>(sizeof(T));  // gemm_tiling.nim:310
-
-  __shared__ T As[BK][BM + 4];
-  __shared__ T Bs[BK][BN + 4];
-
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-
-  const int64_t total_tiles = static_cast<int64_t>(num_tiles) * p.batch;
-
-  for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    const int64_t bi = t / num_tiles;
-    const int tile = static_cast<int>(t - bi * num_tiles);
-    const T *Ab = p.A + bi * p.bsA;
-    const T *Bb = p.B + bi * p.bsB;
-    T *Cb = p.C + bi * p.bsC;
-    const int mb = tile % p.num_m_blocks, nb = tile / p.num_m_blocks;
-    const int64_t m0 = static_cast<int64_t>(mb) * BM, n0 = static_cast<int64_t>(nb) * BN;
-
-    T ra[A_PER_T], rb[B_PER_T];
-    auto load_tiles = [&](int64_t k0, int64_t kend) {
-#pragma unroll
-      for (int i = 0; i < A_PER_T; ++i) {
-        const int idx = tid + i * 256;
-        const int m = p.a_along_m ? (idx % BM) : (idx / BK);
-        const int k = p.a_along_m ? (idx / BM) : (idx % BK);
-        const int64_t gm = m0 + m, gk = k0 + k;
-        ra[i] = (gm < p.M && gk < kend) ? Ab[gm * p.rsA + gk * p.csA] : T(0);
-      }
-#pragma unroll
-      for (int i = 0; i < B_PER_T; ++i) {
-        const int idx = tid + i * 256;
-        const int n = p.b_along_k ? (idx / BK) : (idx % BN);
-        const int k = p.b_along_k ? (idx % BK) : (idx / BN);
-        const int64_t gn = n0 + n, gk = k0 + k;
-        rb[i] = (gn < p.N && gk < kend) ? Bb[gk * p.rsB + gn * p.csB] : T(0);
-      }
-    };
-    auto store_tiles = [&]() {
-#pragma unroll
-      for (int i = 0; i < A_PER_T; ++i) {
-        const int idx = tid + i * 256;
-        const int m = p.a_along_m ? (idx % BM) : (idx / BK);
-        const int k = p.a_along_m ? (idx / BM) : (idx % BK);
-        As[k][m] = ra[i];
-      }
-#pragma unroll
-      for (int i = 0; i < B_PER_T; ++i) {
-        const int idx = tid + i * 256;
-        const int n = p.b_along_k ? (idx / BK) : (idx % BN);
-        const int k = p.b_along_k ? (idx % BK) : (idx / BN);
-        Bs[k][n] = rb[i];
-      }
-    };
-
-    for (int64_t pc = 0; pc < p.K; pc += KC) {  // reference loop 2 (gemm.nim:150)
-      const int64_t kend = (pc + KC < p.K) ? pc + KC : p.K;
-      T acc[TM][TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
-
-      load_tiles(pc, kend);
-      for (int64_t k0 = pc; k0 < kend; k0 += BK) {
-        __syncthreads();  // previous tile fully consumed
-        store_tiles();
-        __syncthreads();
-        if (k0 + BK < kend) load_tiles(k0 + BK, kend);  // in flight during the FMAs below
-        const int kmax = (kend - k0 < BK) ? static_cast<int>(kend - k0) : BK;
-#pragma unroll 4
-        for (int k = 0; k < kmax; ++k) {
-          T a[TM], b[TN];
-#pragma unroll
-          for (int i = 0; i < HM; ++i) {
-            a[i] = As[k][ty * HM + i];
-            a[HM + i] = As[k][BM / 2 + ty * HM + i];
-          }
-#pragma unroll
-          for (int j = 0; j < HN; ++j) {
-            b[j] = Bs[k][tx * HN + j];
-            b[HN + j] = Bs[k][BN / 2 + tx * HN + j];
-          }
-#pragma unroll
-          for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = Op::fma(a[i], b[j], acc[i][j]);
-        }
-      }
-
-      // reference epilogue for this kc block (gemm_ukernel_generic.nim:53-76)
-      const T beta1 = (pc == 0) ? p.beta : T(1);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int64_t gm = m0 + ((i < HM) ? (ty * HM + i) : (BM / 2 + ty * HM + (i - HM)));
-        if (gm >= p.M) continue;
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          const int64_t gn = n0 + ((j < HN) ? (tx * HN + j) : (BN / 2 + tx * HN + (j - HN)));
-          if (gn >= p.N) continue;
-          T *c = Cb + gm * p.rsC + gn * p.csC;
-          T v;
-          if (beta1 == T(0)) v = T(0);
-          else if (beta1 != T(1)) v = Op::mul(*c, beta1);
-          else v = *c;
-          if (p.alpha == T(1)) v = Op::add(v, acc[i][j]);
-          else v = Op::add(v, Op::mul(p.alpha, acc[i][j]));
-          if constexpr (sizeof(T) == 4 && !std::is_integral<T>::value) {
-            if (kend == p.K && (p.bias != nullptr || p.act != 0)) {
-              float f = static_cast<float>(v);
-              if (p.bias) f += p.bias_per_row ? p.bias[gm] : p.bias[gn];
-              if (p.act == 1) f = fmaxf(f, 0.0f);
-              else if (p.act == 2) f = tanhf(f);
-              else if (p.act == 3) f = 1.0f / (1.0f + expf(-f));
-              v = static_cast<T>(f);
-            }
-          }
-          *c = v;
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
+#define LB200_SIMT_KERNEL_NAME gemm_simt_kernel
+#define LB200_SIMT_BATCHED 0
+#include "gemm_simt_kernel.inc"
+#undef LB200_SIMT_KERNEL_NAME
+#undef LB200_SIMT_BATCHED
+#define LB200_SIMT_KERNEL_NAME gemm_simt_batched_kernel
+#define LB200_SIMT_BATCHED 1
+#include "gemm_simt_kernel.inc"
+#undef LB200_SIMT_KERNEL_NAME
+#undef LB200_SIMT_BATCHED
 
 // dynamic shared memory (tests/emu runs this header on host threads, where it is a plain buffer)
 #ifndef LB200_DYN_SMEM

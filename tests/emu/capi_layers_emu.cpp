@@ -98,7 +98,8 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
   const int64_t tiles = simt_plan<T, TMN, TMN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
   p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   const int grid = grid_for(c, tiles * batch, 2);
-  emu::launch(grid, 256, [=]() { gemm_simt_kernel<T, TMN, TMN, 16>(p); });
+  if (batch > 1) emu::launch(grid, 256, [=]() { gemm_simt_batched_kernel<T, TMN, TMN, 16>(p); });
+  else emu::launch(grid, 256, [=]() { gemm_simt_kernel<T, TMN, TMN, 16>(p); });
   COUNT_LAUNCH();
   return LASER_B200_OK;
 }

@@ -20,7 +20,8 @@ static int run(int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA
   p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   if (batch <= 0) return 0;
   if (grid <= 0 || grid > tiles * batch) grid = static_cast<int>(tiles * batch);
-  emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_simt_kernel<T, TM, TN, BK>(p); });
+  if (batch > 1) emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_simt_batched_kernel<T, TM, TN, BK>(p); });
+  else emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_simt_kernel<T, TM, TN, BK>(p); });
   return static_cast<int>(tiles);
 }
 

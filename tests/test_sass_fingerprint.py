@@ -1,6 +1,6 @@
 """CPU-only: the kernels whose timings are quoted (bench.py, profiles/) must be the kernels in
 the shipped library.  profiles/sass_fingerprint.json holds an md5 of the SASS of every tensor-core GEMM
-variant and of the operand-preparation / reduce / skinny-GEMM kernels as they were when last MEASURED on a
+variant, of the exact kernel and of the operand-preparation / reduce / skinny-GEMM kernels as they were when last MEASURED on a
 B200; this test recomputes them from the in-tree build (cuobjdump).  If a kernel was changed on purpose:
 measure it on the GPU, then refresh the file with `python tests/test_sass_fingerprint.py --update`."""
 import hashlib
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILE = os.path.join(ROOT, "profiles", "sass_fingerprint.json")
-MEASURED = ("gemm_tc_kernel", "split_rows_", "pack_general_kernel", "splitk_reduce_kernel", "gemv_warp", "fill_uniform_f32_kernel")
+MEASURED = ("gemm_tc_kernel", "gemm_simt_kernel", "split_rows_", "pack_general_kernel", "splitk_reduce_kernel", "gemv_warp", "fill_uniform_f32_kernel")
 
 
 def fingerprints():
