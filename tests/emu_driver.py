@@ -218,5 +218,21 @@ def tensors():
     print("OK tensors 3")
 
 
+def lifecycle():
+    """init / shutdown / re-init: workspaces, staging buffers and the layer workspace are released and rebuilt"""
+    a, b = rnd((300, 200), 40), rnd((200, 260), 41)
+    ref = ref_gemm(300, 260, 200, 1.0, a, b, 0.0, np.zeros((300, 260), np.float32))
+    for _ in range(2):
+        L.init()
+        c = np.zeros((300, 260), np.float32)
+        L.gemm_strided(300, 260, 200, 1.0, a, 200, 1, b, 260, 1, 0.0, c, 260, 1)          # host entry: staging buffers
+        assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max()
+        out = np.zeros((1, 1, 4, 4), np.float32)
+        L.conv2d_im2col(out, np.ones((1, 1, 4, 4), np.float32), (1, 1, 4, 4), np.ones((1, 1, 3, 3), np.float32), (1, 1, 3, 3), (1, 1), (1, 1))
+        assert out[0, 0, 1, 1] == 9.0 and out[0, 0, 0, 0] == 4.0                           # host conv: layer workspace
+        L.shutdown()
+    print("OK lifecycle 2")
+
+
 if __name__ == "__main__":
     globals()[sys.argv[1]]()

@@ -32,7 +32,7 @@ def run(lib, scenario, **env):
 
 
 @pytest.mark.parametrize("scenario", ["dispatch_and_modes", "strided_operands", "host_entry", "prepacked", "other_types",
-                                      "fused_and_skinny", "tensors"])
+                                      "fused_and_skinny", "tensors", "lifecycle"])
 def test_scenario(emulated_lib, scenario):
     run(emulated_lib, scenario)
 
