@@ -135,6 +135,14 @@ inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int
   std::memcpy(&m, map, sizeof m);
   if (m.magic != emu::kMapMagic) { std::fprintf(stderr, "emu: not an emulated tensor map\n"); std::abort(); }
   unsigned char *dst = static_cast<unsigned char *>(smem_dst);
+  {   // the destination must be this CTA's shared memory, whole box inside it, swizzle-atom (1024 B) aligned
+    const unsigned char *lo = emu::dyn_smem[emu::cta_rank];
+    const size_t box_bytes = static_cast<size_t>(m.box0) * m.box1 * m.esz;
+    if (dst < lo || dst + box_bytes > lo + emu::kDynSmemBytes || ((dst - lo) & 1023)) {
+      std::fprintf(stderr, "emu: TMA destination outside this CTA's shared memory or not 1024-byte aligned\n");
+      std::abort();
+    }
+  }
   for (int r = 0; r < m.box1; ++r)
     for (int e = 0; e < m.box0; ++e) {
       const int64_t i0 = static_cast<int64_t>(c0) + e, i1 = static_cast<int64_t>(c1) + r;
