@@ -376,6 +376,8 @@ def emit(obj):
 
 
 def main():
+    if os.environ.get("LASER_B200_LIB") or os.environ.get("LASER_B200_EMU"):
+        raise SystemExit("bench.py measures the in-tree CUDA library only: unset LASER_B200_LIB / LASER_B200_EMU")
     global GUARD
     GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()

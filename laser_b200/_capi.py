@@ -117,6 +117,11 @@ def lib():
     if _lib is None:
         path = os.environ.get("LASER_B200_LIB") or _build.build()   # override: A/B builds in tools/
         L = ctypes.CDLL(path)
+        # tests/emu can build the library for the CPU (kernels on host threads) to test host logic without
+        # a GPU; such a build marks itself and is only ever accepted inside those tests' own subprocesses
+        if hasattr(L, "laser_b200_is_host_emulation") and os.environ.get("LASER_B200_EMU") != "1":
+            raise RuntimeError("%s is a host-emulation TEST build of liblaser_b200 (tests/emu); refusing to use it as "
+                               "the product library" % path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the header and the library disagree
             fn.restype = res

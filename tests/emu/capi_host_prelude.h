@@ -65,6 +65,8 @@ static CUresult emu_encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuuin
 
 // ---- CUDA runtime ---------------------------------------------------------------------------------------
 extern "C" {
+// marks this build: the Python mirror refuses to load a library exporting it unless LASER_B200_EMU=1
+int laser_b200_is_host_emulation(void) { return 1; }
 inline int emu_device_count_sms() { const char *e = getenv("LASER_B200_EMU_SMS"); return e ? atoi(e) : 8; }
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }

@@ -24,7 +24,7 @@ def emulated_lib():
 
 
 def run(lib, scenario, **env):
-    e = dict(os.environ, LASER_B200_LIB=lib, PYTHONPATH=ROOT, **{k: str(v) for k, v in env.items()})
+    e = dict(os.environ, LASER_B200_LIB=lib, LASER_B200_EMU="1", PYTHONPATH=ROOT, **{k: str(v) for k, v in env.items()})
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_driver.py"), scenario], cwd=ROOT, env=e,
                          capture_output=True, text=True, timeout=1100)
     assert out.returncode == 0 and out.stdout.strip().startswith("OK " + scenario), out.stdout[-1500:] + out.stderr[-3000:]
@@ -51,3 +51,13 @@ def test_host_entry_under_configuration(emulated_lib, env):
     """the panel geometry of the pipelined host-pointer entry and the kernel configuration knobs are read
     from the environment when the library initialises: one process per configuration"""
     run(emulated_lib, "host_entry", **env)
+
+
+def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):
+    """the Python mirror must never use the CPU test build as the product library by accident"""
+    e = dict(os.environ, LASER_B200_LIB=emulated_lib, PYTHONPATH=ROOT)
+    e.pop("LASER_B200_EMU", None)
+    out = subprocess.run([sys.executable, "-c", "import laser_b200 as L; L.lib()"], cwd=ROOT, env=e, capture_output=True, text=True)
+    assert out.returncode != 0 and "host-emulation TEST build" in out.stderr
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], cwd=ROOT, env=e, capture_output=True, text=True)
+    assert out.returncode != 0 and "in-tree CUDA library only" in (out.stderr + out.stdout)
