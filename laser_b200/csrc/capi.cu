@@ -94,6 +94,7 @@ struct Ctx {
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
+  bool tc_batched = false;    // env LASER_B200_TC_BATCHED=1: batches of tensor-core problems as one launch (unmeasured)
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
   int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
@@ -157,6 +158,7 @@ int get_ctx(Ctx **out) {
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
+      if (const char *tb = getenv("LASER_B200_TC_BATCHED")) c.tc_batched = atoi(tb) != 0;
       if (const char *pr = getenv("LASER_B200_PANEL_ROWS")) {
         const int64_t v = atoll(pr) / 256 * 256;   // whole CTA-pair tiles
         if (v >= 256) c.panel_rows = v;
@@ -368,6 +370,32 @@ int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams
   return LASER_B200_OK;
 }
 
+// ---- batch of problems in one launch (gemm_tc_batched_kernel): 3-d tensor maps, box depth 1 ----
+int encode_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer, int64_t nb,
+                int64_t outer_stride_elems, int64_t batch_stride_elems, int box_inner, int box_outer,
+                CUtensorMapSwizzle swz) {
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(nb)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(outer_stride_elems) * esz,
+                                 static_cast<cuuint64_t>(nb > 1 ? batch_stride_elems : outer_stride_elems * outer) * esz};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = c.encode(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LASER_B200_ECUDA, "cuTensorMapEncodeTiled (3-d) failed (%d): inner=%lld outer=%lld batch=%lld",
+                     static_cast<int>(r), (long long)inner, (long long)outer, (long long)nb);
+  return LASER_B200_OK;
+}
+// nb matrices seen as [mn][k] each, stacked densely: K-major [nb][mn][ld], MN-major [nb][k][ld]
+int operand_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, bool mn_major, int64_t mn, int64_t k, int64_t nb,
+                 int64_t ld, int block_mn) {
+  const int block_k = TC_ROW_BYTES / esz, mn_atom = TC_ROW_BYTES / esz;
+  if (!mn_major) return encode_map3(c, map, esz, base, k, mn, nb, ld, mn * ld, block_k, block_mn, CU_TENSOR_MAP_SWIZZLE_128B);
+  return encode_map3(c, map, esz, base, mn, k, nb, ld, k * ld, mn_atom, block_k,
+                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int ESZ>
 int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w, int block_mn,
                     OperandMaps *m, bool *used_ws, cudaStream_t s) {
@@ -524,6 +552,121 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
   rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s);
+  if (rc) return rc;
+  if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
+  return LASER_B200_OK;
+}
+
+template <int ESZ, typename OutT, bool PAIR>
+int launch_tc_batched(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcBatchedParams &p, cudaStream_t s) {
+  const bool a_mn = A.mn_major, b_mn = B.mn_major;
+  const int64_t units_total = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits * p.batch;
+  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
+  const int sched = static_cast<int>(units_total < units ? units_total : units);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define LB200_LAUNCH(AMN, BMN)                                                                   \
+  do {                                                                                           \
+    auto kfn = gemm_tc_batched_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                \
+    static std::atomic<uint32_t> attr_set{0};                                                    \
+    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
+      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
+    }                                                                                            \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
+  } while (0)
+  if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
+  else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
+  else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
+  else LB200_LAUNCH(true, true);
+#undef LB200_LAUNCH
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+
+// One operand of a batch: nb = 1 (shared) or `batch` matrices that must stack densely -- K-major rows one
+// after the other (batch stride = mn * row pitch) or MN-major k-rows one after the other (batch stride =
+// k * pitch); then the whole stack is ONE matrix for the preparation kernels.  Returns -2 when the layout
+// does not stack (the caller falls back to one launch sequence per problem).
+int prepare_operand_stack(Ctx &c, const void *ptr, int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int64_t bs, int64_t nb,
+                          SplitMode mode, const OperandWs &w, int block_mn, OperandMaps *m, bool *used_ws, cudaStream_t s) {
+  Operand one{ptr, mn, k, s_mn, s_k};
+  const Major mj = classify(one, 4);
+  if (mj == GENERAL && nb > 1) return -2;   // a single (shared) matrix of any strides is gathered as usual
+  Operand stack = one;
+  if (nb > 1) {
+    if (mj == K_MAJOR) { if (bs != mn * s_mn) return -2; stack.mn = nb * mn; }
+    else { if (bs != k * s_k) return -2; stack.k = nb * k; }
+  }
+  OperandMaps flat;
+  bool used = false;
+  int rc = prepare_operand<4>(c, stack, mode, w, block_mn, &flat, &used, s);   // the 2-d maps it builds are not used
+  if (rc) return rc;
+  *used_ws = *used_ws || used;
+  const bool mn_major = (mj == MN_MAJOR);   // gathered operands come out K-major
+  const int64_t Cc = mn_major ? mn : k;
+  const int64_t ld = used ? round_up(Cc, 4) : (mn_major ? s_k : s_mn), ld_b = round_up(Cc, 8);
+  const void *hi = used ? w.hi->ptr : ptr;
+  m->mn_major = mn_major;
+  if ((rc = operand_map3(c, &m->hi, 4, hi, mn_major, mn, k, nb, ld, block_mn))) return rc;
+  m->lo = m->xb = m->lb = m->hi;
+  if (mode == SPLIT_TF32) return operand_map3(c, &m->lo, 4, w.lo->ptr, mn_major, mn, k, nb, ld, block_mn);
+  if (mode == SPLIT_MIXED) {
+    if ((rc = operand_map3(c, &m->xb, 2, w.xb->ptr, mn_major, mn, k, nb, ld_b, block_mn))) return rc;
+    return operand_map3(c, &m->lb, 2, w.lb->ptr, mn_major, mn, k, nb, ld_b, block_mn);
+  }
+  return LASER_B200_OK;
+}
+
+// `batch` float32 problems of one shape as ONE tensor-core launch (after at most one preparation launch
+// per operand).  -2: the operands do not stack, nothing was launched.
+int gemm_tc_batched(Ctx &c, int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA,
+                    int64_t csA, int64_t bsA, const float *B, int64_t rsB, int64_t csB, int64_t bsB, float beta, float *C,
+                    int64_t rsC, int64_t csC, int64_t bsC, int npass, cudaStream_t s) {
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL || batch > 0x7fffffffLL / 4 ||
+      batch * M > 0x7fffffffLL || batch * K > 0x7fffffffLL || batch * N > 0x7fffffffLL)
+    return -2;
+  std::lock_guard<std::mutex> lk(c.mu);
+  const SplitMode mode = split_mode(npass);
+  const bool pair = c.cta_pair && M > TC_BLOCK_M;
+  OperandMaps ma, mb;
+  bool used_ws = false;
+  // both operands must stack before anything is launched
+  {
+    Operand oa{A, M, K, rsA, csA}, ob{B, N, K, csB, rsB};
+    const Major ja = classify(oa, 4), jb = classify(ob, 4);
+    if ((ja == GENERAL && bsA != 0) || (jb == GENERAL && bsB != 0)) return -2;
+    if (bsA != 0 && bsA != (ja == K_MAJOR ? M * rsA : K * csA)) return -2;
+    if (bsB != 0 && bsB != (jb == K_MAJOR ? N * csB : K * rsB)) return -2;
+  }
+  CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
+  int rc = prepare_operand_stack(c, A, M, K, rsA, csA, bsA, bsA == 0 ? 1 : batch, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
+  if (rc) return rc;
+  rc = prepare_operand_stack(c, B, N, K, csB, rsB, bsB, bsB == 0 ? 1 : batch, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N,
+                             &mb, &used_ws, s);
+  if (rc) return rc;
+  TcBatchedParams p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
+  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
+  tc_plan<4, true>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, false /* no split-K */, c.sm_count});
+  p.batch = static_cast<int>(batch);
+  p.a_shared = bsA == 0 ? 1 : 0;
+  p.b_shared = bsB == 0 ? 1 : 0;
+  p.bsC = bsC;
+  if (pair) rc = launch_tc_batched<4, float, true>(c, ma, mb, p, s);
+  else rc = launch_tc_batched<4, float, false>(c, ma, mb, p, s);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;

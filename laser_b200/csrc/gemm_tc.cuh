@@ -96,6 +96,14 @@ struct TcParams {
   int64_t split_plane;   // elements between consecutive planes
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
 };
+// gemm_tc_batched_kernel: `batch` problems of one shape per launch; the tensor maps are 3-d, problem b
+// reads matrix b of an operand (matrix 0 if that operand is shared) and writes C + b * bsC.  (A separate
+// struct: the parameter block of the measured single-problem kernel must not change size.)
+struct TcBatchedParams : TcParams {
+  int batch = 1;
+  int a_shared = 0, b_shared = 0;
+  int64_t bsC = 0;
+};
 
 // host side: the part of TcParams that depends only on the problem (p.M, p.N, p.K set by the
 // caller) and on the configuration
@@ -170,6 +178,11 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 
 #define LB200_TC_KERNEL_NAME gemm_tc_kernel
 #define LB200_TC_BATCHED 0
+#include "gemm_tc_kernel.inc"
+#undef LB200_TC_KERNEL_NAME
+#undef LB200_TC_BATCHED
+#define LB200_TC_KERNEL_NAME gemm_tc_batched_kernel
+#define LB200_TC_BATCHED 1
 #include "gemm_tc_kernel.inc"
 #undef LB200_TC_KERNEL_NAME
 #undef LB200_TC_BATCHED

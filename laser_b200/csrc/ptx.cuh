@@ -98,6 +98,16 @@ __device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorM
         "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// 3-D tiled load (box depth 1): the third coordinate selects one matrix of a batch
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src,
                                              int32_t c0, int32_t c1) {
@@ -258,6 +268,15 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUte
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                                 int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 template <uint32_t NCOLS>

@@ -46,8 +46,13 @@ inline cudaError_t cudaFuncSetAttribute(void (*)(KArgs...), cudaFuncAttribute, i
 static CUresult emu_encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuuint32_t rank, void *base, const cuuint64_t *dims,
                                  const cuuint64_t *strides, const cuuint32_t *box, const cuuint32_t *, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
-  if (rank != 2) return CUDA_ERROR_INVALID_VALUE;
+  if (rank != 2 && rank != 3) return CUDA_ERROR_INVALID_VALUE;
   emu::TensorMap2D m;
+  if (rank == 3) {
+    if (box[2] != 1 || (strides[1] & 15) || dims[2] == 0) return CUDA_ERROR_INVALID_VALUE;
+    m.dim2 = static_cast<int64_t>(dims[2]);
+    m.stride2_bytes = static_cast<int64_t>(strides[1]);
+  }
   m.magic = emu::kMapMagic;
   m.base = static_cast<const unsigned char *>(base);
   m.esz = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 2;

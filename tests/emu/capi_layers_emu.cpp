@@ -60,6 +60,7 @@ struct Ctx {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(0x10);
   std::mutex host_mu;
   Buffer stage[3], layer_ws;
+  bool tc_batched = false;   // the tensor-core batch launch is covered by test_emulated_library.py
 };
 Ctx g_ctx;
 int get_ctx(Ctx **out) { *out = &g_ctx; return LASER_B200_OK; }
@@ -105,6 +106,9 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
 }
 // capi.cu: f32_dev -- here every problem takes the exact kernel (the tensor-core paths are
 // covered by test_emulated_tc.py); the path argument is recorded for the dispatch checks
+std::atomic<int> g_f32_mode{LASER_B200_PATH_TF32_BF16C};
+int gemm_tc_batched(Ctx &, int64_t, int64_t, int64_t, int64_t, float, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
+                    int64_t, int64_t, float, float *, int64_t, int64_t, int64_t, int, cudaStream_t) { return -2; }
 int g_last_requested_path = -1;
 int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA, const float *B,
             int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC, int path, void *) {

@@ -35,6 +35,7 @@ struct TensorMap2D {
   int64_t dim0, dim1;        // extents in elements, dim0 innermost
   int64_t stride1_bytes;     // pitch of dim1
   int32_t esz, box0, box1;   // element size, box extents in elements
+  int64_t dim2 = 1, stride2_bytes = 0;   // rank 3: dim2 matrices, stride2 apart (box depth 1)
 };
 constexpr uint64_t kMapMagic = 0x4c42323030544d41ull;
 static_assert(sizeof(TensorMap2D) <= sizeof(CUtensorMap), "fits in the opaque struct");
@@ -130,7 +131,7 @@ inline void prefetch_tensormap(const CUtensorMap *) {}
 inline void prefetch_l2(const void *) {}
 template <int N> inline void setmaxnreg_inc() {}
 template <int N> inline void setmaxnreg_dec() {}
-inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1, long *bytes) {
+inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int32_t c1, long *bytes, int32_t c2 = 0) {
   emu::TensorMap2D m;
   std::memcpy(&m, map, sizeof m);
   if (m.magic != emu::kMapMagic) { std::fprintf(stderr, "emu: not an emulated tensor map\n"); std::abort(); }
@@ -143,6 +144,9 @@ inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int
       std::abort();
     }
   }
+  const bool z_inside = c2 >= 0 && c2 < m.dim2;
+  m.base += static_cast<int64_t>(z_inside ? c2 : 0) * m.stride2_bytes;
+  if (!z_inside) m.dim1 = 0;   // a matrix outside the batch reads as zeros
   for (int r = 0; r < m.box1; ++r)
     for (int e = 0; e < m.box0; ++e) {
       const int64_t i0 = static_cast<int64_t>(c0) + e, i1 = static_cast<int64_t>(c1) + r;
@@ -155,6 +159,12 @@ inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int
 inline void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
   long bytes;
   tma_copy_box(smem_dst, map, c0, c1, &bytes);
+  emu::mb_complete_tx(bar, bytes);
+}
+
+inline void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, int32_t c2) {
+  long bytes;
+  tma_copy_box(smem_dst, map, c0, c1, &bytes, c2);
   emu::mb_complete_tx(bar, bytes);
 }
 
@@ -282,6 +292,11 @@ inline void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *b
 }
 inline void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, uint64_t) {
   tma_load_2d_pair(smem_dst, map, bar, c0, c1);
+}
+inline void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, int32_t c2) {
+  long bytes;
+  tma_copy_box(smem_dst, map, c0, c1, &bytes, c2);
+  emu::mb_complete_tx(emu::peer_ptr(bar, 0), bytes);
 }
 template <uint32_t NCOLS> inline void tmem_alloc_pair(uint32_t *smem_dst) { *smem_dst = 0; }
 template <uint32_t NCOLS> inline void tmem_dealloc_pair(uint32_t) {}

@@ -218,6 +218,41 @@ def tensors():
     print("OK tensors 3")
 
 
+def batched_tc():
+    """LASER_B200_TC_BATCHED=1: a batch of tensor-core problems whose operands stack densely runs as one
+    launch (plus one preparation launch per operand); anything else falls back to one sequence per problem"""
+    n = 0
+    for (batch, M, N, K, share, path, launches) in (
+            (3, 150, 140, 100, "B", L.PATH_AUTO, 3),         # A [b][M][K], B shared
+            (3, 150, 140, 100, "", L.PATH_AUTO, 3),          # both batched
+            (4, 40, 600, 96, "A", L.PATH_AUTO, 3),           # shared filter matrix against a stack of [K][N] (convolution)
+            (2, 300, 260, 72, "B", L.PATH_TF32X3, 3),        # CTA pairs
+            (3, 150, 140, 100, "B", L.PATH_TF32X1, 1),       # no preparation: 3-d maps straight on the caller's memory
+            (3, 20, 400, 27, "A", L.PATH_TF32_BF16C, 3)):    # shared operand of any strides (K = 27: gathered), stacked B
+        nA, nB = (1 if share == "A" else batch), (1 if share == "B" else batch)
+        A = rnd((nA, M, K), 50, -1, 1); B = rnd((nB, K, N), 51, -1, 1); C0 = rnd((batch, M, N), 52, -1, 1)
+        bsA, bsB = (0 if share == "A" else M * K), (0 if share == "B" else K * N)
+        ref = C0.copy()
+        for b in range(batch):
+            O.gemm_strided(M, N, K, 0.5, A[b % nA], K, 1, B[b % nB], N, 1, -1.25, ref[b], N, 1)
+        C = C0.copy()
+        n0 = L.launch_count()
+        L.gemm_strided_batched(batch, M, N, K, 0.5, D(A), K, 1, bsA, D(B), N, 1, bsB, -1.25, D(C), N, 1, M * N, path=path)
+        assert L.launch_count() - n0 == launches, (L.launch_count() - n0, launches, share, path)
+        tol = 3e-3 if path == L.PATH_TF32X1 else 1e-5
+        assert np.abs(C - ref).max() <= tol * np.abs(ref).max(), (batch, M, N, K, share, path)
+        n += 1
+    # a batch stride that is not the dense stack (padding between the matrices): per-problem sequences
+    batch, M, N, K = 2, 150, 140, 100
+    A = rnd((batch, M + 4, K), 53); B = rnd((K, N), 54); C = np.zeros((batch, M, N), np.float32); ref = C.copy()
+    for b in range(batch):
+        O.gemm_strided(M, N, K, 1.0, A[b], K, 1, B, N, 1, 0.0, ref[b], N, 1)
+    n0 = L.launch_count()
+    L.gemm_strided_batched(batch, M, N, K, 1.0, D(A), K, 1, (M + 4) * K, D(B), N, 1, 0, 0.0, D(C), N, 1, M * N)
+    assert L.launch_count() - n0 == 3 * batch and np.abs(C - ref).max() <= 1e-5 * np.abs(ref).max()
+    print("OK batched_tc", n + 1)
+
+
 def lifecycle():
     """init / shutdown / re-init: workspaces, staging buffers and the layer workspace are released and rebuilt"""
     a, b = rnd((300, 200), 40), rnd((200, 260), 41)

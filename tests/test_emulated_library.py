@@ -53,6 +53,11 @@ def test_host_entry_under_configuration(emulated_lib, env):
     run(emulated_lib, "host_entry", **env)
 
 
+def test_batched_tensor_core_launch(emulated_lib):
+    """off by default (not yet measured on a B200): with LASER_B200_TC_BATCHED=1 a stackable batch is one launch"""
+    run(emulated_lib, "batched_tc", LASER_B200_TC_BATCHED=1)
+
+
 def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):
     """the Python mirror must never use the CPU test build as the product library by accident"""
     e = dict(os.environ, LASER_B200_LIB=emulated_lib, PYTHONPATH=ROOT)
