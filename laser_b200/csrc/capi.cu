@@ -94,6 +94,7 @@ struct Ctx {
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
+  int l2_hint = 0;            // env LASER_B200_L2HINT: 0 = the measured kernel (default); 1 A evict_last / B evict_first, 2 the reverse (gemm_tc_hint_kernel, unmeasured)
   bool tc_batched = false;    // env LASER_B200_TC_BATCHED=1: batches of tensor-core problems as one launch (unmeasured)
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
@@ -159,6 +160,7 @@ int get_ctx(Ctx **out) {
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
       if (const char *tb = getenv("LASER_B200_TC_BATCHED")) c.tc_batched = atoi(tb) != 0;
+      if (const char *lh = getenv("LASER_B200_L2HINT")) c.l2_hint = atoi(lh);
       if (const char *pr = getenv("LASER_B200_PANEL_ROWS")) {
         const int64_t v = atoll(pr) / 256 * 256;   // whole CTA-pair tiles
         if (v >= 256) c.panel_rows = v;
@@ -360,10 +362,36 @@ int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams
     }                                                                                            \
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
   } while (0)
-  if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
-  else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
-  else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
-  else LB200_LAUNCH(true, true);
+#define LB200_LAUNCH_HINT(AMN, BMN)                                                              \
+  do {                                                                                           \
+    auto kfn = gemm_tc_hint_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                   \
+    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
+    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
+      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
+    }                                                                                            \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, ph)); \
+  } while (0)
+  bool hinted = false;
+  if constexpr (ESZ == 4) hinted = (c.l2_hint == 1 || c.l2_hint == 2);   // the experiment covers the fp32 kernels only
+  if constexpr (ESZ == 4) if (hinted) {
+    TcHintParams ph;
+    static_cast<TcParams &>(ph) = p;
+    ph.hint_a = c.l2_hint == 1 ? ptx::kEvictLast : ptx::kEvictFirst;
+    ph.hint_b = c.l2_hint == 1 ? ptx::kEvictFirst : ptx::kEvictLast;
+    if (!a_mn && !b_mn) LB200_LAUNCH_HINT(false, false);
+    else if (!a_mn && b_mn) LB200_LAUNCH_HINT(false, true);
+    else if (a_mn && !b_mn) LB200_LAUNCH_HINT(true, false);
+    else LB200_LAUNCH_HINT(true, true);
+  }
+  if (!hinted) {
+    if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
+    else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
+    else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
+    else LB200_LAUNCH(true, true);
+  }
+#undef LB200_LAUNCH_HINT
 #undef LB200_LAUNCH
   COUNT_LAUNCH();
   CHECK_LAUNCH();

@@ -99,6 +99,11 @@ struct TcParams {
 // gemm_tc_batched_kernel: `batch` problems of one shape per launch; the tensor maps are 3-d, problem b
 // reads matrix b of an operand (matrix 0 if that operand is shared) and writes C + b * bsC.  (A separate
 // struct: the parameter block of the measured single-problem kernel must not change size.)
+// gemm_tc_hint_kernel: the single-problem kernel with L2 eviction-priority hints (ptx::kEvict*) on the
+// A / B tile loads
+struct TcHintParams : TcParams {
+  uint64_t hint_a = 0, hint_b = 0;
+};
 struct TcBatchedParams : TcParams {
   int batch = 1;
   int a_shared = 0, b_shared = 0;
@@ -178,12 +183,21 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 
 #define LB200_TC_KERNEL_NAME gemm_tc_kernel
 #define LB200_TC_BATCHED 0
+#define LB200_TC_HINT 0
 #include "gemm_tc_kernel.inc"
 #undef LB200_TC_KERNEL_NAME
+#undef LB200_TC_HINT
+#define LB200_TC_KERNEL_NAME gemm_tc_hint_kernel
+#define LB200_TC_HINT 1
+#include "gemm_tc_kernel.inc"
+#undef LB200_TC_KERNEL_NAME
+#undef LB200_TC_HINT
 #undef LB200_TC_BATCHED
 #define LB200_TC_KERNEL_NAME gemm_tc_batched_kernel
 #define LB200_TC_BATCHED 1
+#define LB200_TC_HINT 0
 #include "gemm_tc_kernel.inc"
+#undef LB200_TC_HINT
 #undef LB200_TC_KERNEL_NAME
 #undef LB200_TC_BATCHED
 

@@ -44,7 +44,7 @@ def test_split_k_planning_and_reduce(emulated_lib):
 
 @pytest.mark.parametrize("env", [dict(LASER_B200_PANEL_ROWS=512), dict(LASER_B200_PANEL_TAPER=1),
                                  dict(LASER_B200_PANEL_ROWS=512, LASER_B200_PANEL_TAPER=1), dict(LASER_B200_CTA_PAIR=0),
-                                 dict(LASER_B200_F32_MODE="tf32x3"),
+                                 dict(LASER_B200_F32_MODE="tf32x3"), dict(LASER_B200_L2HINT=1),
                                  dict(LASER_B200_KC=64, LASER_B200_RASTER=2)],
                          ids=lambda e: ",".join("%s=%s" % (k.replace("LASER_B200_", ""), v) for k, v in e.items()))
 def test_host_entry_under_configuration(emulated_lib, env):

@@ -19,3 +19,5 @@ echo "=== host-pointer entry: panel geometry variants"
 for v in "" "LASER_B200_PANEL_ROWS=512" "LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=512 LASER_B200_PANEL_TAPER=1" "LASER_B200_PANEL_ROWS=2048 LASER_B200_PANEL_TAPER=1"; do env $v timeout 200 python tools/e2e_probe.py 2>> gpurun_out/e2e_probe_err.log | tee -a gpurun_out/e2e_probe.jsonl; done
 echo "=== batched tensor-core launch (first run on a B200)"; LASER_B200_TC_BATCHED=1 timeout 600 python -m pytest tests/test_gpu_zlayers.py -m gpu -q -k "batched or conv2d" 2>&1 | tail -3; LASER_B200_TC_BATCHED=1 timeout 300 python tools/layers_bench.py 2>/dev/null | grep conv2d | sed "s/^/TC_BATCHED /"
 echo "=== ncu full (layer kernels)"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"transpose_batched|im2col_kernel|foreach_strided" -c 8 -o gpurun_out/prof_layers python tools/ncu_layers_target.py > gpurun_out/ncu_layers.log 2>&1; tail -1 gpurun_out/ncu_layers.log
+echo "=== L2 hints / raster (gemm_tc_hint_kernel next to the measured kernel)"
+for v in "" "LASER_B200_L2HINT=1" "LASER_B200_L2HINT=2" "LASER_B200_L2HINT=1 LASER_B200_RASTER=6" "LASER_B200_L2HINT=1 LASER_B200_RASTER=4"; do echo "$v"; env $v timeout 300 python tools/perf_probe.py 2>> gpurun_out/perf_hint_err.log | tail -4 | tee -a gpurun_out/perf_hint.log; done
