@@ -4,7 +4,7 @@ oracle: transposes / NCHW<->NHWC (swapaxes.nim:16-112), im2col convolution
 batched GEMM, copyFrom and forEach on strided views (initialization.nim:80-112, foreach.nim:229-251).
 
 These kernels were written after the round's GPU budget was spent, so their first run on a B200 is the
-round-end run of this file (kept last among the GPU test files for that reason).  Before that they were
+round-end run of this file (which sorts after the validated GPU test files for that reason).  Before that they were
 checked as far as a machine without a GPU allows: the kernel source runs on CPU threads against the
 oracle (tests/test_emulated_kernels.py), the host side of the entry points too
 (tests/test_emulated_layers_host.py), and this very file runs on the CPU against a stand-in library
