@@ -1,4 +1,8 @@
-"""Builds the host-thread emulation harnesses under tests/emu/ (TEST INFRASTRUCTURE, see cuda_emu.h)."""
+"""Builds the host-thread emulation harnesses under tests/emu/ (TEST INFRASTRUCTURE, see cuda_emu.h).
+
+All of them are compiled with -fsanitize=alignment (abort on the first hit): a vector access (float4, the 4-element
+transposition vectors, 16-byte bf16 stores ...) through a pointer that is not aligned to its type is a fault on the GPU
+but silently works on x86, so the emulation would otherwise miss a forgotten alignment guard."""
 import os
 import shutil
 import subprocess
@@ -25,7 +29,7 @@ def build_emu(name, product_headers):
            [os.path.join(CSRC, h) for h in product_headers]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment",
                                "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic"   # stand-ins of CUDA runtime calls must win over a loaded libcudart
                               , srcs[0], "-o", so], env=env)
     return so
@@ -101,7 +105,7 @@ def build_capi_host_emu():
     with open(gen, "w") as f:
         f.write('// GENERATED by tests/emu_build.py from laser_b200/csrc/capi.cu -- do not edit\n#include "capi_host_prelude.h"\n' + src)
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-I", CUDA_INC,
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,
                            "-I", EMU_DIR, "-I", csrc, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic",
                            gen, "-o", so], env=env)
     return so
