@@ -21,7 +21,7 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    if _has_gpu() or os.environ.get("LASER_B200_EMU", "0") == "1":   # EMU: CPU stand-in library, see test_emulated_python_mirror.py
+    if os.environ.get("LASER_B200_EMU", "0") == "1" or _has_gpu():   # EMU: CPU stand-in library, see test_emulated_python_mirror.py
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -78,7 +78,7 @@ def _rewrite_launches(src):
     return "".join(out)
 
 
-def build_capi_host_emu():
+def build_capi_host_emu(asan=False):
     """The whole host side of the library (laser_b200/csrc/capi.cu + capi_layers.inc) compiled for the CPU:
     generated translation unit = tests/emu/capi_host_prelude.h + capi.cu with its kernel launches rewritten."""
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
@@ -88,7 +88,7 @@ def build_capi_host_emu():
         pytest.skip("no g++")
     out_dir = os.path.join(EMU_DIR, "_build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "liblaser_b200_hostemu.so")
+    so = os.path.join(out_dir, "liblaser_b200_hostemu_asan.so" if asan else "liblaser_b200_hostemu.so")
     csrc = os.path.abspath(CSRC)
     deps = [os.path.join(csrc, f) for f in ("capi.cu", "capi_layers.inc", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh",
                                             "ptx.cuh")] + \
@@ -105,7 +105,17 @@ def build_capi_host_emu():
     with open(gen, "w") as f:
         f.write('// GENERATED by tests/emu_build.py from laser_b200/csrc/capi.cu -- do not edit\n#include "capi_host_prelude.h"\n' + src)
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,
+    san = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
+    subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,
                            "-I", EMU_DIR, "-I", csrc, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic",
                            gen, "-o", so], env=env)
     return so
+
+
+def asan_env():
+    """environment of a subprocess that loads an AddressSanitizer build through ctypes"""
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    lib = subprocess.run([gcc, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not lib or not os.path.exists(lib):
+        pytest.skip("libasan not installed")
+    return {"LD_PRELOAD": os.path.realpath(lib), "ASAN_OPTIONS": "detect_leaks=0:abort_on_error=1"}

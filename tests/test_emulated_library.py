@@ -66,3 +66,27 @@ def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):
     assert out.returncode != 0 and "host-emulation TEST build" in out.stderr
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], cwd=ROOT, env=e, capture_output=True, text=True)
     assert out.returncode != 0 and "in-tree CUDA library only" in (out.stderr + out.stdout)
+
+
+ASAN_DEFAULT = ["tensors", "other_types"]
+ASAN_ALL = ["dispatch_and_modes", "strided_operands", "host_entry", "prepacked", "other_types", "fused_and_skinny", "tensors",
+            "lifecycle"]
+
+
+def test_scenarios_under_address_sanitizer():
+    """the emulated library built with -fsanitize=address, loaded under LD_PRELOAD=libasan: any kernel or host
+    code that reads or writes outside a buffer (numpy arrays, library workspaces) aborts -- the CPU analogue of
+    compute-sanitizer memcheck.  Two quick scenarios by default, all of them (and the layer tests) with
+    LASER_B200_EMU_ASAN=1 (about two minutes; clean when last run)."""
+    from emu_build import asan_env
+    lib = build_capi_host_emu(asan=True)
+    full = os.environ.get("LASER_B200_EMU_ASAN", "0") == "1"
+    for sc in (ASAN_ALL if full else ASAN_DEFAULT):
+        run(lib, sc, **asan_env())
+    if full:
+        run(lib, "batched_tc", LASER_B200_TC_BATCHED=1, **asan_env())
+        run(lib, "split_k", LASER_B200_EMU_SMS=32, **asan_env())
+        e = dict(os.environ, LASER_B200_LIB=lib, LASER_B200_EMU="1", PYTHONPATH=ROOT, **asan_env())
+        out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zlayers.py"), "-m", "gpu", "-q",
+                              "-p", "no:cacheprovider"], cwd=ROOT, env=e, capture_output=True, text=True, timeout=2500)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
