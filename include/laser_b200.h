@@ -53,6 +53,10 @@ extern "C" {
 #define LASER_B200_PATH_BF16 4    /* tcgen05 kind::f16 (bf16 inputs, fp32 accumulate)         */
 #define LASER_B200_PATH_TF32_BF16C 5 /* fp32-faithful, mixed: tf32 hi*hi pass + two bf16 passes for the
                                       * hi*lo / lo*hi correction terms (2 tf32-equivalents instead of 3) */
+#define LASER_B200_PATH_BF16X3 6  /* fp32 operands split into two bf16 pieces each (x = h + l, |x - h - l| <= 2^-18 |x|);
+                                   * three kind::f16 passes h*l', l*h', h*h' on the bf16 kernel with fp32 output
+                                   * (1.5 tf32-equivalents per MAC; error <= 3*2^-18 ~ 1.1e-5 per product, random-signed).
+                                   * Opt-in: written after the round's GPU minutes were spent, see DESIGN.md */
 
 /* ---- life cycle -------------------------------------------------------
  * The reference has one piece of import-time state, cpuinfo_initialize()
@@ -77,7 +81,7 @@ int laser_b200_profile_begin(void);
 int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
                            int64_t *prep_launches);
 /* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32_BF16C (default), _TF32X3,
- * _TF32X1 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|simt. */
+ * _TF32X1, _BF16X3 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|bf16x3|simt. */
 int laser_b200_set_f32_mode(int path);
 int laser_b200_get_f32_mode(void);
 

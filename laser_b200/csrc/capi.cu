@@ -172,6 +172,7 @@ int get_ctx(Ctx **out) {
           if (!strcmp(mode, "tf32x3")) m = LASER_B200_PATH_TF32X3;
           if (!strcmp(mode, "tf32x1")) m = LASER_B200_PATH_TF32X1;
           else if (!strcmp(mode, "tf32_bf16c")) m = LASER_B200_PATH_TF32_BF16C;
+          else if (!strcmp(mode, "bf16x3")) m = LASER_B200_PATH_BF16X3;
           else if (!strcmp(mode, "simt")) m = LASER_B200_PATH_SIMT;
         }
         g_f32_mode.store(m);
@@ -330,7 +331,7 @@ struct OperandMaps {
 struct OperandWs {
   Buffer *hi, *lo, *xb, *lb;
 };
-enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2 };
+enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2, SPLIT_BF16X2 = 3 /* fp32 -> two bf16 arrays (xb, lb) */ };
 
 template <int ESZ, typename OutT, bool PAIR>
 int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, cudaStream_t s) {
@@ -448,9 +449,9 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   const int64_t ld_b = round_up(Cc, 8);
   const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
   const size_t bytes_b = static_cast<size_t>(R) * ld_b * 2;
-  if ((rc = ensure(*w.hi, bytes))) return rc;
+  if (mode != SPLIT_BF16X2 && (rc = ensure(*w.hi, bytes))) return rc;
   if (mode == SPLIT_TF32 && (rc = ensure(*w.lo, bytes))) return rc;
-  if (mode == SPLIT_MIXED) {
+  if (mode == SPLIT_MIXED || mode == SPLIT_BF16X2) {
     if ((rc = ensure(*w.xb, bytes_b))) return rc;
     if ((rc = ensure(*w.lb, bytes_b))) return rc;
   }
@@ -464,6 +465,10 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
         split_rows_tf32_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
                                                     static_cast<float *>(w.hi->ptr),
                                                     static_cast<float *>(w.lo->ptr), ld);
+      else if (mode == SPLIT_BF16X2)
+        split_rows_bf16x2_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
+                                                      static_cast<uint16_t *>(w.xb->ptr),
+                                                      static_cast<uint16_t *>(w.lb->ptr), ld_b);
       else
         split_rows_mixed_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
                                                      static_cast<float *>(w.hi->ptr), ld,
@@ -478,7 +483,11 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
     const ET *src = static_cast<const ET *>(o.ptr);
     ET *dhi = static_cast<ET *>(w.hi->ptr);
     if constexpr (ESZ == 4) {
-      if (mode == SPLIT_TF32)
+      if (mode == SPLIT_BF16X2)
+        pack_general_kernel<float, 3><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, nullptr, nullptr, ld,
+                                                           read_along_r, static_cast<uint16_t *>(w.xb->ptr),
+                                                           static_cast<uint16_t *>(w.lb->ptr), ld_b);
+      else if (mode == SPLIT_TF32)
         pack_general_kernel<float, 1><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi,
                                                            static_cast<float *>(w.lo->ptr), ld,
                                                            read_along_r, nullptr, nullptr, 0);
@@ -497,6 +506,13 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   COUNT_LAUNCH();
   CHECK_LAUNCH();
   m->mn_major = (out_mj == MN_MAJOR);
+  if (mode == SPLIT_BF16X2) {
+    // the bf16 kernel's three-pass order reads (hi, lo) = (xb, lb)
+    if ((rc = operand_map(c, &m->hi, 2, w.xb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
+    if ((rc = operand_map(c, &m->lo, 2, w.lb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
+    m->xb = m->lb = m->hi;
+    return LASER_B200_OK;
+  }
   if ((rc = operand_map(c, &m->hi, ESZ, w.hi->ptr, out_mj, o.mn, o.k, ld, block_mn))) return rc;
   m->lo = m->xb = m->lb = m->hi;
   if (mode == SPLIT_TF32) return operand_map(c, &m->lo, ESZ, w.lo->ptr, out_mj, o.mn, o.k, ld, block_mn);
@@ -553,14 +569,16 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
   return prof_close(c, s, &ep, 1);
 }
 
-template <int ESZ, typename OutT>
+// SRC_ESZ: element size of the caller's operands; it differs from the kernel's ESZ only in the
+// BF16X3 mode (fp32 operands split into two bf16 arrays each, multiplied by the bf16 kernel)
+template <int ESZ, typename OutT, int SRC_ESZ = ESZ>
 int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
             int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
             int64_t csC, int npass, cudaStream_t s) {
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
     return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
   std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
-  const SplitMode mode = split_mode(npass);
+  const SplitMode mode = (SRC_ESZ != ESZ) ? SPLIT_BF16X2 : split_mode(npass);
   Operand oa{A, M, K, rsA, csA};
   Operand ob{B, N, K, csB, rsB};
   OperandMaps ma, mb;
@@ -571,11 +589,11 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   const int64_t launches_before = g_launches.load();
   int rc = prof_open(c, s, &ep, 1);
   if (rc) return rc;
-  rc = prepare_operand<ESZ>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
+  rc = prepare_operand<SRC_ESZ>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
   if (rc) return rc;
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
   const bool pair = c.cta_pair && M > TC_BLOCK_M;
-  rc = prepare_operand<ESZ>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
+  rc = prepare_operand<SRC_ESZ>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
@@ -867,6 +885,12 @@ const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_c
       if (rc) return rc;
       g_last_path = path;
       break;
+    case LASER_B200_PATH_BF16X3:
+      // two bf16 pieces per fp32 operand, three passes (h*l', l*h', h*h') of the bf16 kernel, fp32 output
+      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s);
+      if (rc) return rc;
+      g_last_path = path;
+      break;
     default:
       return set_error(LASER_B200_EINVAL, "unknown path %d for float32", path);
   }
@@ -944,7 +968,9 @@ inline bool panel_separable(int64_t rows, int64_t cols, int64_t rs, int64_t cs) 
 
 int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                             int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
-                            float beta, float *C, int64_t rsC, int64_t csC, int npass) {
+                            float beta, float *C, int64_t rsC, int64_t csC, int path) {
+  const bool bf16x3 = (path == LASER_B200_PATH_BF16X3);
+  const int npass = (path == LASER_B200_PATH_TF32X3 || bf16x3) ? 3 : (path == LASER_B200_PATH_TF32_BF16C ? 2 : 1);
   std::lock_guard<std::mutex> host_lk(c.host_mu);
   std::lock_guard<std::mutex> lk(c.mu);
   int rc;
@@ -982,7 +1008,7 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
       CUDA_TRY(cudaEventCreateWithFlags(&c.panel_ev[i], cudaEventDisableTiming));
   }
   cudaStream_t up = c.up, cmp = c.stream, down = c.down;
-  const SplitMode mode = split_mode(npass);
+  const SplitMode mode = bf16x3 ? SPLIT_BF16X2 : split_mode(npass);
   const bool pair = c.cta_pair && panel_rows > TC_BLOCK_M && M > TC_BLOCK_M;
   // staging buffers / workspace may still be in use by an earlier call
   CUDA_TRY(cudaStreamWaitEvent(up, c.ws_free, 0));
@@ -1015,8 +1041,9 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     if ((rc = prepare_operand<4>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, cmp))) return rc;
     // B's tensor maps were built for `pair` (128- vs 256-column boxes): every panel, however
     // short, must run the same kernel variant
-    if ((rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp)))
-      return rc;
+    if (bf16x3) rc = tc_run<2, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
+    else rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
+    if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));
     CUDA_TRY(cudaStreamWaitEvent(down, c.panel_ev[panels + pnl], 0));
     CUDA_TRY(cudaMemcpyAsync(Cp + pc.lo, dC + m0 * rsC + pc.lo, static_cast<size_t>(pc.hi - pc.lo + 1) * 4,
@@ -1025,7 +1052,7 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
   CUDA_TRY(cudaEventRecord(c.ws_free, cmp));
   CUDA_TRY(cudaStreamSynchronize(down));
   CUDA_TRY(cudaStreamSynchronize(cmp));
-  g_last_path = (npass == 3) ? LASER_B200_PATH_TF32X3 : (npass == 2 ? LASER_B200_PATH_TF32_BF16C : LASER_B200_PATH_TF32X1);
+  g_last_path = path;
   return LASER_B200_OK;
 }
 
@@ -1142,8 +1169,8 @@ int64_t laser_b200_launch_count(void) { return g_launches.load(); }
 int laser_b200_last_path(void) { return g_last_path; }
 int laser_b200_set_f32_mode(int path) {
   if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3 &&
-      path != LASER_B200_PATH_TF32_BF16C)
-    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3 or TF32_BF16C");
+      path != LASER_B200_PATH_TF32_BF16C && path != LASER_B200_PATH_BF16X3)
+    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3, TF32_BF16C or BF16X3");
   g_f32_mode.store(path);
   return LASER_B200_OK;
 }
@@ -1210,11 +1237,11 @@ int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, co
     int rc = get_ctx(&c);
     if (rc) return rc;
     const int mode = g_f32_mode.load();
-    const int npass = mode == LASER_B200_PATH_TF32X3 ? 3 : mode == LASER_B200_PATH_TF32_BF16C ? 2
-                      : mode == LASER_B200_PATH_TF32X1 ? 1 : 0;
-    if (npass && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
+    const bool tc_mode = mode == LASER_B200_PATH_TF32X3 || mode == LASER_B200_PATH_TF32_BF16C ||
+                         mode == LASER_B200_PATH_TF32X1 || mode == LASER_B200_PATH_BF16X3;
+    if (tc_mode && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
         span_of(c->panel_rows, N, rsC, csC).dense && rsA > 0 && rsC > 0)
-      return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, npass);
+      return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, mode);
   }
   return host_gemm<float>(M, N, K, A, rsA, csA, B, rsB, csB, beta == 0.0f, C, rsC, csC,
                           [&](const float *a, const float *b, float *c, void *s) {

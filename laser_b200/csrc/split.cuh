@@ -107,10 +107,47 @@ split_rows_mixed_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
   }
 }
 
+// Two-piece bf16 split (LASER_B200_PATH_BF16X3): hb = bf16(x), lb = bf16(x - hb) (the difference is exact
+// in fp32), so x = hb + lb + r with |r| <= 2^-18 |x|.  The three kind::f16 passes hb*lb', lb*hb', hb*hb' then
+// miss only lb*lb' and the r terms: <= 3 * 2^-18 of each product.  Same addressing as split_rows_tf32_kernel;
+// reads 4 bytes and writes 4 bytes per element (the mixed split writes 8).
+__global__ void __launch_bounds__(256)
+split_rows_bf16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
+                         uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b) {
+  const int64_t vec_per_row = (Cc + 3) >> 2;
+  const int64_t total = R * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int64_t c = (i - r * vec_per_row) << 2;
+    const float *s = src + r * src_ld + c;
+    float4 v;
+    if (c + 4 <= Cc) {
+      v = *reinterpret_cast<const float4 *>(s);
+    } else {
+      v.x = s[0];
+      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
+      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
+      v.w = 0.0f;
+    }
+    const uint16_t hx = bf16_rn_bits(v.x), hy = bf16_rn_bits(v.y), hz = bf16_rn_bits(v.z), hw = bf16_rn_bits(v.w);
+    uint2 h, l;
+    h.x = hx | (static_cast<uint32_t>(hy) << 16);
+    h.y = hz | (static_cast<uint32_t>(hw) << 16);
+    l.x = bf16_rn_bits(v.x - __uint_as_float(static_cast<uint32_t>(hx) << 16)) |
+          (static_cast<uint32_t>(bf16_rn_bits(v.y - __uint_as_float(static_cast<uint32_t>(hy) << 16))) << 16);
+    l.y = bf16_rn_bits(v.z - __uint_as_float(static_cast<uint32_t>(hz) << 16)) |
+          (static_cast<uint32_t>(bf16_rn_bits(v.w - __uint_as_float(static_cast<uint32_t>(hw) << 16))) << 16);
+    *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
+    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
+  }
+}
+
 // dst[r*ld + c] = src[r*sr + c*sc] for r < R, c < Cc.  32 x 32 tiles through shared
 // memory so that both the gather (along whichever source stride is smaller) and the
 // store (along c) are coalesced.  SPLIT: also write lo (fp32 only).
-// MODE 0: plain copy; 1: fp32 hi/lo (dst, dst_lo); 2: mixed (dst = hi fp32, xb/lb = bf16 arrays).
+// MODE 0: plain copy; 1: fp32 hi/lo (dst, dst_lo); 2: mixed (dst = hi fp32, xb/lb = bf16 arrays);
+// 3: two bf16 pieces (xb = bf16(x), lb = bf16(x - xb); dst unused).
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr, int64_t sc,
@@ -150,6 +187,10 @@ pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr
           dst[r * ld + c] = h;
           xb[r * ld_b + c] = bf16_rn_bits(v);
           lb[r * ld_b + c] = bf16_rn_bits(v - h);
+        } else if constexpr (MODE == 3) {
+          const uint16_t hbits = bf16_rn_bits(v);
+          xb[r * ld_b + c] = hbits;
+          lb[r * ld_b + c] = bf16_rn_bits(v - __uint_as_float(static_cast<uint32_t>(hbits) << 16));
         } else {
           dst[r * ld + c] = v;
         }

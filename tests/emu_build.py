@@ -22,14 +22,16 @@ def build_emu(name, product_headers):
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     if not gxx:
         pytest.skip("no g++")
-    out_dir = os.path.join(EMU_DIR, "_build")
+    tsan = os.environ.get("LASER_B200_EMU_TSAN", "0") == "1"   # ThreadSanitizer variant (run pytest under LD_PRELOAD=libtsan)
+    out_dir = os.path.join(EMU_DIR, "_build", "tsan") if tsan else os.path.join(EMU_DIR, "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "lib%s.so" % name)
     srcs = [os.path.join(EMU_DIR, name + ".cpp"), os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "ptx_emu.h")] + \
            [os.path.join(CSRC, h) for h in product_headers]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment",
+        san = ["-O1", "-g", "-fsanitize=thread"] if tsan else ["-O2", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
+        subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
                                "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic"   # stand-ins of CUDA runtime calls must win over a loaded libcudart
                               , srcs[0], "-o", so], env=env)
     return so

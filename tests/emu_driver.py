@@ -253,6 +253,55 @@ def batched_tc():
     print("OK batched_tc", n + 1)
 
 
+def bf16x3():
+    """opt-in fp32 mode: two bf16 pieces per operand, three passes of the bf16 tensor-core kernel with fp32 output.
+    Error model: <= 3 * 2^-18 of sum |a||b| from the dropped l*l' and remainder terms (plus fp32 accumulation)."""
+    n = 0
+    # (a) contiguous, sizes around the tile / accumulation-block boundaries, both scalings, both distributions
+    for (M, N, K) in ((200, 300, 150), (130, 40, 70), (257, 260, 129), (300, 9, 333)):
+        for lo, hi in ((0.0, 1.0), (-0.1, 0.1)):
+            a, b, c0 = rnd((M, K), 41, lo, hi), rnd((K, N), 42, lo, hi), rnd((M, N), 43, lo, hi)
+            for alpha, beta in ((1.0, 0.0), (0.5, -1.25)):
+                c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
+                L.gemm_strided(M, N, K, alpha, D(a), K, 1, D(b), N, 1, beta, D(c), N, 1, path=L.PATH_BF16X3)
+                assert L.last_path() == L.PATH_BF16X3
+                exact = alpha * (a.astype(np.float64) @ b.astype(np.float64)) + beta * c0.astype(np.float64)
+                bound = abs(alpha) * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) * (3 * 2.0 ** -18 + 2e-6) \
+                    + np.abs(exact) * 2e-6 + 1e-30
+                assert (np.abs(c - exact) <= bound).all(), (float((np.abs(c - exact) / bound).max()), M, N, K, alpha, beta)
+                if lo == 0.0:   # positive data: the north-star gate, max elementwise relative error vs the reference
+                    ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
+                    if beta == 0.0:
+                        assert (np.abs(c - ref) / np.abs(ref)).max() < 1e-5, (M, N, K)
+                n += 1
+    # (b) every operand class (K-major / MN-major split kernel, gathered general strides) and C of any strides
+    M, N, K = 150, 140, 100
+    a, b, c0 = rnd((M, K), 44), rnd((K, N), 45), rnd((M, N), 46)
+    L.set_f32_mode(L.PATH_BF16X3)
+    assert L.get_f32_mode() == L.PATH_BF16X3
+    for la, lb, lc in [(x, "row", "row") for x in LAYOUTS] + [("row", x, "row") for x in LAYOUTS] + [("col", "col", x) for x in LAYOUTS]:
+        A, oa, rsa, csa = embed(a, la); B, ob, rsb, csb = embed(b, lb); C, oc, rsc, csc = embed(c0, lc)
+        Cref = C.copy()
+        O.gemm_strided(M, N, K, 1.0, A[oa:], rsa, csa, B[ob:], rsb, csb, 2.0, Cref[oc:], rsc, csc)
+        L.gemm_strided(M, N, K, 1.0, D(A, oa), rsa, csa, D(B, ob), rsb, csb, 2.0, D(C, oc), rsc, csc)   # AUTO -> the selected mode
+        assert L.last_path() == L.PATH_BF16X3
+        idx = oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc
+        assert np.abs(C[idx] - Cref[idx]).max() <= 1.5e-5 * np.abs(Cref[idx]).max(), (la, lb, lc)
+        mask = np.ones(C.size, bool); mask[idx.reshape(-1)] = False
+        assert np.array_equal(C[mask], Cref[mask]), (la, lb, lc)
+        n += 1
+    # (c) host-pointer entry in this mode (staged path), and back to the default
+    M, N, K = 2100, 24, 72
+    a, b = rnd((M, K), 47), rnd((K, N), 48)
+    c = np.full((M, N), np.nan, np.float32)
+    L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1)
+    ref = ref_gemm(M, N, K, 1.0, a, b, 0.0, c)
+    assert (np.abs(c - ref) / np.abs(ref)).max() < 1e-5
+    L.set_f32_mode(L.PATH_TF32_BF16C)
+    n += 1
+    print("OK bf16x3", n)
+
+
 def lifecycle():
     """init / shutdown / re-init: workspaces, staging buffers and the layer workspace are released and rebuilt"""
     a, b = rnd((300, 200), 40), rnd((200, 260), 41)

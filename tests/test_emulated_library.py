@@ -58,6 +58,15 @@ def test_batched_tensor_core_launch(emulated_lib):
     run(emulated_lib, "batched_tc", LASER_B200_TC_BATCHED=1)
 
 
+def test_bf16x3_mode(emulated_lib):
+    """opt-in fp32 mode (not yet measured on a B200): fp32 operands split into two bf16 arrays, three passes of the
+    bf16 tensor-core kernel, fp32 output; also selected through the environment, and with a 32-SM machine so that
+    split-K takes part"""
+    run(emulated_lib, "bf16x3")
+    run(emulated_lib, "host_entry", LASER_B200_F32_MODE="bf16x3")
+    run(emulated_lib, "bf16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
+
+
 def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):
     """the Python mirror must never use the CPU test build as the product library by accident"""
     e = dict(os.environ, LASER_B200_LIB=emulated_lib, PYTHONPATH=ROOT)

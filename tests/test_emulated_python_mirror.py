@@ -52,6 +52,11 @@ def test_parity_file_subset_against_the_host_emulated_library():
     assert _run_gpu_files(["test_gpu_parity.py"], ["-k", FAST], 1500) >= 50
 
 
+def test_bf16x3_file_against_the_host_emulated_library():
+    """tests/test_gpu_zy_bf16x3.py (the opt-in two-piece bf16 mode) in full, minus the sizes skipped for the CPU build"""
+    assert _run_gpu_files(["test_gpu_zy_bf16x3.py"], [], 1500) >= 40
+
+
 @pytest.mark.skipif(os.environ.get("LASER_B200_EMU_FULL", "0") != "1", reason="about 18 minutes; set LASER_B200_EMU_FULL=1")
 def test_whole_parity_and_fuzz_files_against_the_host_emulated_library():
     assert _run_gpu_files(["test_gpu_parity.py", "test_gpu_fuzz.py", "test_gpu_prepacked.py", "test_gpu_fused_epilogue.py"], [],
