@@ -19,11 +19,16 @@ void emu_split_rows_mixed(const float *src, int64_t R, int64_t Cc, int64_t src_l
                           uint16_t *xb, uint16_t *lb, int64_t ld_b, int grid) {
   emu::launch(grid, 256, [=]() { split_rows_mixed_kernel(src, R, Cc, src_ld, hi, dst_ld, xb, lb, ld_b); });
 }
-// mode 0: copy, 1: tf32 hi/lo, 2: mixed (hi fp32 + xb/lb bf16)
+void emu_split_rows_bf16x2(const float *src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *hb, uint16_t *lb, int64_t ld_b,
+                           int grid) {
+  emu::launch(grid, 256, [=]() { split_rows_bf16x2_kernel(src, R, Cc, src_ld, hb, lb, ld_b); });
+}
+// mode 0: copy, 1: tf32 hi/lo, 2: mixed (hi fp32 + xb/lb bf16), 3: two bf16 pieces (xb, lb)
 void emu_pack_general_f32(int mode, const float *src, int64_t R, int64_t Cc, int64_t sr, int64_t sc, float *dst,
                           float *dst_lo, int64_t ld, int read_along_r, uint16_t *xb, uint16_t *lb, int64_t ld_b, int grid) {
   if (mode == 0) emu::launch(grid, 256, [=]() { pack_general_kernel<float, 0>(src, R, Cc, sr, sc, dst, dst_lo, ld, read_along_r, xb, lb, ld_b); });
   else if (mode == 1) emu::launch(grid, 256, [=]() { pack_general_kernel<float, 1>(src, R, Cc, sr, sc, dst, dst_lo, ld, read_along_r, xb, lb, ld_b); });
+  else if (mode == 3) emu::launch(grid, 256, [=]() { pack_general_kernel<float, 3>(src, R, Cc, sr, sc, dst, dst_lo, ld, read_along_r, xb, lb, ld_b); });
   else emu::launch(grid, 256, [=]() { pack_general_kernel<float, 2>(src, R, Cc, sr, sc, dst, dst_lo, ld, read_along_r, xb, lb, ld_b); });
 }
 void emu_pack_general_u16(const uint16_t *src, int64_t R, int64_t Cc, int64_t sr, int64_t sc, uint16_t *dst, int64_t ld,

@@ -9,7 +9,7 @@ import pytest
 
 import oracle as O
 from emu_build import build_emu
-from util import f32_to_bf16_bits
+from util import bf16_bits_to_f32, f32_to_bf16_bits
 
 i64, vp, ci, f32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 
@@ -19,11 +19,12 @@ def emu():
     L = ctypes.CDLL(build_emu("split_emu", ["split.cuh"]))
     L.emu_split_rows_tf32.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
     L.emu_split_rows_mixed.argtypes = [vp, i64, i64, i64, vp, i64, vp, vp, i64, ci]
+    L.emu_split_rows_bf16x2.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
     L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, vp, vp, i64, ci]
     L.emu_pack_general_u16.argtypes = [vp, i64, i64, i64, i64, vp, i64, ci, ci]
     L.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.emu_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, ci]
-    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_pack_general_f32", "emu_pack_general_u16",
+    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_split_rows_bf16x2", "emu_pack_general_f32", "emu_pack_general_u16",
               "emu_splitk_reduce", "emu_fill_uniform_f32"):
         getattr(L, n).restype = None
     return L
@@ -63,6 +64,15 @@ def test_split_rows(emu, R, Cc, src_ld):
     assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
     assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - h).reshape(R, Cc))
     assert np.all(hi2[:, Cc:] == 0) and np.all(xb[:, Cc:ld] == 0) and np.all(lb[:, Cc:ld] == 0)
+    # two bf16 pieces (LASER_B200_PATH_BF16X3): h = bf16(x), l = bf16(x - h), remainder <= 2^-18 |x|
+    hb = np.full((R, ldb), 9, np.uint16); lb2 = np.full((R, ldb), 9, np.uint16)
+    emu.emu_split_rows_bf16x2(p(src), R, Cc, src_ld, p(hb), p(lb2), ldb, 3)
+    hbf = bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(R, Cc)
+    assert np.array_equal(hb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
+    assert np.array_equal(lb2[:, :Cc], f32_to_bf16_bits(x - hbf).reshape(R, Cc))
+    assert np.all(hb[:, Cc:ld] == 0) and np.all(lb2[:, Cc:ld] == 0)
+    rec = hbf.astype(np.float64) + bf16_bits_to_f32(lb2[:, :Cc].reshape(-1)).reshape(R, Cc)
+    assert (np.abs(rec - x) <= 2.0 ** -18 * np.abs(x)).all()
 
 
 @pytest.mark.parametrize("R,Cc,sr,sc,along_r", [
@@ -73,7 +83,7 @@ def test_split_rows(emu, R, Cc, src_ld):
     (20, 31, 31, -1, 0),      # columns right-to-left
     (70, 3, 2, 140, 1),
 ])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_pack_general(emu, R, Cc, sr, sc, along_r, mode):
     lo_off = min(0, (R - 1) * sr) + min(0, (Cc - 1) * sc)
     hi_off = max(0, (R - 1) * sr) + max(0, (Cc - 1) * sc)
@@ -90,6 +100,11 @@ def test_pack_general(emu, R, Cc, sr, sc, along_r, mode):
         assert np.array_equal(dst[:, :Cc], x)
     elif mode == 1:
         assert np.array_equal(dst[:, :Cc], h) and np.array_equal(dlo[:, :Cc], tf32_rna(x - h))
+    elif mode == 3:
+        hb = bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(R, Cc)
+        assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
+        assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - hb).reshape(R, Cc))
+        assert np.all(dst == 7)          # the fp32 array is not used by this mode
     else:
         assert np.array_equal(dst[:, :Cc], h)
         assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
