@@ -108,8 +108,9 @@ split_rows_mixed_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
 }
 
 // Two-piece bf16 split (LASER_B200_PATH_BF16X3): hb = bf16(x), lb = bf16(x - hb) (the difference is exact
-// in fp32), so x = hb + lb + r with |r| <= 2^-18 |x|.  The three kind::f16 passes hb*lb', lb*hb', hb*hb' then
-// miss only lb*lb' and the r terms: <= 3 * 2^-18 of each product.  Same addressing as split_rows_tf32_kernel;
+// in fp32), so x = hb + lb + r with |r| <= 2^-16 |x| (bf16 keeps 8 significant bits: each rounding is <= 2^-8 relative).  The three kind::f16 passes hb*lb', lb*hb', hb*hb' then
+// miss only lb*lb' and the r terms: <= 3 * 2^-16 ~ 4.6e-5 of each product in the worst case, random-signed
+// (measured over K = 8192 random products: 3e-7 of sum |a||b|).  Same addressing as split_rows_tf32_kernel;
 // reads 4 bytes and writes 4 bytes per element (the mixed split writes 8).
 __global__ void __launch_bounds__(256)
 split_rows_bf16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,

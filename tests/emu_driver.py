@@ -255,7 +255,8 @@ def batched_tc():
 
 def bf16x3():
     """opt-in fp32 mode: two bf16 pieces per operand, three passes of the bf16 tensor-core kernel with fp32 output.
-    Error model: <= 3 * 2^-18 of sum |a||b| from the dropped l*l' and remainder terms (plus fp32 accumulation)."""
+    Worst case 3 * 2^-16 of sum |a||b| from the dropped l*l' and remainder terms; the errors are random-signed, so on these
+    (fixed, seeded) inputs a four times tighter bar holds with margin and catches a wrong pass order or a lost piece."""
     n = 0
     # (a) contiguous, sizes around the tile / accumulation-block boundaries, both scalings, both distributions
     for (M, N, K) in ((200, 300, 150), (130, 40, 70), (257, 260, 129), (300, 9, 333)):
