@@ -15,8 +15,8 @@ One JSON line on stdout (rank 0).  Extra keys beyond the driver's contract:
   roofline      dominant kernel (gemm_tc_kernel) against the tensor roofline
   cpu_baseline  the reference CPU path (C restatement, oracle/) timed on this box's cores
   modes         device-resident TFLOP/s of the opt-in 1xTF32 fast mode and of bf16; at N=1 also
-                "bf16x3_experimental": the opt-in two-piece bf16 mode, timed and error-checked by a child
-                process after everything else (tools/bf16x3_probe.py)
+                "bf16x3_experimental" / "f16x3_experimental": the opt-in two-piece modes, timed and
+                error-checked by a child process each after everything else (tools/two_piece_probe.py)
 """
 import argparse
 import json
@@ -334,7 +334,8 @@ def run_ours(args):
         if cpu:
             cpu.pop("ms"); cpu.pop("n")
         if world == 1:
-            modes["bf16x3_experimental"] = experimental_mode_probe(MNK)
+            for mode_name in ("bf16x3", "f16x3"):
+                modes[mode_name + "_experimental"] = experimental_mode_probe(mode_name, MNK)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -354,19 +355,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def experimental_mode_probe(n):
-    """Informational, N=1 only, AFTER every measurement of this run: time and error of the opt-in fp32 mode
-    LASER_B200_PATH_BF16X3 (two bf16 pieces per operand, three passes of the bf16 kernel).
-    It was written after the round's GPU minutes were spent, so it runs in a child process with a timeout
-    (tools/bf16x3_probe.py): whatever its first run on silicon does, the line above is already measured."""
+def experimental_mode_probe(mode_name, n):
+    """Informational, N=1 only, AFTER every measurement of this run: time and error of an opt-in fp32 mode
+    (LASER_B200_PATH_BF16X3 / _F16X3: two 16-bit pieces per operand, three passes of the 16-bit kernel; DESIGN.md
+    section 2).  They were written after the round's GPU minutes were spent, so each runs in a child process with a
+    timeout (tools/two_piece_probe.py): whatever its first run on silicon does, the line above is already measured."""
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bf16x3_probe.py"), str(n), "10"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "two_piece_probe.py"), mode_name, str(n), "10"],
                            capture_output=True, text=True, timeout=300, cwd=ROOT)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode == 0 and lines:
             res = json.loads(lines[-1])
-            res["note"] = ("opt-in mode, first measured by this run; error bars: max-elementwise < 1e-4 on U(0,1), normwise < 1.5e-5 on "
-                           "U(-0.1,0.1); does not claim the reference's mean_relative_error <= 1e-5 gate (the default mode does)")
+            res["note"] = ("opt-in mode, first measured by this run; " +
+                           ("error bars: max-elementwise < 1e-4 on U(0,1), normwise < 1.5e-5 on U(-0.1,0.1); does not claim the "
+                            "reference's mean_relative_error <= 1e-5 gate (the default mode does)" if mode_name == "bf16x3" else
+                            "error bars of the fp32-faithful modes (max-elementwise < 1e-4 on U(0,1), normwise < 2e-6 and "
+                            "mean_relative_error <= 1e-5 on U(-0.1,0.1)) for matrices whose entries lie within 2^-17 of their maximum"))
             return res
         return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
     except subprocess.TimeoutExpired:

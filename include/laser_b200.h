@@ -57,6 +57,11 @@ extern "C" {
                                    * three kind::f16 passes h*l', l*h', h*h' on the bf16 kernel with fp32 output
                                    * (1.5 tf32-equivalents per MAC; error <= 3*2^-16 ~ 4.6e-5 per product worst case, random-signed: ~3e-7 of sum|a||b| at K = 8192).
                                    * Opt-in: written after the round's GPU minutes were spent, see DESIGN.md */
+#define LASER_B200_PATH_F16X3 7   /* fp32 operands scaled by a power of two (device-side abs-max of each matrix, no host
+                                   * synchronisation) and split into two FP16 pieces (11 + 11 bits); three kind::f16 passes; the
+                                   * epilogue undoes the scales.  3 instruction times per k-step like BF16X3, accuracy of TF32X3
+                                   * (<= 3*2^-22 per product) for matrices whose entries lie within 2^-17 of their maximum; smaller
+                                   * entries keep absolute precision 2^-39 of the maximum.  Opt-in, unmeasured: see DESIGN.md */
 
 /* ---- life cycle -------------------------------------------------------
  * The reference has one piece of import-time state, cpuinfo_initialize()
@@ -81,7 +86,7 @@ int laser_b200_profile_begin(void);
 int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
                            int64_t *prep_launches);
 /* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32_BF16C (default), _TF32X3,
- * _TF32X1, _BF16X3 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|bf16x3|simt. */
+ * _TF32X1, _BF16X3, _F16X3 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|bf16x3|f16x3|simt. */
 int laser_b200_set_f32_mode(int path);
 int laser_b200_get_f32_mode(void);
 

@@ -8,7 +8,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblaser_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh", "capi_layers.inc",
+HEADERS = ["ptx.cuh", "f16_scale.cuh", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh", "capi_layers.inc",
            "../../include/laser_b200.h"]
 
 NVCC_FLAGS = [

@@ -111,6 +111,7 @@ struct Ctx {
   Buffer stage[3];   // device staging of host A, B, C spans
   Buffer splitk;     // split-K partial-sum planes
   Buffer layer_ws;   // im2col workspace of the host-pointer convolution
+  Buffer f16s;       // F16X3 mode: fp32 bits of max |a| (word 0) and max |b| (word 1), written and read on the device
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
@@ -173,6 +174,7 @@ int get_ctx(Ctx **out) {
           if (!strcmp(mode, "tf32x1")) m = LASER_B200_PATH_TF32X1;
           else if (!strcmp(mode, "tf32_bf16c")) m = LASER_B200_PATH_TF32_BF16C;
           else if (!strcmp(mode, "bf16x3")) m = LASER_B200_PATH_BF16X3;
+          else if (!strcmp(mode, "f16x3")) m = LASER_B200_PATH_F16X3;
           else if (!strcmp(mode, "simt")) m = LASER_B200_PATH_SIMT;
         }
         g_f32_mode.store(m);
@@ -330,8 +332,10 @@ struct OperandMaps {
 };
 struct OperandWs {
   Buffer *hi, *lo, *xb, *lb;
+  int which;   // 0 = A, 1 = B (index of the operand's abs-max word in Ctx::f16s)
 };
-enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2, SPLIT_BF16X2 = 3 /* fp32 -> two bf16 arrays (xb, lb) */ };
+enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2, SPLIT_BF16X2 = 3 /* fp32 -> two bf16 arrays (xb, lb) */,
+                 SPLIT_F16X2 = 4 /* fp32 -> abs-max word + two fp16 arrays of the scaled operand (xb, lb) */ };
 
 template <int ESZ, typename OutT, bool PAIR>
 int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, cudaStream_t s) {
@@ -399,6 +403,49 @@ int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams
   return LASER_B200_OK;
 }
 
+// gemm_tc_f16_kernel (LASER_B200_PATH_F16X3): same grid / cluster / shared-memory configuration as launch_tc
+template <bool PAIR>
+int launch_tc_f16(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, const uint32_t *absmax, cudaStream_t s) {
+  const bool a_mn = A.mn_major, b_mn = B.mn_major;
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;
+  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
+  const int sched = static_cast<int>(tiles < units ? tiles : units);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TcF16Params pf;
+  static_cast<TcParams &>(pf) = p;
+  pf.absmax = absmax;
+#define LB200_LAUNCH_F16(AMN, BMN)                                                               \
+  do {                                                                                           \
+    auto kfn = gemm_tc_f16_kernel<2, AMN, BMN, float, PAIR>;                                     \
+    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
+    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
+      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
+    }                                                                                            \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, pf)); \
+  } while (0)
+  if (!a_mn && !b_mn) LB200_LAUNCH_F16(false, false);
+  else if (!a_mn && b_mn) LB200_LAUNCH_F16(false, true);
+  else if (a_mn && !b_mn) LB200_LAUNCH_F16(true, false);
+  else LB200_LAUNCH_F16(true, true);
+#undef LB200_LAUNCH_F16
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+
 // ---- batch of problems in one launch (gemm_tc_batched_kernel): 3-d tensor maps, box depth 1 ----
 int encode_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer, int64_t nb,
                 int64_t outer_stride_elems, int64_t batch_stride_elems, int box_inner, int box_outer,
@@ -425,6 +472,19 @@ int operand_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, bool mn_ma
                      esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// F16X3 mode: abs-max word of a compact / row-contiguous fp32 operand, then its two fp16 pieces (f16_scale.cuh)
+int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_ld, const OperandWs &w, int64_t ld_b,
+                  int grid, cudaStream_t s) {
+  uint32_t *word = static_cast<uint32_t *>(c.f16s.ptr) + w.which;
+  CUDA_TRY(cudaMemsetAsync(word, 0, sizeof(uint32_t), s));
+  absmax_rows_kernel<<<grid, 256, 0, s>>>(src, R, Cc, src_ld, word);
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  split_rows_f16x2_kernel<<<grid, 256, 0, s>>>(src, R, Cc, src_ld, static_cast<uint16_t *>(w.xb->ptr),
+                                               static_cast<uint16_t *>(w.lb->ptr), ld_b, word);
+  return LASER_B200_OK;   // the caller counts and checks this last launch
+}
+
 template <int ESZ>
 int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w, int block_mn,
                     OperandMaps *m, bool *used_ws, cudaStream_t s) {
@@ -449,9 +509,10 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   const int64_t ld_b = round_up(Cc, 8);
   const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
   const size_t bytes_b = static_cast<size_t>(R) * ld_b * 2;
-  if (mode != SPLIT_BF16X2 && (rc = ensure(*w.hi, bytes))) return rc;
+  if (mode != SPLIT_BF16X2 && !(mode == SPLIT_F16X2 && mj != GENERAL) && (rc = ensure(*w.hi, bytes))) return rc;
   if (mode == SPLIT_TF32 && (rc = ensure(*w.lo, bytes))) return rc;
-  if (mode == SPLIT_MIXED || mode == SPLIT_BF16X2) {
+  if (mode == SPLIT_F16X2 && (rc = ensure(c.f16s, 256))) return rc;
+  if (mode == SPLIT_MIXED || mode == SPLIT_BF16X2 || mode == SPLIT_F16X2) {
     if ((rc = ensure(*w.xb, bytes_b))) return rc;
     if ((rc = ensure(*w.lb, bytes_b))) return rc;
   }
@@ -461,7 +522,9 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
       const int64_t src_ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
       const int64_t items = R * ((Cc + 3) / 4);
       const int grid = grid_for(c, (items + 255) / 256, 8);
-      if (mode == SPLIT_TF32)
+      if (mode == SPLIT_F16X2) {
+        if ((rc = f16x2_prepare(c, static_cast<const float *>(o.ptr), R, Cc, src_ld, w, ld_b, grid, s))) return rc;
+      } else if (mode == SPLIT_TF32)
         split_rows_tf32_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
                                                     static_cast<float *>(w.hi->ptr),
                                                     static_cast<float *>(w.lo->ptr), ld);
@@ -483,7 +546,15 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
     const ET *src = static_cast<const ET *>(o.ptr);
     ET *dhi = static_cast<ET *>(w.hi->ptr);
     if constexpr (ESZ == 4) {
-      if (mode == SPLIT_BF16X2)
+      if (mode == SPLIT_F16X2) {
+        // gather into the compact fp32 array first, then scale + split that (two more passes, general operands only)
+        pack_general_kernel<float, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
+                                                           read_along_r, nullptr, nullptr, 0);
+        COUNT_LAUNCH();
+        CHECK_LAUNCH();
+        const int g2 = grid_for(c, (R * ((Cc + 3) / 4) + 255) / 256, 8);
+        if ((rc = f16x2_prepare(c, dhi, R, Cc, ld, w, ld_b, g2, s))) return rc;
+      } else if (mode == SPLIT_BF16X2)
         pack_general_kernel<float, 3><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, nullptr, nullptr, ld,
                                                            read_along_r, static_cast<uint16_t *>(w.xb->ptr),
                                                            static_cast<uint16_t *>(w.lb->ptr), ld_b);
@@ -506,8 +577,8 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   COUNT_LAUNCH();
   CHECK_LAUNCH();
   m->mn_major = (out_mj == MN_MAJOR);
-  if (mode == SPLIT_BF16X2) {
-    // the bf16 kernel's three-pass order reads (hi, lo) = (xb, lb)
+  if (mode == SPLIT_BF16X2 || mode == SPLIT_F16X2) {
+    // the 16-bit kernel's three-pass order reads (hi, lo) = (xb, lb); TMA moves 16-bit words, whatever their format
     if ((rc = operand_map(c, &m->hi, 2, w.xb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
     if ((rc = operand_map(c, &m->lo, 2, w.lb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
     m->xb = m->lb = m->hi;
@@ -526,14 +597,21 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
 inline SplitMode split_mode(int npass) {
   return (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
 }
-inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3]}; }
-inline OperandWs ws_of_B(Ctx &c) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7]}; }
+inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3], 0}; }
+inline OperandWs ws_of_B(Ctx &c) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7], 1}; }
 
 // launch the tensor-core kernel on prepared operands (c.mu held by the caller)
 template <int ESZ, typename OutT>
 int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMaps &ma,
            const OperandMaps &mb, float beta, OutT *C, int64_t rsC, int64_t csC, int npass, bool pair,
-           cudaStream_t s) {
+           cudaStream_t s, const uint32_t *f16_absmax = nullptr) {
+  // f16_absmax != nullptr: the operands are fp16 pieces of scaled fp32 matrices (F16X3; ESZ == 2, fp32 output only)
+  auto launch = [&](const TcParams &q) -> int {
+    if constexpr (ESZ == 2 && std::is_same<OutT, float>::value) {
+      if (f16_absmax) return pair ? launch_tc_f16<true>(c, ma, mb, q, f16_absmax, s) : launch_tc_f16<false>(c, ma, mb, q, f16_absmax, s);
+    }
+    return pair ? launch_tc<ESZ, OutT, true>(c, ma, mb, q, s) : launch_tc<ESZ, OutT, false>(c, ma, mb, q, s);
+  };
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
@@ -550,8 +628,7 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
       TcParams q = p;
       q.C = c.splitk.ptr; q.rsC = ld; q.csC = 1; q.alpha = 1.0f; q.beta = 0.0f; q.epi = Epilogue();
       q.split_plane = plane;
-      if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, q, s);
-      else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, q, s);
+      rc = launch(q);
       if (rc) return rc;
       const int64_t items = (M * N + 255) / 256;
       splitk_reduce_kernel<<<grid_for(c, items, 8), 256, 0, s>>>(
@@ -563,8 +640,7 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
       return prof_close(c, s, &ep, 2);
     }
   }
-  if (pair) rc = launch_tc<ESZ, OutT, true>(c, ma, mb, p, s);
-  else rc = launch_tc<ESZ, OutT, false>(c, ma, mb, p, s);
+  rc = launch(p);
   if (rc) return rc;
   return prof_close(c, s, &ep, 1);
 }
@@ -574,11 +650,11 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
 template <int ESZ, typename OutT, int SRC_ESZ = ESZ>
 int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
             int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
-            int64_t csC, int npass, cudaStream_t s) {
+            int64_t csC, int npass, cudaStream_t s, SplitMode forced = SPLIT_NONE) {
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
     return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
   std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
-  const SplitMode mode = (SRC_ESZ != ESZ) ? SPLIT_BF16X2 : split_mode(npass);
+  const SplitMode mode = (forced != SPLIT_NONE) ? forced : split_mode(npass);
   Operand oa{A, M, K, rsA, csA};
   Operand ob{B, N, K, csB, rsB};
   OperandMaps ma, mb;
@@ -597,7 +673,8 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   if (rc) return rc;
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
-  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s);
+  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s,
+                         mode == SPLIT_F16X2 ? static_cast<const uint32_t *>(c.f16s.ptr) : nullptr);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;
@@ -887,7 +964,14 @@ const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_c
       break;
     case LASER_B200_PATH_BF16X3:
       // two bf16 pieces per fp32 operand, three passes (h*l', l*h', h*h') of the bf16 kernel, fp32 output
-      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s);
+      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s, SPLIT_BF16X2);
+      if (rc) return rc;
+      g_last_path = path;
+      break;
+    case LASER_B200_PATH_F16X3:
+      // two fp16 pieces of each operand scaled by a power of two (device-side abs-max), three passes of the fp16 flavour
+      // of the kernel, whose epilogue undoes the scales
+      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s, SPLIT_F16X2);
       if (rc) return rc;
       g_last_path = path;
       break;
@@ -1114,6 +1198,7 @@ void laser_b200_shutdown(void) {
     for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     if (c.splitk.ptr) { cudaFree(c.splitk.ptr); c.splitk = Buffer(); }
     if (c.layer_ws.ptr) { cudaFree(c.layer_ws.ptr); c.layer_ws = Buffer(); }
+    if (c.f16s.ptr) { cudaFree(c.f16s.ptr); c.f16s = Buffer(); }
     cudaEventDestroy(c.ws_free);
     for (auto e : c.panel_ev) cudaEventDestroy(e);
     c.panel_ev.clear();
@@ -1169,8 +1254,8 @@ int64_t laser_b200_launch_count(void) { return g_launches.load(); }
 int laser_b200_last_path(void) { return g_last_path; }
 int laser_b200_set_f32_mode(int path) {
   if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3 &&
-      path != LASER_B200_PATH_TF32_BF16C && path != LASER_B200_PATH_BF16X3)
-    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3, TF32_BF16C or BF16X3");
+      path != LASER_B200_PATH_TF32_BF16C && path != LASER_B200_PATH_BF16X3 && path != LASER_B200_PATH_F16X3)
+    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3, TF32_BF16C, BF16X3 or F16X3");
   g_f32_mode.store(path);
   return LASER_B200_OK;
 }

@@ -30,10 +30,14 @@
 // the hi*hi product last over arrays produced by split.cuh: either three tf32 passes
 // (hi*lo, lo*hi, hi*hi) or -- the default -- two bf16 passes for the cross terms at twice
 // the rate plus one tf32 pass (npass = 2).
+// The bf16 instantiation with fp32 output also serves the opt-in BF16X3 mode (fp32 operands as two bf16 arrays each,
+// npass = 3), and gemm_tc_f16_kernel -- the fourth flavour of gemm_tc_kernel.inc -- the opt-in F16X3 mode (two fp16 arrays
+// of the power-of-two-scaled operand; the epilogue undoes the scales, f16_scale.cuh).
 #pragma once
 
 #include <type_traits>
 
+#include "f16_scale.cuh"
 #include "ptx.cuh"
 
 namespace lb200 {
@@ -103,6 +107,11 @@ struct TcParams {
 // A / B tile loads
 struct TcHintParams : TcParams {
   uint64_t hint_a = 0, hint_b = 0;
+};
+// gemm_tc_f16_kernel: fp16 operands (two scaled pieces per fp32 operand); absmax[0] / absmax[1] = fp32 bits of the
+// largest finite |a| / |b|, from which the epilogue derives the unscale factors (f16_scale.cuh)
+struct TcF16Params : TcParams {
+  const uint32_t *absmax = nullptr;
 };
 struct TcBatchedParams : TcParams {
   int batch = 1;
@@ -184,6 +193,8 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 #define LB200_TC_KERNEL_NAME gemm_tc_kernel
 #define LB200_TC_BATCHED 0
 #define LB200_TC_HINT 0
+#define LB200_TC_F16 0
+#define LB200_TC_FMT16 ptx::kFmtBF16
 #include "gemm_tc_kernel.inc"
 #undef LB200_TC_KERNEL_NAME
 #undef LB200_TC_HINT
@@ -197,6 +208,17 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 #define LB200_TC_BATCHED 1
 #define LB200_TC_HINT 0
 #include "gemm_tc_kernel.inc"
+#undef LB200_TC_KERNEL_NAME
+#undef LB200_TC_BATCHED
+#undef LB200_TC_F16
+#undef LB200_TC_FMT16
+#define LB200_TC_KERNEL_NAME gemm_tc_f16_kernel
+#define LB200_TC_BATCHED 0
+#define LB200_TC_F16 1
+#define LB200_TC_FMT16 ptx::kFmtF16
+#include "gemm_tc_kernel.inc"
+#undef LB200_TC_FMT16
+#undef LB200_TC_F16
 #undef LB200_TC_HINT
 #undef LB200_TC_KERNEL_NAME
 #undef LB200_TC_BATCHED

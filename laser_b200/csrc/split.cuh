@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "f16_scale.cuh"
+
 namespace lb200 {
 
 #ifndef LB200_HOST_EMULATION
@@ -139,6 +141,76 @@ split_rows_bf16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, i
           (static_cast<uint32_t>(bf16_rn_bits(v.y - __uint_as_float(static_cast<uint32_t>(hy) << 16))) << 16);
     l.y = bf16_rn_bits(v.z - __uint_as_float(static_cast<uint32_t>(hz) << 16)) |
           (static_cast<uint32_t>(bf16_rn_bits(v.w - __uint_as_float(static_cast<uint32_t>(hw) << 16))) << 16);
+    *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
+    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
+  }
+}
+
+// ---- LASER_B200_PATH_F16X3: two fp16 pieces of the SCALED operand (f16_scale.cuh) -------------------------
+// Largest finite |x| of R rows of Cc contiguous floats (same addressing as the split kernels), as fp32 bits,
+// max-combined into *out (zeroed by the host before the launch): one shared-memory atomic per thread, one
+// global atomic per block.
+__global__ void __launch_bounds__(256)
+absmax_rows_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint32_t *__restrict__ out) {
+  __shared__ uint32_t block_max;
+  if (threadIdx.x == 0) block_max = 0u;
+  __syncthreads();
+  const int64_t vec_per_row = (Cc + 3) >> 2;
+  const int64_t total = R * vec_per_row;
+  uint32_t m = 0u;
+  auto take = [&](float f) {
+    const uint32_t a = __float_as_uint(f) & 0x7fffffffu;
+    if (a < 0x7f800000u && a > m) m = a;      // infinities and NaNs do not set the scale (they propagate as such)
+  };
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int64_t c = (i - r * vec_per_row) << 2;
+    const float *s = src + r * src_ld + c;
+    if (c + 4 <= Cc) {
+      const float4 v = *reinterpret_cast<const float4 *>(s);
+      take(v.x); take(v.y); take(v.z); take(v.w);
+    } else {
+      take(s[0]);
+      if (c + 1 < Cc) take(s[1]);
+      if (c + 2 < Cc) take(s[2]);
+    }
+  }
+  atomicMax(&block_max, m);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(out, block_max);
+}
+
+// hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from *absmax (f16_scale.cuh): x * 2^s = hb + lb + r,
+// |r| <= 2^-22 |x * 2^s| while hb is a normal fp16 number.  Addressing as split_rows_bf16x2_kernel.
+__global__ void __launch_bounds__(256)
+split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
+                        uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b,
+                        const uint32_t *__restrict__ absmax) {
+  const float scale = f16x2_scale(*absmax);
+  const int64_t vec_per_row = (Cc + 3) >> 2;
+  const int64_t total = R * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int64_t c = (i - r * vec_per_row) << 2;
+    const float *s = src + r * src_ld + c;
+    float4 v;
+    if (c + 4 <= Cc) {
+      v = *reinterpret_cast<const float4 *>(s);
+    } else {
+      v.x = s[0];
+      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
+      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
+      v.w = 0.0f;
+    }
+    v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale); v.z = __fmul_rn(v.z, scale); v.w = __fmul_rn(v.w, scale);
+    const uint16_t hx = f16_rn_bits(v.x), hy = f16_rn_bits(v.y), hz = f16_rn_bits(v.z), hw = f16_rn_bits(v.w);
+    uint2 h, l;
+    h.x = hx | (static_cast<uint32_t>(hy) << 16);
+    h.y = hz | (static_cast<uint32_t>(hw) << 16);
+    l.x = f16_rn_bits(__fsub_rn(v.x, f16_bits_to_f32(hx))) | (static_cast<uint32_t>(f16_rn_bits(__fsub_rn(v.y, f16_bits_to_f32(hy)))) << 16);
+    l.y = f16_rn_bits(__fsub_rn(v.z, f16_bits_to_f32(hz))) | (static_cast<uint32_t>(f16_rn_bits(__fsub_rn(v.w, f16_bits_to_f32(hw)))) << 16);
     *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
     *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
   }

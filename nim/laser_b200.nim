@@ -20,7 +20,7 @@ type
   LaserB200Error* = object of CatchableError   # cf. LibraryError in laser/cpuinfo.nim:358-359
 
   GemmPath* {.size: sizeof(cint).} = enum      # LASER_B200_PATH_*
-    pathAuto = 0, pathSimt = 1, pathTf32x1 = 2, pathTf32x3 = 3, pathBf16 = 4, pathTf32Bf16c = 5, pathBf16x3 = 6
+    pathAuto = 0, pathSimt = 1, pathTf32x1 = 2, pathTf32x3 = 3, pathBf16 = 4, pathTf32Bf16c = 5, pathBf16x3 = 6, pathF16x3 = 7
 
 {.push importc, cdecl, dynlib: laserB200Lib.}
 proc laser_b200_init*(): cint

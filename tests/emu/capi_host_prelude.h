@@ -94,6 +94,7 @@ cudaError_t cudaMalloc(void **p, size_t n) { *p = std::aligned_alloc(256, (n + 2
 cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "emulated"; }

@@ -222,7 +222,15 @@ inline float operand_elem(const unsigned char *cta_smem, uint64_t desc, bool mn_
   }
   uint16_t h;
   std::memcpy(&h, cta_smem + off, 2);
-  if (fmt != kFmtBF16) { std::fprintf(stderr, "emu: fp16 operands are not modelled\n"); std::abort(); }
+  if (fmt == kFmtF16) {   // IEEE binary16 (subnormals included), exactly representable in fp32
+    const int e = (h >> 10) & 31, m = h & 1023;
+    float v;
+    if (e == 0) v = std::ldexp(static_cast<float>(m), -24);
+    else if (e == 31) v = m ? std::nanf("") : HUGE_VALF;
+    else v = std::ldexp(static_cast<float>(1024 + m), e - 25);
+    return (h & 0x8000) ? -v : v;
+  }
+  if (fmt != kFmtBF16) { std::fprintf(stderr, "emu: unknown 16-bit operand format\n"); std::abort(); }
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
 }
 

@@ -92,7 +92,7 @@ def build_capi_host_emu(asan=False):
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "liblaser_b200_hostemu_asan.so" if asan else "liblaser_b200_hostemu.so")
     csrc = os.path.abspath(CSRC)
-    deps = [os.path.join(csrc, f) for f in ("capi.cu", "capi_layers.inc", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh",
+    deps = [os.path.join(csrc, f) for f in ("capi.cu", "capi_layers.inc", "f16_scale.cuh", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh",
                                             "ptx.cuh")] + \
            [os.path.join(EMU_DIR, f) for f in ("capi_host_prelude.h", "cuda_emu.h", "ptx_emu.h")] + [os.path.abspath(__file__)]
     if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):

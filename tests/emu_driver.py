@@ -106,6 +106,23 @@ def host_entry():
     print("OK host_entry", n + 1)
 
 
+def host_entry_staged_modes():
+    """host-pointer entry in a mode that has no pipelined variant (f16x3): staged upload, device call, download"""
+    L.init()                                                          # the environment is read when the context is created
+    assert L.get_f32_mode() == L.PATH_F16X3, L.get_f32_mode()       # selected by LASER_B200_F32_MODE
+    n = 0
+    for (M, N, K) in ((300, 70, 200), (2304, 24, 64)):
+        a, b, c0 = rnd((M, K), 81, -1, 1), rnd((K, N), 82, -1, 1), rnd((M, N), 83, -1, 1)
+        for alpha, beta in ((1.0, 0.0), (0.5, -1.25)):
+            c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
+            L.gemm_strided(M, N, K, alpha, a, K, 1, b, N, 1, beta, c, N, 1)
+            assert L.last_path() == L.PATH_F16X3
+            ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
+            assert np.abs(c - ref).max() <= 3e-6 * np.abs(ref).max(), (M, N, K, alpha, beta)
+            n += 1
+    print("OK host_entry_staged_modes", n)
+
+
 def prepacked():
     n = 0
     for (M, N, K) in ((300, 520, 200), (100, 36, 77)):
@@ -253,8 +270,8 @@ def batched_tc():
     print("OK batched_tc", n + 1)
 
 
-def bf16x3():
-    """opt-in fp32 mode: two bf16 pieces per operand, three passes of the bf16 tensor-core kernel with fp32 output.
+def _two_piece_mode(PATH, name, per_product, gate, layouts_tol):
+    """opt-in fp32 modes: two 16-bit pieces per operand, three passes of the 16-bit tensor-core kernel with fp32 output.
     Worst case 3 * 2^-16 of sum |a||b| from the dropped l*l' and remainder terms; the errors are random-signed, so on these
     (fixed, seeded) inputs a four times tighter bar holds with margin and catches a wrong pass order or a lost piece."""
     n = 0
@@ -264,30 +281,30 @@ def bf16x3():
             a, b, c0 = rnd((M, K), 41, lo, hi), rnd((K, N), 42, lo, hi), rnd((M, N), 43, lo, hi)
             for alpha, beta in ((1.0, 0.0), (0.5, -1.25)):
                 c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
-                L.gemm_strided(M, N, K, alpha, D(a), K, 1, D(b), N, 1, beta, D(c), N, 1, path=L.PATH_BF16X3)
-                assert L.last_path() == L.PATH_BF16X3
+                L.gemm_strided(M, N, K, alpha, D(a), K, 1, D(b), N, 1, beta, D(c), N, 1, path=PATH)
+                assert L.last_path() == PATH
                 exact = alpha * (a.astype(np.float64) @ b.astype(np.float64)) + beta * c0.astype(np.float64)
-                bound = abs(alpha) * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) * (3 * 2.0 ** -18 + 2e-6) \
+                bound = abs(alpha) * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) * (per_product + 2e-6) \
                     + np.abs(exact) * 2e-6 + 1e-30
                 assert (np.abs(c - exact) <= bound).all(), (float((np.abs(c - exact) / bound).max()), M, N, K, alpha, beta)
                 if lo == 0.0:   # positive data: the north-star gate, max elementwise relative error vs the reference
                     ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
                     if beta == 0.0:
-                        assert (np.abs(c - ref) / np.abs(ref)).max() < 1e-5, (M, N, K)
+                        assert (np.abs(c - ref) / np.abs(ref)).max() < gate, (M, N, K)
                 n += 1
     # (b) every operand class (K-major / MN-major split kernel, gathered general strides) and C of any strides
     M, N, K = 150, 140, 100
     a, b, c0 = rnd((M, K), 44), rnd((K, N), 45), rnd((M, N), 46)
-    L.set_f32_mode(L.PATH_BF16X3)
-    assert L.get_f32_mode() == L.PATH_BF16X3
+    L.set_f32_mode(PATH)
+    assert L.get_f32_mode() == PATH
     for la, lb, lc in [(x, "row", "row") for x in LAYOUTS] + [("row", x, "row") for x in LAYOUTS] + [("col", "col", x) for x in LAYOUTS]:
         A, oa, rsa, csa = embed(a, la); B, ob, rsb, csb = embed(b, lb); C, oc, rsc, csc = embed(c0, lc)
         Cref = C.copy()
         O.gemm_strided(M, N, K, 1.0, A[oa:], rsa, csa, B[ob:], rsb, csb, 2.0, Cref[oc:], rsc, csc)
         L.gemm_strided(M, N, K, 1.0, D(A, oa), rsa, csa, D(B, ob), rsb, csb, 2.0, D(C, oc), rsc, csc)   # AUTO -> the selected mode
-        assert L.last_path() == L.PATH_BF16X3
+        assert L.last_path() == PATH
         idx = oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc
-        assert np.abs(C[idx] - Cref[idx]).max() <= 1.5e-5 * np.abs(Cref[idx]).max(), (la, lb, lc)
+        assert np.abs(C[idx] - Cref[idx]).max() <= layouts_tol * np.abs(Cref[idx]).max(), (la, lb, lc)
         mask = np.ones(C.size, bool); mask[idx.reshape(-1)] = False
         assert np.array_equal(C[mask], Cref[mask]), (la, lb, lc)
         n += 1
@@ -297,10 +314,47 @@ def bf16x3():
     c = np.full((M, N), np.nan, np.float32)
     L.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, c, N, 1)
     ref = ref_gemm(M, N, K, 1.0, a, b, 0.0, c)
-    assert (np.abs(c - ref) / np.abs(ref)).max() < 1e-5
+    assert (np.abs(c - ref) / np.abs(ref)).max() < gate
     L.set_f32_mode(L.PATH_TF32_BF16C)
     n += 1
-    print("OK bf16x3", n)
+    return n
+
+
+def bf16x3():
+    print("OK bf16x3", _two_piece_mode(L.PATH_BF16X3, "bf16x3", 3 * 2.0 ** -18, 1e-5, 1.5e-5))
+
+
+def f16x3():
+    """two fp16 pieces of the power-of-two-scaled operands (device-side abs-max), fp16 flavour of the kernel whose
+    epilogue undoes the scales: accuracy of tf32x3, and fp32's range although fp16 has 5 exponent bits"""
+    n = _two_piece_mode(L.PATH_F16X3, "f16x3", 3 * 2.0 ** -22, 3e-6, 3e-6)
+    M, N, K = 200, 130, 96
+    a, b = rnd((M, K), 61, -1.0, 1.0), rnd((K, N), 62, -1.0, 1.0)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    absab = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    # operands far outside fp16's range, in both directions, and a zero operand (abs-max word 0: no scaling)
+    for sa, sb in ((1e-20, 1e-10), (1e+15, 3e+12), (1e-30, 1e+25), (7.0, 0.0)):
+        aa, bb = (a * np.float32(sa)).astype(np.float32), (b * np.float32(sb)).astype(np.float32)
+        c = np.full((M, N), np.nan, np.float32)
+        L.gemm_strided(M, N, K, 1.0, D(aa), K, 1, D(bb), N, 1, 0.0, D(c), N, 1, path=L.PATH_F16X3)
+        ex = aa.astype(np.float64) @ bb.astype(np.float64)
+        bound = (np.abs(aa).astype(np.float64) @ np.abs(bb).astype(np.float64)) * (3 * 2.0 ** -22 + 2e-6) + 1e-37
+        assert np.isfinite(c).all() and (np.abs(c - ex) <= bound).all(), (sa, sb, float((np.abs(c - ex) / bound).max()))
+        n += 1
+    # wide dynamic range inside one matrix: entries 2^-30 of the maximum keep ABSOLUTE precision (documented domain
+    # of the mode): error <= 2^-36 * max|a| * sum_k |b| instead of a bound relative to each product
+    aw = a.copy(); aw[::2, :] *= np.float32(2.0 ** -30)
+    c = np.full((M, N), np.nan, np.float32)
+    L.gemm_strided(M, N, K, 1.0, D(aw), K, 1, D(b), N, 1, 0.0, D(c), N, 1, path=L.PATH_F16X3)
+    ex = aw.astype(np.float64) @ b.astype(np.float64)
+    assert (np.abs(c - ex) <= np.abs(aw).astype(np.float64) @ np.abs(b).astype(np.float64) * (3 * 2.0 ** -22 + 2e-6)
+            + np.abs(aw).max() * np.abs(b).astype(np.float64).sum(0)[None, :] * 2.0 ** -36).all()
+    assert (np.abs(c[1::2] - ex[1::2]) <= absab[1::2] * (3 * 2.0 ** -22 + 2e-6)).all()      # the large rows are unaffected
+    # two calls in a row with different ranges: the abs-max words are per call
+    c2 = np.full((M, N), np.nan, np.float32)
+    L.gemm_strided(M, N, K, 1.0, D(a), K, 1, D(b), N, 1, 0.0, D(c2), N, 1, path=L.PATH_F16X3)
+    assert (np.abs(c2 - exact) <= absab * (3 * 2.0 ** -22 + 2e-6)).all()
+    print("OK f16x3", n + 2)
 
 
 def lifecycle():

@@ -60,11 +60,19 @@ def test_batched_tensor_core_launch(emulated_lib):
 
 def test_bf16x3_mode(emulated_lib):
     """opt-in fp32 mode (not yet measured on a B200): fp32 operands split into two bf16 arrays, three passes of the
-    bf16 tensor-core kernel, fp32 output; also selected through the environment, and with a 32-SM machine so that
-    split-K takes part"""
-    run(emulated_lib, "bf16x3")
-    run(emulated_lib, "host_entry", LASER_B200_F32_MODE="bf16x3")
+    bf16 tensor-core kernel, fp32 output.  Here on a 32-SM machine without CTA pairs, so that the single-CTA kernel and
+    split-K take part (the CTA-pair kernel runs the same assertions in test_emulated_python_mirror.py), and selected
+    through the environment for the pipelined host-pointer entry"""
     run(emulated_lib, "bf16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
+    run(emulated_lib, "host_entry", LASER_B200_F32_MODE="bf16x3")
+
+
+def test_f16x3_mode(emulated_lib):
+    """opt-in fp32 mode (not yet measured on a B200): power-of-two scaling from a device-side abs-max, two fp16 pieces,
+    the fp16 flavour of the tensor-core kernel undoing the scales in its epilogue; range cases included.  Same split of
+    the work as test_bf16x3_mode; the host-pointer entry takes the staged path in this mode"""
+    run(emulated_lib, "f16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
+    run(emulated_lib, "host_entry_staged_modes", LASER_B200_F32_MODE="f16x3")
 
 
 def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):

@@ -24,7 +24,7 @@ def emu():
     L.emu_gemm_tc.restype = ci
     L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64,
                               vp, i64, i64, ci, ci, ci, ci, ci, vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
-    S = ctypes.CDLL(build_emu("split_emu", ["split.cuh"]))
+    S = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh"]))
     S.emu_splitk_reduce.restype = None
     S.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.splitk_reduce = S.emu_splitk_reduce

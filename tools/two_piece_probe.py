@@ -1,8 +1,8 @@
-"""Time and error of the opt-in fp32 mode LASER_B200_PATH_BF16X3 on one B200 -> one JSON line on stdout.
+"""Time and error of one opt-in fp32 mode (bf16x3 | f16x3) on one B200 -> one JSON line on stdout.
 
-bench.py runs this in a CHILD process (with a timeout) after all of its own measurements: the mode was written after
-the round's GPU minutes were spent, so its first run on silicon must not be able to take the bench line down with it.
-Also usable by hand:  python tools/bf16x3_probe.py [n] [steps]
+bench.py runs this in a CHILD process per mode (with a timeout) after all of its own measurements: the modes were written
+after the round's GPU minutes were spent, so their first run on silicon must not be able to take the bench line down.
+Also usable by hand:  python tools/two_piece_probe.py bf16x3|f16x3 [n] [steps]
 """
 import json
 import os
@@ -28,33 +28,35 @@ def timed(fn, steps, warmup):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    name = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+    PATH = {"bf16x3": L.PATH_BF16X3, "f16x3": L.PATH_F16X3}[name]
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
     L.init()
     dev = torch.device("cuda", 0)
     A = torch.empty(n * n, dtype=torch.float32, device=dev); B = torch.empty(n * n, dtype=torch.float32, device=dev)
     C = torch.empty(n * n, dtype=torch.float32, device=dev); Cd = torch.empty(n * n, dtype=torch.float32, device=dev)
-    out = {"shape": [n, n, n]}
+    out = {"mode": name, "shape": [n, n, n]}
     # ---- error: against an fp64 product on a slab (2048 rows x 2048 columns x full K), both distributions
     m = min(n, 2048)
     for dist, (lo, hi) in (("P_U(0,1)", (0.0, 1.0)), ("S_U(-0.1,0.1)", (-0.1, 0.1))):
         L.fill_uniform_f32(A, n * n, 42, lo, hi); L.fill_uniform_f32(B, n * n, 43, lo, hi)
         C.fill_(float("nan")); Cd.fill_(float("nan"))
-        L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, C, m, 1, path=L.PATH_BF16X3)
-        assert L.last_path() == L.PATH_BF16X3
+        L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, C, m, 1, path=PATH)
+        assert L.last_path() == PATH
         L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, Cd, m, 1, path=L.PATH_TF32_BF16C)
         torch.cuda.synchronize()
         exact = A.view(n, n)[:m, :].double() @ B.view(n, n)[:, :m].double()
         got = C[:m * m].view(m, m).double(); dflt = Cd[:m * m].view(m, m).double()
         e = {}
-        for name, x in (("bf16x3", got), ("default", dflt)):
+        for label, x in ((name, got), ("default", dflt)):
             d = (x - exact).abs()
-            e[name] = {"max_rel": (d / exact.abs()).max().item(), "normwise": (torch.linalg.norm(x - exact) / torch.linalg.norm(exact)).item(),
+            e[label] = {"max_rel": (d / exact.abs()).max().item(), "normwise": (torch.linalg.norm(x - exact) / torch.linalg.norm(exact)).item(),
                        "mean_relative_error": (d / exact.abs().clamp_min(1e-30)).mean().item()}
         out["error_vs_fp64_%s" % dist] = e
         del exact, got, dflt
     # ---- time at n^3 on the bench's distribution (S), device-resident, split pre-pass included
-    f = lambda: L.gemm_strided(n, n, n, 1.0, A, n, 1, B, n, 1, 0.0, C, n, 1, path=L.PATH_BF16X3)
+    f = lambda: L.gemm_strided(n, n, n, 1.0, A, n, 1, B, n, 1, 0.0, C, n, 1, path=PATH)
     ms = timed(f, steps, 3)
     L.profile_begin()
     for _ in range(3):
