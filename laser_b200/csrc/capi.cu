@@ -1053,7 +1053,8 @@ inline bool panel_separable(int64_t rows, int64_t cols, int64_t rs, int64_t cs) 
 int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                             int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
                             float beta, float *C, int64_t rsC, int64_t csC, int path) {
-  const bool bf16x3 = (path == LASER_B200_PATH_BF16X3);
+  const bool f16x3 = (path == LASER_B200_PATH_F16X3);
+  const bool bf16x3 = (path == LASER_B200_PATH_BF16X3) || f16x3;   // two 16-bit pieces per operand: the 16-bit kernel, three passes
   const int npass = (path == LASER_B200_PATH_TF32X3 || bf16x3) ? 3 : (path == LASER_B200_PATH_TF32_BF16C ? 2 : 1);
   std::lock_guard<std::mutex> host_lk(c.host_mu);
   std::lock_guard<std::mutex> lk(c.mu);
@@ -1092,7 +1093,9 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
       CUDA_TRY(cudaEventCreateWithFlags(&c.panel_ev[i], cudaEventDisableTiming));
   }
   cudaStream_t up = c.up, cmp = c.stream, down = c.down;
-  const SplitMode mode = bf16x3 ? SPLIT_BF16X2 : split_mode(npass);
+  // f16x3: B's abs-max word is written once, A's is rewritten by every panel's preparation -- after the previous panel's
+  // GEMM, whose epilogue reads it, because everything of a panel runs on the compute stream
+  const SplitMode mode = f16x3 ? SPLIT_F16X2 : (bf16x3 ? SPLIT_BF16X2 : split_mode(npass));
   const bool pair = c.cta_pair && panel_rows > TC_BLOCK_M && M > TC_BLOCK_M;
   // staging buffers / workspace may still be in use by an earlier call
   CUDA_TRY(cudaStreamWaitEvent(up, c.ws_free, 0));
@@ -1125,7 +1128,8 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     if ((rc = prepare_operand<4>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, cmp))) return rc;
     // B's tensor maps were built for `pair` (128- vs 256-column boxes): every panel, however
     // short, must run the same kernel variant
-    if (bf16x3) rc = tc_run<2, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
+    if (bf16x3) rc = tc_run<2, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp,
+                                      f16x3 ? static_cast<const uint32_t *>(c.f16s.ptr) : nullptr);
     else rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));
@@ -1323,7 +1327,7 @@ int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, co
     if (rc) return rc;
     const int mode = g_f32_mode.load();
     const bool tc_mode = mode == LASER_B200_PATH_TF32X3 || mode == LASER_B200_PATH_TF32_BF16C ||
-                         mode == LASER_B200_PATH_TF32X1 || mode == LASER_B200_PATH_BF16X3;
+                         mode == LASER_B200_PATH_TF32X1 || mode == LASER_B200_PATH_BF16X3 || mode == LASER_B200_PATH_F16X3;
     if (tc_mode && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
         span_of(c->panel_rows, N, rsC, csC).dense && rsA > 0 && rsC > 0)
       return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, mode);

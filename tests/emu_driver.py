@@ -106,23 +106,6 @@ def host_entry():
     print("OK host_entry", n + 1)
 
 
-def host_entry_staged_modes():
-    """host-pointer entry in a mode that has no pipelined variant (f16x3): staged upload, device call, download"""
-    L.init()                                                          # the environment is read when the context is created
-    assert L.get_f32_mode() == L.PATH_F16X3, L.get_f32_mode()       # selected by LASER_B200_F32_MODE
-    n = 0
-    for (M, N, K) in ((300, 70, 200), (2304, 24, 64)):
-        a, b, c0 = rnd((M, K), 81, -1, 1), rnd((K, N), 82, -1, 1), rnd((M, N), 83, -1, 1)
-        for alpha, beta in ((1.0, 0.0), (0.5, -1.25)):
-            c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
-            L.gemm_strided(M, N, K, alpha, a, K, 1, b, N, 1, beta, c, N, 1)
-            assert L.last_path() == L.PATH_F16X3
-            ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
-            assert np.abs(c - ref).max() <= 3e-6 * np.abs(ref).max(), (M, N, K, alpha, beta)
-            n += 1
-    print("OK host_entry_staged_modes", n)
-
-
 def prepacked():
     n = 0
     for (M, N, K) in ((300, 520, 200), (100, 36, 77)):

@@ -70,9 +70,9 @@ def test_bf16x3_mode(emulated_lib):
 def test_f16x3_mode(emulated_lib):
     """opt-in fp32 mode (not yet measured on a B200): power-of-two scaling from a device-side abs-max, two fp16 pieces,
     the fp16 flavour of the tensor-core kernel undoing the scales in its epilogue; range cases included.  Same split of
-    the work as test_bf16x3_mode; the host-pointer entry takes the staged path in this mode"""
+    the work as test_bf16x3_mode; in the pipelined host-pointer entry every row panel of A gets its own scale"""
     run(emulated_lib, "f16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
-    run(emulated_lib, "host_entry_staged_modes", LASER_B200_F32_MODE="f16x3")
+    run(emulated_lib, "host_entry", LASER_B200_F32_MODE="f16x3")
 
 
 def test_the_emulated_build_is_refused_outside_these_tests(emulated_lib):

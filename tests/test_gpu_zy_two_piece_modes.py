@@ -116,8 +116,8 @@ def test_every_operand_class(which, layout, path):
 
 @pytest.mark.parametrize("path", MODES, ids=mode_ids)
 def test_mode_selection_and_host_pointer_entry(path):
-    """set_f32_mode(mode) makes it the AUTO path of device- and host-pointer calls (bf16x3: the pipelined row-panel
-    path included; f16x3: the staged path); other modes are untouched afterwards"""
+    """set_f32_mode(mode) makes it the AUTO path of device- and host-pointer calls (the pipelined row-panel path
+    included: in f16x3 every row panel of A gets its own scale); other modes are untouched afterwards"""
     L.set_f32_mode(path)
     try:
         assert L.get_f32_mode() == path
