@@ -370,7 +370,7 @@ def experimental_mode_probe(mode_name, n):
                            ("error bars: max-elementwise < 1e-4 on U(0,1), normwise < 1.5e-5 on U(-0.1,0.1); does not claim the "
                             "reference's mean_relative_error <= 1e-5 gate (the default mode does)" if mode_name == "bf16x3" else
                             "error bars of the fp32-faithful modes (max-elementwise < 1e-4 on U(0,1), normwise < 2e-6 and "
-                            "mean_relative_error <= 1e-5 on U(-0.1,0.1)) for matrices whose entries lie within 2^-17 of their maximum"))
+                            "mean_relative_error <= 1e-5 on U(-0.1,0.1)); one power-of-two scale per row of A / column of B, entries within 2^-17 of that maximum keep 22 bits"))
             return res
         return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
     except subprocess.TimeoutExpired:

@@ -57,11 +57,11 @@ extern "C" {
                                    * three kind::f16 passes h*l', l*h', h*h' on the bf16 kernel with fp32 output
                                    * (1.5 tf32-equivalents per MAC; error <= 3*2^-16 ~ 4.6e-5 per product worst case, random-signed: ~3e-7 of sum|a||b| at K = 8192).
                                    * Opt-in: written after the round's GPU minutes were spent, see DESIGN.md */
-#define LASER_B200_PATH_F16X3 7   /* fp32 operands scaled by a power of two (device-side abs-max of each matrix, no host
-                                   * synchronisation) and split into two FP16 pieces (11 + 11 bits); three kind::f16 passes; the
-                                   * epilogue undoes the scales.  3 instruction times per k-step like BF16X3, accuracy of TF32X3
-                                   * (<= 3*2^-22 per product) for matrices whose entries lie within 2^-17 of their maximum; smaller
-                                   * entries keep absolute precision 2^-39 of the maximum.  Opt-in, unmeasured: see DESIGN.md */
+#define LASER_B200_PATH_F16X3 7   /* every row of A and column of B scaled by its own power of two (device-side abs-max along K, no
+                                   * host synchronisation) and split into two FP16 pieces (11 + 11 bits); three kind::f16 passes;
+                                   * the epilogue undoes the scales.  3 instruction times per k-step like BF16X3, accuracy of TF32X3
+                                   * (<= 3*2^-22 per product) for entries within 2^-17 of their row's / column's maximum; smaller
+                                   * entries keep absolute precision 2^-39 of that maximum.  Opt-in, unmeasured: see DESIGN.md */
 
 /* ---- life cycle -------------------------------------------------------
  * The reference has one piece of import-time state, cpuinfo_initialize()

@@ -111,7 +111,8 @@ struct Ctx {
   Buffer stage[3];   // device staging of host A, B, C spans
   Buffer splitk;     // split-K partial-sum planes
   Buffer layer_ws;   // im2col workspace of the host-pointer convolution
-  Buffer f16s;       // F16X3 mode: fp32 bits of max |a| (word 0) and max |b| (word 1), written and read on the device
+  Buffer f16s;       // F16X3 mode: fp32 bits of max_k |a| per row of A (words [0, M)) and of max_k |b| per column of B (from
+                     // f16_b_off on), written and read on the device
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
@@ -332,7 +333,7 @@ struct OperandMaps {
 };
 struct OperandWs {
   Buffer *hi, *lo, *xb, *lb;
-  int which;   // 0 = A, 1 = B (index of the operand's abs-max word in Ctx::f16s)
+  int64_t amax_off;   // F16X3: word offset of the operand's abs-max vector in Ctx::f16s (set by f16_scales)
 };
 enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2, SPLIT_BF16X2 = 3 /* fp32 -> two bf16 arrays (xb, lb) */,
                  SPLIT_F16X2 = 4 /* fp32 -> abs-max word + two fp16 arrays of the scaled operand (xb, lb) */ };
@@ -405,7 +406,7 @@ int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams
 
 // gemm_tc_f16_kernel (LASER_B200_PATH_F16X3): same grid / cluster / shared-memory configuration as launch_tc
 template <bool PAIR>
-int launch_tc_f16(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, const uint32_t *absmax, cudaStream_t s) {
+int launch_tc_f16(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, const F16Scales &sc, cudaStream_t s) {
   const bool a_mn = A.mn_major, b_mn = B.mn_major;
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;
   const int units = PAIR ? c.sm_count / 2 : c.sm_count;
@@ -424,7 +425,8 @@ int launch_tc_f16(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcPa
   cfg.numAttrs = 1;
   TcF16Params pf;
   static_cast<TcParams &>(pf) = p;
-  pf.absmax = absmax;
+  pf.amax_a = sc.a;
+  pf.amax_b = sc.b;
 #define LB200_LAUNCH_F16(AMN, BMN)                                                               \
   do {                                                                                           \
     auto kfn = gemm_tc_f16_kernel<2, AMN, BMN, float, PAIR>;                                     \
@@ -472,16 +474,29 @@ int operand_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, bool mn_ma
                      esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// F16X3 mode: abs-max word of a compact / row-contiguous fp32 operand, then its two fp16 pieces (f16_scale.cuh)
-int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_ld, const OperandWs &w, int64_t ld_b,
-                  int grid, cudaStream_t s) {
-  uint32_t *word = static_cast<uint32_t *>(c.f16s.ptr) + w.which;
-  CUDA_TRY(cudaMemsetAsync(word, 0, sizeof(uint32_t), s));
-  absmax_rows_kernel<<<grid, 256, 0, s>>>(src, R, Cc, src_ld, word);
-  COUNT_LAUNCH();
-  CHECK_LAUNCH();
-  split_rows_f16x2_kernel<<<grid, 256, 0, s>>>(src, R, Cc, src_ld, static_cast<uint16_t *>(w.xb->ptr),
-                                               static_cast<uint16_t *>(w.lb->ptr), ld_b, word);
+// F16X3 mode: abs-max per mn index of a row-contiguous fp32 operand [R][Cc] (mn along R, or along Cc when the operand is
+// MN-major), then its two fp16 pieces (split.cuh, f16_scale.cuh); the caller made room with f16_scales()
+int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_ld, bool mn_along_cols, const OperandWs &w,
+                  int64_t ld_b, int grid, cudaStream_t s) {
+  uint32_t *words = static_cast<uint32_t *>(c.f16s.ptr) + w.amax_off;
+  const int64_t n_mn = mn_along_cols ? Cc : R;
+  if (c.f16s.bytes < static_cast<size_t>(w.amax_off + n_mn) * sizeof(uint32_t))
+    return set_error(LASER_B200_ECUDA, "internal: F16X3 scale buffer not sized for this operand");
+  CUDA_TRY(cudaMemsetAsync(words, 0, static_cast<size_t>(n_mn) * sizeof(uint32_t), s));
+  uint16_t *xb = static_cast<uint16_t *>(w.xb->ptr), *lb = static_cast<uint16_t *>(w.lb->ptr);
+  if (mn_along_cols) {
+    const int64_t items = ((Cc + 3) / 4) * ((R + ABSMAX_COL_ROWS - 1) / ABSMAX_COL_ROWS);
+    absmax_mn_kernel<true><<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(src, R, Cc, src_ld, words);
+    COUNT_LAUNCH();
+    CHECK_LAUNCH();
+    split_rows_f16x2_kernel<true><<<grid, 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+  } else {
+    const int64_t warp_items = R * ((Cc + ABSMAX_ROW_CHUNK - 1) / ABSMAX_ROW_CHUNK);
+    absmax_mn_kernel<false><<<grid_for(c, (warp_items + 7) / 8, 8), 256, 0, s>>>(src, R, Cc, src_ld, words);
+    COUNT_LAUNCH();
+    CHECK_LAUNCH();
+    split_rows_f16x2_kernel<false><<<grid, 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+  }
   return LASER_B200_OK;   // the caller counts and checks this last launch
 }
 
@@ -511,7 +526,6 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   const size_t bytes_b = static_cast<size_t>(R) * ld_b * 2;
   if (mode != SPLIT_BF16X2 && !(mode == SPLIT_F16X2 && mj != GENERAL) && (rc = ensure(*w.hi, bytes))) return rc;
   if (mode == SPLIT_TF32 && (rc = ensure(*w.lo, bytes))) return rc;
-  if (mode == SPLIT_F16X2 && (rc = ensure(c.f16s, 256))) return rc;
   if (mode == SPLIT_MIXED || mode == SPLIT_BF16X2 || mode == SPLIT_F16X2) {
     if ((rc = ensure(*w.xb, bytes_b))) return rc;
     if ((rc = ensure(*w.lb, bytes_b))) return rc;
@@ -523,7 +537,7 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
       const int64_t items = R * ((Cc + 3) / 4);
       const int grid = grid_for(c, (items + 255) / 256, 8);
       if (mode == SPLIT_F16X2) {
-        if ((rc = f16x2_prepare(c, static_cast<const float *>(o.ptr), R, Cc, src_ld, w, ld_b, grid, s))) return rc;
+        if ((rc = f16x2_prepare(c, static_cast<const float *>(o.ptr), R, Cc, src_ld, mj == MN_MAJOR, w, ld_b, grid, s))) return rc;
       } else if (mode == SPLIT_TF32)
         split_rows_tf32_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
                                                     static_cast<float *>(w.hi->ptr),
@@ -553,7 +567,7 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
         COUNT_LAUNCH();
         CHECK_LAUNCH();
         const int g2 = grid_for(c, (R * ((Cc + 3) / 4) + 255) / 256, 8);
-        if ((rc = f16x2_prepare(c, dhi, R, Cc, ld, w, ld_b, g2, s))) return rc;
+        if ((rc = f16x2_prepare(c, dhi, R, Cc, ld, false, w, ld_b, g2, s))) return rc;
       } else if (mode == SPLIT_BF16X2)
         pack_general_kernel<float, 3><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, nullptr, nullptr, ld,
                                                            read_along_r, static_cast<uint16_t *>(w.xb->ptr),
@@ -598,17 +612,22 @@ inline SplitMode split_mode(int npass) {
   return (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
 }
 inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3], 0}; }
-inline OperandWs ws_of_B(Ctx &c) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7], 1}; }
+inline OperandWs ws_of_B(Ctx &c, int64_t amax_off = 0) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7], amax_off}; }
+// F16X3: room for M + N abs-max words; A's vector starts at word 0, B's at the returned offset
+inline int f16_scales(Ctx &c, int64_t M, int64_t N, int64_t *b_off) {
+  *b_off = round_up(M, 64);
+  return ensure(c.f16s, static_cast<size_t>(*b_off + N) * sizeof(uint32_t));
+}
 
 // launch the tensor-core kernel on prepared operands (c.mu held by the caller)
 template <int ESZ, typename OutT>
 int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMaps &ma,
            const OperandMaps &mb, float beta, OutT *C, int64_t rsC, int64_t csC, int npass, bool pair,
-           cudaStream_t s, const uint32_t *f16_absmax = nullptr) {
-  // f16_absmax != nullptr: the operands are fp16 pieces of scaled fp32 matrices (F16X3; ESZ == 2, fp32 output only)
+           cudaStream_t s, const F16Scales *f16 = nullptr) {
+  // f16 != nullptr: the operands are fp16 pieces of scaled fp32 matrices (F16X3; ESZ == 2, fp32 output only)
   auto launch = [&](const TcParams &q) -> int {
     if constexpr (ESZ == 2 && std::is_same<OutT, float>::value) {
-      if (f16_absmax) return pair ? launch_tc_f16<true>(c, ma, mb, q, f16_absmax, s) : launch_tc_f16<false>(c, ma, mb, q, f16_absmax, s);
+      if (f16) return pair ? launch_tc_f16<true>(c, ma, mb, q, *f16, s) : launch_tc_f16<false>(c, ma, mb, q, *f16, s);
     }
     return pair ? launch_tc<ESZ, OutT, true>(c, ma, mb, q, s) : launch_tc<ESZ, OutT, false>(c, ma, mb, q, s);
   };
@@ -665,16 +684,18 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   const int64_t launches_before = g_launches.load();
   int rc = prof_open(c, s, &ep, 1);
   if (rc) return rc;
+  int64_t f16_b_off = 0;
+  if (mode == SPLIT_F16X2 && (rc = f16_scales(c, M, N, &f16_b_off))) return rc;
   rc = prepare_operand<SRC_ESZ>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
   if (rc) return rc;
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
   const bool pair = c.cta_pair && M > TC_BLOCK_M;
-  rc = prepare_operand<SRC_ESZ>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
+  rc = prepare_operand<SRC_ESZ>(c, ob, mode, ws_of_B(c, f16_b_off), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
   if (rc) return rc;
   rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
   if (rc) return rc;
-  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s,
-                         mode == SPLIT_F16X2 ? static_cast<const uint32_t *>(c.f16s.ptr) : nullptr);
+  const F16Scales f16{static_cast<const uint32_t *>(c.f16s.ptr), static_cast<const uint32_t *>(c.f16s.ptr) + f16_b_off};
+  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s, mode == SPLIT_F16X2 ? &f16 : nullptr);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;
@@ -1093,8 +1114,8 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
       CUDA_TRY(cudaEventCreateWithFlags(&c.panel_ev[i], cudaEventDisableTiming));
   }
   cudaStream_t up = c.up, cmp = c.stream, down = c.down;
-  // f16x3: B's abs-max word is written once, A's is rewritten by every panel's preparation -- after the previous panel's
-  // GEMM, whose epilogue reads it, because everything of a panel runs on the compute stream
+  // f16x3: B's abs-max words are written once, A's (one per row of the panel) are rewritten by every panel's preparation --
+  // after the previous panel's GEMM, whose epilogue reads them, because everything of a panel runs on the compute stream
   const SplitMode mode = f16x3 ? SPLIT_F16X2 : (bf16x3 ? SPLIT_BF16X2 : split_mode(npass));
   const bool pair = c.cta_pair && panel_rows > TC_BLOCK_M && M > TC_BLOCK_M;
   // staging buffers / workspace may still be in use by an earlier call
@@ -1107,8 +1128,11 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
   OperandMaps mb;
   bool used_ws = false;
   Operand ob{dB, N, K, csB, rsB};
-  if ((rc = prepare_operand<4>(c, ob, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, cmp)))
+  int64_t f16_b_off = 0;       // f16x3: room for the longest panel's rows of A + the columns of B
+  if (f16x3 && (rc = f16_scales(c, panel_rows < M ? panel_rows : M, N, &f16_b_off))) return rc;
+  if ((rc = prepare_operand<4>(c, ob, mode, ws_of_B(c, f16_b_off), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, cmp)))
     return rc;
+  const F16Scales f16{static_cast<const uint32_t *>(c.f16s.ptr), static_cast<const uint32_t *>(c.f16s.ptr) + f16_b_off};
   // ---- row panels ----
   for (int pnl = 0; pnl < panels; ++pnl) {
     const int64_t m0 = plist[pnl].first;
@@ -1129,7 +1153,7 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     // B's tensor maps were built for `pair` (128- vs 256-column boxes): every panel, however
     // short, must run the same kernel variant
     if (bf16x3) rc = tc_run<2, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp,
-                                      f16x3 ? static_cast<const uint32_t *>(c.f16s.ptr) : nullptr);
+                                      f16x3 ? &f16 : nullptr);
     else rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));

@@ -1,13 +1,15 @@
 // f16_scale.cuh -- range handling of the opt-in fp32 mode LASER_B200_PATH_F16X3 (shared by split.cuh, which
 // scales and splits the operands, and by gemm_tc_f16_kernel, whose epilogue undoes the scales).
 //
-// fp16 has 11 significant bits (bf16: 8) but only 5 exponent bits, so an fp32 matrix is first multiplied by
-// a power of two 2^s that puts its largest finite |x| into [2^14, 2^15), the top binade below fp16's maximum
-// 65504; s is derived ON THE DEVICE from the abs-max word an earlier kernel of the same stream produced
-// (no host synchronisation), by the split kernel and again by the GEMM epilogue, which multiplies alpha by
-// 2^-sA * 2^-sB.  Elements down to 2^-17 of the maximum keep all 22 bits of the two pieces (the low
-// piece, <= 2^-11 of the element, is then still rounded at or above fp16's subnormal spacing 2^-24); smaller ones
-// keep an ABSOLUTE precision of 2^-39 of the maximum -- see DESIGN.md.
+// fp16 has 11 significant bits (bf16: 8) but only 5 exponent bits, so every row of A and every column of B (an
+// "mn index": the vectors that meet in one output element) is first multiplied by its own power of two 2^s, which
+// puts its largest finite |x| into [2^14, 2^15), the top binade below fp16's maximum 65504.  s is derived ON THE
+// DEVICE from the abs-max word an earlier kernel of the same stream produced for that mn index (no host
+// synchronisation), by the split kernel and again by the GEMM epilogue, which multiplies output (i, j) by
+// 2^-sA[i] * 2^-sB[j].  Elements down to 2^-17 of their row's / column's maximum keep all 22 bits of the two pieces
+// (the low piece, <= 2^-11 of the element, is then still rounded at or above fp16's subnormal spacing 2^-24);
+// smaller ones keep an ABSOLUTE precision of 2^-39 of that maximum -- the usual row/column-norm error model of a
+// blocked GEMM.  See DESIGN.md.
 #pragma once
 
 #include <stdint.h>
@@ -18,7 +20,7 @@
 
 namespace lb200 {
 
-// unbiased exponent s of the scale for a matrix whose largest finite |x| has fp32 bits `absmax_bits`
+// unbiased exponent s of the scale for a row / column whose largest finite |x| has fp32 bits `absmax_bits`
 __device__ __forceinline__ int f16x2_scale_exp(uint32_t absmax_bits) {
   const int e = static_cast<int>(absmax_bits >> 23);  // biased exponent (the sign bit is clear)
   if (e == 0) return 0;                               // all zero / subnormal: leave as is

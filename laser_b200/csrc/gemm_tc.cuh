@@ -108,10 +108,13 @@ struct TcParams {
 struct TcHintParams : TcParams {
   uint64_t hint_a = 0, hint_b = 0;
 };
-// gemm_tc_f16_kernel: fp16 operands (two scaled pieces per fp32 operand); absmax[0] / absmax[1] = fp32 bits of the
-// largest finite |a| / |b|, from which the epilogue derives the unscale factors (f16_scale.cuh)
+// gemm_tc_f16_kernel: fp16 operands (two scaled pieces per fp32 operand); amax_a[i] / amax_b[j] = fp32 bits of the largest
+// finite |a| of row i of A / |b| of column j of B, from which the epilogue derives the unscale factors (f16_scale.cuh)
 struct TcF16Params : TcParams {
-  const uint32_t *absmax = nullptr;
+  const uint32_t *amax_a = nullptr, *amax_b = nullptr;
+};
+struct F16Scales {     // host side: where the two abs-max vectors of the current call live (device memory)
+  const uint32_t *a = nullptr, *b = nullptr;
 };
 struct TcBatchedParams : TcParams {
   int batch = 1;

@@ -147,47 +147,85 @@ split_rows_bf16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, i
 }
 
 // ---- LASER_B200_PATH_F16X3: two fp16 pieces of the SCALED operand (f16_scale.cuh) -------------------------
-// Largest finite |x| of R rows of Cc contiguous floats (same addressing as the split kernels), as fp32 bits,
-// max-combined into *out (zeroed by the host before the launch): one shared-memory atomic per thread, one
-// global atomic per block.
+// One scale per mn index of the operand (row of A / column of B), i.e. one abs-max over k per mn.  The prepared
+// layout is [R][Cc] with contiguous rows (as for the other split kernels); mn runs along R for a K-major operand
+// (PER_COL = false: one word per row) and along Cc for an MN-major one (PER_COL = true: one word per column).
+// out[] holds fp32 bit patterns of non-negative finite numbers (ordered like unsigned integers), zeroed by the
+// host before the launch, combined with atomicMax after a local reduction.
+__device__ __forceinline__ uint32_t finite_abs_bits(float f) {
+  const uint32_t a = __float_as_uint(f) & 0x7fffffffu;
+  return a < 0x7f800000u ? a : 0u;     // infinities and NaNs do not set a scale (they propagate as such)
+}
+constexpr int ABSMAX_ROW_CHUNK = 1024;   // floats of one row reduced by one warp pass (32 lanes x 8 x float4)
+constexpr int ABSMAX_COL_ROWS = 64;      // rows of a 4-column strip reduced by one thread
+template <bool PER_COL>
 __global__ void __launch_bounds__(256)
-absmax_rows_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint32_t *__restrict__ out) {
-  __shared__ uint32_t block_max;
-  if (threadIdx.x == 0) block_max = 0u;
-  __syncthreads();
-  const int64_t vec_per_row = (Cc + 3) >> 2;
-  const int64_t total = R * vec_per_row;
-  uint32_t m = 0u;
-  auto take = [&](float f) {
-    const uint32_t a = __float_as_uint(f) & 0x7fffffffu;
-    if (a < 0x7f800000u && a > m) m = a;      // infinities and NaNs do not set the scale (they propagate as such)
-  };
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int64_t c = (i - r * vec_per_row) << 2;
-    const float *s = src + r * src_ld + c;
-    if (c + 4 <= Cc) {
-      const float4 v = *reinterpret_cast<const float4 *>(s);
-      take(v.x); take(v.y); take(v.z); take(v.w);
-    } else {
-      take(s[0]);
-      if (c + 1 < Cc) take(s[1]);
-      if (c + 2 < Cc) take(s[2]);
+absmax_mn_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint32_t *__restrict__ out) {
+  if constexpr (!PER_COL) {
+    // warp w takes (row, chunk) items; lanes read float4s 128 floats apart; butterfly max; one atomic per item
+    const int lane = threadIdx.x & 31;
+    const int64_t chunks = (Cc + ABSMAX_ROW_CHUNK - 1) / ABSMAX_ROW_CHUNK;
+    const int64_t items = R * chunks;
+    const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t it = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; it < items; it += warps) {
+      const int64_t r = it / chunks;
+      const int64_t c0 = (it - r * chunks) * ABSMAX_ROW_CHUNK;
+      const float *row = src + r * src_ld;
+      uint32_t m = 0u;
+#pragma unroll
+      for (int i = 0; i < ABSMAX_ROW_CHUNK / 128; ++i) {
+        const int64_t c = c0 + i * 128 + lane * 4;
+        if (c + 4 <= Cc) {
+          const float4 v = *reinterpret_cast<const float4 *>(row + c);
+          m = max(max(m, finite_abs_bits(v.x)), max(finite_abs_bits(v.y), max(finite_abs_bits(v.z), finite_abs_bits(v.w))));
+        } else {
+          for (int64_t cc = c; cc < Cc; ++cc) m = max(m, finite_abs_bits(row[cc]));
+        }
+      }
+      float mf = __uint_as_float(m);     // non-negative finite: fmaxf orders them like the integers
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+      if (lane == 0) atomicMax(out + r, __float_as_uint(mf));
+    }
+  } else {
+    // thread takes (4-column strip, block of ABSMAX_COL_ROWS rows) items: adjacent threads read adjacent float4s
+    const int64_t strips = (Cc + 3) >> 2;
+    const int64_t rblocks = (R + ABSMAX_COL_ROWS - 1) / ABSMAX_COL_ROWS;
+    const int64_t items = strips * rblocks;
+    for (int64_t it = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; it < items;
+         it += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t rb = it / strips;
+      const int64_t c = (it - rb * strips) << 2;
+      const int64_t r1 = (rb + 1) * ABSMAX_COL_ROWS < R ? (rb + 1) * ABSMAX_COL_ROWS : R;
+      uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+      for (int64_t r = rb * ABSMAX_COL_ROWS; r < r1; ++r) {
+        const float *s = src + r * src_ld + c;
+        if (c + 4 <= Cc) {
+          const float4 v = *reinterpret_cast<const float4 *>(s);
+          m0 = max(m0, finite_abs_bits(v.x)); m1 = max(m1, finite_abs_bits(v.y));
+          m2 = max(m2, finite_abs_bits(v.z)); m3 = max(m3, finite_abs_bits(v.w));
+        } else {
+          m0 = max(m0, finite_abs_bits(s[0]));
+          if (c + 1 < Cc) m1 = max(m1, finite_abs_bits(s[1]));
+          if (c + 2 < Cc) m2 = max(m2, finite_abs_bits(s[2]));
+        }
+      }
+      atomicMax(out + c, m0);
+      if (c + 1 < Cc) atomicMax(out + c + 1, m1);
+      if (c + 2 < Cc) atomicMax(out + c + 2, m2);
+      if (c + 3 < Cc) atomicMax(out + c + 3, m3);
     }
   }
-  atomicMax(&block_max, m);
-  __syncthreads();
-  if (threadIdx.x == 0) atomicMax(out, block_max);
 }
 
-// hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from *absmax (f16_scale.cuh): x * 2^s = hb + lb + r,
-// |r| <= 2^-22 |x * 2^s| while hb is a normal fp16 number.  Addressing as split_rows_bf16x2_kernel.
+// hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from the abs-max word of the element's mn index
+// (f16_scale.cuh): x * 2^s = hb + lb + r, |r| <= 2^-22 |x * 2^s| for elements within 2^-17 of their row's /
+// column's maximum.  Addressing as split_rows_bf16x2_kernel.
+template <bool PER_COL>
 __global__ void __launch_bounds__(256)
 split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
                         uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b,
                         const uint32_t *__restrict__ absmax) {
-  const float scale = f16x2_scale(*absmax);
   const int64_t vec_per_row = (Cc + 3) >> 2;
   const int64_t total = R * vec_per_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -204,7 +242,16 @@ split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
       v.z = (c + 2 < Cc) ? s[2] : 0.0f;
       v.w = 0.0f;
     }
-    v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale); v.z = __fmul_rn(v.z, scale); v.w = __fmul_rn(v.w, scale);
+    float sx, sy, sz, sw;
+    if constexpr (PER_COL) {
+      sx = f16x2_scale(absmax[c]);
+      sy = (c + 1 < Cc) ? f16x2_scale(absmax[c + 1]) : 1.0f;
+      sz = (c + 2 < Cc) ? f16x2_scale(absmax[c + 2]) : 1.0f;
+      sw = (c + 3 < Cc) ? f16x2_scale(absmax[c + 3]) : 1.0f;
+    } else {
+      sx = sy = sz = sw = f16x2_scale(absmax[r]);
+    }
+    v.x = __fmul_rn(v.x, sx); v.y = __fmul_rn(v.y, sy); v.z = __fmul_rn(v.z, sz); v.w = __fmul_rn(v.w, sw);
     const uint16_t hx = f16_rn_bits(v.x), hy = f16_rn_bits(v.y), hz = f16_rn_bits(v.z), hw = f16_rn_bits(v.w);
     uint2 h, l;
     h.x = hx | (static_cast<uint32_t>(hy) << 16);

@@ -110,6 +110,7 @@ inline uint32_t atomicMax(uint32_t *p, uint32_t v) {   // shared or global word;
 }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
+inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 #define threadIdx (emu::t_idx)
 #define blockIdx (emu::b_idx)

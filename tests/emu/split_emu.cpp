@@ -23,12 +23,15 @@ void emu_split_rows_bf16x2(const float *src, int64_t R, int64_t Cc, int64_t src_
                            int grid) {
   emu::launch(grid, 256, [=]() { split_rows_bf16x2_kernel(src, R, Cc, src_ld, hb, lb, ld_b); });
 }
-void emu_absmax_rows(const float *src, int64_t R, int64_t Cc, int64_t src_ld, uint32_t *out, int grid) {
-  emu::launch(grid, 256, [=]() { absmax_rows_kernel(src, R, Cc, src_ld, out); });
+// per_col 0: one abs-max word per row (K-major operand), 1: one per column (MN-major operand)
+void emu_absmax_mn(int per_col, const float *src, int64_t R, int64_t Cc, int64_t src_ld, uint32_t *out, int grid) {
+  if (per_col) emu::launch(grid, 256, [=]() { absmax_mn_kernel<true>(src, R, Cc, src_ld, out); });
+  else emu::launch(grid, 256, [=]() { absmax_mn_kernel<false>(src, R, Cc, src_ld, out); });
 }
-void emu_split_rows_f16x2(const float *src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *hb, uint16_t *lb, int64_t ld_b,
-                          const uint32_t *absmax, int grid) {
-  emu::launch(grid, 256, [=]() { split_rows_f16x2_kernel(src, R, Cc, src_ld, hb, lb, ld_b, absmax); });
+void emu_split_rows_f16x2(int per_col, const float *src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *hb, uint16_t *lb,
+                          int64_t ld_b, const uint32_t *absmax, int grid) {
+  if (per_col) emu::launch(grid, 256, [=]() { split_rows_f16x2_kernel<true>(src, R, Cc, src_ld, hb, lb, ld_b, absmax); });
+  else emu::launch(grid, 256, [=]() { split_rows_f16x2_kernel<false>(src, R, Cc, src_ld, hb, lb, ld_b, absmax); });
 }
 // mode 0: copy, 1: tf32 hi/lo, 2: mixed (hi fp32 + xb/lb bf16), 3: two bf16 pieces (xb, lb)
 void emu_pack_general_f32(int mode, const float *src, int64_t R, int64_t Cc, int64_t sr, int64_t sc, float *dst,

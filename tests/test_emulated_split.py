@@ -20,13 +20,13 @@ def emu():
     L.emu_split_rows_tf32.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
     L.emu_split_rows_mixed.argtypes = [vp, i64, i64, i64, vp, i64, vp, vp, i64, ci]
     L.emu_split_rows_bf16x2.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
-    L.emu_absmax_rows.argtypes = [vp, i64, i64, i64, vp, ci]
-    L.emu_split_rows_f16x2.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp, ci]
+    L.emu_absmax_mn.argtypes = [ci, vp, i64, i64, i64, vp, ci]
+    L.emu_split_rows_f16x2.argtypes = [ci, vp, i64, i64, i64, vp, vp, i64, vp, ci]
     L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, vp, vp, i64, ci]
     L.emu_pack_general_u16.argtypes = [vp, i64, i64, i64, i64, vp, i64, ci, ci]
     L.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.emu_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, ci]
-    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_split_rows_bf16x2", "emu_absmax_rows", "emu_split_rows_f16x2", "emu_pack_general_f32", "emu_pack_general_u16",
+    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_split_rows_bf16x2", "emu_absmax_mn", "emu_split_rows_f16x2", "emu_pack_general_f32", "emu_pack_general_u16",
               "emu_splitk_reduce", "emu_fill_uniform_f32"):
         getattr(L, n).restype = None
     return L
@@ -77,38 +77,44 @@ def test_split_rows(emu, R, Cc, src_ld):
     assert (np.abs(rec - x) <= 2.0 ** -16 * np.abs(x)).all()
 
 
-@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260)])
-@pytest.mark.parametrize("magnitude", [1.0, 1e-20, 3e+18, 0.0])
-def test_f16x2_scale_and_split(emu, R, Cc, src_ld, magnitude):
-    """LASER_B200_PATH_F16X3: abs-max word, power-of-two scale putting the maximum into [2^14, 2^15), two fp16 pieces
-    (numpy's float16 is IEEE binary16 with round-to-nearest-even, the conversion the kernel's software twin restates)"""
+@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100)])
+@pytest.mark.parametrize("per_col", [0, 1])
+def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
+    """LASER_B200_PATH_F16X3: one abs-max word per row (K-major operand) or per column (MN-major operand), a power-of-two
+    scale per word putting that maximum into [2^14, 2^15), two fp16 pieces (numpy's float16 is IEEE binary16 with
+    round-to-nearest-even, the conversion the kernel's software twin restates).  The rows / columns differ by up to
+    2^+-60 in magnitude; one of them is all zero."""
     rng = np.random.default_rng(3)
-    src = (rng.standard_normal((R, src_ld)) * np.float32(magnitude)).astype(np.float32)
-    src[0, 0] = np.inf; src[R - 1, Cc - 1] = np.nan          # non-finite entries must not set the scale
+    src = rng.standard_normal((R, src_ld)).astype(np.float32)
+    n_mn = Cc if per_col else R
+    mags = (2.0 ** rng.integers(-60, 60, n_mn)).astype(np.float32)
+    mags[n_mn // 2] = 0.0
+    src[:, :Cc] *= mags[None, :] if per_col else mags[:, None]
+    src[0, 0] = np.inf; src[R - 1, Cc - 1] = np.nan          # non-finite entries must not set a scale
     src[:, Cc:] = 1e30                                        # nor may anything outside the view
     x = src[:, :Cc]
-    word = np.zeros(1, np.uint32)
-    emu.emu_absmax_rows(p(src), R, Cc, src_ld, p(word), 3)
-    finite = np.abs(x[np.isfinite(x)])
-    assert word[0] == finite.max().view(np.uint32)
-    e = int(word[0] >> 23)
-    s_exp = 0 if e == 0 else int(np.clip(14 - (e - 127), -126, 126))
-    scale = np.float32(2.0 ** s_exp)
+    words = np.zeros(n_mn, np.uint32)
+    emu.emu_absmax_mn(per_col, p(src), R, Cc, src_ld, p(words), 3)
+    want = np.where(np.isfinite(x), np.abs(x), 0).max(axis=0 if per_col else 1).astype(np.float32)
+    assert np.array_equal(words, want.view(np.uint32))
+    e = (words >> 23).astype(np.int64)
+    s_exp = np.where(e == 0, 0, np.clip(14 - (e - 127), -126, 126))
+    scale = (2.0 ** s_exp).astype(np.float32)
     ldb = -(-Cc // 8) * 8; ld = -(-Cc // 4) * 4
     hb = np.full((R, ldb), 9, np.uint16); lb = np.full((R, ldb), 9, np.uint16)
-    emu.emu_split_rows_f16x2(p(src), R, Cc, src_ld, p(hb), p(lb), ldb, p(word), 2)
+    emu.emu_split_rows_f16x2(per_col, p(src), R, Cc, src_ld, p(hb), p(lb), ldb, p(words), 2)
     with np.errstate(invalid="ignore", over="ignore"):
-        xs = x * scale
+        xs = x * (scale[None, :] if per_col else scale[:, None])
         h = xs.astype(np.float16); l = (xs - h.astype(np.float32)).astype(np.float16)
     ok = np.isfinite(x)
     assert np.array_equal(hb[:, :Cc][ok], h.view(np.uint16)[ok]) and np.array_equal(lb[:, :Cc][ok], l.view(np.uint16)[ok])
     assert np.all(hb[:, Cc:ld] == 0) and np.all(lb[:, Cc:ld] == 0)
-    if magnitude:
-        assert 2.0 ** 14 <= np.abs(xs[ok]).max() < 2.0 ** 15
-        big = ok & (np.abs(xs) >= 2.0 ** -3)           # l = xs - h (<= 2^-11 |xs|) is then rounded at or above fp16's subnormal spacing 2^-24: 22 bits
-        rec = h.astype(np.float64) + l.astype(np.float64)
-        assert (np.abs(rec - xs)[big] <= 2.0 ** -22 * np.abs(xs)[big]).all()
-        assert (np.abs(rec - xs)[ok & ~big] <= 2.0 ** -25).all()      # everything else: absolute precision of the fp16 subnormals
+    mx = np.where(ok, np.abs(xs), 0).max(axis=0 if per_col else 1)
+    assert np.all((mx == 0) | ((mx >= 2.0 ** 14) & (mx < 2.0 ** 15)))
+    big = ok & (np.abs(xs) >= 2.0 ** -3)           # l = xs - h (<= 2^-11 |xs|) is then rounded at or above fp16's subnormal spacing 2^-24: 22 bits
+    rec = h.astype(np.float64) + l.astype(np.float64)
+    assert (np.abs(rec - xs)[big] <= 2.0 ** -22 * np.abs(xs)[big]).all()
+    assert (np.abs(rec - xs)[ok & ~big] <= 2.0 ** -25).all()      # everything else: absolute precision of the fp16 subnormals
 
 
 @pytest.mark.parametrize("R,Cc,sr,sc,along_r", [

@@ -10,11 +10,12 @@ tensor-core kernel (fp32 output, kc-blocked fp32 accumulation):
     <= 1e-5 gate is NOT claimed); on the seeded inputs |ours-exact| <= (3*2^-18 + 2e-6) * sum_k |a||b| elementwise, a
     quarter of the worst case 3*2^-16 (random-signed errors; a lost piece or a wrong pass order exceeds it by orders
     of magnitude).
-  * LASER_B200_PATH_F16X3: the operand times 2^s (s from a device-side abs-max, csrc/f16_scale.cuh) as two FP16 pieces,
+  * LASER_B200_PATH_F16X3: every row of A / column of B times its own 2^s (s from a device-side abs-max, csrc/f16_scale.cuh) as two FP16 pieces,
     |x 2^s - h - l| <= 2^-22 |x 2^s|; the fp16 flavour of the kernel, whose epilogue undoes the scales.  Bars: those of the
     fp32-faithful modes of tests/test_gpu_parity.py (U(0,1) max-elementwise < 1e-4, expected ~1e-6; U(-0.1,0.1)
     normwise < 2e-6, mean_relative_error <= 1e-5), |ours-exact| <= (3*2^-22 + 2e-6) * sum_k |a||b|; operands far outside
-    fp16's range; entries below 2^-17 of the matrix maximum keep absolute (not relative) precision.
+    fp16's range; one scale per row of A / column of B; entries below 2^-17 of their own row's / column's maximum keep
+    absolute (not relative) precision.
 """
 import numpy as np
 import pytest
@@ -137,8 +138,8 @@ def test_mode_selection_and_host_pointer_entry(path):
 
 
 def test_f16x3_range_handling():
-    """fp16 has 5 exponent bits: operands far outside its range in both directions, a zero operand, two calls of
-    different ranges in a row, and the documented behaviour for entries far below the matrix maximum"""
+    """fp16 has 5 exponent bits: operands far outside its range in both directions, a zero operand, rows and columns of
+    wildly different magnitude, and the documented behaviour for entries far below their own row's maximum"""
     M, N, K = 200, 130, 96
     a = O.fill_uniform_f32(M * K, 71, -1.0, 1.0).reshape(M, K); b = O.fill_uniform_f32(K * N, 72, -1.0, 1.0).reshape(K, N)
     nan = np.full((M, N), np.nan, np.float32)
@@ -148,12 +149,23 @@ def test_f16x3_range_handling():
         ex = aa.astype(np.float64) @ bb.astype(np.float64)
         bnd = (np.abs(aa).astype(np.float64) @ np.abs(bb).astype(np.float64)) * (3 * 2.0 ** -22 + 2e-6) + 1e-37
         assert np.isfinite(got).all() and (np.abs(got - ex) <= bnd).all(), (sa, sb)
-    aw = a.copy(); aw[::2, :] *= np.float32(2.0 ** -30)
-    got, *_ = run(L.PATH_F16X3, M, N, K, 1.0, aw, "row", b, "row", 0.0, nan, "row")
-    ex = aw.astype(np.float64) @ b.astype(np.float64)
-    per = np.abs(aw).astype(np.float64) @ np.abs(b).astype(np.float64) * (3 * 2.0 ** -22 + 2e-6)
-    assert (np.abs(got - ex) <= per + np.abs(aw).max() * np.abs(b).astype(np.float64).sum(0)[None, :] * 2.0 ** -36).all()
-    assert (np.abs(got[1::2] - ex[1::2]) <= per[1::2]).all()       # rows at full scale are unaffected by the small ones
+    # one scale per row of A and per column of B: rows / columns of wildly different magnitude inside one matrix keep
+    # their full per-product accuracy (block-scaled matrices), in every operand class
+    rs_ = (2.0 ** np.random.default_rng(5).integers(-40, 40, M)).astype(np.float32)
+    cs_ = (2.0 ** np.random.default_rng(6).integers(-40, 40, N)).astype(np.float32)
+    aw, bw = (a * rs_[:, None]).astype(np.float32), (b * cs_[None, :]).astype(np.float32)
+    ex = aw.astype(np.float64) @ bw.astype(np.float64)
+    per = np.abs(aw).astype(np.float64) @ np.abs(bw).astype(np.float64) * (3 * 2.0 ** -22 + 2e-6)
+    for la, lb in (("row", "row"), ("col", "col"), ("padded", "both2"), ("negrow", "misaligned")):
+        got, *_ = run(L.PATH_F16X3, M, N, K, 1.0, aw, la, bw, lb, 0.0, nan, "row")
+        assert np.isfinite(got).all() and (np.abs(got - ex) <= per).all(), (la, lb)
+    # entries far below the maximum of their OWN row keep absolute precision (2^-39 of that maximum): the bound becomes
+    # relative to max_k |a_ik| * sum_k |b_kj|, the row-norm error model of a blocked GEMM (documented domain of the mode)
+    ai = a.copy(); ai[:, ::2] *= np.float32(2.0 ** -30)
+    got, *_ = run(L.PATH_F16X3, M, N, K, 1.0, ai, "row", b, "row", 0.0, nan, "row")
+    ex = ai.astype(np.float64) @ b.astype(np.float64)
+    per = np.abs(ai).astype(np.float64) @ np.abs(b).astype(np.float64) * (3 * 2.0 ** -22 + 2e-6)
+    assert (np.abs(got - ex) <= per + np.abs(ai).max(1)[:, None] * np.abs(b).astype(np.float64).sum(0)[None, :] * 2.0 ** -36).all()
 
 
 @pytest.mark.skipif(EMU, reason="too large for the CPU build")
