@@ -362,7 +362,7 @@ def experimental_mode_probe(mode_name, n):
     timeout (tools/two_piece_probe.py): whatever its first run on silicon does, the line above is already measured."""
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "two_piece_probe.py"), mode_name, str(n), "10"],
-                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+                           capture_output=True, text=True, timeout=180, cwd=ROOT)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode == 0 and lines:
             res = json.loads(lines[-1])
@@ -374,7 +374,7 @@ def experimental_mode_probe(mode_name, n):
             return res
         return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
     except subprocess.TimeoutExpired:
-        return {"error": "timeout after 300 s"}
+        return {"error": "timeout after 180 s"}
     except Exception as exc:   # informational leg: never fatal
         return {"error": repr(exc)}
 
