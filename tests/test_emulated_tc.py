@@ -20,7 +20,7 @@ pytestmark = pytest.mark.timeout(300)
 
 @pytest.fixture(scope="module")
 def emu():
-    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "ptx.cuh"]))
+    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "gemm_tc_kernel.inc", "f16_scale.cuh", "ptx.cuh"]))
     L.emu_gemm_tc.restype = ci
     L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64,
                               vp, i64, i64, ci, ci, ci, ci, ci, vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
