@@ -43,6 +43,8 @@ struct Args {
   int bias_per_row, act;
   float *splitk_ws;          // k_splits planes of M x round_up(N, 4) when split-K triggers
   int *out_k_splits, *out_grid;
+  int f16 = 0;               // 16-bit operands with fp32 output: 0 = bf16 pieces (gemm_tc_kernel), 1 = fp16 pieces (gemm_tc_f16_kernel)
+  const uint32_t *amax_a = nullptr, *amax_b = nullptr;   // f16: abs-max words per row of A / column of B (f16_scale.cuh)
 };
 
 template <int ESZ, bool A_MN, bool B_MN, typename OutT, bool PAIR>
@@ -72,6 +74,17 @@ static int run(const Args &a) {
   if (a.out_grid) *a.out_grid = static_cast<int>(grid);
   if (TcCfg<PAIR>::SMEM_BYTES > static_cast<int>(emu::kDynSmemBytes)) return -3;
   emu::reset_state();
+  if constexpr (ESZ == 2 && std::is_same<OutT, float>::value) {
+    if (a.f16) {   // capi.cu: launch_tc_f16
+      TcF16Params pf;
+      static_cast<TcParams &>(pf) = p;
+      pf.amax_a = a.amax_a; pf.amax_b = a.amax_b;
+      emu::launch(grid, TC_THREADS,
+                  [=]() { gemm_tc_f16_kernel<2, A_MN, B_MN, float, PAIR>(mA0, mA1, mB0, mB1, mA2, mA3, mB2, mB3, pf); },
+                  PAIR ? 2 : 1);
+      return 0;
+    }
+  }
   emu::launch(grid, TC_THREADS,
               [=]() { gemm_tc_kernel<ESZ, A_MN, B_MN, OutT, PAIR>(mA0, mA1, mB0, mB1, mA2, mA3, mB2, mB3, p); },
               PAIR ? 2 : 1);
@@ -99,4 +112,16 @@ extern "C" int emu_gemm_tc(int esz, int a_mn, int b_mn, int pair, int64_t M, int
   if (esz == 4) return dispatch<4, float>(a_mn, b_mn, pair, a);
   if (esz == 2) return dispatch<2, uint16_t>(a_mn, b_mn, pair, a);
   return -1;
+}
+
+// the two-piece fp32 modes (capi.cu: PATH_BF16X3 / PATH_F16X3): 16-bit hi / lo arrays per operand, three passes, fp32 output
+extern "C" int emu_gemm_tc16x3(int f16, int a_mn, int b_mn, int pair, int64_t M, int64_t N, int64_t K, float alpha, float beta,
+                               const void *A0, const void *A1, int64_t ldA, const void *B0, const void *B1, int64_t ldB,
+                               void *C, int64_t rsC, int64_t csC, int kc_faithful, int raster_g, int splitk_enabled, int sm_count,
+                               const float *bias, int bias_per_row, int act, float *splitk_ws, int *out_k_splits, int *out_grid,
+                               const uint32_t *amax_a, const uint32_t *amax_b) {
+  Args a{M, N, K, alpha, beta, {A0, A1, nullptr, nullptr}, {B0, B1, nullptr, nullptr}, ldA, ldA, ldB, ldB, C, rsC, csC, 3, kc_faithful,
+         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, out_k_splits, out_grid};
+  a.f16 = f16; a.amax_a = amax_a; a.amax_b = amax_b;
+  return dispatch<2, float>(a_mn, b_mn, pair, a);
 }

@@ -24,6 +24,8 @@ def emu():
     L.emu_gemm_tc.restype = ci
     L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64,
                               vp, i64, i64, ci, ci, ci, ci, ci, vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.emu_gemm_tc16x3.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, i64, vp, vp, i64, vp, i64, i64, ci, ci, ci, ci,
+                                  vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp]
     S = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh"]))
     S.emu_splitk_reduce.restype = None
     S.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
@@ -62,7 +64,35 @@ def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=F
     bt = np.ascontiguousarray(b.T)              # B seen as [n][k]
     arrs = {"A": [None] * 4, "B": [None] * 4}
     ld = {"A": 0, "B": 0}; ldb = {"A": 0, "B": 0}
-    if mode == "bf16":
+    amax = {"A": None, "B": None}
+    if mode in ("bf16x3", "f16x3"):
+        # two 16-bit pieces per operand (split.cuh: split_rows_bf16x2_kernel / absmax_mn_kernel + split_rows_f16x2_kernel)
+        esz, npass = 2, 3
+        f = np.float64
+        if mode == "bf16x3":
+            def pieces(x):
+                hb = f32_to_bf16_bits(x).reshape(x.shape); hf = bf16_bits_to_f32(hb).reshape(x.shape)
+                lb_ = f32_to_bf16_bits(x - hf).reshape(x.shape)
+                return hb, lb_, hf.astype(f), bf16_bits_to_f32(lb_).reshape(x.shape).astype(f), np.ones(x.shape[0])
+        else:
+            def pieces(x):          # one power-of-two scale per mn index (row of x), from its abs-max word (f16_scale.cuh)
+                words = np.abs(x).max(axis=1).astype(np.float32).view(np.uint32)
+                e = (words >> 23).astype(np.int64)
+                s_exp = np.where(e == 0, 0, np.clip(14 - (e - 127), -126, 126))
+                xs = x * (2.0 ** s_exp).astype(np.float32)[:, None]
+                h16 = xs.astype(np.float16); l16 = (xs - h16.astype(np.float32)).astype(np.float16)
+                pieces.words = words
+                return h16.view(np.uint16), l16.view(np.uint16), h16.astype(f), l16.astype(f), 2.0 ** (-s_exp.astype(f))
+        ha, la, haf, laf, ua = pieces(a)
+        if mode == "f16x3":
+            amax["A"] = pieces.words.copy()
+        hb, lb_, hbf, lbf, ub = pieces(bt)
+        if mode == "f16x3":
+            amax["B"] = pieces.words.copy()
+        arrs["A"][0], ld["A"] = lay(ha, a_mn, 8); arrs["A"][1], _ = lay(la, a_mn, 8)
+        arrs["B"][0], ld["B"] = lay(hb, b_mn, 8); arrs["B"][1], _ = lay(lb_, b_mn, 8)
+        exact = (haf @ lbf.T + laf @ hbf.T + haf @ hbf.T) * ua[:, None] * ub[None, :]
+    elif mode == "bf16":
         esz, npass = 2, 1
         ab, bb = f32_to_bf16_bits(a).reshape(M, K), f32_to_bf16_bits(bt).reshape(N, K)
         arrs["A"][0], ld["A"] = lay(ab, a_mn, 8); arrs["B"][0], ld["B"] = lay(bb, b_mn, 8)
@@ -92,11 +122,17 @@ def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=F
     bias, per_row, act = epi if epi else (None, 0, 0)
     ws = np.zeros(16 * M * (-(-N // 4) * 4), np.float32)
     ks, grid = ci(0), ci(0)
-    rc = emu.emu_gemm_tc(esz, int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
-                         ptr(arrs["A"][0]), ptr(arrs["A"][1]), ptr(arrs["A"][2]), ptr(arrs["A"][3]), ld["A"], ldb["A"],
-                         ptr(arrs["B"][0]), ptr(arrs["B"][1]), ptr(arrs["B"][2]), ptr(arrs["B"][3]), ld["B"], ldb["B"],
-                         ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, npass, kc, raster, splitk, sms,
-                         ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid))
+    if mode in ("bf16x3", "f16x3"):
+        rc = emu.emu_gemm_tc16x3(int(mode == "f16x3"), int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
+                                 ptr(arrs["A"][0]), ptr(arrs["A"][1]), ld["A"], ptr(arrs["B"][0]), ptr(arrs["B"][1]), ld["B"],
+                                 ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, kc, raster, splitk, sms,
+                                 ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]))
+    else:
+        rc = emu.emu_gemm_tc(esz, int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
+                             ptr(arrs["A"][0]), ptr(arrs["A"][1]), ptr(arrs["A"][2]), ptr(arrs["A"][3]), ld["A"], ldb["A"],
+                             ptr(arrs["B"][0]), ptr(arrs["B"][1]), ptr(arrs["B"][2]), ptr(arrs["B"][3]), ld["B"], ldb["B"],
+                             ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, npass, kc, raster, splitk, sms,
+                             ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid))
     assert rc == 0
     if ks.value > 1:     # capi.cu: tc_run -- second kernel of a split-K GEMM
         ldw = -(-N // 4) * 4
@@ -109,7 +145,7 @@ def rnd(shape, seed, lo=-1.0, hi=1.0):
     return O.fill_uniform_f32(int(np.prod(shape)), seed, lo, hi).reshape(shape)
 
 
-@pytest.mark.parametrize("mode", ["tf32x1", "tf32x3", "mixed"])
+@pytest.mark.parametrize("mode", ["tf32x1", "tf32x3", "mixed", "bf16x3", "f16x3"])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("pair", [False, True])
 def test_modes_majorness_and_pairs(emu, mode, a_mn, b_mn, pair):
@@ -124,7 +160,7 @@ def test_modes_majorness_and_pairs(emu, mode, a_mn, b_mn, pair):
     if mode != "tf32x1":                         # the split operands reproduce the fp32 product
         ref = np.zeros((M, N), np.float32)
         O.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, ref, N, 1)
-        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+        assert np.abs(got - ref).max() <= (2e-5 if mode == "bf16x3" else 1e-5) * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("pair", [False, True])
@@ -167,7 +203,7 @@ def test_fused_epilogue(emu, pair, per_row, act):
     assert np.abs(c.reshape(M, N) - want).max() <= 3e-6 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("mode,kc", [("mixed", 64), ("mixed", 128), ("tf32x3", 64), ("tf32x1", 128)])
+@pytest.mark.parametrize("mode,kc", [("mixed", 64), ("mixed", 128), ("tf32x3", 64), ("tf32x1", 128), ("bf16x3", 64), ("f16x3", 128)])
 @pytest.mark.parametrize("pair", [False, True])
 def test_accumulation_blocks_and_ragged_k(emu, mode, kc, pair):
     M, N, K = 140, 100, 333                      # several kc blocks, the last one partial, K % 32 != 0
@@ -179,7 +215,7 @@ def test_accumulation_blocks_and_ragged_k(emu, mode, kc, pair):
 
 
 @pytest.mark.parametrize("pair,M", [(False, 100), (True, 250)])
-@pytest.mark.parametrize("mode", ["mixed", "tf32x3"])
+@pytest.mark.parametrize("mode", ["mixed", "tf32x3", "bf16x3", "f16x3"])
 def test_split_k(emu, pair, M, mode):
     N, K = 200, 700                              # one output tile, long K: the planner splits K over idle SMs
     a, b = rnd((M, K), 11), rnd((K, N), 12)
@@ -219,7 +255,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
-@given(mode=st.sampled_from(["tf32x1", "tf32x3", "mixed", "bf16"]), M=st.integers(1, 300), N=st.integers(1, 300),
+@given(mode=st.sampled_from(["tf32x1", "tf32x3", "mixed", "bf16", "bf16x3", "f16x3"]), M=st.integers(1, 300), N=st.integers(1, 300),
        K=st.integers(1, 400), a_mn=st.booleans(), b_mn=st.booleans(), pair=st.booleans(),
        kc=st.sampled_from([32, 64, 128, 512]), raster=st.sampled_from([0, 1, 3]), sms=st.sampled_from([2, 4, 10]),
        splitk=st.booleans(), ccol=st.booleans(), beta=st.sampled_from([0.0, 1.0, -0.75]), seed=st.integers(0, 2**30))
