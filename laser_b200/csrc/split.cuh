@@ -178,8 +178,10 @@ absmax_mn_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t s
         if (c + 4 <= Cc) {
           const float4 v = *reinterpret_cast<const float4 *>(row + c);
           m = max(max(m, finite_abs_bits(v.x)), max(finite_abs_bits(v.y), max(finite_abs_bits(v.z), finite_abs_bits(v.w))));
-        } else {
-          for (int64_t cc = c; cc < Cc; ++cc) m = max(m, finite_abs_bits(row[cc]));
+        } else if (c < Cc) {   // ragged end of the row: one to three elements
+          m = max(m, finite_abs_bits(row[c]));
+          if (c + 1 < Cc) m = max(m, finite_abs_bits(row[c + 1]));
+          if (c + 2 < Cc) m = max(m, finite_abs_bits(row[c + 2]));
         }
       }
       float mf = __uint_as_float(m);     // non-negative finite: fmaxf orders them like the integers
