@@ -7,6 +7,7 @@ for m in bf16x3 f16x3; do
   echo "=== probe $m"; timeout 200 python tools/two_piece_probe.py $m 8192 10 2> gpurun_out/probe_${m}_err.log | tee gpurun_out/probe_${m}.json | cut -c1-1200
   echo "=== probe $m 4096"; timeout 200 python tools/two_piece_probe.py $m 4096 20 2>> gpurun_out/probe_${m}_err.log | tee gpurun_out/probe_${m}_4096.json | cut -c1-600
 done
+echo "=== accuracy of every fp32 mode vs the oracle and an fp64 product"; timeout 400 python tools/accuracy_probe.py 2>&1 | tee gpurun_out/accuracy_all_modes.log | cut -c1-400
 echo "=== e2e in each mode (host pointers, pipelined)"
 for m in tf32_bf16c bf16x3 f16x3; do echo $m; LASER_B200_F32_MODE=$m timeout 200 python tools/e2e_probe.py 2>> gpurun_out/e2e_modes_err.log | tee -a gpurun_out/e2e_modes.jsonl; done
 echo "=== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_two_piece.csv python tools/ncu_two_piece_target.py > gpurun_out/ncu_two_piece_list.log 2>&1; grep -c . gpurun_out/launches_two_piece.csv
