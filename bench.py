@@ -355,6 +355,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _finite_json(x):
+    """non-finite numbers -> None, recursively: the bench line must stay strict JSON (no NaN / Infinity tokens) whatever an
+    informational leg measured"""
+    import math
+    if isinstance(x, float):
+        return x if math.isfinite(x) else None
+    if isinstance(x, dict):
+        return {k: _finite_json(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite_json(v) for v in x]
+    return x
+
+
 def experimental_mode_probe(mode_name, n):
     """Informational, N=1 only, AFTER every measurement of this run: time and error of an opt-in fp32 mode
     (LASER_B200_PATH_BF16X3 / _F16X3: two 16-bit pieces per operand, three passes of the 16-bit kernel; DESIGN.md
@@ -365,7 +378,7 @@ def experimental_mode_probe(mode_name, n):
                            capture_output=True, text=True, timeout=180, cwd=ROOT)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode == 0 and lines:
-            res = json.loads(lines[-1])
+            res = _finite_json(json.loads(lines[-1]))
             res["note"] = ("opt-in mode, first measured by this run; " +
                            ("error bars: max-elementwise < 1e-4 on U(0,1), normwise < 1.5e-5 on U(-0.1,0.1); does not claim the "
                             "reference's mean_relative_error <= 1e-5 gate (the default mode does)" if mode_name == "bf16x3" else
@@ -397,7 +410,7 @@ GUARD = None
 
 
 def emit(obj):
-    line = json.dumps(obj)
+    line = json.dumps(_finite_json(obj), allow_nan=False)
     if GUARD is not None:
         GUARD.emit(line)
     else:
