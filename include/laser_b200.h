@@ -43,25 +43,21 @@ extern "C" {
 #define LASER_B200_EUNSUPPORTED 5
 
 /* Which kernel family executes a float32 gemm_strided call.
- * AUTO: tensor cores in the default fp32-faithful mode (TF32_BF16C) when the problem is
- *       large enough, exact SIMT otherwise.  The reference's analogue of this switch is its
- *       run-time ISA dispatch, gemm.nim:228-247. */
+ * AUTO: tensor cores in the fp32-faithful mode in force (default F16X3) when the problem is large
+ *       enough, exact SIMT otherwise (M*N*K <= 128^3, the reference's own switch, gemm.nim:140-141).
+ *       The reference's analogue of this choice is its run-time ISA dispatch, gemm.nim:228-247. */
 #define LASER_B200_PATH_AUTO 0
 #define LASER_B200_PATH_SIMT 1    /* exact fp32 FFMA chain, bit-equal to the CPU reference order */
-#define LASER_B200_PATH_TF32X1 2  /* tcgen05 kind::tf32, one pass (fast, ~1e-3 relative)      */
-#define LASER_B200_PATH_TF32X3 3  /* tcgen05 kind::tf32, hi/lo split, three passes (fp32-faithful) */
+#define LASER_B200_PATH_TF32X1 2  /* tcgen05 kind::tf32, one pass over the caller's memory (fast, ~1e-3 relative) */
+#define LASER_B200_PATH_TF32X3 3  /* tcgen05 kind::tf32, hi/lo split, three passes (fp32-faithful, any dynamic range) */
 #define LASER_B200_PATH_BF16 4    /* tcgen05 kind::f16 (bf16 inputs, fp32 accumulate)         */
-#define LASER_B200_PATH_TF32_BF16C 5 /* fp32-faithful, mixed: tf32 hi*hi pass + two bf16 passes for the
-                                      * hi*lo / lo*hi correction terms (2 tf32-equivalents instead of 3) */
-#define LASER_B200_PATH_BF16X3 6  /* fp32 operands split into two bf16 pieces each (x = h + l, |x - h - l| <= 2^-16 |x|);
-                                   * three kind::f16 passes h*l', l*h', h*h' on the bf16 kernel with fp32 output
-                                   * (1.5 tf32-equivalents per MAC; error <= 3*2^-16 ~ 4.6e-5 per product worst case, random-signed: ~3e-7 of sum|a||b| at K = 8192).
-                                   * Opt-in: written after the round's GPU minutes were spent, see DESIGN.md */
-#define LASER_B200_PATH_F16X3 7   /* every row of A and column of B scaled by its own power of two (device-side abs-max along K, no
-                                   * host synchronisation) and split into two FP16 pieces (11 + 11 bits); three kind::f16 passes;
-                                   * the epilogue undoes the scales.  3 instruction times per k-step like BF16X3, accuracy of TF32X3
-                                   * (<= 3*2^-22 per product) for entries within 2^-17 of their row's / column's maximum; smaller
-                                   * entries keep absolute precision 2^-39 of that maximum.  Opt-in, unmeasured: see DESIGN.md */
+/* 5 and 6 were round-1 modes (tf32 + bf16 correction terms; two bf16 pieces): superseded by F16X3, removed */
+#define LASER_B200_PATH_F16X3 7   /* DEFAULT fp32 mode.  Every row of A and column of B is scaled by its own power of two
+                                   * (device-side abs-max along K, no host synchronisation) and split into two FP16 pieces
+                                   * (11 + 11 bits); three kind::f16 passes hi*lo', lo*hi', hi*hi' over tiles loaded once; the
+                                   * epilogue undoes the scales.  1.5 tf32-equivalents per MAC; <= 3*2^-22 per product for
+                                   * entries within 2^-17 of their row's / column's maximum, smaller entries keep an absolute
+                                   * precision of 2^-39 of that maximum (the row/column-norm error model of a blocked GEMM) */
 
 /* ---- life cycle -------------------------------------------------------
  * The reference has one piece of import-time state, cpuinfo_initialize()
@@ -85,8 +81,8 @@ int laser_b200_last_path(void);
 int laser_b200_profile_begin(void);
 int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep_ms,
                            int64_t *prep_launches);
-/* default path for PATH_AUTO float32 calls: LASER_B200_PATH_TF32_BF16C (default), _TF32X3,
- * _TF32X1, _BF16X3, _F16X3 or _SIMT.  Also settable with env LASER_B200_F32_MODE=tf32x3|tf32_bf16c|tf32x1|bf16x3|f16x3|simt. */
+/* default path for PATH_AUTO float32 calls: LASER_B200_PATH_F16X3 (default), _TF32X3, _TF32X1 or _SIMT.
+ * Also settable with env LASER_B200_F32_MODE=f16x3|tf32x3|tf32x1|simt. */
 int laser_b200_set_f32_mode(int path);
 int laser_b200_get_f32_mode(void);
 
@@ -179,9 +175,9 @@ int laser_b200_gemm_strided_f32_epi_dev(int64_t M, int64_t N, int64_t K, float a
  * and gemm_packed   (laser/primitives/matrix_multiplication/gemm_prepacked.nim:63-292).
  * The reference packs an operand once into micro-panels so that repeated products with the same
  * matrix skip the packing pass; here "packing" is the operand preparation of the default
- * fp32-faithful mode (tf32 hi part + bf16 cross-term parts, K-major compact), so repeated
- * products skip the split pre-pass and read TMA-friendly K-major tiles whatever the source
- * strides were.  Packed buffers are opaque DEVICE memory owned by the caller, sized by
+ * fp32-faithful mode (two fp16 pieces of the scaled operand, K-major compact, plus the per-row
+ * scale words), so repeated products skip the preparation pass and read TMA-friendly K-major
+ * tiles whatever the source strides were.  Packed buffers are opaque DEVICE memory owned by the caller, sized by
  * *_mem_required (bytes), 256-byte aligned; like the reference's they are only meaningful to the
  * library build that wrote them ("unsafe to store or serialize", gemm_prepacked.nim:120-123).
  * M, N, K are the extents of the product the operand will take part in (A is M x K, B is K x N). */

@@ -4,8 +4,8 @@ The product is the C-ABI shared library laser_b200/lib/liblaser_b200.so (hand-wr
 tcgen05/TMEM/TMA tensor-core kernels + an exact SIMT kernel); this package is the thin
 host-side mirror of the reference interface on top of it.  See DESIGN.md / INTEGRATION.md.
 """
-from ._capi import (PATH_AUTO, PATH_BF16, PATH_BF16X3, PATH_F16X3, PATH_NAMES, PATH_SIMT, PATH_TF32_BF16C, PATH_TF32X1,
-                    PATH_TF32X3, LaserB200Error, lib, lib_path)
+from ._capi import (PATH_AUTO, PATH_BF16, PATH_F16X3, PATH_NAMES, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, LaserB200Error, lib,
+                    lib_path)
 from .gemm import (DevPtr, fill_uniform_f32, gemm_strided, gemm_strided_fused, get_f32_mode, init, last_path,
                    launch_count, profile_begin, profile_end, set_f32_mode, shutdown,
                    synchronize)

@@ -1,4 +1,7 @@
-"""Builds laser_b200/lib/liblaser_b200.so with nvcc for sm_100a (in-tree, no JIT cache)."""
+"""Builds laser_b200/lib/liblaser_b200.so with nvcc for sm_100a (in-tree, no JIT cache).
+
+One object per translation unit, compiled in parallel (the tcgen05 kernel families are the slow ones), then one link."""
+import concurrent.futures
 import os
 import shutil
 import subprocess
@@ -6,18 +9,21 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "liblaser_b200.so")
-SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "f16_scale.cuh", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh", "capi_layers.inc",
+SOURCES = ["capi.cu", "tc_f16x3.cu", "tc_tf32x3.cu", "tc_tf32x1.cu", "tc_bf16.cu", "multi_gpu.cu"]
+HEADERS = ["ptx.cuh", "f16_scale.cuh", "gemm_tc.cuh", "tc_params.h", "tc_launch.h", "tc_launch_impl.cuh", "gemm_simt.cuh",
+           "gemm_simt_kernel.inc", "split.cuh", "layers.cuh", "capi_layers.inc", "host_common.h",
            "../../include/laser_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",   # NOT -arch=sm_100a: tcgen05 needs the 'a' PTX target
     "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",                            # no libcuda/libcudart link dependency: loads on CPU-only hosts
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-shared", "-cudart", "static",       # no libcuda/libcudart link dependency: loads on CPU-only hosts
+              "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-ldl"]
 
 
 def _nvcc():
@@ -27,25 +33,45 @@ def _nvcc():
     raise RuntimeError("nvcc not found: cannot build liblaser_b200.so")
 
 
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _newest_header():
+    return max((os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h))), default=0.0)
+
+
 def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return _newest_header() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in _sources())
 
 
 def build(force=False, verbose=False):
     """Compile every CUDA source into the in-tree shared library. Returns its path."""
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
+    nvcc = _nvcc()
+    hdr_t = _newest_header()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(path)):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        subprocess.check_call(cmd, env=env)
+        return obj
+
+    srcs = _sources()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, srcs))
+    subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs, env=env)
     return LIB_PATH
 
 

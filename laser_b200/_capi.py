@@ -4,8 +4,8 @@ import os
 
 from . import _build
 
-PATH_AUTO, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, PATH_BF16, PATH_TF32_BF16C, PATH_BF16X3, PATH_F16X3 = 0, 1, 2, 3, 4, 5, 6, 7
-PATH_NAMES = {0: "auto", 1: "simt", 2: "tf32x1", 3: "tf32x3", 4: "bf16", 5: "tf32_bf16c", 6: "bf16x3", 7: "f16x3"}
+PATH_AUTO, PATH_SIMT, PATH_TF32X1, PATH_TF32X3, PATH_BF16, PATH_F16X3 = 0, 1, 2, 3, 4, 7
+PATH_NAMES = {0: "auto", 1: "simt", 2: "tf32x1", 3: "tf32x3", 4: "bf16", 7: "f16x3"}
 E_OK, E_INVAL, E_NODEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, 1, 2, 3, 4, 5
 MAXRANK = 6
 

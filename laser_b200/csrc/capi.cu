@@ -4,7 +4,8 @@
 // three matrix views, pick a kernel family (the reference picks an ISA micro-kernel at
 // run time, gemm.nim:228-247; here: exact SIMT vs tcgen05), prepare the operands
 // (the reference allocates packing Tiles per call, gemm_tiling.nim:312-341; here: TMA
-// tensor maps, plus the hi/lo split workspace for the fp32-faithful mode) and launch.
+// tensor maps, plus the two-piece workspace of the fp32-faithful modes) and launch.
+// The tcgen05 kernels live in their own translation units (tc_*.cu, tc_launch.h).
 // There is no CPU fallback anywhere in this file.
 #include "../../include/laser_b200.h"
 
@@ -24,9 +25,9 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
 #include "layers.cuh"
 #include "split.cuh"
+#include "tc_launch.h"
 
 namespace {
 
@@ -34,9 +35,9 @@ using namespace lb200;
 
 thread_local std::string g_last_error;
 thread_local int g_last_path = 0;
-thread_local Epilogue g_epi;   // fused epilogue of the call in flight on this thread (default: none)
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_f32_mode{-1};
+constexpr int kDefaultF32Mode = LASER_B200_PATH_F16X3;
 
 int set_error(int code, const char *fmt, ...) {
   char buf[512];
@@ -88,17 +89,19 @@ struct MapCacheEntry {
 };
 constexpr int kMapCacheSize = 64;
 
+constexpr int kSchedSlots = 256;   // tile-scheduler counters: one pair of words per launch in flight, used round-robin
+
 struct Ctx {
   MapCacheEntry map_cache[kMapCacheSize];
   int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
-  int l2_hint = 0;            // env LASER_B200_L2HINT: 0 = the measured kernel (default); 1 A evict_last / B evict_first, 2 the reverse (gemm_tc_hint_kernel, unmeasured)
-  bool tc_batched = false;    // env LASER_B200_TC_BATCHED=1: batches of tensor-core problems as one launch (unmeasured)
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
-  int kc_faithful = 128;  // env LASER_B200_KC (K extent per TMEM accumulation block)
+  int kc_faithful = 256;  // env LASER_B200_KC (K extent per TMEM accumulation block, fp32-faithful modes)
+  bool dyn_sched = true;  // env LASER_B200_DYNSCHED=0: static round-robin tiles instead of the atomic counter
+  bool pdl = true;        // env LASER_B200_PDL=0: ordinary launch of the GEMM kernel after the preparation kernels
   bool profiling = false;
   std::vector<EventPair> prof;
   int dev = -1;
@@ -107,12 +110,15 @@ struct Ctx {
   cudaStream_t up = nullptr, down = nullptr;  // H2D / D2H streams of the pipelined host entry
   std::vector<cudaEvent_t> panel_ev;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  Buffer ws[8];      // per operand: hi, lo (fp32) and xb, lb (bf16) -- A then B
+  Buffer ws[4];      // prepared pieces: A piece 0, A piece 1, B piece 0, B piece 1
+  Buffer gather[2];  // F16X3: compact fp32 copy of a general-stride operand (A, B) before it is scaled and split
   Buffer stage[3];   // device staging of host A, B, C spans
   Buffer splitk;     // split-K partial-sum planes
   Buffer layer_ws;   // im2col workspace of the host-pointer convolution
   Buffer f16s;       // F16X3 mode: fp32 bits of max_k |a| per row of A (words [0, M)) and of max_k |b| per column of B (from
                      // f16_b_off on), written and read on the device
+  Buffer sched;      // kSchedSlots x {next unit, pairs done}: the kernel re-zeroes its slot when it ends
+  int sched_next = 0;
   cudaEvent_t ws_free = nullptr;  // recorded after the last kernel that reads ws[]
   std::mutex mu;       // workspace + tensor-map construction
   std::mutex host_mu;  // staging buffers of the host-pointer entry points
@@ -122,6 +128,15 @@ struct Ctx {
 constexpr int kMaxDevices = 32;
 Ctx g_ctx[kMaxDevices];
 std::mutex g_ctx_mu;
+
+int parse_f32_mode(const char *mode) {
+  if (!mode) return kDefaultF32Mode;
+  if (!strcmp(mode, "f16x3")) return LASER_B200_PATH_F16X3;
+  else if (!strcmp(mode, "tf32x3")) return LASER_B200_PATH_TF32X3;
+  else if (!strcmp(mode, "tf32x1")) return LASER_B200_PATH_TF32X1;
+  else if (!strcmp(mode, "simt")) return LASER_B200_PATH_SIMT;
+  return kDefaultF32Mode;
+}
 
 int get_ctx(Ctx **out) {
   int dev = 0;
@@ -153,6 +168,9 @@ int get_ctx(Ctx **out) {
       if (!fn || qres != cudaDriverEntryPointSuccess)
         return set_error(LASER_B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
       c.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+      CUDA_TRY(cudaMalloc(&c.sched.ptr, kSchedSlots * 2 * sizeof(unsigned int)));
+      c.sched.bytes = kSchedSlots * 2 * sizeof(unsigned int);
+      CUDA_TRY(cudaMemset(c.sched.ptr, 0, c.sched.bytes));
       if (const char *kc = getenv("LASER_B200_KC")) {
         const int v = atoi(kc);
         if (v >= 32) c.kc_faithful = v;
@@ -161,25 +179,13 @@ int get_ctx(Ctx **out) {
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
-      if (const char *tb = getenv("LASER_B200_TC_BATCHED")) c.tc_batched = atoi(tb) != 0;
-      if (const char *lh = getenv("LASER_B200_L2HINT")) c.l2_hint = atoi(lh);
+      if (const char *ds = getenv("LASER_B200_DYNSCHED")) c.dyn_sched = atoi(ds) != 0;
+      if (const char *pd = getenv("LASER_B200_PDL")) c.pdl = atoi(pd) != 0;
       if (const char *pr = getenv("LASER_B200_PANEL_ROWS")) {
         const int64_t v = atoll(pr) / 256 * 256;   // whole CTA-pair tiles
         if (v >= 256) c.panel_rows = v;
       }
-      const char *mode = getenv("LASER_B200_F32_MODE");
-      if (g_f32_mode.load() < 0) {
-        int m = LASER_B200_PATH_TF32_BF16C;
-        if (mode) {
-          if (!strcmp(mode, "tf32x3")) m = LASER_B200_PATH_TF32X3;
-          if (!strcmp(mode, "tf32x1")) m = LASER_B200_PATH_TF32X1;
-          else if (!strcmp(mode, "tf32_bf16c")) m = LASER_B200_PATH_TF32_BF16C;
-          else if (!strcmp(mode, "bf16x3")) m = LASER_B200_PATH_BF16X3;
-          else if (!strcmp(mode, "f16x3")) m = LASER_B200_PATH_F16X3;
-          else if (!strcmp(mode, "simt")) m = LASER_B200_PATH_SIMT;
-        }
-        g_f32_mode.store(m);
-      }
+      if (g_f32_mode.load() < 0) g_f32_mode.store(parse_f32_mode(getenv("LASER_B200_F32_MODE")));
       c.ready = true;
     }
   }
@@ -216,6 +222,12 @@ int prof_close(Ctx &c, cudaStream_t s, EventPair *ep, int launches) {
   return LASER_B200_OK;
 }
 
+void prof_abort(Ctx &c, EventPair *ep) {   // an error path after prof_open: the pair is not recorded, so release it here
+  if (!c.profiling) return;
+  cudaEventDestroy(ep->a);
+  cudaEventDestroy(ep->b);
+}
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
   int64_t g = static_cast<int64_t>(c.sm_count) * per_sm;
@@ -231,11 +243,11 @@ inline int grid_for(const Ctx &c, int64_t work_items, int per_sm) {
 template <typename T, int TM, int TN, int BK>
 int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
                 int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
-                int64_t csC, cudaStream_t s, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0,
+                int64_t csC, cudaStream_t s, const Epilogue &epi, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0,
                 int64_t bsC = 0) {
   SimtParams<T> p;
   const int64_t tiles = simt_plan<T, TM, TN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
-  if constexpr (std::is_same<T, float>::value) { p.bias = g_epi.bias; p.bias_per_row = g_epi.bias_per_row; p.act = g_epi.act; }
+  if constexpr (std::is_same<T, float>::value) { p.bias = epi.bias; p.bias_per_row = epi.bias_per_row; p.act = epi.act; }
   if (tiles > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
   p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   const int grid = grid_for(c, tiles * batch, 2);
@@ -249,16 +261,16 @@ int launch_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, in
 template <typename T>
 int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA,
               int64_t csA, const T *B, int64_t rsB, int64_t csB, T beta, T *C, int64_t rsC,
-              int64_t csC, cudaStream_t s, int64_t batch = 1, int64_t bsA = 0, int64_t bsB = 0,
-              int64_t bsC = 0) {
+              int64_t csC, cudaStream_t s, const Epilogue &epi = Epilogue(), int64_t batch = 1, int64_t bsA = 0,
+              int64_t bsB = 0, int64_t bsC = 0) {
 #ifndef LB200_SIMT_BK
 #define LB200_SIMT_BK 16
 #endif
   if constexpr (sizeof(T) == 4)
-    return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, batch,
+    return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi, batch,
                                                bsA, bsB, bsC);
   else
-    return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, batch, bsA, bsB,
+    return launch_simt<T, 4, 4, 16>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi, batch, bsA, bsB,
                                     bsC);
 }
 
@@ -294,6 +306,7 @@ int encode_map(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inne
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(outer_stride_elems) * esz};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   const cuuint32_t estr[2] = {1, 1};
+  // 16-bit tiles travel as BFLOAT16 whatever their format (bf16 / fp16): TMA only moves the words
   const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = c.encode(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -323,181 +336,49 @@ int operand_map(Ctx &c, CUtensorMap *map, int esz, const void *base, Major major
                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// Tensor maps (and workspace arrays) of one operand for the tensor-core kernel.
-//   hi  : the operand itself (single pass) or tf32_rna(x) in fp32 containers
-//   lo  : tf32_rna(x - hi)                       (fp32, 3-pass mode)
-//   xb  : bf16(x),  lb : bf16(x - hi)            (bf16, mixed mode)
+// Tensor maps of one operand for the tensor-core kernel: piece 0 = the operand itself (one pass) or its high piece,
+// piece 1 = its low piece (three-pass modes).
 struct OperandMaps {
-  CUtensorMap hi, lo, xb, lb;
+  CUtensorMap p0, p1;
   bool mn_major = false;
 };
 struct OperandWs {
-  Buffer *hi, *lo, *xb, *lb;
+  Buffer *p0, *p1, *gather;
   int64_t amax_off;   // F16X3: word offset of the operand's abs-max vector in Ctx::f16s (set by f16_scales)
 };
-enum SplitMode { SPLIT_NONE = 0, SPLIT_TF32 = 1, SPLIT_MIXED = 2, SPLIT_BF16X2 = 3 /* fp32 -> two bf16 arrays (xb, lb) */,
-                 SPLIT_F16X2 = 4 /* fp32 -> abs-max word + two fp16 arrays of the scaled operand (xb, lb) */ };
+// how an fp32 operand reaches the kernel
+enum SplitMode {
+  SPLIT_NONE = 0,    // as it is: TMA reads the caller's memory (TF32X1; bf16 operands)
+  SPLIT_TF32 = 1,    // hi = tf32_rna(x), lo = tf32_rna(x - hi) in fp32 containers (TF32X3)
+  SPLIT_F16X2 = 2,   // abs-max word per mn index + two fp16 pieces of the scaled operand (F16X3, the default)
+};
 
-template <int ESZ, typename OutT, bool PAIR>
-int launch_tc(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, cudaStream_t s) {
-  const bool a_mn = A.mn_major, b_mn = B.mn_major;
-  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;  // work units
-  // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than units
-  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
-  const int sched = static_cast<int>(tiles < units ? tiles : units);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define LB200_LAUNCH(AMN, BMN)                                                                   \
-  do {                                                                                           \
-    auto kfn = gemm_tc_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                        \
-    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
-    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
-      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
-    }                                                                                            \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
-  } while (0)
-#define LB200_LAUNCH_HINT(AMN, BMN)                                                              \
-  do {                                                                                           \
-    auto kfn = gemm_tc_hint_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                   \
-    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
-    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
-      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
-    }                                                                                            \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, ph)); \
-  } while (0)
-  bool hinted = false;
-  if constexpr (ESZ == 4) hinted = (c.l2_hint == 1 || c.l2_hint == 2);   // the experiment covers the fp32 kernels only
-  if constexpr (ESZ == 4) if (hinted) {
-    TcHintParams ph;
-    static_cast<TcParams &>(ph) = p;
-    ph.hint_a = c.l2_hint == 1 ? ptx::kEvictLast : ptx::kEvictFirst;
-    ph.hint_b = c.l2_hint == 1 ? ptx::kEvictFirst : ptx::kEvictLast;
-    if (!a_mn && !b_mn) LB200_LAUNCH_HINT(false, false);
-    else if (!a_mn && b_mn) LB200_LAUNCH_HINT(false, true);
-    else if (a_mn && !b_mn) LB200_LAUNCH_HINT(true, false);
-    else LB200_LAUNCH_HINT(true, true);
-  }
-  if (!hinted) {
-    if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
-    else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
-    else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
-    else LB200_LAUNCH(true, true);
-  }
-#undef LB200_LAUNCH_HINT
-#undef LB200_LAUNCH
-  COUNT_LAUNCH();
-  CHECK_LAUNCH();
-  return LASER_B200_OK;
-}
-
-// gemm_tc_f16_kernel (LASER_B200_PATH_F16X3): same grid / cluster / shared-memory configuration as launch_tc
-template <bool PAIR>
-int launch_tc_f16(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcParams &p, const F16Scales &sc, cudaStream_t s) {
-  const bool a_mn = A.mn_major, b_mn = B.mn_major;
-  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;
-  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
-  const int sched = static_cast<int>(tiles < units ? tiles : units);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TcF16Params pf;
-  static_cast<TcParams &>(pf) = p;
-  pf.amax_a = sc.a;
-  pf.amax_b = sc.b;
-#define LB200_LAUNCH_F16(AMN, BMN)                                                               \
-  do {                                                                                           \
-    auto kfn = gemm_tc_f16_kernel<2, AMN, BMN, float, PAIR>;                                     \
-    static std::atomic<uint32_t> attr_set{0};   /* per device: function attributes live in the context */ \
-    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
-      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
-    }                                                                                            \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, pf)); \
-  } while (0)
-  if (!a_mn && !b_mn) LB200_LAUNCH_F16(false, false);
-  else if (!a_mn && b_mn) LB200_LAUNCH_F16(false, true);
-  else if (a_mn && !b_mn) LB200_LAUNCH_F16(true, false);
-  else LB200_LAUNCH_F16(true, true);
-#undef LB200_LAUNCH_F16
-  COUNT_LAUNCH();
-  CHECK_LAUNCH();
-  return LASER_B200_OK;
-}
-
-// ---- batch of problems in one launch (gemm_tc_batched_kernel): 3-d tensor maps, box depth 1 ----
-int encode_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, int64_t inner, int64_t outer, int64_t nb,
-                int64_t outer_stride_elems, int64_t batch_stride_elems, int box_inner, int box_outer,
-                CUtensorMapSwizzle swz) {
-  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(nb)};
-  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(outer_stride_elems) * esz,
-                                 static_cast<cuuint64_t>(nb > 1 ? batch_stride_elems : outer_stride_elems * outer) * esz};
-  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer), 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = c.encode(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(LASER_B200_ECUDA, "cuTensorMapEncodeTiled (3-d) failed (%d): inner=%lld outer=%lld batch=%lld",
-                     static_cast<int>(r), (long long)inner, (long long)outer, (long long)nb);
-  return LASER_B200_OK;
-}
-// nb matrices seen as [mn][k] each, stacked densely: K-major [nb][mn][ld], MN-major [nb][k][ld]
-int operand_map3(Ctx &c, CUtensorMap *map, int esz, const void *base, bool mn_major, int64_t mn, int64_t k, int64_t nb,
-                 int64_t ld, int block_mn) {
-  const int block_k = TC_ROW_BYTES / esz, mn_atom = TC_ROW_BYTES / esz;
-  if (!mn_major) return encode_map3(c, map, esz, base, k, mn, nb, ld, mn * ld, block_k, block_mn, CU_TENSOR_MAP_SWIZZLE_128B);
-  return encode_map3(c, map, esz, base, mn, k, nb, ld, k * ld, mn_atom, block_k,
-                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
-}
-
-// F16X3 mode: abs-max per mn index of a row-contiguous fp32 operand [R][Cc] (mn along R, or along Cc when the operand is
-// MN-major), then its two fp16 pieces (split.cuh, f16_scale.cuh); the caller made room with f16_scales()
+// F16X3 preparation of a row-contiguous fp32 operand [R][Cc] (mn along R, or along Cc when the operand is MN-major):
+// K-major: ONE fused pass (abs-max per row, scale, split; split.cuh).  MN-major: the scale belongs to a column, so the
+// abs-max pass (strip reduction + atomicMax) comes first and the split second.
 int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_ld, bool mn_along_cols, const OperandWs &w,
-                  int64_t ld_b, int grid, cudaStream_t s) {
+                  int64_t ld_b, cudaStream_t s) {
   uint32_t *words = static_cast<uint32_t *>(c.f16s.ptr) + w.amax_off;
   const int64_t n_mn = mn_along_cols ? Cc : R;
   if (c.f16s.bytes < static_cast<size_t>(w.amax_off + n_mn) * sizeof(uint32_t))
     return set_error(LASER_B200_ECUDA, "internal: F16X3 scale buffer not sized for this operand");
-  CUDA_TRY(cudaMemsetAsync(words, 0, static_cast<size_t>(n_mn) * sizeof(uint32_t), s));
-  uint16_t *xb = static_cast<uint16_t *>(w.xb->ptr), *lb = static_cast<uint16_t *>(w.lb->ptr);
+  uint16_t *xb = static_cast<uint16_t *>(w.p0->ptr), *lb = static_cast<uint16_t *>(w.p1->ptr);
   if (mn_along_cols) {
+    CUDA_TRY(cudaMemsetAsync(words, 0, static_cast<size_t>(n_mn) * sizeof(uint32_t), s));
     const int64_t items = ((Cc + 3) / 4) * ((R + ABSMAX_COL_ROWS - 1) / ABSMAX_COL_ROWS);
     absmax_mn_kernel<true><<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(src, R, Cc, src_ld, words);
     COUNT_LAUNCH();
     CHECK_LAUNCH();
+    const int grid = grid_for(c, (R * ((Cc + 3) / 4) + 255) / 256, 8);
     split_rows_f16x2_kernel<true><<<grid, 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+  } else if (Cc <= 4 * 32 * F16ROWS_MAXV) {   // short rows: a warp per row
+    f16x2_rows_fused_kernel<32><<<grid_for(c, (R + 7) / 8, 6), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else {
-    const int64_t warp_items = R * ((Cc + ABSMAX_ROW_CHUNK - 1) / ABSMAX_ROW_CHUNK);
-    absmax_mn_kernel<false><<<grid_for(c, (warp_items + 7) / 8, 8), 256, 0, s>>>(src, R, Cc, src_ld, words);
-    COUNT_LAUNCH();
-    CHECK_LAUNCH();
-    split_rows_f16x2_kernel<false><<<grid, 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+    f16x2_rows_fused_kernel<256><<<grid_for(c, R, 6), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   }
-  return LASER_B200_OK;   // the caller counts and checks this last launch
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
 }
 
 template <int ESZ>
@@ -510,8 +391,8 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   if (mj != GENERAL && mode == SPLIT_NONE) {
     const int64_t ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
     m->mn_major = (mj == MN_MAJOR);
-    if ((rc = operand_map(c, &m->hi, ESZ, o.ptr, mj, o.mn, o.k, ld, block_mn))) return rc;
-    m->lo = m->xb = m->lb = m->hi;
+    if ((rc = operand_map(c, &m->p0, ESZ, o.ptr, mj, o.mn, o.k, ld, block_mn))) return rc;
+    m->p1 = m->p0;
     return LASER_B200_OK;
   }
   *used_ws = true;
@@ -524,131 +405,137 @@ int prepare_operand(Ctx &c, const Operand &o, SplitMode mode, const OperandWs &w
   const int64_t ld_b = round_up(Cc, 8);
   const size_t bytes = static_cast<size_t>(R) * ld * ESZ;
   const size_t bytes_b = static_cast<size_t>(R) * ld_b * 2;
-  if (mode != SPLIT_BF16X2 && !(mode == SPLIT_F16X2 && mj != GENERAL) && (rc = ensure(*w.hi, bytes))) return rc;
-  if (mode == SPLIT_TF32 && (rc = ensure(*w.lo, bytes))) return rc;
-  if (mode == SPLIT_MIXED || mode == SPLIT_BF16X2 || mode == SPLIT_F16X2) {
-    if ((rc = ensure(*w.xb, bytes_b))) return rc;
-    if ((rc = ensure(*w.lb, bytes_b))) return rc;
+  m->mn_major = (out_mj == MN_MAJOR);
+  if constexpr (ESZ == 4) {
+    if (mode == SPLIT_F16X2) {
+      if ((rc = ensure(*w.p0, bytes_b))) return rc;
+      if ((rc = ensure(*w.p1, bytes_b))) return rc;
+      const float *src = static_cast<const float *>(o.ptr);
+      int64_t src_ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
+      if (mj == GENERAL) {
+        // general strides: one coalesced gather into a compact fp32 array (the surviving descendant of pack_A / pack_B),
+        // then the fused scale + split of that
+        if ((rc = ensure(*w.gather, bytes))) return rc;
+        const int64_t tiles = ((o.mn + 31) / 32) * ((o.k + 31) / 32);
+        const int read_along_r = (llabs(o.s_mn) < llabs(o.s_k)) ? 1 : 0;
+        pack_general_kernel<float, 0><<<grid_for(c, tiles, 8), 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k,
+                                                                            static_cast<float *>(w.gather->ptr), nullptr, ld,
+                                                                            read_along_r);
+        COUNT_LAUNCH();
+        CHECK_LAUNCH();
+        src = static_cast<const float *>(w.gather->ptr);
+        src_ld = ld;
+      }
+      if ((rc = f16x2_prepare(c, src, R, Cc, src_ld, out_mj == MN_MAJOR, w, ld_b, s))) return rc;
+      if ((rc = operand_map(c, &m->p0, 2, w.p0->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
+      return operand_map(c, &m->p1, 2, w.p1->ptr, out_mj, o.mn, o.k, ld_b, block_mn);
+    }
   }
+  if ((rc = ensure(*w.p0, bytes))) return rc;
+  if (mode == SPLIT_TF32 && (rc = ensure(*w.p1, bytes))) return rc;
   if (mj != GENERAL) {
-    // TMA-addressable: elementwise split that keeps the operand's major-ness (fp32 only)
+    // TMA-addressable: elementwise split that keeps the operand's major-ness (fp32 only; SPLIT_NONE returned above)
     if constexpr (ESZ == 4) {
       const int64_t src_ld = (mj == K_MAJOR) ? o.s_mn : o.s_k;
       const int64_t items = R * ((Cc + 3) / 4);
-      const int grid = grid_for(c, (items + 255) / 256, 8);
-      if (mode == SPLIT_F16X2) {
-        if ((rc = f16x2_prepare(c, static_cast<const float *>(o.ptr), R, Cc, src_ld, mj == MN_MAJOR, w, ld_b, grid, s))) return rc;
-      } else if (mode == SPLIT_TF32)
-        split_rows_tf32_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
-                                                    static_cast<float *>(w.hi->ptr),
-                                                    static_cast<float *>(w.lo->ptr), ld);
-      else if (mode == SPLIT_BF16X2)
-        split_rows_bf16x2_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
-                                                      static_cast<uint16_t *>(w.xb->ptr),
-                                                      static_cast<uint16_t *>(w.lb->ptr), ld_b);
-      else
-        split_rows_mixed_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(o.ptr), R, Cc, src_ld,
-                                                     static_cast<float *>(w.hi->ptr), ld,
-                                                     static_cast<uint16_t *>(w.xb->ptr),
-                                                     static_cast<uint16_t *>(w.lb->ptr), ld_b);
+      split_rows_tf32_kernel<<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(
+          static_cast<const float *>(o.ptr), R, Cc, src_ld, static_cast<float *>(w.p0->ptr), static_cast<float *>(w.p1->ptr), ld);
     }
   } else {
-    // general strides: one coalesced gather (the surviving descendant of pack_A / pack_B)
     const int64_t tiles = ((o.mn + 31) / 32) * ((o.k + 31) / 32);
     const int read_along_r = (llabs(o.s_mn) < llabs(o.s_k)) ? 1 : 0;
     const int grid = grid_for(c, tiles, 8);
     const ET *src = static_cast<const ET *>(o.ptr);
-    ET *dhi = static_cast<ET *>(w.hi->ptr);
+    ET *d0 = static_cast<ET *>(w.p0->ptr);
     if constexpr (ESZ == 4) {
-      if (mode == SPLIT_F16X2) {
-        // gather into the compact fp32 array first, then scale + split that (two more passes, general operands only)
-        pack_general_kernel<float, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
-                                                           read_along_r, nullptr, nullptr, 0);
-        COUNT_LAUNCH();
-        CHECK_LAUNCH();
-        const int g2 = grid_for(c, (R * ((Cc + 3) / 4) + 255) / 256, 8);
-        if ((rc = f16x2_prepare(c, dhi, R, Cc, ld, false, w, ld_b, g2, s))) return rc;
-      } else if (mode == SPLIT_BF16X2)
-        pack_general_kernel<float, 3><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, nullptr, nullptr, ld,
-                                                           read_along_r, static_cast<uint16_t *>(w.xb->ptr),
-                                                           static_cast<uint16_t *>(w.lb->ptr), ld_b);
-      else if (mode == SPLIT_TF32)
-        pack_general_kernel<float, 1><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi,
-                                                           static_cast<float *>(w.lo->ptr), ld,
-                                                           read_along_r, nullptr, nullptr, 0);
-      else if (mode == SPLIT_MIXED)
-        pack_general_kernel<float, 2><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
-                                                           read_along_r, static_cast<uint16_t *>(w.xb->ptr),
-                                                           static_cast<uint16_t *>(w.lb->ptr), ld_b);
+      if (mode == SPLIT_TF32)
+        pack_general_kernel<float, 1><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, d0, static_cast<float *>(w.p1->ptr),
+                                                           ld, read_along_r);
       else
-        pack_general_kernel<float, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
-                                                           read_along_r, nullptr, nullptr, 0);
+        pack_general_kernel<float, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, d0, nullptr, ld, read_along_r);
     } else {
-      pack_general_kernel<ET, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, dhi, nullptr, ld,
-                                                      read_along_r, nullptr, nullptr, 0);
+      pack_general_kernel<ET, 0><<<grid, 256, 0, s>>>(src, o.mn, o.k, o.s_mn, o.s_k, d0, nullptr, ld, read_along_r);
     }
   }
   COUNT_LAUNCH();
   CHECK_LAUNCH();
-  m->mn_major = (out_mj == MN_MAJOR);
-  if (mode == SPLIT_BF16X2 || mode == SPLIT_F16X2) {
-    // the 16-bit kernel's three-pass order reads (hi, lo) = (xb, lb); TMA moves 16-bit words, whatever their format
-    if ((rc = operand_map(c, &m->hi, 2, w.xb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
-    if ((rc = operand_map(c, &m->lo, 2, w.lb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
-    m->xb = m->lb = m->hi;
-    return LASER_B200_OK;
-  }
-  if ((rc = operand_map(c, &m->hi, ESZ, w.hi->ptr, out_mj, o.mn, o.k, ld, block_mn))) return rc;
-  m->lo = m->xb = m->lb = m->hi;
-  if (mode == SPLIT_TF32) return operand_map(c, &m->lo, ESZ, w.lo->ptr, out_mj, o.mn, o.k, ld, block_mn);
-  if (mode == SPLIT_MIXED) {
-    if ((rc = operand_map(c, &m->xb, 2, w.xb->ptr, out_mj, o.mn, o.k, ld_b, block_mn))) return rc;
-    return operand_map(c, &m->lb, 2, w.lb->ptr, out_mj, o.mn, o.k, ld_b, block_mn);
-  }
+  if ((rc = operand_map(c, &m->p0, ESZ, w.p0->ptr, out_mj, o.mn, o.k, ld, block_mn))) return rc;
+  m->p1 = m->p0;
+  if (mode == SPLIT_TF32) return operand_map(c, &m->p1, ESZ, w.p1->ptr, out_mj, o.mn, o.k, ld, block_mn);
   return LASER_B200_OK;
 }
 
-inline SplitMode split_mode(int npass) {
-  return (npass == 3) ? SPLIT_TF32 : (npass == 2) ? SPLIT_MIXED : SPLIT_NONE;
-}
-inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.ws[2], &c.ws[3], 0}; }
-inline OperandWs ws_of_B(Ctx &c, int64_t amax_off = 0) { return OperandWs{&c.ws[4], &c.ws[5], &c.ws[6], &c.ws[7], amax_off}; }
+inline OperandWs ws_of_A(Ctx &c) { return OperandWs{&c.ws[0], &c.ws[1], &c.gather[0], 0}; }
+inline OperandWs ws_of_B(Ctx &c, int64_t amax_off = 0) { return OperandWs{&c.ws[2], &c.ws[3], &c.gather[1], amax_off}; }
 // F16X3: room for M + N abs-max words; A's vector starts at word 0, B's at the returned offset
 inline int f16_scales(Ctx &c, int64_t M, int64_t N, int64_t *b_off) {
   *b_off = round_up(M, 64);
   return ensure(c.f16s, static_cast<size_t>(*b_off + N) * sizeof(uint32_t));
 }
+struct F16Scales {     // where the two abs-max vectors of the current call live (device memory)
+  const uint32_t *a = nullptr, *b = nullptr;
+};
+
+// kernel family of a tensor-core call
+enum TcKind { TC_TF32X1, TC_TF32X3, TC_BF16, TC_F16X3 };
+inline TcKind tc_kind_of_path(int path) {
+  return path == LASER_B200_PATH_TF32X1 ? TC_TF32X1 : path == LASER_B200_PATH_TF32X3 ? TC_TF32X3 : TC_F16X3;
+}
+inline SplitMode split_mode(TcKind k) { return k == TC_TF32X3 ? SPLIT_TF32 : k == TC_F16X3 ? SPLIT_F16X2 : SPLIT_NONE; }
 
 // launch the tensor-core kernel on prepared operands (c.mu held by the caller)
-template <int ESZ, typename OutT>
-int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMaps &ma,
-           const OperandMaps &mb, float beta, OutT *C, int64_t rsC, int64_t csC, int npass, bool pair,
-           cudaStream_t s, const F16Scales *f16 = nullptr) {
-  // f16 != nullptr: the operands are fp16 pieces of scaled fp32 matrices (F16X3; ESZ == 2, fp32 output only)
-  auto launch = [&](const TcParams &q) -> int {
-    if constexpr (ESZ == 2 && std::is_same<OutT, float>::value) {
-      if (f16) return pair ? launch_tc_f16<true>(c, ma, mb, q, *f16, s) : launch_tc_f16<false>(c, ma, mb, q, *f16, s);
-    }
-    return pair ? launch_tc<ESZ, OutT, true>(c, ma, mb, q, s) : launch_tc<ESZ, OutT, false>(c, ma, mb, q, s);
-  };
-  TcParams p;
+template <typename OutT>
+int tc_run(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, const OperandMaps &ma,
+           const OperandMaps &mb, float beta, OutT *C, int64_t rsC, int64_t csC, bool pair, cudaStream_t s,
+           const Epilogue &epi, const F16Scales *f16 = nullptr, bool after_prep = false) {
+  TcLaunch l;
+  l.a0 = ma.p0; l.a1 = ma.p1; l.b0 = mb.p0; l.b1 = mb.p1;
+  l.a_mn = ma.mn_major; l.b_mn = mb.mn_major;
+  l.pair = pair;
+  l.pdl = c.pdl && after_prep;   // the preceding kernel of the stream is one of ours and calls launch_dependents
+  l.dev = c.dev; l.sm_count = c.sm_count; l.stream = s;
+  TcParams &p = l.p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
-  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
-  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count});
+  p.C = C; p.rsC = rsC; p.csC = csC; p.zero = 0; p.epi = epi;
+  if (f16) { p.amax_a = f16->a; p.amax_b = f16->b; }
+  const int npass = (kind == TC_TF32X3 || kind == TC_F16X3) ? 3 : 1;
+  const TcPlanCfg cfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count};
+  if (kind == TC_BF16 || kind == TC_F16X3) tc_plan<2, std::is_same<OutT, float>::value>(p, npass, pair, cfg);
+  else tc_plan<4, std::is_same<OutT, float>::value>(p, npass, pair, cfg);
+  if (c.dyn_sched) {
+    p.sched = static_cast<unsigned int *>(c.sched.ptr) + 2 * c.sched_next;
+    c.sched_next = (c.sched_next + 1) % kSchedSlots;
+  }
+  auto launch = [&](const TcLaunch &q) -> int {
+    int e;
+    switch (kind) {
+      case TC_TF32X1: e = launch_tc_tf32x1(q); break;
+      case TC_TF32X3: e = launch_tc_tf32x3(q); break;
+      case TC_BF16: e = launch_tc_bf16(q); break;
+      default: e = launch_tc_f16x3(q); break;
+    }
+    COUNT_LAUNCH();
+    if (e != 0) {
+      cudaGetLastError();
+      return set_error(e == static_cast<int>(cudaErrorMemoryAllocation) ? LASER_B200_ENOMEM : LASER_B200_ECUDA,
+                       "tensor-core kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(e)));
+    }
+    CHECK_LAUNCH();
+    return LASER_B200_OK;
+  };
   EventPair ep;
   int rc = prof_open(c, s, &ep, 0);
   if (rc) return rc;
   if (p.k_splits > 1) {
     if constexpr (std::is_same<OutT, float>::value) {
-      // partial sums of split s go to plane s of the workspace; a second kernel reduces
+      // partial sums of split s go to plane s of the workspace; a second kernel reduces (it also undoes the F16X3 scales)
       const int64_t ld = round_up(N, 4);
       const int64_t plane = M * ld;
-      if ((rc = ensure(c.splitk, static_cast<size_t>(p.k_splits) * plane * sizeof(float)))) return rc;
-      TcParams q = p;
-      q.C = c.splitk.ptr; q.rsC = ld; q.csC = 1; q.alpha = 1.0f; q.beta = 0.0f; q.epi = Epilogue();
-      q.split_plane = plane;
-      rc = launch(q);
-      if (rc) return rc;
+      if ((rc = ensure(c.splitk, static_cast<size_t>(p.k_splits) * plane * sizeof(float)))) { prof_abort(c, &ep); return rc; }
+      TcLaunch q = l;
+      q.p.C = c.splitk.ptr; q.p.rsC = ld; q.p.csC = 1; q.p.alpha = 1.0f; q.p.beta = 0.0f; q.p.epi = Epilogue();
+      q.p.split_plane = plane;
+      if ((rc = launch(q))) { prof_abort(c, &ep); return rc; }
       const int64_t items = (M * N + 255) / 256;
       splitk_reduce_kernel<<<grid_for(c, items, 8), 256, 0, s>>>(
           static_cast<const float *>(c.splitk.ptr), p.k_splits, M, N, ld, plane, alpha, beta, C, rsC, csC,
@@ -659,21 +546,19 @@ int tc_run(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const OperandMa
       return prof_close(c, s, &ep, 2);
     }
   }
-  rc = launch(p);
-  if (rc) return rc;
+  if ((rc = launch(l))) { prof_abort(c, &ep); return rc; }
   return prof_close(c, s, &ep, 1);
 }
 
-// SRC_ESZ: element size of the caller's operands; it differs from the kernel's ESZ only in the
-// BF16X3 mode (fp32 operands split into two bf16 arrays each, multiplied by the bf16 kernel)
-template <int ESZ, typename OutT, int SRC_ESZ = ESZ>
-int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
+// SRC_ESZ: element size of the caller's operands (4: fp32 in any of the three tensor-core modes, 2: bf16)
+template <int SRC_ESZ, typename OutT>
+int gemm_tc(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
             int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
-            int64_t csC, int npass, cudaStream_t s, SplitMode forced = SPLIT_NONE) {
+            int64_t csC, cudaStream_t s, const Epilogue &epi) {
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
     return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
   std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
-  const SplitMode mode = (forced != SPLIT_NONE) ? forced : split_mode(npass);
+  const SplitMode mode = split_mode(kind);
   Operand oa{A, M, K, rsA, csA};
   Operand ob{B, N, K, csB, rsB};
   OperandMaps ma, mb;
@@ -685,132 +570,20 @@ int gemm_tc(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const void *A,
   int rc = prof_open(c, s, &ep, 1);
   if (rc) return rc;
   int64_t f16_b_off = 0;
-  if (mode == SPLIT_F16X2 && (rc = f16_scales(c, M, N, &f16_b_off))) return rc;
+  if (mode == SPLIT_F16X2 && (rc = f16_scales(c, M, N, &f16_b_off))) { prof_abort(c, &ep); return rc; }
   rc = prepare_operand<SRC_ESZ>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
-  if (rc) return rc;
+  if (rc) { prof_abort(c, &ep); return rc; }
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
   const bool pair = c.cta_pair && M > TC_BLOCK_M;
   rc = prepare_operand<SRC_ESZ>(c, ob, mode, ws_of_B(c, f16_b_off), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
-  if (rc) return rc;
-  rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - launches_before));
+  if (rc) { prof_abort(c, &ep); return rc; }
+  const int prep_launches = static_cast<int>(g_launches.load() - launches_before);
+  rc = prof_close(c, s, &ep, prep_launches);
   if (rc) return rc;
   const F16Scales f16{static_cast<const uint32_t *>(c.f16s.ptr), static_cast<const uint32_t *>(c.f16s.ptr) + f16_b_off};
-  rc = tc_run<ESZ, OutT>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, npass, pair, s, mode == SPLIT_F16X2 ? &f16 : nullptr);
-  if (rc) return rc;
-  if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
-  return LASER_B200_OK;
-}
-
-template <int ESZ, typename OutT, bool PAIR>
-int launch_tc_batched(Ctx &c, const OperandMaps &A, const OperandMaps &B, const TcBatchedParams &p, cudaStream_t s) {
-  const bool a_mn = A.mn_major, b_mn = B.mn_major;
-  const int64_t units_total = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits * p.batch;
-  const int units = PAIR ? c.sm_count / 2 : c.sm_count;
-  const int sched = static_cast<int>(units_total < units ? units_total : units);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(PAIR ? 2 * sched : sched);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<PAIR>::SMEM_BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define LB200_LAUNCH(AMN, BMN)                                                                   \
-  do {                                                                                           \
-    auto kfn = gemm_tc_batched_kernel<ESZ, AMN, BMN, OutT, PAIR>;                                \
-    static std::atomic<uint32_t> attr_set{0};                                                    \
-    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                           \
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                    TcCfg<PAIR>::SMEM_BYTES));                                   \
-      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                 \
-    }                                                                                            \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, A.hi, A.lo, B.hi, B.lo, A.xb, A.lb, B.xb, B.lb, p));  \
-  } while (0)
-  if (!a_mn && !b_mn) LB200_LAUNCH(false, false);
-  else if (!a_mn && b_mn) LB200_LAUNCH(false, true);
-  else if (a_mn && !b_mn) LB200_LAUNCH(true, false);
-  else LB200_LAUNCH(true, true);
-#undef LB200_LAUNCH
-  COUNT_LAUNCH();
-  CHECK_LAUNCH();
-  return LASER_B200_OK;
-}
-
-// One operand of a batch: nb = 1 (shared) or `batch` matrices that must stack densely -- K-major rows one
-// after the other (batch stride = mn * row pitch) or MN-major k-rows one after the other (batch stride =
-// k * pitch); then the whole stack is ONE matrix for the preparation kernels.  Returns -2 when the layout
-// does not stack (the caller falls back to one launch sequence per problem).
-int prepare_operand_stack(Ctx &c, const void *ptr, int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int64_t bs, int64_t nb,
-                          SplitMode mode, const OperandWs &w, int block_mn, OperandMaps *m, bool *used_ws, cudaStream_t s) {
-  Operand one{ptr, mn, k, s_mn, s_k};
-  const Major mj = classify(one, 4);
-  if (mj == GENERAL && nb > 1) return -2;   // a single (shared) matrix of any strides is gathered as usual
-  Operand stack = one;
-  if (nb > 1) {
-    if (mj == K_MAJOR) { if (bs != mn * s_mn) return -2; stack.mn = nb * mn; }
-    else { if (bs != k * s_k) return -2; stack.k = nb * k; }
-  }
-  OperandMaps flat;
-  bool used = false;
-  int rc = prepare_operand<4>(c, stack, mode, w, block_mn, &flat, &used, s);   // the 2-d maps it builds are not used
-  if (rc) return rc;
-  *used_ws = *used_ws || used;
-  const bool mn_major = (mj == MN_MAJOR);   // gathered operands come out K-major
-  const int64_t Cc = mn_major ? mn : k;
-  const int64_t ld = used ? round_up(Cc, 4) : (mn_major ? s_k : s_mn), ld_b = round_up(Cc, 8);
-  const void *hi = used ? w.hi->ptr : ptr;
-  m->mn_major = mn_major;
-  if ((rc = operand_map3(c, &m->hi, 4, hi, mn_major, mn, k, nb, ld, block_mn))) return rc;
-  m->lo = m->xb = m->lb = m->hi;
-  if (mode == SPLIT_TF32) return operand_map3(c, &m->lo, 4, w.lo->ptr, mn_major, mn, k, nb, ld, block_mn);
-  if (mode == SPLIT_MIXED) {
-    if ((rc = operand_map3(c, &m->xb, 2, w.xb->ptr, mn_major, mn, k, nb, ld_b, block_mn))) return rc;
-    return operand_map3(c, &m->lb, 2, w.lb->ptr, mn_major, mn, k, nb, ld_b, block_mn);
-  }
-  return LASER_B200_OK;
-}
-
-// `batch` float32 problems of one shape as ONE tensor-core launch (after at most one preparation launch
-// per operand).  -2: the operands do not stack, nothing was launched.
-int gemm_tc_batched(Ctx &c, int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA,
-                    int64_t csA, int64_t bsA, const float *B, int64_t rsB, int64_t csB, int64_t bsB, float beta, float *C,
-                    int64_t rsC, int64_t csC, int64_t bsC, int npass, cudaStream_t s) {
-  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL || batch > 0x7fffffffLL / 4 ||
-      batch * M > 0x7fffffffLL || batch * K > 0x7fffffffLL || batch * N > 0x7fffffffLL)
-    return -2;
-  std::lock_guard<std::mutex> lk(c.mu);
-  const SplitMode mode = split_mode(npass);
-  const bool pair = c.cta_pair && M > TC_BLOCK_M;
-  OperandMaps ma, mb;
-  bool used_ws = false;
-  // both operands must stack before anything is launched
-  {
-    Operand oa{A, M, K, rsA, csA}, ob{B, N, K, csB, rsB};
-    const Major ja = classify(oa, 4), jb = classify(ob, 4);
-    if ((ja == GENERAL && bsA != 0) || (jb == GENERAL && bsB != 0)) return -2;
-    if (bsA != 0 && bsA != (ja == K_MAJOR ? M * rsA : K * csA)) return -2;
-    if (bsB != 0 && bsB != (jb == K_MAJOR ? N * csB : K * rsB)) return -2;
-  }
-  CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
-  int rc = prepare_operand_stack(c, A, M, K, rsA, csA, bsA, bsA == 0 ? 1 : batch, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s);
-  if (rc) return rc;
-  rc = prepare_operand_stack(c, B, N, K, csB, rsB, bsB, bsB == 0 ? 1 : batch, mode, ws_of_B(c), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N,
-                             &mb, &used_ws, s);
-  if (rc) return rc;
-  TcBatchedParams p;
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
-  p.C = C; p.rsC = rsC; p.csC = csC; p.npass = npass; p.zero = 0; p.epi = g_epi;
-  tc_plan<4, true>(p, npass, pair, TcPlanCfg{c.kc_faithful, c.raster_g, false /* no split-K */, c.sm_count});
-  p.batch = static_cast<int>(batch);
-  p.a_shared = bsA == 0 ? 1 : 0;
-  p.b_shared = bsB == 0 ? 1 : 0;
-  p.bsC = bsC;
-  if (pair) rc = launch_tc_batched<4, float, true>(c, ma, mb, p, s);
-  else rc = launch_tc_batched<4, float, false>(c, ma, mb, p, s);
+  // (with profiling on, an event record sits between the last preparation kernel and the GEMM: no dependent launch then)
+  rc = tc_run<OutT>(c, kind, M, N, K, alpha, ma, mb, beta, C, rsC, csC, pair, s, epi, mode == SPLIT_F16X2 ? &f16 : nullptr,
+                    prep_launches > 0 && !c.profiling);
   if (rc) return rc;
   if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   return LASER_B200_OK;
@@ -820,27 +593,27 @@ int gemm_tc_batched(Ctx &c, int64_t batch, int64_t M, int64_t N, int64_t K, floa
 //                      pre-packed operands (gemm_prepacked.nim:63-292)
 // ---------------------------------------------------------------------------------------
 // Layout of a packed operand seen as [mn][k] (A: mn = M, B: mn = N), a pure function of (mn, k):
-//   [hi : mn x ld  fp32][xb : mn x ld_b bf16][lb : mn x ld_b bf16], sections 256-byte aligned,
-//   ld = round_up(k, 4), ld_b = round_up(k, 8): compact K-major arrays of the mixed mode.
+//   [h : mn x ld_b fp16][l : mn x ld_b fp16][abs-max words : mn x u32], sections 256-byte aligned,
+//   ld_b = round_up(k, 8): the compact K-major pieces of the default (F16X3) mode together with the
+//   per-row scale words the epilogue needs -- a repeated product skips the whole preparation pass.
 int finish(Ctx &c, cudaStream_t user, cudaStream_t s);
 
 struct PackedLayout {
-  int64_t ld, ld_b;
-  size_t off_hi, off_xb, off_lb, bytes;
+  int64_t ld_b;
+  size_t off_h, off_l, off_amax, bytes;
 };
 inline PackedLayout packed_layout(int64_t mn, int64_t k) {
   PackedLayout L;
-  L.ld = round_up(k, 4);
   L.ld_b = round_up(k, 8);
   auto al = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
-  L.off_hi = 0;
-  L.off_xb = al(static_cast<size_t>(mn) * L.ld * 4);
-  L.off_lb = L.off_xb + al(static_cast<size_t>(mn) * L.ld_b * 2);
-  L.bytes = L.off_lb + al(static_cast<size_t>(mn) * L.ld_b * 2);
+  L.off_h = 0;
+  L.off_l = al(static_cast<size_t>(mn) * L.ld_b * 2);
+  L.off_amax = L.off_l + al(static_cast<size_t>(mn) * L.ld_b * 2);
+  L.bytes = L.off_amax + al(static_cast<size_t>(mn) * sizeof(uint32_t));
   return L;
 }
 
-int prepack_dev(void *dst, int64_t mn, int64_t k, const float *src, int64_t s_mn, int64_t s_k,
+int prepack_dev(int which, void *dst, int64_t mn, int64_t k, const float *src, int64_t s_mn, int64_t s_k,
                 void *stream) {
   if (mn < 0 || k < 0) return set_error(LASER_B200_EINVAL, "negative extent");
   if (mn == 0 || k == 0) return LASER_B200_OK;
@@ -852,25 +625,47 @@ int prepack_dev(void *dst, int64_t mn, int64_t k, const float *src, int64_t s_mn
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
   const PackedLayout L = packed_layout(mn, k);
   uint8_t *base = static_cast<uint8_t *>(dst);
-  const int64_t tiles = ((mn + 31) / 32) * ((k + 31) / 32);
-  const int read_along_r = (llabs(s_mn) < llabs(s_k)) ? 1 : 0;
-  pack_general_kernel<float, 2><<<grid_for(*c, tiles, 8), 256, 0, s>>>(
-      src, mn, k, s_mn, s_k, reinterpret_cast<float *>(base + L.off_hi), nullptr, L.ld, read_along_r,
-      reinterpret_cast<uint16_t *>(base + L.off_xb), reinterpret_cast<uint16_t *>(base + L.off_lb), L.ld_b);
-  COUNT_LAUNCH();
-  CHECK_LAUNCH();
+  uint16_t *h = reinterpret_cast<uint16_t *>(base + L.off_h), *l = reinterpret_cast<uint16_t *>(base + L.off_l);
+  uint32_t *amax = reinterpret_cast<uint32_t *>(base + L.off_amax);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);   // the gather buffer is workspace
+    Operand o{src, mn, k, s_mn, s_k};
+    const float *rows = src;
+    int64_t rows_ld = s_mn;
+    if (classify(o, 4) != K_MAJOR) {
+      // anything that is not K-major already (MN-major, general strides) is gathered into compact K-major rows first
+      CUDA_TRY(cudaStreamWaitEvent(s, c->ws_free, 0));
+      const int64_t ld = round_up(k, 4);
+      Buffer &g = c->gather[which];
+      if ((rc = ensure(g, static_cast<size_t>(mn) * ld * 4))) return rc;
+      const int64_t tiles = ((mn + 31) / 32) * ((k + 31) / 32);
+      const int read_along_r = (llabs(s_mn) < llabs(s_k)) ? 1 : 0;
+      pack_general_kernel<float, 0><<<grid_for(*c, tiles, 8), 256, 0, s>>>(src, mn, k, s_mn, s_k, static_cast<float *>(g.ptr),
+                                                                           nullptr, ld, read_along_r);
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      rows = static_cast<const float *>(g.ptr);
+      rows_ld = ld;
+    }
+    if (k <= 4 * 32 * F16ROWS_MAXV)
+      f16x2_rows_fused_kernel<32><<<grid_for(*c, (mn + 7) / 8, 6), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
+    else
+      f16x2_rows_fused_kernel<256><<<grid_for(*c, mn, 6), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
+    COUNT_LAUNCH();
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaEventRecord(c->ws_free, s));
+  }
   return finish(*c, static_cast<cudaStream_t>(stream), s);
 }
 
-int packed_maps(Ctx &c, const void *packed, int64_t mn, int64_t k, int block_mn, OperandMaps *m) {
+int packed_maps(Ctx &c, const void *packed, int64_t mn, int64_t k, int block_mn, OperandMaps *m, const uint32_t **amax) {
   const PackedLayout L = packed_layout(mn, k);
   const uint8_t *base = static_cast<const uint8_t *>(packed);
   int rc;
   m->mn_major = false;
-  if ((rc = operand_map(c, &m->hi, 4, base + L.off_hi, K_MAJOR, mn, k, L.ld, block_mn))) return rc;
-  m->lo = m->hi;
-  if ((rc = operand_map(c, &m->xb, 2, base + L.off_xb, K_MAJOR, mn, k, L.ld_b, block_mn))) return rc;
-  return operand_map(c, &m->lb, 2, base + L.off_lb, K_MAJOR, mn, k, L.ld_b, block_mn);
+  *amax = reinterpret_cast<const uint32_t *>(base + L.off_amax);
+  if ((rc = operand_map(c, &m->p0, 2, base + L.off_h, K_MAJOR, mn, k, L.ld_b, block_mn))) return rc;
+  return operand_map(c, &m->p1, 2, base + L.off_l, K_MAJOR, mn, k, L.ld_b, block_mn);
 }
 
 // A: either raw (A != nullptr) or packed (packedA != nullptr); B always packed
@@ -891,23 +686,31 @@ int gemm_packed_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A
     std::lock_guard<std::mutex> lk(c.mu);
     const bool pair = c.cta_pair && M > TC_BLOCK_M;
     OperandMaps ma, mb;
+    F16Scales f16;
     bool used_ws = false;
+    int prep_launches = 0;
     CUDA_TRY(cudaStreamWaitEvent(s, c.ws_free, 0));
     if (packedA) {
-      if ((rc = packed_maps(c, packedA, M, K, TC_BLOCK_M, &ma))) return rc;
+      if ((rc = packed_maps(c, packedA, M, K, TC_BLOCK_M, &ma, &f16.a))) return rc;
     } else {
       Operand oa{A, M, K, rsA, csA};
       EventPair ep;
       const int64_t before = g_launches.load();
+      int64_t b_off = 0;
+      if ((rc = f16_scales(c, M, 0, &b_off))) return rc;
       if ((rc = prof_open(c, s, &ep, 1))) return rc;
-      if ((rc = prepare_operand<4>(c, oa, SPLIT_MIXED, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s))) return rc;
-      if ((rc = prof_close(c, s, &ep, static_cast<int>(g_launches.load() - before)))) return rc;
+      if ((rc = prepare_operand<4>(c, oa, SPLIT_F16X2, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, s))) { prof_abort(c, &ep); return rc; }
+      prep_launches = static_cast<int>(g_launches.load() - before);
+      if ((rc = prof_close(c, s, &ep, prep_launches))) return rc;
+      f16.a = static_cast<const uint32_t *>(c.f16s.ptr);
     }
-    if ((rc = packed_maps(c, packedB, N, K, pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb))) return rc;
-    if ((rc = tc_run<4, float>(c, M, N, K, alpha, ma, mb, beta, C, rsC, csC, 2, pair, s))) return rc;
+    if ((rc = packed_maps(c, packedB, N, K, pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &f16.b))) return rc;
+    if ((rc = tc_run<float>(c, TC_F16X3, M, N, K, alpha, ma, mb, beta, C, rsC, csC, pair, s, Epilogue(), &f16,
+                            prep_launches > 0 && !c.profiling)))
+      return rc;
     if (used_ws) CUDA_TRY(cudaEventRecord(c.ws_free, s));
   }
-  g_last_path = LASER_B200_PATH_TF32_BF16C;
+  g_last_path = LASER_B200_PATH_F16X3;
   return finish(c, static_cast<cudaStream_t>(stream), s);
 }
 
@@ -927,9 +730,27 @@ int finish(Ctx &, cudaStream_t user, cudaStream_t s) {
   return LASER_B200_OK;
 }
 
+inline bool is_tc_mode(int mode) {
+  return mode == LASER_B200_PATH_F16X3 || mode == LASER_B200_PATH_TF32X3 || mode == LASER_B200_PATH_TF32X1;
+}
+// What PATH_AUTO resolves to -- ONE predicate for the device-pointer and the host-pointer entry points:
+//   work <= 128^3 (the reference's own switch, gemm.nim:140-141): exact kernel -- a 128 x 256 tensor-core tile would be
+//       mostly padding;
+//   mode SIMT: exact kernel for every shape (the mode documented as bit-identical to the CPU reference), before any shortcut;
+//   N <= 4 tall problems without a fused epilogue: warp-shuffle GEMV (-1);
+//   otherwise the fp32 mode in force.
+int resolve_auto(int64_t M, int64_t N, int64_t K, const Epilogue &epi) {
+  const double work = static_cast<double>(M) * N * K;
+  if (work <= 128.0 * 128.0 * 128.0) return LASER_B200_PATH_SIMT;
+  const int mode = g_f32_mode.load();
+  if (mode == LASER_B200_PATH_SIMT) return LASER_B200_PATH_SIMT;
+  if (N <= 4 && M >= 1024 && !epi.bias && !epi.act) return -1;
+  return mode < 0 ? kDefaultF32Mode : mode;
+}
+
 int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
             const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
-            int path, void *stream) {
+            int path, void *stream, const Epilogue &epi = Epilogue()) {
   int rc = check_args(M, N, K, A, B, C);
   if (rc == -1) return LASER_B200_OK;
   if (rc) return rc;
@@ -937,18 +758,11 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
   rc = get_ctx(&c);
   if (rc) return rc;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-  if (path == LASER_B200_PATH_AUTO) {
-    // the reference switches behaviour at M*N*K > 128^3 (gemm.nim:140-141); below that
-    // a 128x256 tensor-core tile is mostly padding and the exact kernel is used
-    const double work = static_cast<double>(M) * N * K;
-    if (work <= 128.0 * 128.0 * 128.0) path = LASER_B200_PATH_SIMT;
-    else if (N <= 4 && M >= 1024 && !g_epi.bias && !g_epi.act) path = -1;  // skinny: warp-shuffle GEMV
-    else path = g_f32_mode.load();
-  }
+  if (path == LASER_B200_PATH_AUTO) path = resolve_auto(M, N, K, epi);
   switch (path) {
     case -1: {
       const int grid = grid_for(*c, (M + 7) / 8, 8);
-const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+      const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
       const size_t bsmem = static_cast<size_t>(N) * K * sizeof(float);
       const bool use_smem = vec && bsmem <= 96 * 1024;
 #define LB200_GEMV(NV)                                                                                         \
@@ -971,28 +785,16 @@ const bool vec = (csA == 1) && (rsA % 4 == 0) && (K % 4 == 0) && ((reinterpret_c
       break;
     }
     case LASER_B200_PATH_SIMT:
-      rc = gemm_simt<float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s);
+      rc = gemm_simt<float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi);
       if (rc) return rc;
       g_last_path = LASER_B200_PATH_SIMT;
       break;
     case LASER_B200_PATH_TF32X1:
     case LASER_B200_PATH_TF32X3:
-    case LASER_B200_PATH_TF32_BF16C:
-      rc = gemm_tc<4, float>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC,
-                             path == LASER_B200_PATH_TF32X3 ? 3 : (path == LASER_B200_PATH_TF32_BF16C ? 2 : 1), s);
-      if (rc) return rc;
-      g_last_path = path;
-      break;
-    case LASER_B200_PATH_BF16X3:
-      // two bf16 pieces per fp32 operand, three passes (h*l', l*h', h*h') of the bf16 kernel, fp32 output
-      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s, SPLIT_BF16X2);
-      if (rc) return rc;
-      g_last_path = path;
-      break;
     case LASER_B200_PATH_F16X3:
-      // two fp16 pieces of each operand scaled by a power of two (device-side abs-max), three passes of the fp16 flavour
-      // of the kernel, whose epilogue undoes the scales
-      rc = gemm_tc<2, float, 4>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 3, s, SPLIT_F16X2);
+      // F16X3 (default): two fp16 pieces of each operand scaled by a power of two per row of A / column of B (device-side
+      // abs-max), three passes, the epilogue undoes the scales.  TF32X3: hi/lo tf32 pieces, three passes.  TF32X1: one pass.
+      rc = gemm_tc<4, float>(*c, tc_kind_of_path(path), M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi);
       if (rc) return rc;
       g_last_path = path;
       break;
@@ -1029,7 +831,7 @@ int bf16_dev(int64_t M, int64_t N, int64_t K, float alpha, const uint16_t *A, in
   rc = get_ctx(&c);
   if (rc) return rc;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-  rc = gemm_tc<2, uint16_t>(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, 1, s);
+  rc = gemm_tc<2, uint16_t>(*c, TC_BF16, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, Epilogue());
   if (rc) return rc;
   g_last_path = LASER_B200_PATH_BF16;
   return finish(*c, static_cast<cudaStream_t>(stream), s);
@@ -1074,12 +876,24 @@ inline bool panel_separable(int64_t rows, int64_t cols, int64_t rs, int64_t cs) 
 int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                             int64_t rsA, int64_t csA, const float *B, int64_t rsB, int64_t csB,
                             float beta, float *C, int64_t rsC, int64_t csC, int path) {
-  const bool f16x3 = (path == LASER_B200_PATH_F16X3);
-  const bool bf16x3 = (path == LASER_B200_PATH_BF16X3) || f16x3;   // two 16-bit pieces per operand: the 16-bit kernel, three passes
-  const int npass = (path == LASER_B200_PATH_TF32X3 || bf16x3) ? 3 : (path == LASER_B200_PATH_TF32_BF16C ? 2 : 1);
+  const TcKind kind = tc_kind_of_path(path);
+  const bool f16x3 = (kind == TC_F16X3);
   std::lock_guard<std::mutex> host_lk(c.host_mu);
   std::lock_guard<std::mutex> lk(c.mu);
   int rc;
+  // Once the first copy is queued the caller's A, B, C are in use by the device: no return -- error or not -- before the
+  // three streams have drained (the caller may free or reuse the buffers as soon as this function returns).
+  struct Drain {
+    Ctx &c;
+    bool armed = false;
+    ~Drain() {
+      if (!armed) return;
+      cudaStreamSynchronize(c.up);
+      cudaStreamSynchronize(c.stream);
+      cudaStreamSynchronize(c.down);
+      cudaEventRecord(c.ws_free, c.stream);
+    }
+  } drain{c};
   const int64_t panel_rows = c.panel_rows;
   // row panels (first row, rows).  The time after the last byte of A has crossed the bus is one
   // panel's split + GEMM + D2H: optionally the last panel is cut finer (halves down to 256 rows).
@@ -1116,12 +930,13 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
   cudaStream_t up = c.up, cmp = c.stream, down = c.down;
   // f16x3: B's abs-max words are written once, A's (one per row of the panel) are rewritten by every panel's preparation --
   // after the previous panel's GEMM, whose epilogue reads them, because everything of a panel runs on the compute stream
-  const SplitMode mode = f16x3 ? SPLIT_F16X2 : (bf16x3 ? SPLIT_BF16X2 : split_mode(npass));
+  const SplitMode mode = split_mode(kind);
   const bool pair = c.cta_pair && panel_rows > TC_BLOCK_M && M > TC_BLOCK_M;
   // staging buffers / workspace may still be in use by an earlier call
   CUDA_TRY(cudaStreamWaitEvent(up, c.ws_free, 0));
   CUDA_TRY(cudaStreamWaitEvent(cmp, c.ws_free, 0));
   // ---- B: upload once, prepare once ----
+  drain.armed = true;
   CUDA_TRY(cudaMemcpyAsync(dB + sb.lo, B + sb.lo, nb, cudaMemcpyHostToDevice, up));
   CUDA_TRY(cudaEventRecord(c.panel_ev[2 * panels], up));
   CUDA_TRY(cudaStreamWaitEvent(cmp, c.panel_ev[2 * panels], 0));
@@ -1152,9 +967,8 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
     if ((rc = prepare_operand<4>(c, oa, mode, ws_of_A(c), TC_BLOCK_M, &ma, &used_ws, cmp))) return rc;
     // B's tensor maps were built for `pair` (128- vs 256-column boxes): every panel, however
     // short, must run the same kernel variant
-    if (bf16x3) rc = tc_run<2, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp,
-                                      f16x3 ? &f16 : nullptr);
-    else rc = tc_run<4, float>(c, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, npass, pair, cmp);
+    rc = tc_run<float>(c, kind, mp, N, K, alpha, ma, mb, beta, dC + m0 * rsC, rsC, csC, pair, cmp, Epilogue(),
+                       f16x3 ? &f16 : nullptr, mode != SPLIT_NONE && !c.profiling);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.panel_ev[panels + pnl], cmp));
     CUDA_TRY(cudaStreamWaitEvent(down, c.panel_ev[panels + pnl], 0));
@@ -1164,6 +978,7 @@ int host_gemm_f32_pipelined(Ctx &c, int64_t M, int64_t N, int64_t K, float alpha
   CUDA_TRY(cudaEventRecord(c.ws_free, cmp));
   CUDA_TRY(cudaStreamSynchronize(down));
   CUDA_TRY(cudaStreamSynchronize(cmp));
+  drain.armed = false;
   g_last_path = path;
   return LASER_B200_OK;
 }
@@ -1195,7 +1010,10 @@ int host_gemm(int64_t M, int64_t N, int64_t K, const T *A, int64_t rsA, int64_t 
   // elements outside the view that must survive the round trip
   if (!beta_zero || !sc.dense) CUDA_TRY(cudaMemcpyAsync(dC, C + sc.lo, nc, cudaMemcpyHostToDevice, s));
   rc = run(dA - sa.lo, dB - sb.lo, dC - sc.lo, static_cast<void *>(s));
-  if (rc) return rc;
+  if (rc) {   // copies from the caller's buffers may still be in flight
+    cudaStreamSynchronize(s);
+    return rc;
+  }
   CUDA_TRY(cudaMemcpyAsync(C + sc.lo, dC, nc, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return LASER_B200_OK;
@@ -1227,6 +1045,10 @@ void laser_b200_shutdown(void) {
     if (c.splitk.ptr) { cudaFree(c.splitk.ptr); c.splitk = Buffer(); }
     if (c.layer_ws.ptr) { cudaFree(c.layer_ws.ptr); c.layer_ws = Buffer(); }
     if (c.f16s.ptr) { cudaFree(c.f16s.ptr); c.f16s = Buffer(); }
+    for (auto &b : c.gather) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
+    if (c.sched.ptr) { cudaFree(c.sched.ptr); c.sched = Buffer(); }
+    c.sched_next = 0;
+    for (auto &e : c.map_cache) e.valid = false;
     cudaEventDestroy(c.ws_free);
     for (auto e : c.panel_ev) cudaEventDestroy(e);
     c.panel_ev.clear();
@@ -1277,19 +1099,19 @@ int laser_b200_profile_end(double *gemm_ms, int64_t *gemm_launches, double *prep
 }
 
 const char *laser_b200_last_error(void) { return g_last_error.c_str(); }
-int laser_b200_version(void) { return 100; }
+int laser_b200_version(void) { return 200; }
 int64_t laser_b200_launch_count(void) { return g_launches.load(); }
 int laser_b200_last_path(void) { return g_last_path; }
 int laser_b200_set_f32_mode(int path) {
   if (path != LASER_B200_PATH_SIMT && path != LASER_B200_PATH_TF32X1 && path != LASER_B200_PATH_TF32X3 &&
-      path != LASER_B200_PATH_TF32_BF16C && path != LASER_B200_PATH_BF16X3 && path != LASER_B200_PATH_F16X3)
-    return set_error(LASER_B200_EINVAL, "f32 mode must be SIMT, TF32X1, TF32X3, TF32_BF16C, BF16X3 or F16X3");
+      path != LASER_B200_PATH_F16X3)
+    return set_error(LASER_B200_EINVAL, "f32 mode must be F16X3, TF32X3, TF32X1 or SIMT");
   g_f32_mode.store(path);
   return LASER_B200_OK;
 }
 int laser_b200_get_f32_mode(void) {
   const int m = g_f32_mode.load();
-  return m < 0 ? LASER_B200_PATH_TF32_BF16C : m;
+  return m < 0 ? parse_f32_mode(getenv("LASER_B200_F32_MODE")) : m;
 }
 
 // ---- device-resident -----------------------------------------------------------------
@@ -1303,15 +1125,14 @@ int laser_b200_gemm_strided_f32_epi_dev(int64_t M, int64_t N, int64_t K, float a
                                         int64_t rsA, int64_t csA, const float *B, int64_t rsB,
                                         int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
                                         const laser_b200_epilogue *epi, int path, void *stream) {
+  Epilogue e;
   if (epi) {
     if (epi->activation < 0 || epi->activation > 3) return set_error(LASER_B200_EINVAL, "unknown activation %d", epi->activation);
-    g_epi.bias = epi->bias;
-    g_epi.bias_per_row = epi->bias_per_row ? 1 : 0;
-    g_epi.act = epi->activation;
+    e.bias = epi->bias;
+    e.bias_per_row = epi->bias_per_row ? 1 : 0;
+    e.act = epi->activation;
   }
-  const int rc = f32_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, path, stream);
-  g_epi = Epilogue();
-  return rc;
+  return f32_dev(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, path, stream, e);
 }
 int laser_b200_gemm_strided_f64_dev(int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                                     int64_t rsA, int64_t csA, const double *B, int64_t rsB,
@@ -1344,15 +1165,13 @@ int laser_b200_gemm_strided_f32(int64_t M, int64_t N, int64_t K, float alpha, co
                                 float beta, float *C, int64_t rsC, int64_t csC) {
   // large tensor-core problems whose row panels are separate address ranges: overlap the
   // PCIe transfers with the compute, panel by panel
-  if (M >= 2048 && N > 4 && K > 0 && A && B && C &&
+  if (M >= 2048 && K > 0 && A && B && C &&
       M <= 0x7fffffffLL && N <= 0x7fffffffLL && K <= 0x7fffffffLL) {
     Ctx *c;
     int rc = get_ctx(&c);
     if (rc) return rc;
-    const int mode = g_f32_mode.load();
-    const bool tc_mode = mode == LASER_B200_PATH_TF32X3 || mode == LASER_B200_PATH_TF32_BF16C ||
-                         mode == LASER_B200_PATH_TF32X1 || mode == LASER_B200_PATH_BF16X3 || mode == LASER_B200_PATH_F16X3;
-    if (tc_mode && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
+    const int mode = resolve_auto(M, N, K, Epilogue());   // the kernel family the device entry would pick
+    if (is_tc_mode(mode) && panel_separable(c->panel_rows, K, rsA, csA) && panel_separable(c->panel_rows, N, rsC, csC) &&
         span_of(c->panel_rows, N, rsC, csC).dense && rsA > 0 && rsC > 0)
       return host_gemm_f32_pipelined(*c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, mode);
   }
@@ -1411,12 +1230,12 @@ size_t laser_b200_gemm_prepackB_mem_required_f32(int64_t M, int64_t N, int64_t K
 int laser_b200_gemm_prepackA_f32_dev(void *dst, int64_t M, int64_t N, int64_t K, const float *A,
                                      int64_t rsA, int64_t csA, void *stream) {
   (void)N;
-  return prepack_dev(dst, M, K, A, rsA, csA, stream);
+  return prepack_dev(0, dst, M, K, A, rsA, csA, stream);
 }
 int laser_b200_gemm_prepackB_f32_dev(void *dst, int64_t M, int64_t N, int64_t K, const float *B,
                                      int64_t rsB, int64_t csB, void *stream) {
   (void)M;
-  return prepack_dev(dst, N, K, B, csB, rsB, stream);   // B seen as [n][k]
+  return prepack_dev(1, dst, N, K, B, csB, rsB, stream);   // B seen as [n][k]
 }
 int laser_b200_gemm_packed_f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const void *packedA,
                                    const void *packedB, float beta, float *C, int64_t rsC, int64_t csC,

@@ -86,28 +86,6 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "r"(c0), "r"(c1)
       : "memory");
 }
-// The same with an L2 eviction-priority hint (64-bit cache policy, see kEvict*).
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull,
-                   kEvictLast = 0x14F0000000000000ull;   // createpolicy.fractional.L2::evict_* 1.0
-__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                                 int32_t c0, int32_t c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
-        "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-// 3-D tiled load (box depth 1): the third coordinate selects one matrix of a batch
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                            int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
-        "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src,
                                              int32_t c0, int32_t c1) {
@@ -251,6 +229,46 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+// shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_addr(const void *p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// arrive (count 1, release at cluster scope) on the copy of this mbarrier in CTA `rank`: orders this thread's earlier
+// writes -- including st.shared::cluster into that CTA -- before the arrival
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr(bar, rank)) : "memory");
+}
+// arrive WITHOUT release semantics (no memory barrier is emitted): for consumers that only signal "I have read the slot";
+// `count` is threaded through a register so that the caller can make the arrival data-dependent on what it read
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t *bar, uint32_t rank, uint32_t count) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr(bar, rank)), "r"(count)
+               : "memory");
+}
+// wait on this CTA's mbarrier with acquire at cluster scope (the data it guards was written by the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 32-bit store into the shared memory of CTA `rank` (same offset as `p` in this CTA)
+__device__ __forceinline__ void st_shared_cluster_s32(int *p, uint32_t rank, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr(p, rank)), "r"(v) : "memory");
+}
+// programmatic dependent launch: wait until the kernels this launch depends on have completed and flushed (no-op when
+// the kernel was launched without the attribute); launch_dependents lets the next kernel of the stream start its prologue
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // TMA load into THIS CTA's shared memory, transaction bytes credited to the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
                                                  int32_t c0, int32_t c1) {
@@ -259,24 +277,6 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                                      int32_t c0, int32_t c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
-        "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                                 int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
-        "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 template <uint32_t NCOLS>

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "f16_scale.cuh"
+#include "ptx.cuh"
 
 namespace lb200 {
 
@@ -35,11 +36,18 @@ inline float tf32_rna(float x) {
 }
 #endif
 
+// low piece of the hi/lo split; 0 when hi is not finite (x = +-inf, or |x| so close to FLT_MAX that hi rounded up to inf:
+// x - hi would be NaN and poison the whole row / column of C, where the reference's FMA chain gives +-inf)
+__device__ __forceinline__ float tf32_lo(float x, float hi) {
+  return ((__float_as_uint(hi) & 0x7f800000u) == 0x7f800000u) ? 0.0f : tf32_rna(x - hi);
+}
+
 // src: R rows of Cc contiguous floats, leading dimension src_ld (16-byte aligned rows).
 // hi/lo: compact, leading dimension dst_ld (multiple of 4).
 __global__ void __launch_bounds__(256)
 split_rows_tf32_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
                        float *__restrict__ hi, float *__restrict__ lo, int64_t dst_ld) {
+  ptx::griddep_launch_dependents();   // the next kernel of the stream may start its prologue (it waits for our results)
   const int64_t vec_per_row = (Cc + 3) >> 2;
   const int64_t total = R * vec_per_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -57,92 +65,12 @@ split_rows_tf32_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int
       v.w = 0.0f;
     }
     float4 h, l;
-    h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-    h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-    h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-    h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+    h.x = tf32_rna(v.x); l.x = tf32_lo(v.x, h.x);
+    h.y = tf32_rna(v.y); l.y = tf32_lo(v.y, h.y);
+    h.z = tf32_rna(v.z); l.z = tf32_lo(v.z, h.z);
+    h.w = tf32_rna(v.w); l.w = tf32_lo(v.w, h.w);
     *reinterpret_cast<float4 *>(hi + r * dst_ld + c) = h;
     *reinterpret_cast<float4 *>(lo + r * dst_ld + c) = l;
-  }
-}
-
-__device__ __forceinline__ uint16_t bf16_rn_bits(float f) {
-  uint32_t u = __float_as_uint(f);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>(u >> 16);
-}
-
-// Mixed-precision split: hi = tf32_rna(x) (fp32 container, feeds the tf32 hi*hi pass),
-// xb = bf16(x) and lb = bf16(x - hi) (feed the two bf16 cross-term passes, which run at twice
-// the tf32 rate).  Same addressing as split_rows_tf32_kernel; bf16 rows have pitch ld_b.
-__global__ void __launch_bounds__(256)
-split_rows_mixed_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
-                        float *__restrict__ hi, int64_t dst_ld, uint16_t *__restrict__ xb,
-                        uint16_t *__restrict__ lb, int64_t ld_b) {
-  const int64_t vec_per_row = (Cc + 3) >> 2;
-  const int64_t total = R * vec_per_row;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int64_t c = (i - r * vec_per_row) << 2;
-    const float *s = src + r * src_ld + c;
-    float4 v;
-    if (c + 4 <= Cc) {
-      v = *reinterpret_cast<const float4 *>(s);
-    } else {
-      v.x = s[0];
-      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
-      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
-      v.w = 0.0f;
-    }
-    float4 h;
-    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-    *reinterpret_cast<float4 *>(hi + r * dst_ld + c) = h;
-    uint2 b, l;
-    b.x = bf16_rn_bits(v.x) | (static_cast<uint32_t>(bf16_rn_bits(v.y)) << 16);
-    b.y = bf16_rn_bits(v.z) | (static_cast<uint32_t>(bf16_rn_bits(v.w)) << 16);
-    l.x = bf16_rn_bits(v.x - h.x) | (static_cast<uint32_t>(bf16_rn_bits(v.y - h.y)) << 16);
-    l.y = bf16_rn_bits(v.z - h.z) | (static_cast<uint32_t>(bf16_rn_bits(v.w - h.w)) << 16);
-    *reinterpret_cast<uint2 *>(xb + r * ld_b + c) = b;
-    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
-  }
-}
-
-// Two-piece bf16 split (LASER_B200_PATH_BF16X3): hb = bf16(x), lb = bf16(x - hb) (the difference is exact
-// in fp32), so x = hb + lb + r with |r| <= 2^-16 |x| (bf16 keeps 8 significant bits: each rounding is <= 2^-8 relative).  The three kind::f16 passes hb*lb', lb*hb', hb*hb' then
-// miss only lb*lb' and the r terms: <= 3 * 2^-16 ~ 4.6e-5 of each product in the worst case, random-signed
-// (measured over K = 8192 random products: 3e-7 of sum |a||b|).  Same addressing as split_rows_tf32_kernel;
-// reads 4 bytes and writes 4 bytes per element (the mixed split writes 8).
-__global__ void __launch_bounds__(256)
-split_rows_bf16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
-                         uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b) {
-  const int64_t vec_per_row = (Cc + 3) >> 2;
-  const int64_t total = R * vec_per_row;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int64_t c = (i - r * vec_per_row) << 2;
-    const float *s = src + r * src_ld + c;
-    float4 v;
-    if (c + 4 <= Cc) {
-      v = *reinterpret_cast<const float4 *>(s);
-    } else {
-      v.x = s[0];
-      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
-      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
-      v.w = 0.0f;
-    }
-    const uint16_t hx = bf16_rn_bits(v.x), hy = bf16_rn_bits(v.y), hz = bf16_rn_bits(v.z), hw = bf16_rn_bits(v.w);
-    uint2 h, l;
-    h.x = hx | (static_cast<uint32_t>(hy) << 16);
-    h.y = hz | (static_cast<uint32_t>(hw) << 16);
-    l.x = bf16_rn_bits(v.x - __uint_as_float(static_cast<uint32_t>(hx) << 16)) |
-          (static_cast<uint32_t>(bf16_rn_bits(v.y - __uint_as_float(static_cast<uint32_t>(hy) << 16))) << 16);
-    l.y = bf16_rn_bits(v.z - __uint_as_float(static_cast<uint32_t>(hz) << 16)) |
-          (static_cast<uint32_t>(bf16_rn_bits(v.w - __uint_as_float(static_cast<uint32_t>(hw) << 16))) << 16);
-    *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
-    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
   }
 }
 
@@ -220,14 +148,107 @@ absmax_mn_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t s
   }
 }
 
+// the two fp16 pieces of an already scaled value: h = fp16(x), l = fp16(x - h) (the difference is exact in fp32);
+// l = 0 when h is not finite (x = +-inf / NaN: x - h would be NaN)
+__device__ __forceinline__ void f16x2_pieces(float x, uint16_t &h, uint16_t &l) {
+  h = f16_rn_bits(x);
+  l = ((h & 0x7c00u) == 0x7c00u) ? static_cast<uint16_t>(0) : f16_rn_bits(__fsub_rn(x, f16_bits_to_f32(h)));
+}
+__device__ __forceinline__ float4 load_row_vec(const float *row, int64_t c, int64_t Cc) {
+  float4 v;
+  if (c + 4 <= Cc) {
+    v = *reinterpret_cast<const float4 *>(row + c);
+  } else {   // ragged end of the row: one to three elements
+    v.x = row[c];
+    v.y = (c + 1 < Cc) ? row[c + 1] : 0.0f;
+    v.z = (c + 2 < Cc) ? row[c + 2] : 0.0f;
+    v.w = 0.0f;
+  }
+  return v;
+}
+__device__ __forceinline__ void store_f16x2_vec(float4 v, float s, uint16_t *hrow, uint16_t *lrow, int64_t c) {
+  uint16_t hx, hy, hz, hw, lx, ly, lz, lw;
+  f16x2_pieces(__fmul_rn(v.x, s), hx, lx);
+  f16x2_pieces(__fmul_rn(v.y, s), hy, ly);
+  f16x2_pieces(__fmul_rn(v.z, s), hz, lz);
+  f16x2_pieces(__fmul_rn(v.w, s), hw, lw);
+  uint2 h, l;
+  h.x = hx | (static_cast<uint32_t>(hy) << 16);
+  h.y = hz | (static_cast<uint32_t>(hw) << 16);
+  l.x = lx | (static_cast<uint32_t>(ly) << 16);
+  l.y = lz | (static_cast<uint32_t>(lw) << 16);
+  *reinterpret_cast<uint2 *>(hrow + c) = h;
+  *reinterpret_cast<uint2 *>(lrow + c) = l;
+}
+
+// K-major operand (rows contiguous, ONE scale per row): abs-max, scale and split in a single pass over HBM.  A group
+// of threads -- a warp for short rows, the whole CTA otherwise -- reads its row into registers (F16ROWS_MAXV float4 per
+// thread; what is left of a longer row is read twice, the second time from L2), reduces the abs-max, writes the word and
+// both fp16 pieces: 4 bytes read + 4 written per element, against 8 + 4 for abs-max and split as two kernels.
+constexpr int F16ROWS_MAXV = 8;
+template <int GROUP>
+__global__ void __launch_bounds__(256)
+f16x2_rows_fused_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *__restrict__ hb,
+                        uint16_t *__restrict__ lb, int64_t ld_b, uint32_t *__restrict__ absmax) {
+  static_assert(GROUP == 32 || GROUP == 256, "a warp or the CTA per row");
+  __shared__ uint32_t red[2][8];
+  ptx::griddep_launch_dependents();
+  const int tid = static_cast<int>(threadIdx.x) % GROUP;
+  const int64_t per_cta = 256 / GROUP;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * per_cta + static_cast<int64_t>(threadIdx.x) / GROUP;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * per_cta;
+  const int64_t nvec = (Cc + 3) >> 2;
+  int parity = 0;
+  // GROUP == 256: every thread of the CTA runs the same number of iterations (the loop holds a __syncthreads)
+  for (int64_t r = first; r < R; r += step) {
+    const float *row = src + r * src_ld;
+    float4 v[F16ROWS_MAXV];
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < F16ROWS_MAXV; ++i) {
+      const int64_t idx = tid + static_cast<int64_t>(i) * GROUP;
+      if (idx < nvec) {
+        v[i] = load_row_vec(row, idx << 2, Cc);
+        m = max(max(m, finite_abs_bits(v[i].x)), max(finite_abs_bits(v[i].y), max(finite_abs_bits(v[i].z), finite_abs_bits(v[i].w))));
+      }
+    }
+    for (int64_t idx = tid + static_cast<int64_t>(F16ROWS_MAXV) * GROUP; idx < nvec; idx += GROUP) {
+      const float4 t = load_row_vec(row, idx << 2, Cc);
+      m = max(max(m, finite_abs_bits(t.x)), max(finite_abs_bits(t.y), max(finite_abs_bits(t.z), finite_abs_bits(t.w))));
+    }
+    float mf = __uint_as_float(m);     // non-negative finite: fmaxf orders them like the integers
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    m = __float_as_uint(mf);
+    if constexpr (GROUP == 256) {
+      if ((threadIdx.x & 31) == 0) red[parity][threadIdx.x >> 5] = m;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = max(m, red[parity][w]);
+      parity ^= 1;   // the next row uses the other buffer: one barrier per row is enough
+    }
+    if (tid == 0) absmax[r] = m;
+    const float s = f16x2_scale(m);
+    uint16_t *hrow = hb + r * ld_b, *lrow = lb + r * ld_b;
+#pragma unroll
+    for (int i = 0; i < F16ROWS_MAXV; ++i) {
+      const int64_t idx = tid + static_cast<int64_t>(i) * GROUP;
+      if (idx < nvec) store_f16x2_vec(v[i], s, hrow, lrow, idx << 2);
+    }
+    for (int64_t idx = tid + static_cast<int64_t>(F16ROWS_MAXV) * GROUP; idx < nvec; idx += GROUP)
+      store_f16x2_vec(load_row_vec(row, idx << 2, Cc), s, hrow, lrow, idx << 2);
+  }
+}
+
 // hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from the abs-max word of the element's mn index
 // (f16_scale.cuh): x * 2^s = hb + lb + r, |r| <= 2^-22 |x * 2^s| for elements within 2^-17 of their row's /
-// column's maximum.  Addressing as split_rows_bf16x2_kernel.
+// column's maximum.  Addressing as split_rows_tf32_kernel.
 template <bool PER_COL>
 __global__ void __launch_bounds__(256)
 split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
                         uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b,
                         const uint32_t *__restrict__ absmax) {
+  ptx::griddep_launch_dependents();   // the next kernel of the stream may start its prologue (it waits for our results)
   const int64_t vec_per_row = (Cc + 3) >> 2;
   const int64_t total = R * vec_per_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -253,13 +274,16 @@ split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
     } else {
       sx = sy = sz = sw = f16x2_scale(absmax[r]);
     }
-    v.x = __fmul_rn(v.x, sx); v.y = __fmul_rn(v.y, sy); v.z = __fmul_rn(v.z, sz); v.w = __fmul_rn(v.w, sw);
-    const uint16_t hx = f16_rn_bits(v.x), hy = f16_rn_bits(v.y), hz = f16_rn_bits(v.z), hw = f16_rn_bits(v.w);
+    uint16_t hx, hy, hz, hw, lx, ly, lz, lw;
+    f16x2_pieces(__fmul_rn(v.x, sx), hx, lx);
+    f16x2_pieces(__fmul_rn(v.y, sy), hy, ly);
+    f16x2_pieces(__fmul_rn(v.z, sz), hz, lz);
+    f16x2_pieces(__fmul_rn(v.w, sw), hw, lw);
     uint2 h, l;
     h.x = hx | (static_cast<uint32_t>(hy) << 16);
     h.y = hz | (static_cast<uint32_t>(hw) << 16);
-    l.x = f16_rn_bits(__fsub_rn(v.x, f16_bits_to_f32(hx))) | (static_cast<uint32_t>(f16_rn_bits(__fsub_rn(v.y, f16_bits_to_f32(hy)))) << 16);
-    l.y = f16_rn_bits(__fsub_rn(v.z, f16_bits_to_f32(hz))) | (static_cast<uint32_t>(f16_rn_bits(__fsub_rn(v.w, f16_bits_to_f32(hw)))) << 16);
+    l.x = lx | (static_cast<uint32_t>(ly) << 16);
+    l.y = lz | (static_cast<uint32_t>(lw) << 16);
     *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
     *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
   }
@@ -268,13 +292,12 @@ split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
 // dst[r*ld + c] = src[r*sr + c*sc] for r < R, c < Cc.  32 x 32 tiles through shared
 // memory so that both the gather (along whichever source stride is smaller) and the
 // store (along c) are coalesced.  SPLIT: also write lo (fp32 only).
-// MODE 0: plain copy; 1: fp32 hi/lo (dst, dst_lo); 2: mixed (dst = hi fp32, xb/lb = bf16 arrays);
-// 3: two bf16 pieces (xb = bf16(x), lb = bf16(x - xb); dst unused).
+// MODE 0: plain copy; 1: fp32 hi/lo pieces (dst, dst_lo).
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr, int64_t sc,
-                    T *__restrict__ dst, T *__restrict__ dst_lo, int64_t ld, int read_along_r,
-                    uint16_t *__restrict__ xb, uint16_t *__restrict__ lb, int64_t ld_b) {
+                    T *__restrict__ dst, T *__restrict__ dst_lo, int64_t ld, int read_along_r) {
+  ptx::griddep_launch_dependents();   // the next kernel of the stream may start its prologue (it waits for our results)
   __shared__ T tile[32][33];
   const int64_t tiles_c = (Cc + 31) >> 5;
   const int64_t tiles_r = (R + 31) >> 5;
@@ -303,16 +326,7 @@ pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr
         if constexpr (MODE == 1) {
           const float h = tf32_rna(v);
           dst[r * ld + c] = h;
-          dst_lo[r * ld + c] = tf32_rna(v - h);
-        } else if constexpr (MODE == 2) {
-          const float h = tf32_rna(v);
-          dst[r * ld + c] = h;
-          xb[r * ld_b + c] = bf16_rn_bits(v);
-          lb[r * ld_b + c] = bf16_rn_bits(v - h);
-        } else if constexpr (MODE == 3) {
-          const uint16_t hbits = bf16_rn_bits(v);
-          xb[r * ld_b + c] = hbits;
-          lb[r * ld_b + c] = bf16_rn_bits(v - __uint_as_float(static_cast<uint32_t>(hbits) << 16));
+          dst_lo[r * ld + c] = tf32_lo(v, h);
         } else {
           dst[r * ld + c] = v;
         }

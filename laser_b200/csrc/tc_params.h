@@ -1,0 +1,113 @@
+// tc_params.h -- host-visible part of the tensor-core GEMM: tile constants, the kernel's parameter block and the launch
+// planning (no device code: capi.cu includes this without instantiating the kernel, see tc_launch.h)
+#pragma once
+
+#include <stdint.h>
+
+namespace lb200 {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_N = 256;
+constexpr int TC_ROW_BYTES = 128;  // one swizzle row; BLOCK_K = 128 / sizeof(element)
+constexpr int TC_A_TILE_BYTES = TC_BLOCK_M * TC_ROW_BYTES;  // 16 KB: 128 rows x 128 B
+template <int NPASS, bool PAIR> struct TcCfg {
+  static constexpr int PIECES = (NPASS == 3) ? 2 : 1;
+  static constexpr int B_COLS = PAIR ? TC_BLOCK_N / 2 : TC_BLOCK_N;
+  static constexpr int B_TILE_BYTES = B_COLS * TC_ROW_BYTES;
+  static constexpr int A_STAGE_BYTES = PIECES * TC_A_TILE_BYTES;
+  static constexpr int B_STAGE_BYTES = PIECES * B_TILE_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 32 / 48 KB (1 pass), 64 / 96 KB (3 passes)
+#ifdef TC_STAGES_OVERRIDE
+  static constexpr int STAGES = TC_STAGES_OVERRIDE;
+#else
+  static constexpr int STAGES = (NPASS == 3) ? (PAIR ? 3 : 2) : (PAIR ? 6 : 4);   // 192 KB of tiles in every variant
+#endif
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, scheduler slot*/;
+};
+constexpr int TC_ACC_STAGES = 2;
+constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512: all of TMEM
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 tile scheduler | warps 4-11: epilogue (2 warpgroups)
+constexpr int TC_THREADS = 384;
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_EPI_WARPS = TC_EPI_THREADS / 32;
+constexpr int TC_EPI_COLS = TC_BLOCK_N / 2;  // columns owned by one epilogue thread
+constexpr int TC_REGS_CTRL = 56;   // setmaxnreg for the producer/MMA warpgroup
+constexpr int TC_REGS_EPI = 216;   // ... and for the epilogue warpgroups (running sums)
+
+// fused epilogue: v -> act(v + bias)   (gemm.nim:196 "elementwise epilogue fusion")
+struct Epilogue {
+  const float *bias = nullptr;
+  int bias_per_row = 0;
+  int act = 0;  // 0 none, 1 relu, 2 tanh, 3 sigmoid
+};
+struct TcParams {
+  int64_t M, N, K;
+  float alpha, beta;
+  void *C;
+  int64_t rsC, csC;
+  int kb_per_block;   // k-tiles per TMEM accumulation block (>= 1)
+  uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
+  int raster_g;       // m-blocks per raster group (see tile_coords)
+  Epilogue epi;
+  // split-K (few output tiles, long K): unit u = (tile, split) covers the K range of one split
+  // and writes its raw partial sums to plane `split` of a workspace (C points at it, alpha = 1,
+  // beta = 0); splitk_reduce_kernel then adds the planes in order and applies alpha/beta/epilogue
+  int k_splits;          // >= 1
+  int kb_per_split;      // k-tiles per split
+  int64_t split_plane;   // elements between consecutive planes
+  int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
+  // SCALED: fp32 bits of the largest finite |a| of row i of A / |b| of column j of B (f16_scale.cuh)
+  const uint32_t *amax_a = nullptr, *amax_b = nullptr;
+  // tile scheduler: word 0 = next unit (atomicAdd), word 1 = pairs that have drawn their last unit (the last one zeroes
+  // both words for the next launch that uses this slot).  nullptr: static round-robin (unit = pair index + i * pairs)
+  unsigned int *sched = nullptr;
+};
+
+// host side: the part of TcParams that depends only on the problem (p.M, p.N, p.K set by the
+// caller) and on the configuration
+struct TcPlanCfg {
+  int kc_faithful;      // K extent per TMEM accumulation block in the fp32-faithful modes
+  int raster_g;         // 0 = default
+  bool splitk_enabled;
+  int sm_count;
+};
+template <int ESZ, bool OUT_F32>
+inline void tc_plan(TcParams &p, int npass, bool pair, const TcPlanCfg &cfg) {
+  const int block_k = TC_ROW_BYTES / ESZ;  // k-tile
+  const int num_kb = static_cast<int>((p.K + block_k - 1) / block_k);
+  {
+    // K extent accumulated inside the tensor core before the epilogue warps add the block
+    // to their fp32 running sums (the analogue of the reference's kc, gemm_tiling.nim:310).
+    // Only the fp32-faithful modes need short chains.
+    const int kc = (npass == 3) ? cfg.kc_faithful : 0;
+    p.kb_per_block = (kc > 0) ? (kc + block_k - 1) / block_k : num_kb;
+    if (p.kb_per_block < 1) p.kb_per_block = 1;
+    if (p.kb_per_block > num_kb) p.kb_per_block = num_kb;
+  }
+  p.raster_g = cfg.raster_g > 0 ? cfg.raster_g : (pair ? 8 : 16);
+  const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+  p.num_m_blocks = static_cast<int>((p.M + tile_m - 1) / tile_m);
+  p.num_n_blocks = static_cast<int>((p.N + TC_BLOCK_N - 1) / TC_BLOCK_N);
+  // ---- split-K: too few output tiles to fill the machine and a long K (fp32 output only) ----
+  p.k_splits = 1;
+  p.split_plane = 0;
+  p.kb_per_split = num_kb;
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int units = pair ? cfg.sm_count / 2 : cfg.sm_count;
+  if constexpr (OUT_F32) {
+    const int blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;   // accumulation blocks along K
+    int S = static_cast<int>(units / (tiles > 0 ? tiles : 1));
+    // every split keeps >= 512 K-elements
+    const int min_tiles = 512 / block_k;
+    const int min_blocks = (min_tiles + p.kb_per_block - 1) / p.kb_per_block;
+    if (S > blocks / min_blocks) S = blocks / min_blocks;
+    if (S > 16) S = 16;
+    if (cfg.splitk_enabled && S >= 2) {
+      const int blocks_per_split = (blocks + S - 1) / S;
+      p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;
+      p.kb_per_split = blocks_per_split * p.kb_per_block;
+    }
+  }
+}
+
+}  // namespace lb200

@@ -18,7 +18,7 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._capi import (PATH_AUTO, PATH_BF16, PATH_SIMT, PATH_TF32_BF16C, PATH_TF32X1, PATH_TF32X3,
+from ._capi import (PATH_AUTO, PATH_BF16, PATH_F16X3, PATH_SIMT, PATH_TF32X1, PATH_TF32X3,
                     LaserB200Error, check, lib)
 
 __all__ = ["gemm_strided", "gemm_strided_fused", "DevPtr", "last_path", "launch_count", "set_f32_mode", "get_f32_mode",

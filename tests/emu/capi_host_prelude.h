@@ -38,6 +38,8 @@ inline cudaError_t emu_launch_ex(const cudaLaunchConfig_t *cfg, void (*kernel)(K
   return cudaSuccess;
 }
 
+#define LB200_LAUNCH_EX emu_launch_ex   // tc_launch_impl.cuh
+
 // the C++ overload of cuda_runtime.h (function pointer instead of const void *) exists under nvcc only
 template <typename... KArgs>
 inline cudaError_t cudaFuncSetAttribute(void (*)(KArgs...), cudaFuncAttribute, int) { return cudaSuccess; }

@@ -38,7 +38,6 @@ using namespace lb200;
 thread_local std::string g_last_error;
 thread_local int g_last_path = 0;
 struct Epilogue { const float *bias = nullptr; int bias_per_row = 0; int act = 0; };
-thread_local Epilogue g_epi;
 std::atomic<int64_t> g_launches{0};
 
 int set_error(int code, const char *fmt, ...) {
@@ -60,7 +59,6 @@ struct Ctx {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(0x10);
   std::mutex host_mu;
   Buffer stage[3], layer_ws;
-  bool tc_batched = false;   // the tensor-core batch launch is covered by test_emulated_library.py
 };
 Ctx g_ctx;
 int get_ctx(Ctx **out) { *out = &g_ctx; return LASER_B200_OK; }
@@ -92,8 +90,8 @@ inline void launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned bloc
 // capi.cu: gemm_simt -- the exact kernel with the library's tile configurations
 template <typename T>
 int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t rsA, int64_t csA, const T *B, int64_t rsB,
-              int64_t csB, T beta, T *C, int64_t rsC, int64_t csC, cudaStream_t, int64_t batch = 1, int64_t bsA = 0,
-              int64_t bsB = 0, int64_t bsC = 0) {
+              int64_t csB, T beta, T *C, int64_t rsC, int64_t csC, cudaStream_t, const Epilogue & = Epilogue(), int64_t batch = 1,
+              int64_t bsA = 0, int64_t bsB = 0, int64_t bsC = 0) {
   constexpr int TMN = sizeof(T) == 4 ? 8 : 4;
   SimtParams<T> p;
   const int64_t tiles = simt_plan<T, TMN, TMN>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
@@ -106,9 +104,12 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
 }
 // capi.cu: f32_dev -- here every problem takes the exact kernel (the tensor-core paths are
 // covered by test_emulated_tc.py); the path argument is recorded for the dispatch checks
-std::atomic<int> g_f32_mode{LASER_B200_PATH_TF32_BF16C};
-int gemm_tc_batched(Ctx &, int64_t, int64_t, int64_t, int64_t, float, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
-                    int64_t, int64_t, float, float *, int64_t, int64_t, int64_t, int, cudaStream_t) { return -2; }
+std::atomic<int> g_f32_mode{LASER_B200_PATH_F16X3};
+// capi.cu: resolve_auto
+int resolve_auto(int64_t M, int64_t N, int64_t K, const Epilogue &) {
+  if (static_cast<double>(M) * N * K <= 128.0 * 128.0 * 128.0) return LASER_B200_PATH_SIMT;
+  return g_f32_mode.load();
+}
 int g_last_requested_path = -1;
 int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA, const float *B,
             int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC, int path, void *) {

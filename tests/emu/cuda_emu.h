@@ -49,6 +49,7 @@ inline pthread_barrier_t cta_barrier[kMaxCluster];  // __syncthreads
 inline pthread_barrier_t cluster_barrier;           // barrier.cluster / end of a cluster's run
 inline pthread_barrier_t warp_barrier[kMaxCluster][32];   // one per warp (shuffles, __syncwarp)
 inline float warp_scratch[kMaxCluster][1024];
+inline int warp_scratch_i[kMaxCluster][1024];
 alignas(1024) inline unsigned char dyn_smem[kMaxCluster][kDynSmemBytes];   // dynamic shared memory
 inline unsigned char *dyn_smem_ptr() { return dyn_smem[cta_rank]; }
 
@@ -108,6 +109,8 @@ inline uint32_t atomicMax(uint32_t *p, uint32_t v) {   // shared or global word;
   }
   return old;
 }
+inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
@@ -118,6 +121,15 @@ inline emu::Idx &blockDim = emu::b_dim;   // plain references, not macros: `cfg.
 inline emu::Idx &gridDim = emu::g_dim;
 inline void __syncthreads() { pthread_barrier_wait(&emu::cta_barrier[emu::cta_rank]); }
 inline void __syncwarp() { pthread_barrier_wait(&emu::warp_barrier[emu::cta_rank][emu::t_idx.x >> 5]); }
+// full-mask broadcast of `v` from lane `src`: every lane of the warp must call it
+inline int __shfl_sync(unsigned, int v, int src) {
+  const unsigned t = emu::t_idx.x, w = t >> 5, r = emu::cta_rank;
+  emu::warp_scratch_i[r][t] = v;
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+  const int out = emu::warp_scratch_i[r][(t & ~31u) + static_cast<unsigned>(src)];
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+  return out;
+}
 // full-mask butterfly shuffle: every lane of the warp must call it (true for the reductions it is used in)
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   const unsigned t = emu::t_idx.x, w = t >> 5, r = emu::cta_rank;

@@ -293,6 +293,14 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 inline uint32_t cluster_ctarank() { return emu::cta_rank; }
 inline void cluster_sync() { pthread_barrier_wait(&emu::cluster_barrier); }
 inline void mbar_arrive_leader(uint64_t *bar) { emu::mb_arrive(emu::peer_ptr(bar, 0), 0); }
+inline void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) { emu::mb_arrive(emu::peer_ptr(bar, rank), 0); }
+inline void mbar_arrive_cluster_relaxed(uint64_t *bar, uint32_t rank, uint32_t count) {
+  for (uint32_t i = 0; i < count; ++i) emu::mb_arrive(emu::peer_ptr(bar, rank), 0);
+}
+inline void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
+inline void st_shared_cluster_s32(int *p, uint32_t rank, int v) { *reinterpret_cast<volatile int *>(emu::peer_ptr(p, rank)) = v; }
+inline void griddep_wait() {}
+inline void griddep_launch_dependents() {}
 inline void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
   long bytes;
   tma_copy_box(smem_dst, map, c0, c1, &bytes);               // into THIS CTA's shared memory

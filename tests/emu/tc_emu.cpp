@@ -34,26 +34,29 @@ static CUtensorMap operand_map(int esz, const void *base, bool mn_major, int64_t
 struct Args {
   int64_t M, N, K;
   float alpha, beta;
-  const void *A[4], *B[4];   // hi, lo (fp32 containers) and xb, lb (bf16), see capi.cu: OperandMaps
-  int64_t ldA, ldA_b, ldB, ldB_b;
+  const void *A[2], *B[2];   // piece 0 / piece 1, see capi.cu: OperandMaps
+  int64_t ldA, ldB;
   void *C;
   int64_t rsC, csC;
-  int npass, kc_faithful, raster_g, splitk_enabled, sm_count;
+  int kc_faithful, raster_g, splitk_enabled, sm_count;
   const float *bias;
   int bias_per_row, act;
   float *splitk_ws;          // k_splits planes of M x round_up(N, 4) when split-K triggers
   int *out_k_splits, *out_grid;
-  int f16 = 0;               // 16-bit operands with fp32 output: 0 = bf16 pieces (gemm_tc_kernel), 1 = fp16 pieces (gemm_tc_f16_kernel)
-  const uint32_t *amax_a = nullptr, *amax_b = nullptr;   // f16: abs-max words per row of A / column of B (f16_scale.cuh)
+  const uint32_t *amax_a, *amax_b;   // SCALED: abs-max words per row of A / column of B (f16_scale.cuh)
+  int dyn_sched;             // 1: tiles drawn from an atomic counter (capi.cu: Ctx::sched), 0: static round-robin
 };
 
-template <int ESZ, bool A_MN, bool B_MN, typename OutT, bool PAIR>
+static unsigned int g_sched[2] = {0u, 0u};
+
+template <int ESZ, uint32_t FMT16, int NPASS, typename OutT, bool SCALED, bool A_MN, bool B_MN, bool PAIR>
 static int run(const Args &a) {
   TcParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.alpha = a.alpha; p.beta = a.beta;
-  p.C = a.C; p.rsC = a.rsC; p.csC = a.csC; p.npass = a.npass; p.zero = 0;
+  p.C = a.C; p.rsC = a.rsC; p.csC = a.csC; p.zero = 0;
   p.epi.bias = a.bias; p.epi.bias_per_row = a.bias_per_row; p.epi.act = a.act;
-  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, a.npass, PAIR, TcPlanCfg{a.kc_faithful, a.raster_g, a.splitk_enabled != 0, a.sm_count});
+  p.amax_a = a.amax_a; p.amax_b = a.amax_b;
+  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, NPASS, PAIR, TcPlanCfg{a.kc_faithful, a.raster_g, a.splitk_enabled != 0, a.sm_count});
   if (a.out_k_splits) *a.out_k_splits = p.k_splits;
   if (p.k_splits > 1) {   // capi.cu: tc_run -- raw partial sums into the planes, reduced by splitk_reduce_kernel
     if (!a.splitk_ws) return -2;
@@ -61,39 +64,30 @@ static int run(const Args &a) {
     p.C = a.splitk_ws; p.rsC = ld; p.csC = 1; p.alpha = 1.0f; p.beta = 0.0f; p.epi = Epilogue();
     p.split_plane = a.M * ld;
   }
+  if (a.dyn_sched) {
+    if (g_sched[0] != 0u || g_sched[1] != 0u) return -4;   // the previous launch must have re-armed its slot
+    p.sched = g_sched;
+  }
   const int b_block = PAIR ? TC_BLOCK_N / 2 : TC_BLOCK_N;
   const CUtensorMap mA0 = operand_map(ESZ, a.A[0], A_MN, a.M, a.K, a.ldA, TC_BLOCK_M), mA1 = operand_map(ESZ, a.A[1], A_MN, a.M, a.K, a.ldA, TC_BLOCK_M);
-  const CUtensorMap mA2 = operand_map(2, a.A[2], A_MN, a.M, a.K, a.ldA_b, TC_BLOCK_M), mA3 = operand_map(2, a.A[3], A_MN, a.M, a.K, a.ldA_b, TC_BLOCK_M);
   const CUtensorMap mB0 = operand_map(ESZ, a.B[0], B_MN, a.N, a.K, a.ldB, b_block), mB1 = operand_map(ESZ, a.B[1], B_MN, a.N, a.K, a.ldB, b_block);
-  const CUtensorMap mB2 = operand_map(2, a.B[2], B_MN, a.N, a.K, a.ldB_b, b_block), mB3 = operand_map(2, a.B[3], B_MN, a.N, a.K, a.ldB_b, b_block);
-  // capi.cu: launch_tc -- persistent: one CTA (pair) per SM (pair of SMs), never more than work units
+  // tc_launch_impl.cuh: launch_tc_one -- persistent: one CTA (pair) per SM (pair of SMs), never more than work units
   const int64_t units_total = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;
   const int units = PAIR ? a.sm_count / 2 : a.sm_count;
   const int sched = static_cast<int>(units_total < units ? units_total : units);
   const unsigned grid = PAIR ? 2 * sched : sched;
   if (a.out_grid) *a.out_grid = static_cast<int>(grid);
-  if (TcCfg<PAIR>::SMEM_BYTES > static_cast<int>(emu::kDynSmemBytes)) return -3;
+  if (TcCfg<NPASS, PAIR>::SMEM_BYTES > static_cast<int>(emu::kDynSmemBytes)) return -3;
   emu::reset_state();
-  if constexpr (ESZ == 2 && std::is_same<OutT, float>::value) {
-    if (a.f16) {   // capi.cu: launch_tc_f16
-      TcF16Params pf;
-      static_cast<TcParams &>(pf) = p;
-      pf.amax_a = a.amax_a; pf.amax_b = a.amax_b;
-      emu::launch(grid, TC_THREADS,
-                  [=]() { gemm_tc_f16_kernel<2, A_MN, B_MN, float, PAIR>(mA0, mA1, mB0, mB1, mA2, mA3, mB2, mB3, pf); },
-                  PAIR ? 2 : 1);
-      return 0;
-    }
-  }
   emu::launch(grid, TC_THREADS,
-              [=]() { gemm_tc_kernel<ESZ, A_MN, B_MN, OutT, PAIR>(mA0, mA1, mB0, mB1, mA2, mA3, mB2, mB3, p); },
+              [=]() { gemm_tc_kernel<ESZ, FMT16, NPASS, A_MN, B_MN, OutT, PAIR, SCALED>(mA0, mA1, mB0, mB1, p); },
               PAIR ? 2 : 1);
   return 0;
 }
 
-template <int ESZ, typename OutT>
+template <int ESZ, uint32_t FMT16, int NPASS, typename OutT, bool SCALED>
 static int dispatch(int a_mn, int b_mn, int pair, const Args &a) {
-#define GO(AMN, BMN) (pair ? run<ESZ, AMN, BMN, OutT, true>(a) : run<ESZ, AMN, BMN, OutT, false>(a))
+#define GO(AMN, BMN) (pair ? run<ESZ, FMT16, NPASS, OutT, SCALED, AMN, BMN, true>(a) : run<ESZ, FMT16, NPASS, OutT, SCALED, AMN, BMN, false>(a))
   if (!a_mn && !b_mn) return GO(false, false);
   if (!a_mn && b_mn) return GO(false, true);
   if (a_mn && !b_mn) return GO(true, false);
@@ -101,27 +95,19 @@ static int dispatch(int a_mn, int b_mn, int pair, const Args &a) {
 #undef GO
 }
 
-extern "C" int emu_gemm_tc(int esz, int a_mn, int b_mn, int pair, int64_t M, int64_t N, int64_t K, float alpha, float beta,
-                           const void *A0, const void *A1, const void *A2, const void *A3, int64_t ldA, int64_t ldA_b,
-                           const void *B0, const void *B1, const void *B2, const void *B3, int64_t ldB, int64_t ldB_b,
-                           void *C, int64_t rsC, int64_t csC, int npass, int kc_faithful, int raster_g, int splitk_enabled,
+// kind: 0 tf32x1, 1 tf32x3, 2 bf16, 3 f16x3 (tc_launch.h: the four kernel families)
+extern "C" int emu_gemm_tc(int kind, int a_mn, int b_mn, int pair, int64_t M, int64_t N, int64_t K, float alpha, float beta,
+                           const void *A0, const void *A1, int64_t ldA, const void *B0, const void *B1, int64_t ldB,
+                           void *C, int64_t rsC, int64_t csC, int kc_faithful, int raster_g, int splitk_enabled,
                            int sm_count, const float *bias, int bias_per_row, int act, float *splitk_ws, int *out_k_splits,
-                           int *out_grid) {
-  Args a{M, N, K, alpha, beta, {A0, A1, A2, A3}, {B0, B1, B2, B3}, ldA, ldA_b, ldB, ldB_b, C, rsC, csC, npass, kc_faithful,
-         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, out_k_splits, out_grid};
-  if (esz == 4) return dispatch<4, float>(a_mn, b_mn, pair, a);
-  if (esz == 2) return dispatch<2, uint16_t>(a_mn, b_mn, pair, a);
-  return -1;
-}
-
-// the two-piece fp32 modes (capi.cu: PATH_BF16X3 / PATH_F16X3): 16-bit hi / lo arrays per operand, three passes, fp32 output
-extern "C" int emu_gemm_tc16x3(int f16, int a_mn, int b_mn, int pair, int64_t M, int64_t N, int64_t K, float alpha, float beta,
-                               const void *A0, const void *A1, int64_t ldA, const void *B0, const void *B1, int64_t ldB,
-                               void *C, int64_t rsC, int64_t csC, int kc_faithful, int raster_g, int splitk_enabled, int sm_count,
-                               const float *bias, int bias_per_row, int act, float *splitk_ws, int *out_k_splits, int *out_grid,
-                               const uint32_t *amax_a, const uint32_t *amax_b) {
-  Args a{M, N, K, alpha, beta, {A0, A1, nullptr, nullptr}, {B0, B1, nullptr, nullptr}, ldA, ldA, ldB, ldB, C, rsC, csC, 3, kc_faithful,
-         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, out_k_splits, out_grid};
-  a.f16 = f16; a.amax_a = amax_a; a.amax_b = amax_b;
-  return dispatch<2, float>(a_mn, b_mn, pair, a);
+                           int *out_grid, const uint32_t *amax_a, const uint32_t *amax_b, int dyn_sched) {
+  Args a{M, N, K, alpha, beta, {A0, A1}, {B0, B1}, ldA, ldB, C, rsC, csC, kc_faithful,
+         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, out_k_splits, out_grid, amax_a, amax_b, dyn_sched};
+  switch (kind) {
+    case 0: return dispatch<4, ptx::kFmtBF16, 1, float, false>(a_mn, b_mn, pair, a);
+    case 1: return dispatch<4, ptx::kFmtBF16, 3, float, false>(a_mn, b_mn, pair, a);
+    case 2: return dispatch<2, ptx::kFmtBF16, 1, uint16_t, false>(a_mn, b_mn, pair, a);
+    case 3: return dispatch<2, ptx::kFmtF16, 3, float, true>(a_mn, b_mn, pair, a);
+    default: return -1;
+  }
 }

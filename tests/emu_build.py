@@ -92,20 +92,26 @@ def build_capi_host_emu(asan=False):
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "liblaser_b200_hostemu_asan.so" if asan else "liblaser_b200_hostemu.so")
     csrc = os.path.abspath(CSRC)
-    deps = [os.path.join(csrc, f) for f in ("capi.cu", "capi_layers.inc", "f16_scale.cuh", "gemm_tc.cuh", "gemm_tc_kernel.inc", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh", "layers.cuh",
-                                            "ptx.cuh")] + \
+    units = ["capi.cu", "tc_f16x3.cu", "tc_tf32x3.cu", "tc_tf32x1.cu", "tc_bf16.cu"]   # laser_b200/_build.py: SOURCES
+    units = [u for u in units + ["multi_gpu.cu"] if os.path.exists(os.path.join(csrc, u))]
+    deps = [os.path.join(csrc, f) for f in units + ["capi_layers.inc", "f16_scale.cuh", "gemm_tc.cuh", "tc_params.h", "tc_launch.h",
+                                                    "tc_launch_impl.cuh", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh",
+                                                    "layers.cuh", "ptx.cuh", "host_common.h"] if os.path.exists(os.path.join(csrc, f))] + \
            [os.path.join(EMU_DIR, f) for f in ("capi_host_prelude.h", "cuda_emu.h", "ptx_emu.h")] + [os.path.abspath(__file__)]
     if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
-    src = open(os.path.join(csrc, "capi.cu")).read()
-    assert src.count("<<<") >= 10
-    src = _rewrite_launches(src)
-    src = src.replace("cudaLaunchKernelEx(&cfg, kfn,", "emu_launch_ex(&cfg, kfn,")
-    src = src.replace('#include "../../include/laser_b200.h"', '#include "%s"' % os.path.join(csrc, "..", "..", "include", "laser_b200.h"))
-    assert "<<<" not in src and "cudaLaunchKernelEx" not in src
+    # ONE generated translation unit: the prelude, then every source of the library with its kernel launches rewritten
+    parts = []
+    for u in units:
+        src = open(os.path.join(csrc, u)).read()
+        src = _rewrite_launches(src)
+        src = src.replace('#include "../../include/laser_b200.h"', '#include "%s"' % os.path.join(csrc, "..", "..", "include", "laser_b200.h"))
+        assert "<<<" not in src and "cudaLaunchKernelEx" not in src
+        parts.append("// ---- %s\n%s" % (u, src))
+    assert parts[0].count("emu_launch_kernel(") >= 10
     gen = os.path.join(out_dir, "capi_host_emu.cpp")
     with open(gen, "w") as f:
-        f.write('// GENERATED by tests/emu_build.py from laser_b200/csrc/capi.cu -- do not edit\n#include "capi_host_prelude.h"\n' + src)
+        f.write('// GENERATED by tests/emu_build.py from laser_b200/csrc/*.cu -- do not edit\n#include "capi_host_prelude.h"\n' + "\n".join(parts))
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     san = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
     subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,

@@ -38,13 +38,13 @@ def test_scenario(emulated_lib, scenario):
 
 
 def test_split_k_planning_and_reduce(emulated_lib):
-    assert run(emulated_lib, "split_k", LASER_B200_EMU_SMS=32).endswith("4")        # split A, split B, GEMM, reduce
-    assert run(emulated_lib, "no_split_k", LASER_B200_EMU_SMS=32, LASER_B200_SPLITK=0).endswith("3")
+    assert run(emulated_lib, "split_k", LASER_B200_EMU_SMS=32).endswith("5")        # prepare A, abs-max B, split B, GEMM, reduce
+    assert run(emulated_lib, "no_split_k", LASER_B200_EMU_SMS=32, LASER_B200_SPLITK=0).endswith("4")
 
 
 @pytest.mark.parametrize("env", [dict(LASER_B200_PANEL_ROWS=512), dict(LASER_B200_PANEL_TAPER=1),
                                  dict(LASER_B200_PANEL_ROWS=512, LASER_B200_PANEL_TAPER=1), dict(LASER_B200_CTA_PAIR=0),
-                                 dict(LASER_B200_F32_MODE="tf32x3"), dict(LASER_B200_L2HINT=1),
+                                 dict(LASER_B200_F32_MODE="tf32x3"), dict(LASER_B200_DYNSCHED=0),
                                  dict(LASER_B200_KC=64, LASER_B200_RASTER=2)],
                          ids=lambda e: ",".join("%s=%s" % (k.replace("LASER_B200_", ""), v) for k, v in e.items()))
 def test_host_entry_under_configuration(emulated_lib, env):
@@ -53,24 +53,11 @@ def test_host_entry_under_configuration(emulated_lib, env):
     run(emulated_lib, "host_entry", **env)
 
 
-def test_batched_tensor_core_launch(emulated_lib):
-    """off by default (not yet measured on a B200): with LASER_B200_TC_BATCHED=1 a stackable batch is one launch"""
-    run(emulated_lib, "batched_tc", LASER_B200_TC_BATCHED=1)
-
-
-def test_bf16x3_mode(emulated_lib):
-    """opt-in fp32 mode (not yet measured on a B200): fp32 operands split into two bf16 arrays, three passes of the
-    bf16 tensor-core kernel, fp32 output.  Here on a 32-SM machine without CTA pairs, so that the single-CTA kernel and
-    split-K take part (the CTA-pair kernel runs the same assertions in test_emulated_python_mirror.py), and selected
-    through the environment for the pipelined host-pointer entry"""
-    run(emulated_lib, "bf16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
-    run(emulated_lib, "host_entry", LASER_B200_F32_MODE="bf16x3")
-
-
 def test_f16x3_mode(emulated_lib):
-    """opt-in fp32 mode (not yet measured on a B200): power-of-two scaling from a device-side abs-max, two fp16 pieces,
-    the fp16 flavour of the tensor-core kernel undoing the scales in its epilogue; range cases included.  Same split of
-    the work as test_bf16x3_mode; in the pipelined host-pointer entry every row panel of A gets its own scale"""
+    """the default fp32 mode: power-of-two scaling from a device-side abs-max, two fp16 pieces, the kernel undoing the
+    scales in its epilogue; range cases included.  Here on a 32-SM machine without CTA pairs, so that the single-CTA
+    kernel and split-K take part (the CTA-pair kernel runs the same assertions in test_emulated_python_mirror.py); in
+    the pipelined host-pointer entry every row panel of A gets its own scale"""
     run(emulated_lib, "f16x3", LASER_B200_EMU_SMS=32, LASER_B200_CTA_PAIR=0, LASER_B200_KC=64)
     run(emulated_lib, "host_entry", LASER_B200_F32_MODE="f16x3")
 
@@ -101,7 +88,6 @@ def test_scenarios_under_address_sanitizer():
     for sc in (ASAN_ALL if full else ASAN_DEFAULT):
         run(lib, sc, **asan_env())
     if full:
-        run(lib, "batched_tc", LASER_B200_TC_BATCHED=1, **asan_env())
         run(lib, "split_k", LASER_B200_EMU_SMS=32, **asan_env())
         e = dict(os.environ, LASER_B200_LIB=lib, LASER_B200_EMU="1", PYTHONPATH=ROOT, **asan_env())
         out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zlayers.py"), "-m", "gpu", "-q",

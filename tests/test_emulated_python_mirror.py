@@ -52,9 +52,9 @@ def test_parity_file_subset_against_the_host_emulated_library():
     assert _run_gpu_files(["test_gpu_parity.py"], ["-k", FAST], 1500) >= 50
 
 
-def test_two_piece_mode_file_against_the_host_emulated_library():
-    """tests/test_gpu_zy_two_piece_modes.py (the opt-in bf16x3 and f16x3 modes) in full, minus the sizes skipped for the CPU build"""
-    assert _run_gpu_files(["test_gpu_zy_two_piece_modes.py"], [], 1500) >= 85
+def test_f16x3_mode_file_against_the_host_emulated_library():
+    """tests/test_gpu_zy_f16x3_mode.py (the default fp32 mode) in full, minus the sizes skipped for the CPU build"""
+    assert _run_gpu_files(["test_gpu_zy_f16x3_mode.py"], [], 1500) >= 40
 
 
 @pytest.mark.skipif(os.environ.get("LASER_B200_EMU_FULL", "0") != "1", reason="about 18 minutes; set LASER_B200_EMU_FULL=1")

@@ -18,15 +18,14 @@ i64, vp, ci, f32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 def emu():
     L = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh"]))
     L.emu_split_rows_tf32.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
-    L.emu_split_rows_mixed.argtypes = [vp, i64, i64, i64, vp, i64, vp, vp, i64, ci]
-    L.emu_split_rows_bf16x2.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
+    L.emu_f16x2_rows_fused.argtypes = [ci, vp, i64, i64, i64, vp, vp, i64, vp, ci]
     L.emu_absmax_mn.argtypes = [ci, vp, i64, i64, i64, vp, ci]
     L.emu_split_rows_f16x2.argtypes = [ci, vp, i64, i64, i64, vp, vp, i64, vp, ci]
-    L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, vp, vp, i64, ci]
+    L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, ci]
     L.emu_pack_general_u16.argtypes = [vp, i64, i64, i64, i64, vp, i64, ci, ci]
     L.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.emu_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, ci]
-    for n in ("emu_split_rows_tf32", "emu_split_rows_mixed", "emu_split_rows_bf16x2", "emu_absmax_mn", "emu_split_rows_f16x2", "emu_pack_general_f32", "emu_pack_general_u16",
+    for n in ("emu_split_rows_tf32", "emu_f16x2_rows_fused", "emu_absmax_mn", "emu_split_rows_f16x2", "emu_pack_general_f32", "emu_pack_general_u16",
               "emu_splitk_reduce", "emu_fill_uniform_f32"):
         getattr(L, n).restype = None
     return L
@@ -60,21 +59,6 @@ def test_split_rows(emu, R, Cc, src_ld):
     assert np.array_equal(hi[:, :Cc], h) and np.array_equal(lo[:, :Cc], tf32_rna(x - h))
     assert np.all(hi[:, Cc:] == 0) and np.all(lo[:, Cc:] == 0)        # k padding is zero (it feeds the MMA)
     assert np.abs((hi[:, :Cc].astype(np.float64) + lo[:, :Cc]) - x).max() <= 2.0 ** -21 * np.abs(x).max()
-    hi2 = np.full((R, ld), 9, np.float32); xb = np.full((R, ldb), 9, np.uint16); lb = np.full((R, ldb), 9, np.uint16)
-    emu.emu_split_rows_mixed(p(src), R, Cc, src_ld, p(hi2), ld, p(xb), p(lb), ldb, 2)
-    assert np.array_equal(hi2[:, :Cc], h)
-    assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
-    assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - h).reshape(R, Cc))
-    assert np.all(hi2[:, Cc:] == 0) and np.all(xb[:, Cc:ld] == 0) and np.all(lb[:, Cc:ld] == 0)
-    # two bf16 pieces (LASER_B200_PATH_BF16X3): h = bf16(x), l = bf16(x - h), remainder <= 2^-16 |x|
-    hb = np.full((R, ldb), 9, np.uint16); lb2 = np.full((R, ldb), 9, np.uint16)
-    emu.emu_split_rows_bf16x2(p(src), R, Cc, src_ld, p(hb), p(lb2), ldb, 3)
-    hbf = bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(R, Cc)
-    assert np.array_equal(hb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
-    assert np.array_equal(lb2[:, :Cc], f32_to_bf16_bits(x - hbf).reshape(R, Cc))
-    assert np.all(hb[:, Cc:ld] == 0) and np.all(lb2[:, Cc:ld] == 0)
-    rec = hbf.astype(np.float64) + bf16_bits_to_f32(lb2[:, :Cc].reshape(-1)).reshape(R, Cc)
-    assert (np.abs(rec - x) <= 2.0 ** -16 * np.abs(x)).all()
 
 
 @pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100)])
@@ -109,6 +93,13 @@ def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
     ok = np.isfinite(x)
     assert np.array_equal(hb[:, :Cc][ok], h.view(np.uint16)[ok]) and np.array_equal(lb[:, :Cc][ok], l.view(np.uint16)[ok])
     assert np.all(hb[:, Cc:ld] == 0) and np.all(lb[:, Cc:ld] == 0)
+    assert np.all(lb[:, :Cc][~ok] == 0)            # non-finite entries: the low piece is 0 (x - h would be NaN)
+    if not per_col:                                 # the fused single-pass kernel (the path K-major operands take)
+        for group, grid in ((32, 2), (256, 3)):
+            w2 = np.full(n_mn, 77, np.uint32); hb2 = np.full((R, ldb), 9, np.uint16); lb2 = np.full((R, ldb), 9, np.uint16)
+            emu.emu_f16x2_rows_fused(group, p(src), R, Cc, src_ld, p(hb2), p(lb2), ldb, p(w2), grid)
+            assert np.array_equal(w2, words)
+            assert np.array_equal(hb2[:, :ld], hb[:, :ld]) and np.array_equal(lb2[:, :ld], lb[:, :ld])
     mx = np.where(ok, np.abs(xs), 0).max(axis=0 if per_col else 1)
     assert np.all((mx == 0) | ((mx >= 2.0 ** 14) & (mx < 2.0 ** 15)))
     big = ok & (np.abs(xs) >= 2.0 ** -3)           # l = xs - h (<= 2^-11 |xs|) is then rounded at or above fp16's subnormal spacing 2^-24: 22 bits
@@ -125,7 +116,7 @@ def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
     (20, 31, 31, -1, 0),      # columns right-to-left
     (70, 3, 2, 140, 1),
 ])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1])
 def test_pack_general(emu, R, Cc, sr, sc, along_r, mode):
     lo_off = min(0, (R - 1) * sr) + min(0, (Cc - 1) * sc)
     hi_off = max(0, (R - 1) * sr) + max(0, (Cc - 1) * sc)
@@ -136,21 +127,12 @@ def test_pack_general(emu, R, Cc, sr, sc, along_r, mode):
     ld = -(-Cc // 4) * 4; ldb = -(-Cc // 8) * 8
     dst = np.full((R, ld), 7, np.float32); dlo = np.full((R, ld), 7, np.float32)
     xb = np.full((R, ldb), 7, np.uint16); lb = np.full((R, ldb), 7, np.uint16)
-    emu.emu_pack_general_f32(mode, p(buf, -lo_off), R, Cc, sr, sc, p(dst), p(dlo), ld, along_r, p(xb), p(lb), ldb, 4)
+    emu.emu_pack_general_f32(mode, p(buf, -lo_off), R, Cc, sr, sc, p(dst), p(dlo), ld, along_r, 4)
     h = tf32_rna(x)
     if mode == 0:
         assert np.array_equal(dst[:, :Cc], x)
-    elif mode == 1:
-        assert np.array_equal(dst[:, :Cc], h) and np.array_equal(dlo[:, :Cc], tf32_rna(x - h))
-    elif mode == 3:
-        hb = bf16_bits_to_f32(f32_to_bf16_bits(x)).reshape(R, Cc)
-        assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
-        assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - hb).reshape(R, Cc))
-        assert np.all(dst == 7)          # the fp32 array is not used by this mode
     else:
-        assert np.array_equal(dst[:, :Cc], h)
-        assert np.array_equal(xb[:, :Cc], f32_to_bf16_bits(x).reshape(R, Cc))
-        assert np.array_equal(lb[:, :Cc], f32_to_bf16_bits(x - h).reshape(R, Cc))
+        assert np.array_equal(dst[:, :Cc], h) and np.array_equal(dlo[:, :Cc], tf32_rna(x - h))
     assert np.all(dst[:, Cc:] == 7)      # the gather never writes the padding (the host zeroes it once)
 
 

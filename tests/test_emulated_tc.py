@@ -18,15 +18,16 @@ i64, vp, ci, f32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 pytestmark = pytest.mark.timeout(300)
 
 
+KIND = {"tf32x1": 0, "tf32x3": 1, "bf16": 2, "f16x3": 3}
+
+
 @pytest.fixture(scope="module")
 def emu():
-    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "gemm_tc_kernel.inc", "f16_scale.cuh", "ptx.cuh"]))
+    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "tc_params.h", "f16_scale.cuh", "ptx.cuh"]))
     L.emu_gemm_tc.restype = ci
-    L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64,
-                              vp, i64, i64, ci, ci, ci, ci, ci, vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
-    L.emu_gemm_tc16x3.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, i64, vp, vp, i64, vp, i64, i64, ci, ci, ci, ci,
-                                  vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp]
-    S = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh"]))
+    L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, i64, vp, vp, i64, vp, i64, i64, ci, ci, ci, ci,
+                              vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp, ci]
+    S = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh", "ptx.cuh"]))
     S.emu_splitk_reduce.restype = None
     S.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.splitk_reduce = S.emu_splitk_reduce
@@ -56,83 +57,51 @@ def ptr(a):
 
 
 def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=False, pair=False, kc=128, raster=0,
-           splitk=1, sms=4, epi=None, c_base=None):
+           splitk=1, sms=4, epi=None, c_base=None, dyn=1):
     """a: logical (M, K) fp32; b: logical (K, N) fp32; c: flat output buffer (float32, or uint16 for bf16).
     Returns (expected sum A*B in float64 under the mode's operand model, k_splits, grid)."""
     M, K = a.shape
     N = b.shape[1]
     bt = np.ascontiguousarray(b.T)              # B seen as [n][k]
-    arrs = {"A": [None] * 4, "B": [None] * 4}
-    ld = {"A": 0, "B": 0}; ldb = {"A": 0, "B": 0}
+    arrs = {"A": [None] * 2, "B": [None] * 2}
+    ld = {"A": 0, "B": 0}
     amax = {"A": None, "B": None}
-    if mode in ("bf16x3", "f16x3"):
-        # two 16-bit pieces per operand (split.cuh: split_rows_bf16x2_kernel / absmax_mn_kernel + split_rows_f16x2_kernel)
-        esz, npass = 2, 3
-        f = np.float64
-        if mode == "bf16x3":
-            def pieces(x):
-                hb = f32_to_bf16_bits(x).reshape(x.shape); hf = bf16_bits_to_f32(hb).reshape(x.shape)
-                lb_ = f32_to_bf16_bits(x - hf).reshape(x.shape)
-                return hb, lb_, hf.astype(f), bf16_bits_to_f32(lb_).reshape(x.shape).astype(f), np.ones(x.shape[0])
-        else:
-            def pieces(x):          # one power-of-two scale per mn index (row of x), from its abs-max word (f16_scale.cuh)
-                words = np.abs(x).max(axis=1).astype(np.float32).view(np.uint32)
-                e = (words >> 23).astype(np.int64)
-                s_exp = np.where(e == 0, 0, np.clip(14 - (e - 127), -126, 126))
-                xs = x * (2.0 ** s_exp).astype(np.float32)[:, None]
-                h16 = xs.astype(np.float16); l16 = (xs - h16.astype(np.float32)).astype(np.float16)
-                pieces.words = words
-                return h16.view(np.uint16), l16.view(np.uint16), h16.astype(f), l16.astype(f), 2.0 ** (-s_exp.astype(f))
-        ha, la, haf, laf, ua = pieces(a)
-        if mode == "f16x3":
-            amax["A"] = pieces.words.copy()
-        hb, lb_, hbf, lbf, ub = pieces(bt)
-        if mode == "f16x3":
-            amax["B"] = pieces.words.copy()
+    f = np.float64
+    if mode == "f16x3":
+        # two fp16 pieces of the scaled operand (split.cuh: f16x2_rows_fused_kernel / absmax_mn_kernel + split_rows_f16x2_kernel)
+        def pieces(x):          # one power-of-two scale per mn index (row of x), from its abs-max word (f16_scale.cuh)
+            words = np.abs(x).max(axis=1).astype(np.float32).view(np.uint32)
+            e = (words >> 23).astype(np.int64)
+            s_exp = np.where(e == 0, 0, np.clip(14 - (e - 127), -126, 126))
+            xs = x * (2.0 ** s_exp).astype(np.float32)[:, None]
+            h16 = xs.astype(np.float16); l16 = (xs - h16.astype(np.float32)).astype(np.float16)
+            return h16.view(np.uint16), l16.view(np.uint16), h16.astype(f), l16.astype(f), 2.0 ** (-s_exp.astype(f)), words
+        ha, la, haf, laf, ua, amax["A"] = pieces(a)
+        hb, lb_, hbf, lbf, ub, amax["B"] = pieces(bt)
         arrs["A"][0], ld["A"] = lay(ha, a_mn, 8); arrs["A"][1], _ = lay(la, a_mn, 8)
         arrs["B"][0], ld["B"] = lay(hb, b_mn, 8); arrs["B"][1], _ = lay(lb_, b_mn, 8)
         exact = (haf @ lbf.T + laf @ hbf.T + haf @ hbf.T) * ua[:, None] * ub[None, :]
     elif mode == "bf16":
-        esz, npass = 2, 1
         ab, bb = f32_to_bf16_bits(a).reshape(M, K), f32_to_bf16_bits(bt).reshape(N, K)
         arrs["A"][0], ld["A"] = lay(ab, a_mn, 8); arrs["B"][0], ld["B"] = lay(bb, b_mn, 8)
         exact = bf16_bits_to_f32(ab).astype(np.float64) @ bf16_bits_to_f32(bb).astype(np.float64).T
+    elif mode == "tf32x1":
+        arrs["A"][0], ld["A"] = lay(a, a_mn, 4); arrs["B"][0], ld["B"] = lay(bt, b_mn, 4)
+        exact = tf32_trunc(a).astype(np.float64) @ tf32_trunc(bt).astype(np.float64).T
     else:
-        esz = 4
-        npass = {"tf32x1": 1, "tf32x3": 3, "mixed": 2}[mode]
-        if mode == "tf32x1":
-            arrs["A"][0], ld["A"] = lay(a, a_mn, 4); arrs["B"][0], ld["B"] = lay(bt, b_mn, 4)
-            exact = tf32_trunc(a).astype(np.float64) @ tf32_trunc(bt).astype(np.float64).T
-        else:
-            ha, hb = tf32_rna(a), tf32_rna(bt)
-            arrs["A"][0], ld["A"] = lay(ha, a_mn, 4); arrs["B"][0], ld["B"] = lay(hb, b_mn, 4)
-            if mode == "tf32x3":
-                la, lb_ = tf32_rna(a - ha), tf32_rna(bt - hb)
-                arrs["A"][1], _ = lay(la, a_mn, 4); arrs["B"][1], _ = lay(lb_, b_mn, 4)
-                f = np.float64
-                exact = ha.astype(f) @ lb_.astype(f).T + la.astype(f) @ hb.astype(f).T + ha.astype(f) @ hb.astype(f).T
-            else:
-                xa, xb = f32_to_bf16_bits(a).reshape(M, K), f32_to_bf16_bits(bt).reshape(N, K)
-                lwa, lwb = f32_to_bf16_bits(a - ha).reshape(M, K), f32_to_bf16_bits(bt - hb).reshape(N, K)
-                arrs["A"][2], ldb["A"] = lay(xa, a_mn, 8); arrs["A"][3], _ = lay(lwa, a_mn, 8)
-                arrs["B"][2], ldb["B"] = lay(xb, b_mn, 8); arrs["B"][3], _ = lay(lwb, b_mn, 8)
-                f = np.float64
-                g = lambda bits: bf16_bits_to_f32(bits).astype(f)
-                exact = g(xa) @ g(lwb).T + g(lwa) @ g(xb).T + ha.astype(f) @ hb.astype(f).T
+        assert mode == "tf32x3"
+        ha, hb = tf32_rna(a), tf32_rna(bt)
+        la, lb_ = tf32_rna(a - ha), tf32_rna(bt - hb)
+        arrs["A"][0], ld["A"] = lay(ha, a_mn, 4); arrs["B"][0], ld["B"] = lay(hb, b_mn, 4)
+        arrs["A"][1], _ = lay(la, a_mn, 4); arrs["B"][1], _ = lay(lb_, b_mn, 4)
+        exact = ha.astype(f) @ lb_.astype(f).T + la.astype(f) @ hb.astype(f).T + ha.astype(f) @ hb.astype(f).T
     bias, per_row, act = epi if epi else (None, 0, 0)
     ws = np.zeros(16 * M * (-(-N // 4) * 4), np.float32)
     ks, grid = ci(0), ci(0)
-    if mode in ("bf16x3", "f16x3"):
-        rc = emu.emu_gemm_tc16x3(int(mode == "f16x3"), int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
-                                 ptr(arrs["A"][0]), ptr(arrs["A"][1]), ld["A"], ptr(arrs["B"][0]), ptr(arrs["B"][1]), ld["B"],
-                                 ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, kc, raster, splitk, sms,
-                                 ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]))
-    else:
-        rc = emu.emu_gemm_tc(esz, int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
-                             ptr(arrs["A"][0]), ptr(arrs["A"][1]), ptr(arrs["A"][2]), ptr(arrs["A"][3]), ld["A"], ldb["A"],
-                             ptr(arrs["B"][0]), ptr(arrs["B"][1]), ptr(arrs["B"][2]), ptr(arrs["B"][3]), ld["B"], ldb["B"],
-                             ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, npass, kc, raster, splitk, sms,
-                             ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid))
+    rc = emu.emu_gemm_tc(KIND[mode], int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
+                         ptr(arrs["A"][0]), ptr(arrs["A"][1]), ld["A"], ptr(arrs["B"][0]), ptr(arrs["B"][1]), ld["B"],
+                         ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, kc, raster, splitk, sms,
+                         ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]), dyn)
     assert rc == 0
     if ks.value > 1:     # capi.cu: tc_run -- second kernel of a split-K GEMM
         ldw = -(-N // 4) * 4
@@ -145,14 +114,15 @@ def rnd(shape, seed, lo=-1.0, hi=1.0):
     return O.fill_uniform_f32(int(np.prod(shape)), seed, lo, hi).reshape(shape)
 
 
-@pytest.mark.parametrize("mode", ["tf32x1", "tf32x3", "mixed", "bf16x3", "f16x3"])
+@pytest.mark.parametrize("mode", ["tf32x1", "tf32x3", "f16x3"])
+@pytest.mark.parametrize("dyn", [0, 1])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("pair", [False, True])
-def test_modes_majorness_and_pairs(emu, mode, a_mn, b_mn, pair):
+def test_modes_majorness_and_pairs(emu, mode, dyn, a_mn, b_mn, pair):
     M, N, K = 200, 300, 150                      # ragged in all three dimensions
     a, b = rnd((M, K), 1), rnd((K, N), 2)
     c = np.full(M * N + 64, -9.0, np.float32)
-    exact, ks, grid = run_tc(emu, mode, a, b, c, N, 1, a_mn=a_mn, b_mn=b_mn, pair=pair, sms=2)
+    exact, ks, grid = run_tc(emu, mode, a, b, c, N, 1, a_mn=a_mn, b_mn=b_mn, pair=pair, sms=2, dyn=dyn)
     assert ks == 1 and grid == 2                 # 4 (2 pair-) tiles on 2 CTAs (1 pair): the persistent loop iterates
     got = c[:M * N].reshape(M, N)
     assert np.abs(got - exact).max() <= 2e-6 * np.abs(exact).max()
@@ -160,7 +130,7 @@ def test_modes_majorness_and_pairs(emu, mode, a_mn, b_mn, pair):
     if mode != "tf32x1":                         # the split operands reproduce the fp32 product
         ref = np.zeros((M, N), np.float32)
         O.gemm_strided(M, N, K, 1.0, a, K, 1, b, N, 1, 0.0, ref, N, 1)
-        assert np.abs(got - ref).max() <= (2e-5 if mode == "bf16x3" else 1e-5) * np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("pair", [False, True])
@@ -183,7 +153,7 @@ def test_epilogue_paths(emu, pair, layout, alpha, beta):
     if beta != 0.0:
         buf[idx] = c0
     before = buf.copy()
-    exact, _, _ = run_tc(emu, "mixed", a, b, buf, rs, cs, alpha=alpha, beta=beta, pair=pair, sms=4)
+    exact, _, _ = run_tc(emu, "f16x3", a, b, buf, rs, cs, alpha=alpha, beta=beta, pair=pair, sms=4)
     want = alpha * exact + (beta * c0 if beta != 0.0 else 0.0)
     assert np.abs(buf[idx] - want).max() <= 3e-6 * max(1.0, np.abs(want).max())
     mask = np.ones(size, bool); mask[idx.reshape(-1)] = False
@@ -197,13 +167,13 @@ def test_fused_epilogue(emu, pair, per_row, act):
     a, b = rnd((M, K), 6), rnd((K, N), 7)
     bias = rnd((M if per_row else N,), 8)
     c = np.zeros(M * N, np.float32)
-    exact, _, _ = run_tc(emu, "mixed", a, b, c, N, 1, pair=pair, epi=(bias, per_row, act))
+    exact, _, _ = run_tc(emu, "f16x3", a, b, c, N, 1, pair=pair, epi=(bias, per_row, act))
     v = exact + (bias[:, None] if per_row else bias[None, :])
     want = {1: np.maximum(v, 0), 2: np.tanh(v), 3: 1 / (1 + np.exp(-v))}[act]
     assert np.abs(c.reshape(M, N) - want).max() <= 3e-6 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("mode,kc", [("mixed", 64), ("mixed", 128), ("tf32x3", 64), ("tf32x1", 128), ("bf16x3", 64), ("f16x3", 128)])
+@pytest.mark.parametrize("mode,kc", [("f16x3", 64), ("f16x3", 128), ("f16x3", 256), ("tf32x3", 64), ("tf32x1", 128)])
 @pytest.mark.parametrize("pair", [False, True])
 def test_accumulation_blocks_and_ragged_k(emu, mode, kc, pair):
     M, N, K = 140, 100, 333                      # several kc blocks, the last one partial, K % 32 != 0
@@ -215,9 +185,9 @@ def test_accumulation_blocks_and_ragged_k(emu, mode, kc, pair):
 
 
 @pytest.mark.parametrize("pair,M", [(False, 100), (True, 250)])
-@pytest.mark.parametrize("mode", ["mixed", "tf32x3", "bf16x3", "f16x3"])
+@pytest.mark.parametrize("mode", ["tf32x3", "f16x3"])
 def test_split_k(emu, pair, M, mode):
-    N, K = 200, 700                              # one output tile, long K: the planner splits K over idle SMs
+    N, K = 200, 1400                             # one output tile, long K: the planner splits K over idle SMs
     a, b = rnd((M, K), 11), rnd((K, N), 12)
     c0 = rnd((M, N), 13)
     c = c0.reshape(-1).copy()
@@ -255,11 +225,11 @@ from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
-@given(mode=st.sampled_from(["tf32x1", "tf32x3", "mixed", "bf16", "bf16x3", "f16x3"]), M=st.integers(1, 300), N=st.integers(1, 300),
+@given(mode=st.sampled_from(["tf32x1", "tf32x3", "bf16", "f16x3"]), dyn=st.sampled_from([0, 1]), M=st.integers(1, 300), N=st.integers(1, 300),
        K=st.integers(1, 400), a_mn=st.booleans(), b_mn=st.booleans(), pair=st.booleans(),
        kc=st.sampled_from([32, 64, 128, 512]), raster=st.sampled_from([0, 1, 3]), sms=st.sampled_from([2, 4, 10]),
        splitk=st.booleans(), ccol=st.booleans(), beta=st.sampled_from([0.0, 1.0, -0.75]), seed=st.integers(0, 2**30))
-def test_property_random_configurations(emu, mode, M, N, K, a_mn, b_mn, pair, kc, raster, sms, splitk, ccol, beta, seed):
+def test_property_random_configurations(emu, mode, dyn, M, N, K, a_mn, b_mn, pair, kc, raster, sms, splitk, ccol, beta, seed):
     if pair and M <= 128:
         pair = False                              # capi.cu: pairs only when there are at least two 128-row blocks
     a, b = rnd((M, K), seed), rnd((K, N), seed + 1)
@@ -270,7 +240,7 @@ def test_property_random_configurations(emu, mode, M, N, K, a_mn, b_mn, pair, kc
         c0b = f32_to_bf16_bits(c0).reshape(M, N)
         buf = np.zeros(M * N, np.uint16); buf[idx] = c0b
         exact, _, _ = run_tc(emu, mode, a, b, buf, rs, cs, beta=beta, a_mn=a_mn, b_mn=b_mn, pair=pair, kc=kc, raster=raster,
-                             splitk=int(splitk), sms=sms)
+                             splitk=int(splitk), sms=sms, dyn=dyn)
         want = exact + beta * bf16_bits_to_f32(c0b)
         assert np.abs(bf16_bits_to_f32(buf[idx]) - want).max() <= 2.0 ** -8 * max(1.0, np.abs(want).max())
         return
@@ -278,6 +248,6 @@ def test_property_random_configurations(emu, mode, M, N, K, a_mn, b_mn, pair, kc
     if beta != 0.0:
         buf[idx] = c0
     exact, ks, _ = run_tc(emu, mode, a, b, buf, rs, cs, beta=beta, a_mn=a_mn, b_mn=b_mn, pair=pair, kc=kc, raster=raster,
-                          splitk=int(splitk), sms=sms)
+                          splitk=int(splitk), sms=sms, dyn=dyn)
     want = exact + (beta * c0 if beta != 0.0 else 0.0)
     assert np.abs(buf[idx] - want).max() <= 4e-6 * max(1.0, np.abs(want).max()), (ks,)

@@ -15,7 +15,7 @@ ACTS = {"none": lambda x: x, "relu": lambda x: np.maximum(x, 0), "tanh": np.tanh
 
 @pytest.mark.parametrize("act", list(ACTS))
 @pytest.mark.parametrize("per_row", [False, True])
-@pytest.mark.parametrize("path", [L.PATH_SIMT, L.PATH_TF32_BF16C, L.PATH_TF32X3])
+@pytest.mark.parametrize("path", [L.PATH_SIMT, L.PATH_F16X3, L.PATH_TF32X3])
 @pytest.mark.parametrize("ldc", [520, 523])
 def test_fused_bias_activation(act, per_row, path, ldc):
     M, N, K = 300, 520, 700

@@ -11,7 +11,7 @@ from util import LAYOUTS, embed, extract
 pytestmark = pytest.mark.gpu
 import laser_b200 as L  # noqa: E402
 
-PATHS = [L.PATH_SIMT, L.PATH_TF32_BF16C, L.PATH_TF32X3, L.PATH_AUTO]
+PATHS = [L.PATH_SIMT, L.PATH_F16X3, L.PATH_TF32X3, L.PATH_AUTO]
 
 
 def one_case(rng):

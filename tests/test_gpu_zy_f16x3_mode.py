@@ -1,21 +1,13 @@
-"""GPU parity tests of the two opt-in "two 16-bit pieces" fp32 modes (written after the round's GPU minutes were spent:
-first B200 run = the round-end suite, hence the late position among the GPU files; the same file runs against the
-host-emulated library in the CPU suite, tests/test_emulated_python_mirror.py).
+"""GPU parity tests of the DEFAULT fp32 mode, LASER_B200_PATH_F16X3 (the same file runs against the host-emulated library
+in the CPU suite, tests/test_emulated_python_mirror.py).
 
-Both split every fp32 operand into two 16-bit arrays and run the three-pass order h*l', l*h', h*h' of the 16-bit
-tensor-core kernel (fp32 output, kc-blocked fp32 accumulation):
-  * LASER_B200_PATH_BF16X3: h = bf16(x), l = bf16(x - h), |x - h - l| <= 2^-16 |x|; the GPU-validated bf16 kernel.
-    Bars: U(0,1) max |ours-ref|/|ref| < 1e-4 (BASELINE.json gate; expected ~1e-6); U(-0.1,0.1) normwise < 1.5e-5
-    (expected ~5e-6; the default mode's bar is 2e-6 -- the price of the mode; the reference's mean_relative_error
-    <= 1e-5 gate is NOT claimed); on the seeded inputs |ours-exact| <= (3*2^-18 + 2e-6) * sum_k |a||b| elementwise, a
-    quarter of the worst case 3*2^-16 (random-signed errors; a lost piece or a wrong pass order exceeds it by orders
-    of magnitude).
-  * LASER_B200_PATH_F16X3: every row of A / column of B times its own 2^s (s from a device-side abs-max, csrc/f16_scale.cuh) as two FP16 pieces,
-    |x 2^s - h - l| <= 2^-22 |x 2^s|; the fp16 flavour of the kernel, whose epilogue undoes the scales.  Bars: those of the
-    fp32-faithful modes of tests/test_gpu_parity.py (U(0,1) max-elementwise < 1e-4, expected ~1e-6; U(-0.1,0.1)
-    normwise < 2e-6, mean_relative_error <= 1e-5), |ours-exact| <= (3*2^-22 + 2e-6) * sum_k |a||b|; operands far outside
-    fp16's range; one scale per row of A / column of B; entries below 2^-17 of their own row's / column's maximum keep
-    absolute (not relative) precision.
+Every row of A / column of B is multiplied by its own 2^s (s from a device-side abs-max, csrc/f16_scale.cuh) and split
+into two FP16 arrays, |x 2^s - h - l| <= 2^-22 |x 2^s|; the kernel runs the three-pass order h*l', l*h', h*h' (fp32
+output, kc-blocked fp32 accumulation) and its epilogue undoes the scales.  Bars: those of the fp32-faithful modes of
+tests/test_gpu_parity.py (U(0,1) max-elementwise < 1e-4, expected ~1e-6; U(-0.1,0.1) normwise < 2e-6,
+mean_relative_error <= 1e-5), |ours-exact| <= (3*2^-22 + 2e-6) * sum_k |a||b|; operands far outside fp16's range; one
+scale per row of A / column of B; entries below 2^-17 of their own row's / column's maximum keep absolute (not
+relative) precision.
 """
 import numpy as np
 import pytest
@@ -33,10 +25,10 @@ def dptr(t, off=0):
     return L.DevPtr(t.data_ptr() + off * t.element_size(), "f32")
 
 
-MODES = [L.PATH_BF16X3, L.PATH_F16X3]
-PER_PRODUCT = {L.PATH_BF16X3: 3 * 2.0 ** -18, L.PATH_F16X3: 3 * 2.0 ** -22}
-NORMWISE_S = {L.PATH_BF16X3: 1.5e-5, L.PATH_F16X3: 2e-6}
-LAYOUT_TOL = {L.PATH_BF16X3: 1.5e-5, L.PATH_F16X3: 3e-6}
+MODES = [L.PATH_F16X3]
+PER_PRODUCT = {L.PATH_F16X3: 3 * 2.0 ** -22}
+NORMWISE_S = {L.PATH_F16X3: 2e-6}
+LAYOUT_TOL = {L.PATH_F16X3: 3e-6}
 mode_ids = lambda p: L.PATH_NAMES[p]
 
 
@@ -99,9 +91,8 @@ def test_error_bound_and_gates(shape, ab, path):
 @pytest.mark.parametrize("which", ["A", "B", "C"])
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_every_operand_class(which, layout, path):
-    """K-major / MN-major operands go through the elementwise split kernels, general strides through the gather
-    (bf16x3: pack_general_kernel<float, 3>; f16x3: gather to fp32, then abs-max + split); C of any strides; nothing
-    outside the C view is written"""
+    """K-major operands go through the fused scale + split kernel, MN-major ones through abs-max + split, general strides
+    through the gather to fp32 first; C of any strides; nothing outside the C view is written"""
     M, N, K = 150, 140, 100
     a = O.fill_uniform_f32(M * K, 54, 0, 1).reshape(M, K); b = O.fill_uniform_f32(K * N, 55, 0, 1).reshape(K, N)
     c0 = O.fill_uniform_f32(M * N, 56, 0, 1).reshape(M, N)
@@ -118,7 +109,10 @@ def test_every_operand_class(which, layout, path):
 @pytest.mark.parametrize("path", MODES, ids=mode_ids)
 def test_mode_selection_and_host_pointer_entry(path):
     """set_f32_mode(mode) makes it the AUTO path of device- and host-pointer calls (the pipelined row-panel path
-    included: in f16x3 every row panel of A gets its own scale); other modes are untouched afterwards"""
+    included: every row panel of A gets its own scale); another mode set before is replaced, and F16X3 is what a fresh
+    process starts with (tests/test_gpu_parity.py: test_env_selects_f32_mode)"""
+    L.set_f32_mode(L.PATH_TF32X3)
+    assert L.get_f32_mode() == L.PATH_TF32X3
     L.set_f32_mode(path)
     try:
         assert L.get_f32_mode() == path
@@ -133,8 +127,8 @@ def test_mode_selection_and_host_pointer_entry(path):
                 O.gemm_strided(M, N, K, alpha, a, K, 1, b, N, 1, beta, ref, N, 1)
                 assert np.abs(c - ref).max() <= LAYOUT_TOL[path] * np.abs(ref).max(), (M, N, K, alpha, beta)
     finally:
-        L.set_f32_mode(L.PATH_TF32_BF16C)
-    assert L.get_f32_mode() == L.PATH_TF32_BF16C
+        L.set_f32_mode(L.PATH_F16X3)
+    assert L.get_f32_mode() == L.PATH_F16X3
 
 
 def test_f16x3_range_handling():
@@ -170,9 +164,9 @@ def test_f16x3_range_handling():
 
 @pytest.mark.skipif(EMU, reason="too large for the CPU build")
 @pytest.mark.parametrize("path", MODES, ids=mode_ids)
-def test_large_square_agrees_with_the_default_mode(path):
-    """4096^3 (BASELINE.json configs[1] shape) on U(0,1): against the default fp32-faithful mode, which the parity file
-    pins to the oracle; and the transposed-A layout of configs[2]"""
+def test_large_square_agrees_with_the_tf32x3_mode(path):
+    """4096^3 (BASELINE.json configs[1] shape) on U(0,1): against the independent fp32-faithful mode TF32X3 (other operand
+    pieces, other MMA kind); and the transposed-A layout of configs[2]"""
     import torch
     n = 4096
     a = torch.empty(n * n, device="cuda"); b = torch.empty(n * n, device="cuda")
@@ -180,7 +174,7 @@ def test_large_square_agrees_with_the_default_mode(path):
     c1 = torch.full((n, n), float("nan"), device="cuda"); c2 = torch.full((n, n), float("nan"), device="cuda")
     for (rsa, csa) in ((n, 1), (1, n)):
         L.gemm_strided(n, n, n, 1.0, a, rsa, csa, b, n, 1, 0.0, c1, n, 1, path=path)
-        L.gemm_strided(n, n, n, 1.0, a, rsa, csa, b, n, 1, 0.0, c2, n, 1, path=L.PATH_TF32_BF16C)
+        L.gemm_strided(n, n, n, 1.0, a, rsa, csa, b, n, 1, 0.0, c2, n, 1, path=L.PATH_TF32X3)
         torch.cuda.synchronize()
         rel = ((c1 - c2).abs() / c2.abs()).max().item()
         assert rel < 1e-5, rel
