@@ -199,6 +199,42 @@ int laser_b200_gemm_packedB_f32_dev(int64_t M, int64_t N, int64_t K, float alpha
                                     float beta, float *C, int64_t rowStrideC, int64_t colStrideC,
                                     void *stream);
 
+/* ---- row panels of C across the GPUs of one box ---------------------------------
+ * The reference parallelises this split inside gemm_strided itself: its `ic` loop hands every worker a row block of A
+ * and C while all workers share one packed panel of B (gemm.nim:160-176).  Here a worker is a GPU: rank r owns rows of
+ * A and C (never moved); B lives on `root` and is broadcast ONCE per product over NCCL (NVLink 5 / NVSwitch) on a
+ * communication stream, while the rank's rows of A are already being prepared; no collective inside the MMA loop, no
+ * reduction.  NCCL is bound at run time (dlopen of libnccl.so.2); without it these entries return LASER_B200_EUNSUPPORTED.
+ *
+ *   comm_get_unique_id / comm_init_rank   one process (or thread) per GPU: rank 0 obtains the 128-byte id, hands it to
+ *                                         the others by any means, every rank calls init_rank with ITS device current
+ *   comm_init_all                         one process driving devices 0 .. ngpus-1 (ncclCommInitAll)
+ *   rowshard_partition                    the row range of a rank: ceil(M / nranks) rounded up to the 256-row tile
+ *   gemm_rowsharded_f32_dev               per-rank entry, DEVICE pointers on the communicator's device, asynchronous on
+ *                                         `stream`: C_local <- alpha * A_local * B + beta * C_local with B (K x N, dense in
+ *                                         memory) valid on `root` and overwritten by the broadcast on every other rank
+ *   gemm_rowsharded_f32                   the reference signature with HOST pointers on `ngpus` devices of this process:
+ *                                         row panels of A (and of C when beta != 0) go to their device, B to device 0,
+ *                                         one broadcast, every device its rows, C comes back; synchronous */
+typedef struct laser_b200_comm laser_b200_comm;
+#define LASER_B200_UNIQUE_ID_BYTES 128
+int laser_b200_comm_get_unique_id(void *id128);
+int laser_b200_comm_init_rank(laser_b200_comm **comm, int nranks, int rank, const void *id128);
+int laser_b200_comm_init_all(laser_b200_comm **comms, int ngpus);
+int laser_b200_comm_destroy(laser_b200_comm *comm);
+int laser_b200_comm_rank(const laser_b200_comm *comm);
+int laser_b200_comm_size(const laser_b200_comm *comm);
+void laser_b200_rowshard_partition(int64_t M, int nranks, int rank, int64_t *first_row, int64_t *rows);
+int laser_b200_gemm_rowsharded_f32_dev(laser_b200_comm *comm, int64_t M_local, int64_t N, int64_t K, float alpha,
+                                       const float *A_local, int64_t rowStrideA, int64_t colStrideA,
+                                       float *B, int64_t rowStrideB, int64_t colStrideB, int root,
+                                       float beta, float *C_local, int64_t rowStrideC, int64_t colStrideC,
+                                       void *stream);
+int laser_b200_gemm_rowsharded_f32(int ngpus, int64_t M, int64_t N, int64_t K, float alpha,
+                                   const float *A, int64_t rowStrideA, int64_t colStrideA,
+                                   const float *B, int64_t rowStrideB, int64_t colStrideB,
+                                   float beta, float *C, int64_t rowStrideC, int64_t colStrideC);
+
 /* ---- device storage for the Tensor contract ----------------------------
  * Device analogue of allocCpuStorage (laser/tensor/allocator.nim:17-29: 64-byte
  * aligned, owned by the storage object) and of copyFromRaw / setZero

@@ -68,6 +68,16 @@ SIGNATURES = {
     "laser_b200_gemm_prepackB_f32_dev": (ctypes.c_int, [vp, i64, i64, i64, vp, i64, i64, vp]),
     "laser_b200_gemm_packed_f32_dev": (ctypes.c_int, [i64, i64, i64, f32, vp, vp, f32, vp, i64, i64, vp]),
     "laser_b200_gemm_packedB_f32_dev": (ctypes.c_int, [i64, i64, i64, f32, vp, i64, i64, vp, f32, vp, i64, i64, vp]),
+    "laser_b200_comm_get_unique_id": (ctypes.c_int, [vp]),
+    "laser_b200_comm_init_rank": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp]),
+    "laser_b200_comm_init_all": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
+    "laser_b200_comm_destroy": (ctypes.c_int, [vp]),
+    "laser_b200_comm_rank": (ctypes.c_int, [vp]),
+    "laser_b200_comm_size": (ctypes.c_int, [vp]),
+    "laser_b200_rowshard_partition": (None, [i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+    "laser_b200_gemm_rowsharded_f32_dev": (ctypes.c_int, [vp, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, ctypes.c_int, f32, vp,
+                                                          i64, i64, vp]),
+    "laser_b200_gemm_rowsharded_f32": (ctypes.c_int, [ctypes.c_int, i64, i64, i64, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, i64]),
     "laser_b200_malloc": (ctypes.c_int, [ctypes.POINTER(vp), sz]),
     "laser_b200_free": (ctypes.c_int, [vp]),
     "laser_b200_memcpy_h2d": (ctypes.c_int, [vp, vp, sz]),

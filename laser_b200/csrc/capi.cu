@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -38,6 +39,7 @@ thread_local int g_last_path = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_f32_mode{-1};
 constexpr int kDefaultF32Mode = LASER_B200_PATH_F16X3;
+void multi_shutdown();   // capi_multi.inc
 
 int set_error(int code, const char *fmt, ...) {
   char buf[512];
@@ -99,7 +101,11 @@ struct Ctx {
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
-  int kc_faithful = 256;  // env LASER_B200_KC (K extent per TMEM accumulation block, fp32-faithful modes)
+  // K extent per TMEM accumulation block of the fp32-faithful modes (env LASER_B200_KC).  Measured on the round-2 kernel at
+  // 8192^3 (profiles/r02_kc_sweep.md): 128 -> 2.147 ms, 256 -> 2.111 ms, 512 -> 2.044 ms, while the truncation bias of the
+  // tensor core's accumulator doubles with every step (mean_relative_error on U(-0.1,0.1): 3.4e-6 / 6.5e-6 / 1.2e-5 against the
+  // reference's 1e-5 gate): 128 keeps a 3x margin for 1.7 % of the time
+  int kc_faithful = 128;
   bool dyn_sched = true;  // env LASER_B200_DYNSCHED=0: static round-robin tiles instead of the atomic counter
   bool pdl = true;        // env LASER_B200_PDL=0: ordinary launch of the GEMM kernel after the preparation kernels
   bool profiling = false;
@@ -369,12 +375,12 @@ int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_l
     absmax_mn_kernel<true><<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(src, R, Cc, src_ld, words);
     COUNT_LAUNCH();
     CHECK_LAUNCH();
-    const int grid = grid_for(c, (R * ((Cc + 3) / 4) + 255) / 256, 8);
-    split_rows_f16x2_kernel<true><<<grid, 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+    const int64_t split_items = ((Cc + 255) / 256) * ((R + SPLIT_ROWS - 1) / SPLIT_ROWS);
+    split_rows_f16x2_kernel<true><<<grid_for(c, split_items, 8), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else if (Cc <= 4 * 32 * F16ROWS_MAXV) {   // short rows: a warp per row
-    f16x2_rows_fused_kernel<32><<<grid_for(c, (R + 7) / 8, 6), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+    f16x2_rows_fused_kernel<32><<<grid_for(c, (R + 7) / 8, 4), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else {
-    f16x2_rows_fused_kernel<256><<<grid_for(c, R, 6), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+    f16x2_rows_fused_kernel<256><<<grid_for(c, R, 4), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   }
   COUNT_LAUNCH();
   CHECK_LAUNCH();
@@ -554,7 +560,9 @@ int tc_run(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, co
 template <int SRC_ESZ, typename OutT>
 int gemm_tc(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, const void *A, int64_t rsA,
             int64_t csA, const void *B, int64_t rsB, int64_t csB, float beta, OutT *C, int64_t rsC,
-            int64_t csC, cudaStream_t s, const Epilogue &epi) {
+            int64_t csC, cudaStream_t s, const Epilogue &epi, cudaEvent_t b_ready = nullptr) {
+  // b_ready: B becomes valid only when this event has fired (the row-sharded driver: B is in flight on the communication
+  // stream); everything that does not read B -- the preparation of A -- is queued before the wait
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL)
     return set_error(LASER_B200_EUNSUPPORTED, "tensor-core path: extents must fit in int32");
   std::lock_guard<std::mutex> lk(c.mu);  // workspace + descriptor construction are per context
@@ -575,6 +583,7 @@ int gemm_tc(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, c
   if (rc) { prof_abort(c, &ep); return rc; }
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two 128-row blocks
   const bool pair = c.cta_pair && M > TC_BLOCK_M;
+  if (b_ready) CUDA_TRY(cudaStreamWaitEvent(s, b_ready, 0));
   rc = prepare_operand<SRC_ESZ>(c, ob, mode, ws_of_B(c, f16_b_off), pair ? TC_BLOCK_N / 2 : TC_BLOCK_N, &mb, &used_ws, s);
   if (rc) { prof_abort(c, &ep); return rc; }
   const int prep_launches = static_cast<int>(g_launches.load() - launches_before);
@@ -648,9 +657,9 @@ int prepack_dev(int which, void *dst, int64_t mn, int64_t k, const float *src, i
       rows_ld = ld;
     }
     if (k <= 4 * 32 * F16ROWS_MAXV)
-      f16x2_rows_fused_kernel<32><<<grid_for(*c, (mn + 7) / 8, 6), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
+      f16x2_rows_fused_kernel<32><<<grid_for(*c, (mn + 7) / 8, 4), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
     else
-      f16x2_rows_fused_kernel<256><<<grid_for(*c, mn, 6), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
+      f16x2_rows_fused_kernel<256><<<grid_for(*c, mn, 4), 256, 0, s>>>(rows, mn, k, rows_ld, h, l, L.ld_b, amax);
     COUNT_LAUNCH();
     CHECK_LAUNCH();
     CUDA_TRY(cudaEventRecord(c->ws_free, s));
@@ -750,7 +759,7 @@ int resolve_auto(int64_t M, int64_t N, int64_t K, const Epilogue &epi) {
 
 int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
             const float *B, int64_t rsB, int64_t csB, float beta, float *C, int64_t rsC, int64_t csC,
-            int path, void *stream, const Epilogue &epi = Epilogue()) {
+            int path, void *stream, const Epilogue &epi = Epilogue(), cudaEvent_t b_ready = nullptr) {
   int rc = check_args(M, N, K, A, B, C);
   if (rc == -1) return LASER_B200_OK;
   if (rc) return rc;
@@ -759,6 +768,7 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
   if (rc) return rc;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
   if (path == LASER_B200_PATH_AUTO) path = resolve_auto(M, N, K, epi);
+  if (b_ready && !is_tc_mode(path)) CUDA_TRY(cudaStreamWaitEvent(s, b_ready, 0));   // no separate preparation of A to overlap
   switch (path) {
     case -1: {
       const int grid = grid_for(*c, (M + 7) / 8, 8);
@@ -794,7 +804,7 @@ int f32_dev(int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_
     case LASER_B200_PATH_F16X3:
       // F16X3 (default): two fp16 pieces of each operand scaled by a power of two per row of A / column of B (device-side
       // abs-max), three passes, the epilogue undoes the scales.  TF32X3: hi/lo tf32 pieces, three passes.  TF32X1: one pass.
-      rc = gemm_tc<4, float>(*c, tc_kind_of_path(path), M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi);
+      rc = gemm_tc<4, float>(*c, tc_kind_of_path(path), M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi, b_ready);
       if (rc) return rc;
       g_last_path = path;
       break;
@@ -1032,6 +1042,7 @@ int laser_b200_init(void) {
 }
 
 void laser_b200_shutdown(void) {
+  multi_shutdown();
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   int cur = 0;
   cudaGetDevice(&cur);
@@ -1350,3 +1361,4 @@ int laser_b200_fill_uniform_f32_dev(float *dst_dev, int64_t n, uint64_t seed, fl
 }  // extern "C"
 
 #include "capi_layers.inc"
+#include "capi_multi.inc"

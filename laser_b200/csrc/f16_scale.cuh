@@ -77,4 +77,33 @@ inline float f16_bits_to_f32(uint16_t h) {
 }
 #endif
 
+// The two fp16 pieces of TWO already scaled values, packed (element 0 in the low half): h = fp16(x), l = fp16(x - h) -- the
+// difference is exact in fp32 -- and l = 0 when h is not finite (x = +-inf / NaN: x - h would be NaN).  The conversion pipe
+// (XU, a quarter of the FP32 rate) is what bounds the preparation kernels, so: ONE packed cvt.rn.f16x2.f32 for the two high
+// pieces, their fp32 values rebuilt with integer ops (no cvt.f32.f16), one packed cvt for the two low pieces -- one XU
+// instruction per element instead of three.
+__device__ __forceinline__ float f16_bits_to_f32_alu(uint32_t v) {   // v: 16 bits, finite
+  const uint32_t u = v & 0x7fffu;
+  const float normal = __uint_as_float((u << 13) + 0x38000000u);                       // (e + 112) << 23 | m << 13
+  const float subnormal = __uint_as_float(0x38800000u + (u << 13)) - __uint_as_float(0x38800000u);   // m * 2^-24, exact
+  const float mag = (u < 0x0400u) ? subnormal : normal;
+  return (v & 0x8000u) ? -mag : mag;
+}
+__device__ __forceinline__ void f16x2_pieces2(float x0, float x1, uint32_t &h2, uint32_t &l2) {
+#ifndef LB200_HOST_EMULATION
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x1), "f"(x0));   // d = {upper: first source, lower: second source}
+  const uint32_t v0 = h2 & 0xffffu, v1 = h2 >> 16;
+  float d0 = __fsub_rn(x0, f16_bits_to_f32_alu(v0)), d1 = __fsub_rn(x1, f16_bits_to_f32_alu(v1));
+  if ((v0 & 0x7c00u) == 0x7c00u) d0 = 0.0f;
+  if ((v1 & 0x7c00u) == 0x7c00u) d1 = 0.0f;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+#else
+  const uint16_t a0 = f16_rn_bits(x0), a1 = f16_rn_bits(x1);
+  const uint16_t b0 = ((a0 & 0x7c00u) == 0x7c00u) ? static_cast<uint16_t>(0) : f16_rn_bits(__fsub_rn(x0, f16_bits_to_f32_alu(a0)));
+  const uint16_t b1 = ((a1 & 0x7c00u) == 0x7c00u) ? static_cast<uint16_t>(0) : f16_rn_bits(__fsub_rn(x1, f16_bits_to_f32_alu(a1)));
+  h2 = a0 | (static_cast<uint32_t>(a1) << 16);
+  l2 = b0 | (static_cast<uint32_t>(b1) << 16);
+#endif
+}
+
 }  // namespace lb200

@@ -148,12 +148,6 @@ absmax_mn_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t s
   }
 }
 
-// the two fp16 pieces of an already scaled value: h = fp16(x), l = fp16(x - h) (the difference is exact in fp32);
-// l = 0 when h is not finite (x = +-inf / NaN: x - h would be NaN)
-__device__ __forceinline__ void f16x2_pieces(float x, uint16_t &h, uint16_t &l) {
-  h = f16_rn_bits(x);
-  l = ((h & 0x7c00u) == 0x7c00u) ? static_cast<uint16_t>(0) : f16_rn_bits(__fsub_rn(x, f16_bits_to_f32(h)));
-}
 __device__ __forceinline__ float4 load_row_vec(const float *row, int64_t c, int64_t Cc) {
   float4 v;
   if (c + 4 <= Cc) {
@@ -166,19 +160,16 @@ __device__ __forceinline__ float4 load_row_vec(const float *row, int64_t c, int6
   }
   return v;
 }
-__device__ __forceinline__ void store_f16x2_vec(float4 v, float s, uint16_t *hrow, uint16_t *lrow, int64_t c) {
-  uint16_t hx, hy, hz, hw, lx, ly, lz, lw;
-  f16x2_pieces(__fmul_rn(v.x, s), hx, lx);
-  f16x2_pieces(__fmul_rn(v.y, s), hy, ly);
-  f16x2_pieces(__fmul_rn(v.z, s), hz, lz);
-  f16x2_pieces(__fmul_rn(v.w, s), hw, lw);
+__device__ __forceinline__ void store_f16x2_vec4(float4 v, float sx, float sy, float sz, float sw, uint16_t *hrow, uint16_t *lrow,
+                                                 int64_t c) {
   uint2 h, l;
-  h.x = hx | (static_cast<uint32_t>(hy) << 16);
-  h.y = hz | (static_cast<uint32_t>(hw) << 16);
-  l.x = lx | (static_cast<uint32_t>(ly) << 16);
-  l.y = lz | (static_cast<uint32_t>(lw) << 16);
+  f16x2_pieces2(__fmul_rn(v.x, sx), __fmul_rn(v.y, sy), h.x, l.x);
+  f16x2_pieces2(__fmul_rn(v.z, sz), __fmul_rn(v.w, sw), h.y, l.y);
   *reinterpret_cast<uint2 *>(hrow + c) = h;
   *reinterpret_cast<uint2 *>(lrow + c) = l;
+}
+__device__ __forceinline__ void store_f16x2_vec(float4 v, float s, uint16_t *hrow, uint16_t *lrow, int64_t c) {
+  store_f16x2_vec4(v, s, s, s, s, hrow, lrow, c);
 }
 
 // K-major operand (rows contiguous, ONE scale per row): abs-max, scale and split in a single pass over HBM.  A group
@@ -187,7 +178,7 @@ __device__ __forceinline__ void store_f16x2_vec(float4 v, float s, uint16_t *hro
 // both fp16 pieces: 4 bytes read + 4 written per element, against 8 + 4 for abs-max and split as two kernels.
 constexpr int F16ROWS_MAXV = 8;
 template <int GROUP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 f16x2_rows_fused_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *__restrict__ hb,
                         uint16_t *__restrict__ lb, int64_t ld_b, uint32_t *__restrict__ absmax) {
   static_assert(GROUP == 32 || GROUP == 256, "a warp or the CTA per row");
@@ -242,50 +233,37 @@ f16x2_rows_fused_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
 
 // hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from the abs-max word of the element's mn index
 // (f16_scale.cuh): x * 2^s = hb + lb + r, |r| <= 2^-22 |x * 2^s| for elements within 2^-17 of their row's /
-// column's maximum.  Addressing as split_rows_tf32_kernel.
+// column's maximum.  [R][Cc] row-contiguous arrays in and out.  Work item = (strip of 256 columns, block of
+// SPLIT_ROWS rows): a thread owns 4 columns of the strip -- for PER_COL their four scales are computed once -- and walks
+// the rows of the block, adjacent threads reading adjacent float4s.
+constexpr int SPLIT_ROWS = 64;
 template <bool PER_COL>
 __global__ void __launch_bounds__(256)
 split_rows_f16x2_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld,
                         uint16_t *__restrict__ hb, uint16_t *__restrict__ lb, int64_t ld_b,
                         const uint32_t *__restrict__ absmax) {
   ptx::griddep_launch_dependents();   // the next kernel of the stream may start its prologue (it waits for our results)
-  const int64_t vec_per_row = (Cc + 3) >> 2;
-  const int64_t total = R * vec_per_row;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int64_t c = (i - r * vec_per_row) << 2;
-    const float *s = src + r * src_ld + c;
-    float4 v;
-    if (c + 4 <= Cc) {
-      v = *reinterpret_cast<const float4 *>(s);
-    } else {
-      v.x = s[0];
-      v.y = (c + 1 < Cc) ? s[1] : 0.0f;
-      v.z = (c + 2 < Cc) ? s[2] : 0.0f;
-      v.w = 0.0f;
-    }
-    float sx, sy, sz, sw;
+  const int tx = static_cast<int>(threadIdx.x) & 63, ty = static_cast<int>(threadIdx.x) >> 6;   // 64 float4 columns x 4 row lanes
+  const int64_t strips = (Cc + 255) >> 8;
+  const int64_t rblocks = (R + SPLIT_ROWS - 1) / SPLIT_ROWS;
+  for (int64_t it = blockIdx.x; it < strips * rblocks; it += gridDim.x) {
+    const int64_t rb = it / strips;
+    const int64_t c = ((it - rb * strips) << 8) + (tx << 2);
+    if (c >= Cc) continue;
+    float sx = 1.0f, sy = 1.0f, sz = 1.0f, sw = 1.0f;
     if constexpr (PER_COL) {
       sx = f16x2_scale(absmax[c]);
       sy = (c + 1 < Cc) ? f16x2_scale(absmax[c + 1]) : 1.0f;
       sz = (c + 2 < Cc) ? f16x2_scale(absmax[c + 2]) : 1.0f;
       sw = (c + 3 < Cc) ? f16x2_scale(absmax[c + 3]) : 1.0f;
-    } else {
-      sx = sy = sz = sw = f16x2_scale(absmax[r]);
     }
-    uint16_t hx, hy, hz, hw, lx, ly, lz, lw;
-    f16x2_pieces(__fmul_rn(v.x, sx), hx, lx);
-    f16x2_pieces(__fmul_rn(v.y, sy), hy, ly);
-    f16x2_pieces(__fmul_rn(v.z, sz), hz, lz);
-    f16x2_pieces(__fmul_rn(v.w, sw), hw, lw);
-    uint2 h, l;
-    h.x = hx | (static_cast<uint32_t>(hy) << 16);
-    h.y = hz | (static_cast<uint32_t>(hw) << 16);
-    l.x = lx | (static_cast<uint32_t>(ly) << 16);
-    l.y = lz | (static_cast<uint32_t>(lw) << 16);
-    *reinterpret_cast<uint2 *>(hb + r * ld_b + c) = h;
-    *reinterpret_cast<uint2 *>(lb + r * ld_b + c) = l;
+    const int64_t r1 = (rb + 1) * SPLIT_ROWS < R ? (rb + 1) * SPLIT_ROWS : R;
+#pragma unroll 4
+    for (int64_t r = rb * SPLIT_ROWS + ty; r < r1; r += 4) {
+      const float4 v = load_row_vec(src + r * src_ld, c, Cc);
+      if constexpr (!PER_COL) sx = sy = sz = sw = f16x2_scale(absmax[r]);
+      store_f16x2_vec4(v, sx, sy, sz, sw, hb + r * ld_b, lb + r * ld_b, c);
+    }
   }
 }
 

@@ -1,32 +1,27 @@
-"""Row-panel sharding of a large GEMM across the GPUs of one box (one process per GPU).
+"""Row-panel sharding of a large GEMM across the GPUs of one box: the Python mirror of
+laser_b200_gemm_rowsharded_f32_dev / laser_b200_gemm_rowsharded_f32 (include/laser_b200.h).
 
-The reference parallelises exactly this way on a CPU: its `ic` loop hands each worker a
-row block of A and C while all workers share one packed panel of B per `pc` iteration, and
-beta is applied on the first K-panel only (gemm.nim:150-176).  Here:
+The reference parallelises exactly this way on a CPU: its `ic` loop hands each worker a row block of A
+and C while all workers share one packed panel of B (gemm.nim:160-176).  Here a worker is a GPU:
   * rank r owns rows [start_r, stop_r) of A and C (never moved);
-  * B lives on `src` and is broadcast once over NCCL/NVLink (torch.distributed) -- no
-    collective inside the MMA loop, no reduction.  With n_panels > 1 the broadcast is cut in
-    K-panels and panel i+1 is in flight while the GEMM consumes panel i with beta' = beta
-    (i == 0) or 1 (i > 0), the reference's own rule for its K blocks.  Measured on 2 and 4
-    B200s (tools/rowshard_probe.py): one panel is fastest -- a 256 MB broadcast costs 0.45 ms
-    against a 3.6 ms GEMM, while every extra K-panel costs a C read-modify-write pass and a
-    kernel ramp -- so n_panels defaults to 1.
-  * overlap_prepack (LASER_B200_ROWSHARD_OVERLAP=1; off by default until measured): the
-    rank's own rows of A are prepared (gemm_prepackA) on a side stream while the broadcast of
-    B is in flight, so only B's preparation and the product follow the collective.
-The host logic is backend-agnostic (tested on CPU with gloo + the oracle as gemm_fn).
+  * B lives on `src` and is broadcast ONCE per product over NCCL / NVLink by the library itself (ncclBroadcast on
+    a communication stream of the communicator) -- no collective inside the MMA loop, no reduction;
+  * the scale + split of the rank's rows of A is queued before the wait for B, so it overlaps the transfer.
+Everything on the data path happens behind the C ABI; torch.distributed is used only to hand the 128-byte NCCL
+unique id from rank 0 to the other ranks when the communicator is created (any backend: gloo, nccl).
 """
-import os
+import ctypes
 
-import torch
-import torch.distributed as dist
+from ._capi import check, lib
+from .gemm import _current_stream, _resolve
 
-__all__ = ["partition_rows", "k_panels", "gemm_rowsharded"]
+__all__ = ["partition_rows", "Comm", "comm_init_all", "comm_init_rank", "comm_from_torch_distributed", "gemm_rowsharded",
+           "gemm_rowsharded_dev", "gemm_rowsharded_host"]
 
 
-def partition_rows(M, world_size, align=128):
-    """[(start, stop)] per rank: ceil(M / world) rounded up to the CTA tile height; the
-    last ranks take what is left (possibly nothing)."""
+def partition_rows(M, world_size, align=256):
+    """[(start, stop)] per rank: ceil(M / world) rounded up to the CTA-pair tile height; the last ranks take what is
+    left (possibly nothing).  Same rule as laser_b200_rowshard_partition (align = 256)."""
     per = -(-M // world_size)
     per = -(-per // align) * align
     out = []
@@ -36,79 +31,113 @@ def partition_rows(M, world_size, align=128):
     return out
 
 
-def k_panels(K, n_panels, align=32):
-    """Split K in at most n_panels panels whose sizes are multiples of `align` (one TMA
-    k-block) except possibly the last."""
-    n_panels = max(1, min(int(n_panels), -(-K // align)))
-    per = -(-K // n_panels)
-    per = -(-per // align) * align
-    out, k0 = [], 0
-    while k0 < K:
-        out.append((k0, min(K, k0 + per)))
-        k0 += per
-    return out
+def partition_rows_c(M, world_size, rank):
+    """(start, stop) of `rank` as the library computes it."""
+    a, n = ctypes.c_int64(), ctypes.c_int64()
+    lib().laser_b200_rowshard_partition(int(M), int(world_size), int(rank), ctypes.byref(a), ctypes.byref(n))
+    return a.value, a.value + n.value
 
 
-_packed_cache = {}   # (device, M, N, K) -> (packedA, packedB, side stream)
+class Comm:
+    """Owner of a laser_b200_comm handle (one rank of a row-sharded product on one device)."""
+
+    def __init__(self, handle):
+        self.handle = ctypes.c_void_p(handle)
+
+    @property
+    def rank(self):
+        return lib().laser_b200_comm_rank(self.handle)
+
+    @property
+    def size(self):
+        return lib().laser_b200_comm_size(self.handle)
+
+    def destroy(self):
+        if self.handle:
+            check(lib().laser_b200_comm_destroy(self.handle))
+            self.handle = ctypes.c_void_p(None)
 
 
-def _packed_buffers(device, M, N, K):
-    from . import prepacked as pp
-    key = (str(device), M, N, K)
-    if key not in _packed_cache:
-        _packed_cache.clear()          # one shape at a time: the buffers are as large as the operands
-        _packed_cache[key] = (pp.alloc_packed(pp.gemm_prepackA_mem_required(M, N, K)),
-                              pp.alloc_packed(pp.gemm_prepackB_mem_required(M, N, K)),
-                              torch.cuda.Stream(device=device))
-    return _packed_cache[key]
+def comm_get_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    check(lib().laser_b200_comm_get_unique_id(buf))
+    return buf.raw
 
 
-def _overlap_applicable(A_local, B, C_local, n_panels, M_local):
-    from .gemm import get_f32_mode
-    return (n_panels == 1 and M_local > 0 and A_local.is_cuda and A_local.dtype == torch.float32
-            and B.dtype == torch.float32 and C_local.dtype == torch.float32 and get_f32_mode() in (0, 5))
+def comm_init_rank(nranks, rank, unique_id):
+    """The calling thread's current CUDA device joins a communicator of `nranks` (one process or thread per GPU)."""
+    h = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+    check(lib().laser_b200_comm_init_rank(ctypes.byref(h), int(nranks), int(rank), buf))
+    return Comm(h.value)
 
 
-def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, group=None,
-                    n_panels=None, gemm_fn=None, broadcast=True, overlap_prepack=None):
-    """C_local <- alpha * A_local @ B + beta * C_local on every rank.
+def comm_init_all(ngpus):
+    """One process driving devices 0 .. ngpus-1: a list of `ngpus` communicators (rank d on device d)."""
+    arr = (ctypes.c_void_p * ngpus)()
+    check(lib().laser_b200_comm_init_all(arr, int(ngpus)))
+    return [Comm(arr[d]) for d in range(ngpus)]
 
-    A_local: (M_local, K) tensor view (any strides), C_local: (M_local, N) view,
-    B: (K, N) row-major contiguous tensor on every rank, valid on `src` only (unless
-    broadcast=False).  gemm_fn has the gemm_strided signature (default: the CUDA library)."""
-    if n_panels is None:     # default 1 (measured best in round 1); env override for A/B runs of bench.py
-        n_panels = int(os.environ.get("LASER_B200_ROWSHARD_PANELS", "1"))
-    if overlap_prepack is None:
-        overlap_prepack = os.environ.get("LASER_B200_ROWSHARD_OVERLAP", "0") == "1"
-    overlap = bool(overlap_prepack) and gemm_fn is None and _overlap_applicable(A_local, B, C_local, n_panels, M_local)
-    if gemm_fn is None:
-        from .gemm import gemm_strided as gemm_fn
-    assert B.dim() == 2 and B.shape[0] == K and B.shape[1] == N and B.is_contiguous()
-    panels = k_panels(K, n_panels)
-    works = []
-    if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
-        for (k0, k1) in panels:  # all panels are queued now; NCCL streams them in order
-            works.append(dist.broadcast(B[k0:k1], src=src, group=group, async_op=True))
+
+_dist_comms = {}
+
+
+def comm_from_torch_distributed(group=None):
+    """The communicator of this rank of a torch.distributed job (created once per group): rank 0 draws the NCCL unique
+    id, torch.distributed carries the 128 bytes to the other ranks, every rank joins with its current device."""
+    import torch.distributed as dist
+    key = id(group)
+    if key not in _dist_comms:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [comm_get_unique_id() if rank == 0 and world > 1 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        _dist_comms[key] = comm_init_rank(world, rank, box[0])
+    return _dist_comms[key]
+
+
+def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, comm=None, group=None, stream=None, gemm_fn=None):
+    """C_local <- alpha * A_local @ B + beta * C_local on every rank (device buffers on this rank's GPU).
+
+    A_local: (M_local, K) view (any strides), C_local: (M_local, N) view, B: (K, N) dense tensor on every rank, valid on
+    `src` only -- the other ranks' copies are overwritten by the broadcast.  gemm_fn (tests of the host logic only): a
+    gemm_strided-like callable that stands in for the library, with torch.distributed doing the broadcast."""
     rsA, csA = (A_local.stride(0), A_local.stride(1)) if M_local > 0 else (K, 1)
     rsC, csC = (C_local.stride(0), C_local.stride(1)) if M_local > 0 else (N, 1)
-    if overlap:
-        from . import prepacked as pp
-        pa, pb, side = _packed_buffers(A_local.device, M_local, N, K)
-        cur = torch.cuda.current_stream(A_local.device)
-        side.wait_stream(cur)                      # A (and the packed buffers' last readers) are ordered on cur
-        with torch.cuda.stream(side):
-            pp.gemm_prepackA(pa, M_local, N, K, A_local, rsA, csA)
-        if works:
-            works[0].wait()                        # cur waits for B
-        pp.gemm_prepackB(pb, M_local, N, K, B, N, 1)
-        cur.wait_stream(side)
-        pp.gemm_packed(M_local, N, K, alpha, pa, pb, beta, C_local, rsC, csC)
+    rsB, csB = B.stride(0), B.stride(1)
+    if gemm_fn is not None:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(B, src=src, group=group)
+        if M_local > 0:
+            gemm_fn(M_local, N, K, alpha, A_local, rsA, csA, B, rsB, csB, beta, C_local, rsC, csC)
         return C_local
-    for i, (k0, k1) in enumerate(panels):
-        if works:
-            works[i].wait()  # NCCL: the current stream waits for panel i; gloo: host wait
-        if M_local == 0:
-            continue
-        gemm_fn(M_local, N, k1 - k0, alpha, A_local[:, k0:k1], rsA, csA, B[k0:k1], N, 1,
-                beta if i == 0 else 1.0, C_local, rsC, csC)
+    if comm is None:
+        comm = comm_from_torch_distributed(group)
+    return gemm_rowsharded_dev(comm, M_local, N, K, alpha, A_local, rsA, csA, B, rsB, csB, src, beta, C_local, rsC, csC, stream)
+
+
+def gemm_rowsharded_dev(comm, M_local, N, K, alpha, A_local, rsA, csA, B, rsB, csB, root, beta, C_local, rsC, csC, stream=None):
+    """laser_b200_gemm_rowsharded_f32_dev with explicit element strides (device buffers: torch CUDA tensors, Tensor, DevPtr)."""
+    pb, tb, db = _resolve(B)
+    if not db or tb != "f32":
+        raise TypeError("gemm_rowsharded takes float32 device buffers")
+    pa = pc = 0
+    if M_local > 0:
+        pa, ta, da = _resolve(A_local); pc, tc, dc = _resolve(C_local)
+        if not (da and dc and ta == tc == "f32"):
+            raise TypeError("gemm_rowsharded takes float32 device buffers")
+    if stream is None:
+        stream = _current_stream()
+    check(lib().laser_b200_gemm_rowsharded_f32_dev(comm.handle, int(M_local), int(N), int(K), float(alpha), pa, rsA, csA, pb, rsB,
+                                                   csB, int(root), float(beta), pc, rsC, csC, stream))
     return C_local
+
+
+def gemm_rowsharded_host(ngpus, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC):
+    """The reference signature with HOST (numpy) buffers, row panels spread over `ngpus` devices of this process."""
+    pa, ta, da = _resolve(A); pb, tb, db = _resolve(B); pc, tc, dc = _resolve(C)
+    if da or db or dc or not (ta == tb == tc == "f32"):
+        raise TypeError("gemm_rowsharded_host takes float32 numpy arrays")
+    check(lib().laser_b200_gemm_rowsharded_f32(int(ngpus), int(M), int(N), int(K), float(alpha), pa, rsA, csA, pb, rsB, csB,
+                                               float(beta), pc, rsC, csC))

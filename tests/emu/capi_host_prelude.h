@@ -75,8 +75,16 @@ extern "C" {
 // marks this build: the Python mirror refuses to load a library exporting it unless LASER_B200_EMU=1
 int laser_b200_is_host_emulation(void) { return 1; }
 inline int emu_device_count_sms() { const char *e = getenv("LASER_B200_EMU_SMS"); return e ? atoi(e) : 8; }
-cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+// "devices": an index per thread (one context of the library each, like real devices); how many there are comes from the test
+static thread_local int emu_current_device = 0;
+inline int emu_device_count() { const char *e = getenv("LASER_B200_EMU_DEVICES"); return e ? atoi(e) : 1; }
+cudaError_t cudaGetDevice(int *d) { *d = emu_current_device; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) {
+  if (d < 0 || d >= emu_device_count()) return cudaErrorInvalidDevice;
+  emu_current_device = d;
+  return cudaSuccess;
+}
+cudaError_t cudaGetDeviceCount(int *n) { *n = emu_device_count(); return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp *p, int) {
   std::memset(p, 0, sizeof *p);
   p->major = 10; p->minor = 0; p->multiProcessorCount = emu_device_count_sms();

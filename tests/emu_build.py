@@ -93,10 +93,9 @@ def build_capi_host_emu(asan=False):
     so = os.path.join(out_dir, "liblaser_b200_hostemu_asan.so" if asan else "liblaser_b200_hostemu.so")
     csrc = os.path.abspath(CSRC)
     units = ["capi.cu", "tc_f16x3.cu", "tc_tf32x3.cu", "tc_tf32x1.cu", "tc_bf16.cu"]   # laser_b200/_build.py: SOURCES
-    units = [u for u in units + ["multi_gpu.cu"] if os.path.exists(os.path.join(csrc, u))]
     deps = [os.path.join(csrc, f) for f in units + ["capi_layers.inc", "f16_scale.cuh", "gemm_tc.cuh", "tc_params.h", "tc_launch.h",
                                                     "tc_launch_impl.cuh", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh",
-                                                    "layers.cuh", "ptx.cuh", "host_common.h"] if os.path.exists(os.path.join(csrc, f))] + \
+                                                    "layers.cuh", "ptx.cuh", "capi_multi.inc"] if os.path.exists(os.path.join(csrc, f))] + \
            [os.path.join(EMU_DIR, f) for f in ("capi_host_prelude.h", "cuda_emu.h", "ptx_emu.h")] + [os.path.abspath(__file__)]
     if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
@@ -116,7 +115,20 @@ def build_capi_host_emu(asan=False):
     san = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
     subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,
                            "-I", EMU_DIR, "-I", csrc, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic",
-                           gen, "-o", so], env=env)
+                           gen, "-o", so, "-ldl"], env=env)
+    return so
+
+
+def build_fake_nccl():
+    """tests/emu/fake_nccl.c -> a shared library the emulated build loads through LASER_B200_NCCL_LIB"""
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    out_dir = os.path.join(EMU_DIR, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    src, so = os.path.join(EMU_DIR, "fake_nccl.c"), os.path.join(out_dir, "libfake_nccl.so")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call([gcc, "-O1", "-fPIC", "-shared", src, "-o", so])
     return so
 
 

@@ -313,6 +313,50 @@ def f16x3():
     print("OK f16x3", n + 2)
 
 
+def rowsharded():
+    """the multi-GPU entry points behind the C ABI (capi_multi.inc) on LASER_B200_EMU_DEVICES emulated devices with a stand-in
+    NCCL (tests/emu/fake_nccl.c): the host-pointer entry (uploads, one broadcast of B inside an NCCL group, every device its
+    row panel, downloads) and the per-rank device entry driven the way a single-process caller must drive it"""
+    import ctypes
+    from laser_b200 import rowshard as RS
+    ndev = int(os.environ["LASER_B200_EMU_DEVICES"])
+    n = 0
+    for (M, N, K, alpha, beta) in ((700, 140, 100, 1.0, 0.0), (1000, 64, 72, 0.5, -1.25), (200, 40, 64, 1.0, 2.0)):
+        a, b, c0 = rnd((M, K), 70), rnd((K, N), 71), rnd((M, N), 72)
+        c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
+        RS.gemm_rowsharded_host(ndev, M, N, K, alpha, a, K, 1, b, N, 1, beta, c, N, 1)
+        ref = ref_gemm(M, N, K, alpha, a, b, beta, c0)
+        assert np.abs(c - ref).max() <= 1e-5 * np.abs(ref).max(), (M, N, K)
+        assert RS.partition_rows(M, ndev) == [RS.partition_rows_c(M, ndev, r) for r in range(ndev)]
+        n += 1
+    # per-rank device entry (one process or thread per GPU in real use; played here rank after rank, the root first, which
+    # is the order the stream dependencies impose anyway): B valid on the root only, every rank its rows
+    fake = ctypes.CDLL(os.environ["LASER_B200_NCCL_LIB"])
+    cudart_set = L.lib().cudaSetDevice
+    comms = RS.comm_init_all(ndev)
+    assert [cm.rank for cm in comms] == list(range(ndev)) and all(cm.size == ndev for cm in comms)
+    M, N, K = 900, 72, 80
+    a, bfull, c0 = rnd((M, K), 73), rnd((K, N), 74), rnd((M, N), 75)
+    parts = RS.partition_rows(M, ndev)
+    Bs = [bfull.copy() if r == 1 else np.full((K, N), np.nan, np.float32) for r in range(ndev)]   # root = rank 1
+    Cs = [c0[lo:hi].copy() for lo, hi in parts]
+    calls0 = fake.fake_nccl_broadcast_calls()
+    for r in [1] + [x for x in range(ndev) if x != 1]:
+        lo, hi = parts[r]
+        assert cudart_set(r) == 0
+        RS.gemm_rowsharded_dev(comms[r], hi - lo, N, K, 0.5, D(a[lo:hi]) if hi > lo else None, K, 1, D(Bs[r]), N, 1, 1, -1.25,
+                               D(Cs[r]) if hi > lo else None, N, 1, stream=1)
+    cudart_set(0)
+    assert fake.fake_nccl_broadcast_calls() - calls0 == ndev
+    ref = ref_gemm(M, N, K, 0.5, a, bfull, -1.25, c0)
+    for r, (lo, hi) in enumerate(parts):
+        assert np.array_equal(Bs[r], bfull), r
+        assert hi == lo or np.abs(Cs[r] - ref[lo:hi]).max() <= 1e-5 * np.abs(ref).max(), r     # (a rank may own no rows)
+    for cm in comms:
+        cm.destroy()
+    print("OK rowsharded", n + 1)
+
+
 def lifecycle():
     """init / shutdown / re-init: workspaces, staging buffers and the layer workspace are released and rebuilt"""
     a, b = rnd((300, 200), 40), rnd((200, 260), 41)

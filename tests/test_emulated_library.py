@@ -12,7 +12,7 @@ import sys
 
 import pytest
 
-from emu_build import build_capi_host_emu
+from emu_build import build_capi_host_emu, build_fake_nccl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.timeout(1200)
@@ -51,6 +51,12 @@ def test_host_entry_under_configuration(emulated_lib, env):
     """the panel geometry of the pipelined host-pointer entry and the kernel configuration knobs are read
     from the environment when the library initialises: one process per configuration"""
     run(emulated_lib, "host_entry", **env)
+
+
+@pytest.mark.parametrize("ndev", [2, 3])
+def test_rowsharded_entry_points_with_a_stand_in_nccl(emulated_lib, ndev):
+    """laser_b200_gemm_rowsharded_f32 / _f32_dev on 2 and 3 emulated devices (3: uneven row panels, the last rank short)"""
+    run(emulated_lib, "rowsharded", LASER_B200_EMU_DEVICES=ndev, LASER_B200_NCCL_LIB=build_fake_nccl())
 
 
 def test_f16x3_mode(emulated_lib):

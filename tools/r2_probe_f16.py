@@ -13,11 +13,11 @@ def timeit(fn, iters=8, warm=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
-PATH = {"f16x3": L.PATH_F16X3, "mixed": L.PATH_TF32_BF16C, "tf32x1": L.PATH_TF32X1}
+PATH = {"f16x3": L.PATH_F16X3, "tf32x3": L.PATH_TF32X3, "tf32x1": L.PATH_TF32X1}
 for n in (4096, 8192):
     a = torch.rand(n, n, device="cuda") - 0.5; b = torch.rand(n, n, device="cuda") - 0.5; c = torch.empty(n, n, device="cuda")
     at = a.t().contiguous(); bt = b.t().contiguous()
-    for name in ("f16x3", "mixed", "tf32x1"):
+    for name in ("f16x3", "tf32x3", "tf32x1"):
         p = PATH[name]
         for lay, fn in (("A row, B row", lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1, path=p)),
                         ("A^T(col), B row", lambda: L.gemm_strided(n, n, n, 1.0, at, 1, n, b, n, 1, 0.0, c, n, 1, path=p)),
@@ -32,6 +32,6 @@ for n in (4096, 8192):
 # M=32768 single GPU (strong-scaling baseline)
 n = 8192; m = 32768
 a = torch.rand(m, n, device="cuda") - 0.5; b = torch.rand(n, n, device="cuda") - 0.5; c = torch.empty(m, n, device="cuda")
-for name in ("f16x3", "mixed"):
+for name in ("f16x3",):
     ms = timeit(lambda: L.gemm_strided(m, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1, path=PATH[name]), iters=4, warm=2)
     print("M=32768 N=K=8192 %-7s %.3f ms %.1f TFLOP/s" % (name, ms, 2.0 * m * n * n / ms / 1e9), flush=True)

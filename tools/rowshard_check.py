@@ -24,7 +24,7 @@ else:
     B.fill_(float("nan"))
 B = B.view(K, N)
 C = torch.full((Ml, N), 3.0, dtype=torch.float32, device="cuda")
-gemm_rowsharded(Ml, N, K, 0.5, A, B, -1.25, C, src=0, n_panels=4)
+gemm_rowsharded(Ml, N, K, 0.5, A, B, -1.25, C, src=0)      # the C ABI: NCCL broadcast of B + this rank's rows
 torch.cuda.synchronize()
 assert not torch.isnan(B).any(), "broadcast of B incomplete"
 rows = np.unique(np.random.default_rng(rank).integers(0, Ml, 24))

@@ -1,4 +1,4 @@
-"""Time and error of one opt-in fp32 mode (bf16x3 | f16x3) on one B200 -> one JSON line on stdout.
+"""Time and error of one fp32 tensor-core mode (f16x3 | tf32x3 | tf32x1) next to tf32x3 on one B200 -> one JSON line on stdout.
 
 bench.py runs this in a CHILD process per mode (with a timeout) after all of its own measurements: the modes were written
 after the round's GPU minutes were spent, so their first run on silicon must not be able to take the bench line down.
@@ -28,8 +28,8 @@ def timed(fn, steps, warmup):
 
 
 def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
-    PATH = {"bf16x3": L.PATH_BF16X3, "f16x3": L.PATH_F16X3}[name]
+    name = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
+    PATH = {"f16x3": L.PATH_F16X3, "tf32x3": L.PATH_TF32X3, "tf32x1": L.PATH_TF32X1}[name]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
     L.init()
@@ -44,12 +44,12 @@ def main():
         C.fill_(float("nan")); Cd.fill_(float("nan"))
         L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, C, m, 1, path=PATH)
         assert L.last_path() == PATH
-        L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, Cd, m, 1, path=L.PATH_TF32_BF16C)
+        L.gemm_strided(m, m, n, 1.0, A, n, 1, B, n, 1, 0.0, Cd, m, 1, path=L.PATH_TF32X3)
         torch.cuda.synchronize()
         exact = A.view(n, n)[:m, :].double() @ B.view(n, n)[:, :m].double()
         got = C[:m * m].view(m, m).double(); dflt = Cd[:m * m].view(m, m).double()
         e = {}
-        for label, x in ((name, got), ("default", dflt)):
+        for label, x in ((name, got), ("tf32x3", dflt)):
             d = (x - exact).abs()
             e[label] = {"max_rel": (d / exact.abs()).max().item(), "normwise": (torch.linalg.norm(x - exact) / torch.linalg.norm(exact)).item(),
                        "mean_relative_error": (d / exact.abs().clamp_min(1e-30)).mean().item()}
@@ -62,11 +62,11 @@ def main():
     for _ in range(3):
         f()
     prof = L.profile_end()
-    msd = timed(lambda: L.gemm_strided(n, n, n, 1.0, A, n, 1, B, n, 1, 0.0, Cd, n, 1, path=L.PATH_TF32_BF16C), steps, 3)
+    msd = timed(lambda: L.gemm_strided(n, n, n, 1.0, A, n, 1, B, n, 1, 0.0, Cd, n, 1, path=L.PATH_TF32X3), steps, 3)
     flops = 2.0 * n * n * n
     out.update({"ms": ms, "tflops": flops / ms / 1e9, "kernel_ms": prof["gemm_ms"] / max(1, prof["gemm_launches"]),
-                "prep_ms_per_step": prof["prep_ms"] / 3, "default_mode_ms_same_process": msd,
-                "speedup_vs_default": msd / ms})
+                "prep_ms_per_step": prof["prep_ms"] / 3, "tf32x3_ms_same_process": msd,
+                "speedup_vs_tf32x3": msd / ms})
     print(json.dumps(out), flush=True)
 
 
