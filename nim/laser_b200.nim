@@ -20,7 +20,7 @@ type
   LaserB200Error* = object of CatchableError   # cf. LibraryError in laser/cpuinfo.nim:358-359
 
   GemmPath* {.size: sizeof(cint).} = enum      # LASER_B200_PATH_*
-    pathAuto = 0, pathSimt = 1, pathTf32x1 = 2, pathTf32x3 = 3, pathBf16 = 4, pathTf32Bf16c = 5, pathBf16x3 = 6, pathF16x3 = 7
+    pathAuto = 0, pathSimt = 1, pathTf32x1 = 2, pathTf32x3 = 3, pathBf16 = 4, pathF16x3 = 7   # 7: the default fp32 mode
 
 {.push importc, cdecl, dynlib: laserB200Lib.}
 proc laser_b200_init*(): cint
@@ -43,6 +43,32 @@ proc laser_b200_gemm_strided_i64*(M, N, K: int64, alpha: int64,
     A: ptr int64, rowStrideA, colStrideA: int64,
     B: ptr int64, rowStrideB, colStrideB: int64,
     beta: int64, C: ptr int64, rowStrideC, colStrideC: int64): cint
+# bf16 (a dtype the reference does not have: BASELINE.json config 4): buffers hold bf16 bit patterns, alpha / beta and the
+# accumulation are float32, C is rounded to nearest-even
+proc laser_b200_gemm_strided_bf16*(M, N, K: int64, alpha: float32,
+    A: ptr uint16, rowStrideA, colStrideA: int64,
+    B: ptr uint16, rowStrideB, colStrideB: int64,
+    beta: float32, C: ptr uint16, rowStrideC, colStrideC: int64): cint
+proc laser_b200_gemm_strided_bf16_dev*(M, N, K: int64, alpha: float32,
+    A: ptr uint16, rowStrideA, colStrideA: int64,
+    B: ptr uint16, rowStrideB, colStrideB: int64,
+    beta: float32, C: ptr uint16, rowStrideC, colStrideC: int64, stream: pointer): cint
+# row panels of C across the GPUs of the box (the `ic` loop of gemm.nim:160-176 with GPUs as workers)
+proc laser_b200_comm_get_unique_id*(id128: pointer): cint
+proc laser_b200_comm_init_rank*(comm: ptr pointer, nranks, rank: cint, id128: pointer): cint
+proc laser_b200_comm_init_all*(comms: ptr pointer, ngpus: cint): cint
+proc laser_b200_comm_destroy*(comm: pointer): cint
+proc laser_b200_comm_rank*(comm: pointer): cint
+proc laser_b200_comm_size*(comm: pointer): cint
+proc laser_b200_rowshard_partition*(M: int64, nranks, rank: cint, firstRow, rows: ptr int64)
+proc laser_b200_gemm_rowsharded_f32_dev*(comm: pointer, M_local, N, K: int64, alpha: float32,
+    A_local: ptr float32, rowStrideA, colStrideA: int64,
+    B: ptr float32, rowStrideB, colStrideB: int64, root: cint,
+    beta: float32, C_local: ptr float32, rowStrideC, colStrideC: int64, stream: pointer): cint
+proc laser_b200_gemm_rowsharded_f32*(ngpus: cint, M, N, K: int64, alpha: float32,
+    A: ptr float32, rowStrideA, colStrideA: int64,
+    B: ptr float32, rowStrideB, colStrideB: int64,
+    beta: float32, C: ptr float32, rowStrideC, colStrideC: int64): cint
 proc laser_b200_gemm_strided_f32_dev*(M, N, K: int64, alpha: float32,
     A: ptr float32, rowStrideA, colStrideA: int64,
     B: ptr float32, rowStrideB, colStrideB: int64,
@@ -70,6 +96,28 @@ proc laser_b200_memset_zero*(dst: pointer, bytes: csize_t): cint
 template check(code: cint) =
   if code != 0:
     raise newException(LaserB200Error, $laser_b200_last_error())
+
+# ---- bf16 and multi-GPU flavours of the same call ------------------------------------------------------
+type BFloat16* = distinct uint16     # bit pattern of a bfloat16
+
+proc gemm_strided*(M, N, K: int, alpha: float32,
+                   A: ptr BFloat16, rowStrideA, colStrideA: int,
+                   B: ptr BFloat16, rowStrideB, colStrideB: int,
+                   beta: float32,
+                   C: ptr BFloat16, rowStrideC, colStrideC: int) =
+  check laser_b200_gemm_strided_bf16(M, N, K, alpha, cast[ptr uint16](A), rowStrideA, colStrideA,
+                                     cast[ptr uint16](B), rowStrideB, colStrideB, beta,
+                                     cast[ptr uint16](C), rowStrideC, colStrideC)
+
+proc gemm_strided_rowsharded*(ngpus: int, M, N, K: int, alpha: float32,
+                              A: ptr float32, rowStrideA, colStrideA: int,
+                              B: ptr float32, rowStrideB, colStrideB: int,
+                              beta: float32,
+                              C: ptr float32, rowStrideC, colStrideC: int) =
+  ## gemm_strided on host matrices with the row blocks of A and C spread over `ngpus` GPUs of this process and one
+  ## NCCL broadcast of B (the reference's `ic` loop, gemm.nim:160-176, with GPUs as workers)
+  check laser_b200_gemm_rowsharded_f32(ngpus.cint, M, N, K, alpha, A, rowStrideA, colStrideA,
+                                       B, rowStrideB, colStrideB, beta, C, rowStrideC, colStrideC)
 
 # ---- the drop-in overloads: same parameter list as gemm.nim:184-193 -------------------
 proc gemm_strided*(M, N, K: int, alpha: float32,

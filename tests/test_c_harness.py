@@ -12,10 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "c_harness", "gemm_harness.c")
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "gemm_harness")
+def build(tmp_path, src=SRC, name="gemm_harness"):
+    exe = str(tmp_path / name)
     libdir = os.path.dirname(L.lib_path())
-    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), SRC,
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
                            "-o", exe, "-L", libdir, "-llaser_b200", "-lm", "-Wl,-rpath," + libdir])
     return exe
 
@@ -32,3 +32,25 @@ def test_c_caller_on_gpu(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "max relative error" in out.stdout
+
+
+def test_multi_gpu_harness_compiles_as_c(tmp_path):
+    build(tmp_path, os.path.join(ROOT, "tests", "c_harness", "rowshard_harness.c"), "rowshard_harness")
+
+
+@pytest.mark.gpu
+def test_c_caller_row_shards_over_two_gpus(tmp_path):
+    """laser_b200_gemm_rowsharded_f32 from plain C on 2 (and, when present, 4) GPUs of this box: NCCL bound at run time"""
+    torch = pytest.importorskip("torch")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    exe = build(tmp_path, os.path.join(ROOT, "tests", "c_harness", "rowshard_harness.c"), "rowshard_harness")
+    env = dict(os.environ)
+    nccl_dir = os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib")
+    if os.path.isdir(nccl_dir):      # a plain C process: point the loader at the NCCL torch ships if the system has none
+        env["LD_LIBRARY_PATH"] = env.get("LD_LIBRARY_PATH", "") + ":" + os.path.abspath(nccl_dir)
+    for g in ([2, 4] if n >= 4 else [2]):
+        out = subprocess.run([exe, str(g)], capture_output=True, text=True, timeout=600, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "max error relative" in out.stdout

@@ -23,6 +23,26 @@ def test_rowsharded_nccl():
     assert out.stdout.count("max_rel_err") == n
 
 
+def test_host_entry_row_shards_over_the_gpus_of_this_process():
+    """laser_b200_gemm_rowsharded_f32: host buffers, one process driving 2 (4) devices, NCCL group broadcast of B"""
+    import numpy as np
+    import oracle as O
+    from laser_b200 import rowshard as RS
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for g in ([2, 4] if n >= 4 else [2]):
+        for (M, N, K, alpha, beta) in ((4096, 1024, 1536, 1.0, 0.0), (3000, 520, 900, 0.5, -1.25)):
+            a = O.fill_uniform_f32(M * K, 3, -1, 1).reshape(M, K); b = O.fill_uniform_f32(K * N, 4, -1, 1).reshape(K, N)
+            c0 = O.fill_uniform_f32(M * N, 5, -1, 1).reshape(M, N)
+            c = c0.copy() if beta else np.full((M, N), np.nan, np.float32)
+            RS.gemm_rowsharded_host(g, M, N, K, alpha, a, K, 1, b, N, 1, beta, c, N, 1)
+            want = c0.copy()
+            O.cpu_gemm_strided_f32(M, N, K, alpha, a.reshape(-1), K, 1, b.reshape(-1), N, 1, beta, want.reshape(-1), N, 1)
+            assert O.normwise_relative_error(c, want) < 2e-6, (g, M, N, K)
+
+
 def test_one_process_two_devices():
     """A single process driving two GPUs through the C ABI (per-device context, tensor-map cache,
     function attributes): the second device must behave like the first."""
