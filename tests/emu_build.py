@@ -3,6 +3,8 @@
 All of them are compiled with -fsanitize=alignment (abort on the first hit): a vector access (float4, the 4-element
 transposition vectors, 16-byte bf16 stores ...) through a pointer that is not aligned to its type is a fault on the GPU
 but silently works on x86, so the emulation would otherwise miss a forgotten alignment guard."""
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -13,6 +15,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
 CSRC = os.path.join(HERE, "..", "laser_b200", "csrc")
 CUDA_INC = "/usr/local/cuda/include"
+
+
+@contextlib.contextmanager
+def _build_lock(so):
+    """pytest-xdist workers may ask for the same library at once: one builds (into a temporary name, renamed when
+    complete), the others wait for the lock and find it up to date."""
+    with open(so + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _compile(cmd, so, env=None):
+    tmp = "%s.tmp%d" % (so, os.getpid())
+    subprocess.check_call(cmd + ["-o", tmp], env=env)
+    os.replace(tmp, so)
 
 
 def build_emu(name, product_headers):
@@ -28,12 +48,14 @@ def build_emu(name, product_headers):
     so = os.path.join(out_dir, "lib%s.so" % name)
     srcs = [os.path.join(EMU_DIR, name + ".cpp"), os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "ptx_emu.h")] + \
            [os.path.join(CSRC, h) for h in product_headers]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        san = ["-O1", "-g", "-fsanitize=thread"] if tsan else ["-O2", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
-        subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic"   # stand-ins of CUDA runtime calls must win over a loaded libcudart
-                              , srcs[0], "-o", so], env=env)
+    with _build_lock(so):
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+            san = ["-O1", "-g", "-fsanitize=thread"] if tsan else ["-O2", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"]
+            _compile([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
+                                    "-I", CUDA_INC, "-I", EMU_DIR, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi",
+                                    "-Wl,-Bsymbolic",   # stand-ins of CUDA runtime calls must win over a loaded libcudart
+                                    srcs[0]], so, env=env)
     return so
 
 
@@ -97,6 +119,11 @@ def build_capi_host_emu(asan=False):
                                                     "tc_launch_impl.cuh", "gemm_simt.cuh", "gemm_simt_kernel.inc", "split.cuh",
                                                     "layers.cuh", "ptx.cuh", "capi_multi.inc"] if os.path.exists(os.path.join(csrc, f))] + \
            [os.path.join(EMU_DIR, f) for f in ("capi_host_prelude.h", "cuda_emu.h", "ptx_emu.h")] + [os.path.abspath(__file__)]
+    with _build_lock(so):
+        return _build_capi_host_emu_locked(so, deps, units, csrc, out_dir, gxx, asan)
+
+
+def _build_capi_host_emu_locked(so, deps, units, csrc, out_dir, gxx, asan):
     if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
     # ONE generated translation unit: the prelude, then every source of the library with its kernel launches rewritten
@@ -108,14 +135,14 @@ def build_capi_host_emu(asan=False):
         assert "<<<" not in src and "cudaLaunchKernelEx" not in src
         parts.append("// ---- %s\n%s" % (u, src))
     assert parts[0].count("emu_launch_kernel(") >= 10
-    gen = os.path.join(out_dir, "capi_host_emu.cpp")
+    gen = os.path.join(out_dir, "capi_host_emu_asan.cpp" if asan else "capi_host_emu.cpp")
     with open(gen, "w") as f:
         f.write('// GENERATED by tests/emu_build.py from laser_b200/csrc/*.cu -- do not edit\n#include "capi_host_prelude.h"\n' + "\n".join(parts))
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     san = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
-    subprocess.check_call([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", CUDA_INC,
-                           "-I", EMU_DIR, "-I", csrc, "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic",
-                           gen, "-o", so, "-ldl"], env=env)
+    _compile([gxx] + san + ["-std=c++17", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment",
+                            "-fno-sanitize-recover=alignment", "-I", CUDA_INC, "-I", EMU_DIR, "-I", csrc, "-Wno-attributes",
+                            "-Wno-unknown-pragmas", "-Wno-psabi", "-Wl,-Bsymbolic", gen, "-ldl"], so, env=env)
     return so
 
 
@@ -127,8 +154,9 @@ def build_fake_nccl():
     out_dir = os.path.join(EMU_DIR, "_build")
     os.makedirs(out_dir, exist_ok=True)
     src, so = os.path.join(EMU_DIR, "fake_nccl.c"), os.path.join(out_dir, "libfake_nccl.so")
-    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
-        subprocess.check_call([gcc, "-O1", "-fPIC", "-shared", src, "-o", so])
+    with _build_lock(so):
+        if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+            _compile([gcc, "-O1", "-fPIC", "-shared", src], so)
     return so
 
 
