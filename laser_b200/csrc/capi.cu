@@ -534,18 +534,18 @@ int tc_run(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, co
   if (rc) return rc;
   if (p.k_splits > 1) {
     if constexpr (std::is_same<OutT, float>::value) {
-      // partial sums of split s go to plane s of the workspace; a second kernel reduces (it also undoes the F16X3 scales)
-      const int64_t ld = round_up(N, 4);
-      const int64_t plane = M * ld;
-      if ((rc = ensure(c.splitk, static_cast<size_t>(p.k_splits) * plane * sizeof(float)))) { prof_abort(c, &ep); return rc; }
-      TcLaunch q = l;
-      q.p.C = c.splitk.ptr; q.p.rsC = ld; q.p.csC = 1; q.p.alpha = 1.0f; q.p.beta = 0.0f; q.p.epi = Epilogue();
-      q.p.split_plane = plane;
-      if ((rc = launch(q))) { prof_abort(c, &ep); return rc; }
-      const int64_t items = (M * N + 255) / 256;
-      splitk_reduce_kernel<<<grid_for(c, items, 8), 256, 0, s>>>(
-          static_cast<const float *>(c.splitk.ptr), p.k_splits, M, N, ld, plane, alpha, beta, C, rsC, csC,
-          p.epi.bias, p.epi.bias_per_row, p.epi.act);
+      // units past the direct tiles write raw partial sums to tile-local planes of the workspace (tc_params.h); a second
+      // kernel adds the planes of those tiles and applies alpha / beta / epilogue
+      const int64_t ws_floats = tc_split_ws_floats(p, pair);
+      if ((rc = ensure(c.splitk, static_cast<size_t>(ws_floats) * sizeof(float)))) { prof_abort(c, &ep); return rc; }
+      p.split_ws = static_cast<float *>(c.splitk.ptr);
+      if ((rc = launch(l))) { prof_abort(c, &ep); return rc; }
+      const int n_tail = p.num_m_blocks * p.num_n_blocks - p.n_direct;
+      const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+      const int64_t items = (static_cast<int64_t>(n_tail) * tile_m * (TC_BLOCK_N / 4) + 255) / 256;
+      splitk_tail_reduce_kernel<<<grid_for(c, items, 8), 256, 0, s>>>(
+          static_cast<const float *>(c.splitk.ptr), p.k_splits, n_tail, p.n_direct, p.num_m_blocks, p.num_n_blocks, p.raster_g,
+          tile_m, M, N, alpha, beta, C, rsC, csC, p.epi.bias, p.epi.bias_per_row, p.epi.act);
       COUNT_LAUNCH();
       CHECK_LAUNCH();
       CUDA_TRY(cudaEventRecord(c.ws_free, s));  // the planes are workspace too

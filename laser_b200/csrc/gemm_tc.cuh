@@ -58,19 +58,6 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int G, int &mb, int &nb) {
-  // groups of G m-blocks sweep n together: the concurrently resident tiles (148 of 128 x 256, or
-  // 74 pairs of 256 x 256) then cover a near-square patch, which minimises the A + B panels one
-  // wave pulls through L2 (G = 16 single-CTA tiles / 8 pair tiles = 2048 rows)
-  const int per_group = G * num_n;
-  const int g = t / per_group;
-  const int first_m = g * G;
-  const int gsz = min(G, num_m - first_m);
-  const int r = t - g * per_group;
-  mb = first_m + r % gsz;
-  nb = r / gsz;
-}
-
 __device__ __forceinline__ float bf16_bits_to_f32(uint16_t h) {
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
 }
@@ -113,11 +100,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_kb = static_cast<int>((p.K + BLOCK_K - 1) / BLOCK_K);
-  const int num_units = num_tiles * p.k_splits;  // work units of the persistent scheduler
-  // K range [kb_lo, kb_hi) of split sp, in k-tiles
-  auto split_range = [&](int sp, int &kb_lo, int &kb_hi) {
-    kb_lo = min(num_kb, sp * p.kb_per_split);
-    kb_hi = min(num_kb, kb_lo + p.kb_per_split);
+  // work units of the persistent scheduler: the direct tiles, then k_splits K-ranges of each of the other tiles (tc_params.h)
+  const int num_units = p.n_direct + (num_tiles - p.n_direct) * p.k_splits;
+  // unit -> tile t, K range [kb_lo, kb_hi) in k-tiles, split index sp (-1: a direct tile)
+  auto decode_unit = [&](int u, int &t, int &sp, int &kb_lo, int &kb_hi) {
+    if (u < p.n_direct) {
+      t = u; sp = -1; kb_lo = 0; kb_hi = num_kb;
+    } else {
+      const int v = u - p.n_direct;
+      const int i = v / p.k_splits;
+      t = p.n_direct + i;
+      sp = v - i * p.k_splits;
+      kb_lo = min(num_kb, sp * p.kb_per_split);
+      kb_hi = min(num_kb, kb_lo + p.kb_per_split);
+    }
   };
   // consumers of the scheduler slot: producer thread of each CTA, the MMA thread, lane 0 of each epilogue warp
   constexpr int SCHED_CONSUMERS = PAIR ? (2 + TC_EPI_WARPS) + (1 + TC_EPI_WARPS) : (2 + TC_EPI_WARPS);
@@ -236,10 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (;;) {
         const int u = next_unit(sched_phase);
         if (u < 0) break;
-        const int t = u / p.k_splits;
-        int mb, nb, kb_lo, kb_hi;
+        int t, sp, mb, nb, kb_lo, kb_hi;
+        decode_unit(u, t, sp, kb_lo, kb_hi);
         tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
-        split_range(u - t * p.k_splits, kb_lo, kb_hi);
         // pair: this CTA's 128 rows of A and its half of the B columns
         const int m0 = mb * TILE_M + static_cast<int>(cta_rank) * TC_BLOCK_M;
         const int n0 = nb * TC_BLOCK_N + static_cast<int>(cta_rank) * (TC_BLOCK_N - Cfg::B_COLS);
@@ -277,8 +272,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (;;) {
         const int u = next_unit(sched_phase);
         if (u < 0) break;
-        int kb_lo, kb_hi;
-        split_range(u % p.k_splits, kb_lo, kb_hi);
+        int t, sp, kb_lo, kb_hi;
+        decode_unit(u, t, sp, kb_lo, kb_hi);
         for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += p.kb_per_block) {
           const int kb1 = min(kb_hi, kb0 + p.kb_per_block);
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -335,34 +330,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int h = (warp_idx - 4) >> 2;   // column half
     int acc = 0;
     uint32_t acc_phase = 0, sched_phase = 0;
-    const bool vec_ok = (p.csC == 1) && ((p.rsC * sizeof(OutT)) % 16 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        ((p.split_plane * sizeof(OutT)) % 16 == 0);
+    const bool vec_ok_c = (p.csC == 1) && ((p.rsC * sizeof(OutT)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     for (;;) {
       int u = 0;
       if (lane == 0) u = next_unit(sched_phase);
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u < 0) break;
-      const int t = u / p.k_splits;
-      int mb, nb, kb_lo, kb_hi;
+      int t, sp, mb, nb, kb_lo, kb_hi;
+      decode_unit(u, t, sp, kb_lo, kb_hi);
       tile_coords(t, p.num_m_blocks, p.num_n_blocks, p.raster_g, mb, nb);
-      split_range(u - t * p.k_splits, kb_lo, kb_hi);
       const int num_blocks = (kb_hi - kb_lo + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
-      OutT *__restrict__ C = reinterpret_cast<OutT *>(p.C) + (u - t * p.k_splits) * p.split_plane;
-      const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;
+      const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;   // of the product
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
+      // where this thread's 128 sums go.  Direct tile: its row of C, with alpha / beta / bias / activation.  Split unit: row
+      // (tile-local) of plane [sp][t - n_direct] of the workspace, raw (only the operand scales are undone).
+      const bool split_unit = sp >= 0;
+      OutT *crow_base;          // element (row, col0)
+      int64_t cs_u;             // column stride
+      int64_t ncols;            // columns of this thread's segment that exist
+      bool vec_ok;
+      float alpha_u, beta_u;
+      if (!split_unit) {
+        crow_base = reinterpret_cast<OutT *>(p.C) + (row < p.M ? row : 0) * p.rsC + col0 * p.csC;
+        cs_u = p.csC; ncols = p.N - col0; vec_ok = vec_ok_c; alpha_u = p.alpha; beta_u = p.beta;
+      } else {
+        const int64_t plane = static_cast<int64_t>(sp) * (num_tiles - p.n_direct) + (t - p.n_direct);
+        crow_base = reinterpret_cast<OutT *>(p.split_ws) +
+                    (plane * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane) * TC_BLOCK_N + h * TC_EPI_COLS;
+        cs_u = 1; ncols = TC_EPI_COLS; vec_ok = true; alpha_u = 1.0f; beta_u = 0.0f;
+      }
       // SCALED: undo the power-of-two scale of this thread's row of A (f16_scale.cuh); the abs-max words were written by
-      // earlier kernels of this stream.  The factors of B's columns are applied per element (col_unscale)
-      float alpha_eff = p.alpha;
-      if constexpr (SCALED) alpha_eff = p.alpha * (row < p.M ? f16x2_unscale(p.amax_a[row]) : 1.0f);
-      auto col_unscale = [&](int64_t col) -> float {
-        if constexpr (SCALED) return f16x2_unscale(p.amax_b[col]);
-        else return 1.0f;
+      // earlier kernels of this stream.  The factors of B's 128 columns of this warp are fetched NOW, four per lane (lane l
+      // holds columns col0 + 4l .. 4l + 3), and handed out by warp shuffles when the tile is stored: fetching them per
+      // element at store time put a dependent global load in front of each of the 32 vector stores, ~13k cycles per tile
+      // during which the tensor core ran out of free accumulator stages (ncu source page, round 2).
+      const bool row_ok = row < p.M || split_unit;   // (rows past M of a split tile: zeros into the workspace)
+      float alpha_eff = alpha_u;
+      float cs[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+      if constexpr (SCALED) {
+        alpha_eff = alpha_u * (row < p.M ? f16x2_unscale(p.amax_a[row]) : 1.0f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t c = col0 + 4 * lane + i;
+          if (c < p.N) cs[i] = f16x2_unscale(p.amax_b[c]);
+        }
+      }
+      // factor of column col0 + j (j warp-uniform); every lane of the warp must call it
+      auto col_unscale = [&](int j) -> float {
+        if constexpr (SCALED) {
+          const float v = (j & 3) == 0 ? cs[0] : (j & 3) == 1 ? cs[1] : (j & 3) == 2 ? cs[2] : cs[3];
+          return __shfl_sync(0xffffffffu, v, j >> 2);
+        } else {
+          return 1.0f;
+        }
       };
-      if (p.beta != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {
+      if (beta_u != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {
         // beta != 0: pull this thread's 512 bytes of old C into L2 now; they are needed only
         // after the whole K loop of the tile, so the latency is free
-        const OutT *cp = C + row * p.rsC + col0;
+        const OutT *cp = crow_base;
 #pragma unroll
         for (int l = 0; l < TC_EPI_COLS * static_cast<int>(sizeof(OutT)) / 128; ++l) {
           if (col0 + l * (128 / static_cast<int>(sizeof(OutT))) < p.N)
@@ -396,19 +421,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       // ---- C <- alpha * sum + beta * C  (gemm_ukernel_generic.nim:53-76 semantics) ----
-      if (row < p.M && col0 < p.N) {
-        OutT *crow = C + row * p.rsC;
-        const bool has_epi = (p.epi.bias != nullptr) || (p.epi.act != 0);
-        const float row_bias = (p.epi.bias && p.epi.bias_per_row) ? p.epi.bias[row] : 0.0f;
-        if (vec_ok && col0 + TC_EPI_COLS <= p.N) {
+      // control flow is warp-uniform down to the loads / stores themselves (col_unscale shuffles): only `row_ok` is per lane
+      if (col0 < p.N) {
+        const bool has_epi = !split_unit && ((p.epi.bias != nullptr) || (p.epi.act != 0));
+        const float row_bias = (has_epi && p.epi.bias && p.epi.bias_per_row && row_ok) ? p.epi.bias[row] : 0.0f;
+        if (vec_ok && ncols >= TC_EPI_COLS) {
           if constexpr (sizeof(OutT) == 4) {
-            float4 *dst = reinterpret_cast<float4 *>(crow + col0);
+            float4 *dst = reinterpret_cast<float4 *>(crow_base);
             // batches of 4 x 16 B: with beta != 0 the four loads of a batch are in flight
             // together (the old C lines were prefetched into L2 when the tile started)
 #pragma unroll
             for (int b8 = 0; b8 < TC_EPI_COLS / 16; ++b8) {
               float4 o[4];
-              if (p.beta != 0.0f) {
+              if (beta_u != 0.0f && row_ok) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = dst[b8 * 4 + e];
               }
@@ -421,16 +446,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 v.z = alpha_eff * run[4 * v4 + 2];
                 v.w = alpha_eff * run[4 * v4 + 3];
                 if constexpr (SCALED) {
-                  v.x *= col_unscale(col0 + 4 * v4 + 0);
-                  v.y *= col_unscale(col0 + 4 * v4 + 1);
-                  v.z *= col_unscale(col0 + 4 * v4 + 2);
-                  v.w *= col_unscale(col0 + 4 * v4 + 3);
+                  v.x *= col_unscale(4 * v4 + 0);
+                  v.y *= col_unscale(4 * v4 + 1);
+                  v.z *= col_unscale(4 * v4 + 2);
+                  v.w *= col_unscale(4 * v4 + 3);
                 }
-                if (p.beta != 0.0f) {
-                  v.x = fmaf(p.beta, o[e].x, v.x);
-                  v.y = fmaf(p.beta, o[e].y, v.y);
-                  v.z = fmaf(p.beta, o[e].z, v.z);
-                  v.w = fmaf(p.beta, o[e].w, v.w);
+                if (beta_u != 0.0f && row_ok) {
+                  v.x = fmaf(beta_u, o[e].x, v.x);
+                  v.y = fmaf(beta_u, o[e].y, v.y);
+                  v.z = fmaf(beta_u, o[e].z, v.z);
+                  v.w = fmaf(beta_u, o[e].w, v.w);
                 }
                 if (has_epi) {
                   float4 bv = make_float4(row_bias, row_bias, row_bias, row_bias);
@@ -444,23 +469,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   v.z = epi_act(v.z + bv.z, p.epi.act);
                   v.w = epi_act(v.w + bv.w, p.epi.act);
                 }
-                dst[v4] = v;
+                if (row_ok) dst[v4] = v;
               }
             }
           } else {
-            uint4 *dst = reinterpret_cast<uint4 *>(crow + col0);
+            uint4 *dst = reinterpret_cast<uint4 *>(crow_base);
 #pragma unroll
             for (int v8 = 0; v8 < TC_EPI_COLS / 8; ++v8) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = alpha_eff * run[8 * v8 + e] * col_unscale(col0 + 8 * v8 + e);
-              if (p.beta != 0.0f) {
+              for (int e = 0; e < 8; ++e) f[e] = alpha_eff * run[8 * v8 + e] * col_unscale(8 * v8 + e);
+              if (beta_u != 0.0f && row_ok) {
                 const uint4 o = dst[v8];
                 const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  f[2 * e] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] & 0xffff)), f[2 * e]);
-                  f[2 * e + 1] = fmaf(p.beta, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
+                  f[2 * e] = fmaf(beta_u, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] & 0xffff)), f[2 * e]);
+                  f[2 * e + 1] = fmaf(beta_u, bf16_bits_to_f32(static_cast<uint16_t>(ow[e] >> 16)), f[2 * e + 1]);
                 }
               }
               if (has_epi) {
@@ -475,22 +500,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               w.y = f32_to_bf16_bits(f[2]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[3])) << 16);
               w.z = f32_to_bf16_bits(f[4]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[5])) << 16);
               w.w = f32_to_bf16_bits(f[6]) | (static_cast<uint32_t>(f32_to_bf16_bits(f[7])) << 16);
-              dst[v8] = w;
+              if (row_ok) dst[v8] = w;
             }
           }
         } else {
           // any C strides / ragged right edge: scalar, predicated; one running pointer so
           // that the unrolled loop does not keep 128 addresses live
-          OutT *dst = crow + col0 * p.csC;
-          const int64_t ncols = p.N - col0;
+          OutT *dst = crow_base;
 #pragma unroll
           for (int j = 0; j < TC_EPI_COLS; ++j) {
-            if (j < ncols) {
-              float v = alpha_eff * run[j];
-              if constexpr (SCALED) v *= col_unscale(col0 + j);
-              if (p.beta != 0.0f) {
-                if constexpr (sizeof(OutT) == 4) v = fmaf(p.beta, *dst, v);
-                else v = fmaf(p.beta, bf16_bits_to_f32(*dst), v);
+            float v = alpha_eff * run[j];
+            if constexpr (SCALED) v *= col_unscale(j);
+            if (j < ncols && row_ok) {
+              if (beta_u != 0.0f) {
+                if constexpr (sizeof(OutT) == 4) v = fmaf(beta_u, *dst, v);
+                else v = fmaf(beta_u, bf16_bits_to_f32(*dst), v);
               }
               if (has_epi) {
                 const float bv = (p.epi.bias && !p.epi.bias_per_row) ? p.epi.bias[col0 + j] : row_bias;
@@ -499,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if constexpr (sizeof(OutT) == 4) *dst = v;
               else *dst = f32_to_bf16_bits(v);
             }
-            dst += p.csC;
+            dst += cs_u;
           }
         }
       }

@@ -19,6 +19,7 @@
 
 #include "f16_scale.cuh"
 #include "ptx.cuh"
+#include "tc_params.h"
 
 namespace lb200 {
 
@@ -314,28 +315,48 @@ pack_general_kernel(const T *__restrict__ src, int64_t R, int64_t Cc, int64_t sr
   }
 }
 
-// Second half of a split-K GEMM: C <- act(alpha * sum_s ws[s] + beta * C + bias), planes added in
-// the fixed order s = 0 .. S-1 (deterministic).  ws: S planes of M x ld (row-major, fp32).
+// Second half of a split-K GEMM (tc_params.h): C <- act(alpha * sum_s ws[s][i] + beta * C + bias) over the split tiles
+// n_direct + i, i < n_tail, planes added in the fixed order s = 0 .. S-1 (deterministic).  ws: [S][n_tail][tile_m][TC_BLOCK_N]
+// fp32, tile-local.  Item = four consecutive columns of one tile row.
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float *__restrict__ ws, int S, int64_t M, int64_t N, int64_t ld,
-                     int64_t plane, float alpha, float beta, float *__restrict__ C, int64_t rsC,
-                     int64_t csC, const float *__restrict__ bias, int bias_per_row, int act) {
-  const int64_t total = M * N;
+splitk_tail_reduce_kernel(const float *__restrict__ ws, int S, int n_tail, int n_direct, int num_m, int num_n, int raster_g,
+                          int tile_m, int64_t M, int64_t N, float alpha, float beta, float *__restrict__ C, int64_t rsC,
+                          int64_t csC, const float *__restrict__ bias, int bias_per_row, int act) {
+  constexpr int V = TC_BLOCK_N / 4;   // float4 per tile row
+  const int64_t per_tile = static_cast<int64_t>(tile_m) * V;
+  const int64_t total = static_cast<int64_t>(n_tail) * per_tile;
+  const int64_t plane = total * 4;    // floats between consecutive split planes
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / N, c = i - r * N;
-    float sum = ws[r * ld + c];
-    for (int s = 1; s < S; ++s) sum = __fadd_rn(sum, ws[s * plane + r * ld + c]);
-    float *dst = C + r * rsC + c * csC;
-    float v = alpha * sum;
-    if (beta != 0.0f) v = fmaf(beta, *dst, v);
-    if (bias != nullptr || act != 0) {
-      if (bias) v += bias_per_row ? bias[r] : bias[c];
-      if (act == 1) v = fmaxf(v, 0.0f);
-      else if (act == 2) v = tanhf(v);
-      else if (act == 3) v = 1.0f / (1.0f + expf(-v));
+    const int ti = static_cast<int>(i / per_tile);
+    const int64_t rem = i - ti * per_tile;
+    const int r_l = static_cast<int>(rem / V), c4 = static_cast<int>(rem - static_cast<int64_t>(r_l) * V);
+    int mb, nb;
+    tile_coords(n_direct + ti, num_m, num_n, raster_g, mb, nb);
+    const int64_t r = static_cast<int64_t>(mb) * tile_m + r_l, c = static_cast<int64_t>(nb) * TC_BLOCK_N + 4 * c4;
+    if (r >= M || c >= N) continue;
+    const float *src = ws + i * 4;
+    float4 sum = *reinterpret_cast<const float4 *>(src);
+    for (int sp = 1; sp < S; ++sp) {
+      const float4 t = *reinterpret_cast<const float4 *>(src + sp * plane);
+      sum.x = __fadd_rn(sum.x, t.x); sum.y = __fadd_rn(sum.y, t.y); sum.z = __fadd_rn(sum.z, t.z); sum.w = __fadd_rn(sum.w, t.w);
     }
-    *dst = v;
+    const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+    float *dst = C + r * rsC + c * csC;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e < N) {
+        float v = alpha * sv[e];
+        if (beta != 0.0f) v = fmaf(beta, dst[e * csC], v);
+        if (bias != nullptr || act != 0) {
+          if (bias) v += bias_per_row ? bias[r] : bias[c + e];
+          if (act == 1) v = fmaxf(v, 0.0f);
+          else if (act == 2) v = tanhf(v);
+          else if (act == 3) v = 1.0f / (1.0f + expf(-v));
+        }
+        dst[e * csC] = v;
+      }
+    }
   }
 }
 

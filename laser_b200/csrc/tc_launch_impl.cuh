@@ -16,7 +16,7 @@ namespace lb200 {
 template <int ESZ, uint32_t FMT16, int NPASS, typename OutT, bool SCALED, bool PAIR, bool A_MN, bool B_MN>
 int launch_tc_one(const TcLaunch &l) {
   using Cfg = TcCfg<NPASS, PAIR>;
-  const int64_t units_total = static_cast<int64_t>(l.p.num_m_blocks) * l.p.num_n_blocks * l.p.k_splits;  // work units
+  const int64_t units_total = tc_units(l.p);  // work units
   // persistent: one CTA (or one CTA pair) per SM (pair of SMs), never more CTAs than units
   const int units = PAIR ? l.sm_count / 2 : l.sm_count;
   const int sched = static_cast<int>(units_total < units ? units_total : units);

@@ -4,6 +4,12 @@
 
 #include <stdint.h>
 
+#if defined(__CUDACC__) || defined(LB200_HOST_EMULATION)
+#define LB200_HD __host__ __device__
+#else
+#define LB200_HD
+#endif
+
 namespace lb200 {
 
 constexpr int TC_BLOCK_M = 128;
@@ -49,12 +55,17 @@ struct TcParams {
   uint32_t zero;      // always 0; opaque to the compiler (see the epilogue)
   int raster_g;       // m-blocks per raster group (see tile_coords)
   Epilogue epi;
-  // split-K (few output tiles, long K): unit u = (tile, split) covers the K range of one split
-  // and writes its raw partial sums to plane `split` of a workspace (C points at it, alpha = 1,
-  // beta = 0); splitk_reduce_kernel then adds the planes in order and applies alpha/beta/epilogue
+  // split-K.  Tiles [0, n_direct) (raster order, tile_coords) are computed over all of K and stored through the epilogue
+  // into C.  Each of the remaining `num tiles - n_direct` tiles is cut in k_splits K-ranges of kb_per_split k-tiles; unit
+  // n_direct + i * k_splits + s computes range s of tile n_direct + i and writes its raw partial sums (scales undone, no
+  // alpha / beta / bias / activation) to the tile-local plane [s][i] of split_ws; splitk_tail_reduce_kernel then adds the
+  // planes in order and applies alpha / beta / epilogue.  Two uses: few output tiles and a long K (n_direct = 0: every
+  // tile is split), and the partial last wave of a persistent launch (n_direct = the tiles of the full waves: the
+  // remainder of 4096^3's 256 pair-tiles on 74 SM pairs runs as 68 half-K units instead of 34 full ones: 3.5 waves, not 4)
+  int n_direct;          // == num_m_blocks * num_n_blocks when nothing is split
   int k_splits;          // >= 1
   int kb_per_split;      // k-tiles per split
-  int64_t split_plane;   // elements between consecutive planes
+  float *split_ws = nullptr;   // [k_splits][split tiles][tile rows][TC_BLOCK_N] fp32
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
   // SCALED: fp32 bits of the largest finite |a| of row i of A / |b| of column j of B (f16_scale.cuh)
   const uint32_t *amax_a = nullptr, *amax_b = nullptr;
@@ -62,6 +73,19 @@ struct TcParams {
   // both words for the next launch that uses this slot).  nullptr: static round-robin (unit = pair index + i * pairs)
   unsigned int *sched = nullptr;
 };
+
+// raster order of the output tiles: groups of G m-blocks sweep n together, so that the concurrently resident tiles (148 of
+// 128 x 256, or 74 pairs of 256 x 256) cover a near-square patch, which minimises the A + B panels one wave pulls through
+// L2 (G = 16 single-CTA tiles / 8 pair tiles = 2048 rows)
+LB200_HD inline void tile_coords(int t, int num_m, int num_n, int G, int &mb, int &nb) {
+  const int per_group = G * num_n;
+  const int g = t / per_group;
+  const int first_m = g * G;
+  const int gsz = (G < num_m - first_m) ? G : (num_m - first_m);
+  const int r = t - g * per_group;
+  mb = first_m + r % gsz;
+  nb = r / gsz;
+}
 
 // host side: the part of TcParams that depends only on the problem (p.M, p.N, p.K set by the
 // caller) and on the configuration
@@ -88,26 +112,44 @@ inline void tc_plan(TcParams &p, int npass, bool pair, const TcPlanCfg &cfg) {
   const int tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
   p.num_m_blocks = static_cast<int>((p.M + tile_m - 1) / tile_m);
   p.num_n_blocks = static_cast<int>((p.N + TC_BLOCK_N - 1) / TC_BLOCK_N);
-  // ---- split-K: too few output tiles to fill the machine and a long K (fp32 output only) ----
-  p.k_splits = 1;
-  p.split_plane = 0;
-  p.kb_per_split = num_kb;
+  // ---- split-K (fp32 output only): too few output tiles to fill the machine and a long K, or a thin last wave ----
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  p.k_splits = 1;
+  p.kb_per_split = num_kb;
+  p.n_direct = static_cast<int>(tiles);
+  p.split_ws = nullptr;
   const int units = pair ? cfg.sm_count / 2 : cfg.sm_count;
   if constexpr (OUT_F32) {
     const int blocks = (num_kb + p.kb_per_block - 1) / p.kb_per_block;   // accumulation blocks along K
-    int S = static_cast<int>(units / (tiles > 0 ? tiles : 1));
     // every split keeps >= 512 K-elements
     const int min_tiles = 512 / block_k;
     const int min_blocks = (min_tiles + p.kb_per_block - 1) / p.kb_per_block;
-    if (S > blocks / min_blocks) S = blocks / min_blocks;
-    if (S > 16) S = 16;
-    if (cfg.splitk_enabled && S >= 2) {
+    const int max_s = blocks / min_blocks < 16 ? blocks / min_blocks : 16;
+    // tiles that do not fill a wave of their own: all of them when there are fewer than `units`, else the remainder
+    const int64_t rem = tiles < units ? tiles : tiles % units;
+    int S = rem > 0 ? static_cast<int>(units / rem) : 1;
+    if (S > max_s) S = max_s;
+    // a remainder behind full waves (S >= 2: at most half a wave of tiles) is split when a tile is long enough for half
+    // of it to outweigh the reduce kernel
+    const bool worth = S >= 2 && (tiles < units || p.K >= 2048);
+    if (cfg.splitk_enabled && worth && units > 0) {
       const int blocks_per_split = (blocks + S - 1) / S;
       p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;
       p.kb_per_split = blocks_per_split * p.kb_per_block;
+      if (p.k_splits >= 2) p.n_direct = static_cast<int>(tiles - rem);
+      else { p.k_splits = 1; p.kb_per_split = num_kb; }
     }
   }
+}
+// work units of a planned launch, and the fp32 words of its split-K workspace (0: nothing is split)
+inline int64_t tc_units(const TcParams &p) {
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  return p.n_direct + (tiles - p.n_direct) * p.k_splits;
+}
+inline int64_t tc_split_ws_floats(const TcParams &p, bool pair) {
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int64_t tile_m = pair ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+  return (tiles - p.n_direct) * p.k_splits * tile_m * TC_BLOCK_N;
 }
 
 }  // namespace lb200

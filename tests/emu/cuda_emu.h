@@ -130,6 +130,14 @@ inline int __shfl_sync(unsigned, int v, int src) {
   pthread_barrier_wait(&emu::warp_barrier[r][w]);
   return out;
 }
+inline float __shfl_sync(unsigned, float v, int src) {
+  const unsigned t = emu::t_idx.x, w = t >> 5, r = emu::cta_rank;
+  emu::warp_scratch[r][t] = v;
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+  const float out = emu::warp_scratch[r][(t & ~31u) + static_cast<unsigned>(src)];
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+  return out;
+}
 // full-mask butterfly shuffle: every lane of the warp must call it (true for the reductions it is used in)
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   const unsigned t = emu::t_idx.x, w = t >> 5, r = emu::cta_rank;

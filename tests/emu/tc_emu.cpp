@@ -7,6 +7,7 @@
 #include "cuda_emu.h"
 
 #include "../../laser_b200/csrc/gemm_tc.cuh"
+#include "../../laser_b200/csrc/split.cuh"
 
 using namespace lb200;
 
@@ -41,7 +42,8 @@ struct Args {
   int kc_faithful, raster_g, splitk_enabled, sm_count;
   const float *bias;
   int bias_per_row, act;
-  float *splitk_ws;          // k_splits planes of M x round_up(N, 4) when split-K triggers
+  float *splitk_ws;          // tile-local planes of the split tiles (tc_params.h: tc_split_ws_floats)
+  int64_t splitk_ws_floats;
   int *out_k_splits, *out_grid;
   const uint32_t *amax_a, *amax_b;   // SCALED: abs-max words per row of A / column of B (f16_scale.cuh)
   int dyn_sched;             // 1: tiles drawn from an atomic counter (capi.cu: Ctx::sched), 0: static round-robin
@@ -57,12 +59,10 @@ static int run(const Args &a) {
   p.epi.bias = a.bias; p.epi.bias_per_row = a.bias_per_row; p.epi.act = a.act;
   p.amax_a = a.amax_a; p.amax_b = a.amax_b;
   tc_plan<ESZ, std::is_same<OutT, float>::value>(p, NPASS, PAIR, TcPlanCfg{a.kc_faithful, a.raster_g, a.splitk_enabled != 0, a.sm_count});
-  if (a.out_k_splits) *a.out_k_splits = p.k_splits;
-  if (p.k_splits > 1) {   // capi.cu: tc_run -- raw partial sums into the planes, reduced by splitk_reduce_kernel
-    if (!a.splitk_ws) return -2;
-    const int64_t ld = (a.N + 3) / 4 * 4;
-    p.C = a.splitk_ws; p.rsC = ld; p.csC = 1; p.alpha = 1.0f; p.beta = 0.0f; p.epi = Epilogue();
-    p.split_plane = a.M * ld;
+  if (a.out_k_splits) { a.out_k_splits[0] = p.k_splits; a.out_k_splits[1] = p.n_direct; }
+  if (p.k_splits > 1) {   // capi.cu: tc_run -- raw partial sums of the split tiles into the planes, reduced by splitk_tail_reduce_kernel
+    if (!a.splitk_ws || a.splitk_ws_floats < tc_split_ws_floats(p, PAIR)) return -2;
+    p.split_ws = a.splitk_ws;
   }
   if (a.dyn_sched) {
     if (g_sched[0] != 0u || g_sched[1] != 0u) return -4;   // the previous launch must have re-armed its slot
@@ -72,7 +72,7 @@ static int run(const Args &a) {
   const CUtensorMap mA0 = operand_map(ESZ, a.A[0], A_MN, a.M, a.K, a.ldA, TC_BLOCK_M), mA1 = operand_map(ESZ, a.A[1], A_MN, a.M, a.K, a.ldA, TC_BLOCK_M);
   const CUtensorMap mB0 = operand_map(ESZ, a.B[0], B_MN, a.N, a.K, a.ldB, b_block), mB1 = operand_map(ESZ, a.B[1], B_MN, a.N, a.K, a.ldB, b_block);
   // tc_launch_impl.cuh: launch_tc_one -- persistent: one CTA (pair) per SM (pair of SMs), never more than work units
-  const int64_t units_total = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks * p.k_splits;
+  const int64_t units_total = tc_units(p);
   const int units = PAIR ? a.sm_count / 2 : a.sm_count;
   const int sched = static_cast<int>(units_total < units ? units_total : units);
   const unsigned grid = PAIR ? 2 * sched : sched;
@@ -82,6 +82,22 @@ static int run(const Args &a) {
   emu::launch(grid, TC_THREADS,
               [=]() { gemm_tc_kernel<ESZ, FMT16, NPASS, A_MN, B_MN, OutT, PAIR, SCALED>(mA0, mA1, mB0, mB1, p); },
               PAIR ? 2 : 1);
+  if (p.k_splits > 1) {
+    if constexpr (std::is_same<OutT, float>::value) {
+      const int n_tail = p.num_m_blocks * p.num_n_blocks - p.n_direct;
+      const int tile_m = PAIR ? 2 * TC_BLOCK_M : TC_BLOCK_M;
+      const float *ws = a.splitk_ws;
+      const TcParams q = p;
+      float *C = static_cast<float *>(a.C);
+      const Args b = a;
+      emu::launch(3, 256, [=]() {
+        splitk_tail_reduce_kernel(ws, q.k_splits, n_tail, q.n_direct, q.num_m_blocks, q.num_n_blocks, q.raster_g, tile_m, b.M, b.N,
+                                  b.alpha, b.beta, C, b.rsC, b.csC, b.bias, b.bias_per_row, b.act);
+      });
+    } else {
+      return -5;
+    }
+  }
   return 0;
 }
 
@@ -99,10 +115,10 @@ static int dispatch(int a_mn, int b_mn, int pair, const Args &a) {
 extern "C" int emu_gemm_tc(int kind, int a_mn, int b_mn, int pair, int64_t M, int64_t N, int64_t K, float alpha, float beta,
                            const void *A0, const void *A1, int64_t ldA, const void *B0, const void *B1, int64_t ldB,
                            void *C, int64_t rsC, int64_t csC, int kc_faithful, int raster_g, int splitk_enabled,
-                           int sm_count, const float *bias, int bias_per_row, int act, float *splitk_ws, int *out_k_splits,
+                           int sm_count, const float *bias, int bias_per_row, int act, float *splitk_ws, int64_t splitk_ws_floats, int *out_k_splits,
                            int *out_grid, const uint32_t *amax_a, const uint32_t *amax_b, int dyn_sched) {
   Args a{M, N, K, alpha, beta, {A0, A1}, {B0, B1}, ldA, ldB, C, rsC, csC, kc_faithful,
-         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, out_k_splits, out_grid, amax_a, amax_b, dyn_sched};
+         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, splitk_ws_floats, out_k_splits, out_grid, amax_a, amax_b, dyn_sched};
   switch (kind) {
     case 0: return dispatch<4, ptx::kFmtBF16, 1, float, false>(a_mn, b_mn, pair, a);
     case 1: return dispatch<4, ptx::kFmtBF16, 3, float, false>(a_mn, b_mn, pair, a);
