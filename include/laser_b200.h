@@ -385,6 +385,10 @@ int laser_b200_foreach_views(int op, laser_b200_tensor_view *out, const laser_b2
 int laser_b200_debug_classify(int elem_size, const void *base, int64_t s_mn, int64_t s_k);
 int laser_b200_debug_span(int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
                           int64_t *lo, int64_t *hi, int *dense);
+/* launches of the fp64 tensor-core kernel (mma.sync DMMA, csrc/gemm_dmma.cuh) since the library was loaded: float64
+ * problems whose 128 x 128 tiles fill at least half of the SMs take it instead of the CUDA-core kernel (same FMA chain
+ * per element, bit for bit; LASER_B200_F64_DMMA=0 turns it off) -- gemm.nim:234-246, the float64 row of the dispatch */
+int64_t laser_b200_debug_f64_dmma_launches(void);
 
 /* ---- synthetic inputs ---------------------------------------------------
  * Counter-based uniform generator, bit-identical to the CPU oracle's

@@ -112,6 +112,7 @@ SIGNATURES = {
     "laser_b200_foreach_views": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(TensorView), ctypes.POINTER(TensorView),
                                                 ctypes.POINTER(TensorView), ctypes.POINTER(TensorView), f64, vp]),
     "laser_b200_debug_classify": (ctypes.c_int, [ctypes.c_int, vp, i64, i64]),
+    "laser_b200_debug_f64_dmma_launches": (i64, []),
     "laser_b200_debug_span": (ctypes.c_int, [i64, i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64),
                                              ctypes.POINTER(ctypes.c_int)]),
     "laser_b200_fill_uniform_f32_dev": (ctypes.c_int, [vp, i64, u64, f32, f32, vp]),

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
+#include "gemm_dmma.cuh"
 #include "layers.cuh"
 #include "split.cuh"
 #include "tc_launch.h"
@@ -37,6 +38,7 @@ using namespace lb200;
 thread_local std::string g_last_error;
 thread_local int g_last_path = 0;
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_dmma_launches{0};   // launches of the fp64 tensor-core kernel (debug counter)
 std::atomic<int> g_f32_mode{-1};
 constexpr int kDefaultF32Mode = LASER_B200_PATH_F16X3;
 void multi_shutdown();   // capi_multi.inc
@@ -98,6 +100,9 @@ struct Ctx {
   int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
+  bool f64_dmma = true;        // env LASER_B200_F64_DMMA=0: fp64 problems stay on the CUDA-core kernel
+  bool prep_ring = true;       // env LASER_B200_PREP_RING=0: register-only preparation kernel for K-major operands
+  bool ring_attr_set = false;
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
@@ -184,6 +189,8 @@ int get_ctx(Ctx **out) {
       if (const char *cp = getenv("LASER_B200_CTA_PAIR")) c.cta_pair = atoi(cp) != 0;
       if (const char *rg = getenv("LASER_B200_RASTER")) c.raster_g = atoi(rg);
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
+      if (const char *pr = getenv("LASER_B200_PREP_RING")) c.prep_ring = atoi(pr) != 0;
+      if (const char *dm = getenv("LASER_B200_F64_DMMA")) c.f64_dmma = atoi(dm) != 0;
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
       if (const char *ds = getenv("LASER_B200_DYNSCHED")) c.dyn_sched = atoi(ds) != 0;
       if (const char *pd = getenv("LASER_B200_PDL")) c.pdl = atoi(pd) != 0;
@@ -272,6 +279,22 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
 #ifndef LB200_SIMT_BK
 #define LB200_SIMT_BK 16
 #endif
+  if constexpr (std::is_same<T, double>::value) {
+    // fp64 tensor cores (mma.sync DMMA, gemm_dmma.cuh) once the 128 x 128 tiles fill at least half of the SMs: the same
+    // FMA chain per element as the CUDA-core kernel, bit for bit, so the choice is a matter of speed only
+    const int64_t tiles128 = ((M + DMMA_BM - 1) / DMMA_BM) * ((N + DMMA_BN - 1) / DMMA_BN) * batch;
+    if (c.f64_dmma && 2 * tiles128 >= c.sm_count) {
+      SimtParams<double> p;
+      const int64_t tiles = dmma_plan(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+      if (tiles * batch > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
+      p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+      gemm_dmma_kernel<<<grid_for(c, tiles * batch, 1), 256, DMMA_SMEM_BYTES, s>>>(p);
+      g_dmma_launches.fetch_add(1);
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      return LASER_B200_OK;
+    }
+  }
   if constexpr (sizeof(T) == 4)
     return launch_simt<T, 8, 8, LB200_SIMT_BK>(c, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, s, epi, batch,
                                                bsA, bsB, bsC);
@@ -379,6 +402,14 @@ int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_l
     split_rows_f16x2_kernel<true><<<grid_for(c, split_items, 8), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else if (Cc <= 4 * 32 * F16ROWS_MAXV) {   // short rows: a warp per row
     f16x2_rows_fused_kernel<32><<<grid_for(c, (R + 7) / 8, 4), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+  } else if (c.prep_ring && f16x2_rows_ring_ok(src, Cc, src_ld)) {   // rows prefetched into a shared-memory ring by the copy engine
+    const size_t smem = f16x2_rows_ring_smem(Cc);
+    if (!c.ring_attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(f16x2_rows_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(f16x2_rows_ring_smem(4 * 256 * F16ROWS_MAXV))));
+      c.ring_attr_set = true;
+    }
+    f16x2_rows_ring_kernel<<<grid_for(c, R, 2), 256, smem, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else {
     f16x2_rows_fused_kernel<256><<<grid_for(c, R, 4), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   }
@@ -1330,6 +1361,8 @@ int laser_b200_matmul_views(const laser_b200_tensor_view *A, const laser_b200_te
   }
 #undef LB200_RAW
 }
+
+int64_t laser_b200_debug_f64_dmma_launches(void) { return g_dmma_launches.load(); }
 
 int laser_b200_debug_classify(int elem_size, const void *base, int64_t s_mn, int64_t s_k) {
   if (elem_size != 2 && elem_size != 4) return -1;

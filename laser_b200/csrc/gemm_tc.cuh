@@ -342,52 +342,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int num_blocks = (kb_hi - kb_lo + p.kb_per_block - 1) / p.kb_per_block;  // accumulation blocks
       const int64_t row = static_cast<int64_t>(mb) * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane;   // of the product
       const int64_t col0 = static_cast<int64_t>(nb) * TC_BLOCK_N + h * TC_EPI_COLS;
-      // where this thread's 128 sums go.  Direct tile: its row of C, with alpha / beta / bias / activation.  Split unit: row
-      // (tile-local) of plane [sp][t - n_direct] of the workspace, raw (only the operand scales are undone).
       const bool split_unit = sp >= 0;
-      OutT *crow_base;          // element (row, col0)
-      int64_t cs_u;             // column stride
-      int64_t ncols;            // columns of this thread's segment that exist
-      bool vec_ok;
-      float alpha_u, beta_u;
-      if (!split_unit) {
-        crow_base = reinterpret_cast<OutT *>(p.C) + (row < p.M ? row : 0) * p.rsC + col0 * p.csC;
-        cs_u = p.csC; ncols = p.N - col0; vec_ok = vec_ok_c; alpha_u = p.alpha; beta_u = p.beta;
-      } else {
-        const int64_t plane = static_cast<int64_t>(sp) * (num_tiles - p.n_direct) + (t - p.n_direct);
-        crow_base = reinterpret_cast<OutT *>(p.split_ws) +
-                    (plane * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane) * TC_BLOCK_N + h * TC_EPI_COLS;
-        cs_u = 1; ncols = TC_EPI_COLS; vec_ok = true; alpha_u = 1.0f; beta_u = 0.0f;
-      }
-      // SCALED: undo the power-of-two scale of this thread's row of A (f16_scale.cuh); the abs-max words were written by
-      // earlier kernels of this stream.  The factors of B's 128 columns of this warp are fetched NOW, four per lane (lane l
-      // holds columns col0 + 4l .. 4l + 3), and handed out by warp shuffles when the tile is stored: fetching them per
-      // element at store time put a dependent global load in front of each of the 32 vector stores, ~13k cycles per tile
-      // during which the tensor core ran out of free accumulator stages (ncu source page, round 2).
-      const bool row_ok = row < p.M || split_unit;   // (rows past M of a split tile: zeros into the workspace)
-      float alpha_eff = alpha_u;
-      float cs[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+      // SCALED: the abs-max words were written by earlier kernels of this stream.  The word of this thread's row of A and the
+      // words of B's 128 columns of this warp are fetched NOW, four per lane (lane l holds columns col0 + 4l .. 4l + 3), and
+      // handed out by warp shuffles when the tile is stored: fetching them per element at store time put a dependent global
+      // load in front of each of the 32 vector stores, ~13k cycles per tile during which the tensor core ran out of free
+      // accumulator stages (ncu source page, round 2).  Everything else the store needs is derived after the K loop, so
+      // that only these five words stay live next to the 128 running sums.
+      uint32_t amax_row = 0u, amax_col[4] = {0u, 0u, 0u, 0u};
       if constexpr (SCALED) {
-        alpha_eff = alpha_u * (row < p.M ? f16x2_unscale(p.amax_a[row]) : 1.0f);
+        if (row < p.M) amax_row = p.amax_a[row];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int64_t c = col0 + 4 * lane + i;
-          if (c < p.N) cs[i] = f16x2_unscale(p.amax_b[c]);
+          if (c < p.N) amax_col[i] = p.amax_b[c];
         }
       }
-      // factor of column col0 + j (j warp-uniform); every lane of the warp must call it
-      auto col_unscale = [&](int j) -> float {
-        if constexpr (SCALED) {
-          const float v = (j & 3) == 0 ? cs[0] : (j & 3) == 1 ? cs[1] : (j & 3) == 2 ? cs[2] : cs[3];
-          return __shfl_sync(0xffffffffu, v, j >> 2);
-        } else {
-          return 1.0f;
-        }
-      };
-      if (beta_u != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {
+      if (!split_unit && p.beta != 0.0f && row < p.M && col0 < p.N && p.csC == 1) {
         // beta != 0: pull this thread's 512 bytes of old C into L2 now; they are needed only
         // after the whole K loop of the tile, so the latency is free
-        const OutT *cp = crow_base;
+        const OutT *cp = reinterpret_cast<const OutT *>(p.C) + row * p.rsC + col0;
 #pragma unroll
         for (int l = 0; l < TC_EPI_COLS * static_cast<int>(sizeof(OutT)) / 128; ++l) {
           if (col0 + l * (128 / static_cast<int>(sizeof(OutT))) < p.N)
@@ -420,6 +394,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         else ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      // where this thread's 128 sums go.  Direct tile: its row of C, with alpha / beta / bias / activation.  Split unit: row
+      // (tile-local) of plane [sp][t - n_direct] of the workspace, raw (only the operand scales are undone).
+      OutT *crow_base;          // element (row, col0)
+      int64_t cs_u;             // column stride
+      int64_t ncols;            // columns of this thread's segment that exist
+      bool vec_ok;
+      float alpha_u, beta_u;
+      if (!split_unit) {
+        crow_base = reinterpret_cast<OutT *>(p.C) + (row < p.M ? row : 0) * p.rsC + col0 * p.csC;
+        cs_u = p.csC; ncols = p.N - col0; vec_ok = vec_ok_c; alpha_u = p.alpha; beta_u = p.beta;
+      } else {
+        const int64_t plane = static_cast<int64_t>(sp) * (num_tiles - p.n_direct) + (t - p.n_direct);
+        crow_base = reinterpret_cast<OutT *>(p.split_ws) +
+                    (plane * TILE_M + cta_rank * TC_BLOCK_M + q * 32 + lane) * TC_BLOCK_N + h * TC_EPI_COLS;
+        cs_u = 1; ncols = TC_EPI_COLS; vec_ok = true; alpha_u = 1.0f; beta_u = 0.0f;
+      }
+      const bool row_ok = row < p.M || split_unit;   // (rows past M of a split tile: zeros into the workspace)
+      float alpha_eff = alpha_u;
+      float cs[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+      if constexpr (SCALED) {
+        alpha_eff = alpha_u * f16x2_unscale(amax_row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cs[i] = f16x2_unscale(amax_col[i]);
+      }
+      // factor of column col0 + j (j warp-uniform); every lane of the warp must call it
+      auto col_unscale = [&](int j) -> float {
+        if constexpr (SCALED) {
+          const float v = (j & 3) == 0 ? cs[0] : (j & 3) == 1 ? cs[1] : (j & 3) == 2 ? cs[2] : cs[3];
+          return __shfl_sync(0xffffffffu, v, j >> 2);
+        } else {
+          return 1.0f;
+        }
+      };
       // ---- C <- alpha * sum + beta * C  (gemm_ukernel_generic.nim:53-76 semantics) ----
       // control flow is warp-uniform down to the loads / stores themselves (col_unscale shuffles): only `row_ok` is per lane
       if (col0 < p.N) {

@@ -232,6 +232,86 @@ f16x2_rows_fused_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, in
   }
 }
 
+// The same single pass with the rows PREFETCHED by the copy engine: thread 0 keeps F16RING_BUFS rows of the CTA in flight as
+// bulk copies into a shared-memory ring (cp.async.bulk, one instruction per row, completion on an mbarrier), the CTA picks a
+// landed row up into registers, reduces its abs-max (the one __syncthreads per row doubles as "the buffer is free again":
+// every thread has read its part by then), scales, splits and stores.  The register-only kernel above alternates between
+// "all loads in flight" and "converting": 47 % of the HBM rate at 8192 x 8192 (ncu, round 2); here the loads of the next
+// rows never stop.  Needs 16-byte aligned rows of at most 256 * F16ROWS_MAXV float4 (the host checks).
+constexpr int F16RING_BUFS = 3;
+__global__ void __launch_bounds__(256, 2)
+f16x2_rows_ring_kernel(const float *__restrict__ src, int64_t R, int64_t Cc, int64_t src_ld, uint16_t *__restrict__ hb,
+                       uint16_t *__restrict__ lb, int64_t ld_b, uint32_t *__restrict__ absmax) {
+  LB200_DYN_SMEM(uint8_t, ring_raw);
+  __shared__ uint32_t red[2][8];
+  __shared__ uint64_t full[F16RING_BUFS];   // (8-byte aligned by type)
+  ptx::griddep_launch_dependents();
+  uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ring_raw) + 127) & ~static_cast<uintptr_t>(127));
+  const uint32_t row_bytes = static_cast<uint32_t>(Cc) * 4u;
+  const uint32_t buf_bytes = (row_bytes + 127u) & ~127u;
+  const int tid = static_cast<int>(threadIdx.x);
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int nvec = static_cast<int>(Cc >> 2);
+  if (tid == 0) {
+    for (int i = 0; i < F16RING_BUFS; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_barrier_init();
+    for (int i = 0; i < F16RING_BUFS; ++i) {
+      const int64_t r = first + i * step;
+      if (r < R) {
+        ptx::mbar_arrive_expect_tx(&full[i], row_bytes);
+        ptx::bulk_load_1d(ring + i * buf_bytes, src + r * src_ld, row_bytes, &full[i]);
+      }
+    }
+  }
+  __syncthreads();
+  int b = 0, parity = 0;
+  uint32_t phase = 0;
+  for (int64_t r = first; r < R; r += step) {
+    ptx::mbar_wait(&full[b], phase);
+    const float4 *row = reinterpret_cast<const float4 *>(ring + b * buf_bytes);
+    float4 v[F16ROWS_MAXV];
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < F16ROWS_MAXV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < nvec) {
+        v[i] = row[idx];
+        m = max(max(m, finite_abs_bits(v[i].x)), max(finite_abs_bits(v[i].y), max(finite_abs_bits(v[i].z), finite_abs_bits(v[i].w))));
+      }
+    }
+    float mf = __uint_as_float(m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    if ((tid & 31) == 0) red[parity][tid >> 5] = __float_as_uint(mf);
+    __syncthreads();   // the maxima of the eight warps are there AND every thread has taken its part of the row out of the ring
+    if (tid == 0) {
+      const int64_t rn = r + F16RING_BUFS * step;
+      if (rn < R) {
+        ptx::mbar_arrive_expect_tx(&full[b], row_bytes);
+        ptx::bulk_load_1d(ring + b * buf_bytes, src + rn * src_ld, row_bytes, &full[b]);
+      }
+    }
+    m = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = max(m, red[parity][w]);
+    parity ^= 1;
+    if (tid == 0) absmax[r] = m;
+    const float s = f16x2_scale(m);
+    uint16_t *hrow = hb + r * ld_b, *lrow = lb + r * ld_b;
+#pragma unroll
+    for (int i = 0; i < F16ROWS_MAXV; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < nvec) store_f16x2_vec(v[i], s, hrow, lrow, static_cast<int64_t>(idx) << 2);
+    }
+    if (++b == F16RING_BUFS) { b = 0; phase ^= 1u; }
+  }
+}
+inline size_t f16x2_rows_ring_smem(int64_t Cc) { return static_cast<size_t>(F16RING_BUFS) * ((Cc * 4 + 127) / 128 * 128) + 128; }
+inline bool f16x2_rows_ring_ok(const float *src, int64_t Cc, int64_t src_ld) {
+  return Cc % 4 == 0 && src_ld % 4 == 0 && Cc > 4 * 32 * F16ROWS_MAXV && Cc <= 4 * 256 * F16ROWS_MAXV &&
+         (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+
 // hb = fp16(x * 2^s), lb = fp16(x * 2^s - hb) with s from the abs-max word of the element's mn index
 // (f16_scale.cuh): x * 2^s = hb + lb + r, |r| <= 2^-22 |x * 2^s| for elements within 2^-17 of their row's /
 // column's maximum.  [R][Cc] row-contiguous arrays in and out.  Work item = (strip of 256 columns, block of

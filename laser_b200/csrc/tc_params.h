@@ -38,7 +38,7 @@ constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_EPI_WARPS = TC_EPI_THREADS / 32;
 constexpr int TC_EPI_COLS = TC_BLOCK_N / 2;  // columns owned by one epilogue thread
 constexpr int TC_REGS_CTRL = 56;   // setmaxnreg for the producer/MMA warpgroup
-constexpr int TC_REGS_EPI = 216;   // ... and for the epilogue warpgroups (running sums)
+constexpr int TC_REGS_EPI = 224;   // ... and for the epilogue warpgroups (running sums): 4 x 32 x 56 + 8 x 32 x 224 = the 64512 of the launch
 
 // fused epilogue: v -> act(v + bias)   (gemm.nim:196 "elementwise epilogue fusion")
 struct Epilogue {
@@ -94,6 +94,7 @@ struct TcPlanCfg {
   int raster_g;         // 0 = default
   bool splitk_enabled;
   int sm_count;
+  int tail_min_k = 2048;   // shortest K for which the remainder behind full waves is split
 };
 template <int ESZ, bool OUT_F32>
 inline void tc_plan(TcParams &p, int npass, bool pair, const TcPlanCfg &cfg) {
@@ -131,7 +132,7 @@ inline void tc_plan(TcParams &p, int npass, bool pair, const TcPlanCfg &cfg) {
     if (S > max_s) S = max_s;
     // a remainder behind full waves (S >= 2: at most half a wave of tiles) is split when a tile is long enough for half
     // of it to outweigh the reduce kernel
-    const bool worth = S >= 2 && (tiles < units || p.K >= 2048);
+    const bool worth = S >= 2 && (tiles < units || p.K >= cfg.tail_min_k);
     if (cfg.splitk_enabled && worth && units > 0) {
       const int blocks_per_split = (blocks + S - 1) / S;
       p.k_splits = (blocks + blocks_per_split - 1) / blocks_per_split;

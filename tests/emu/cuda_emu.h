@@ -50,6 +50,7 @@ inline pthread_barrier_t cluster_barrier;           // barrier.cluster / end of 
 inline pthread_barrier_t warp_barrier[kMaxCluster][32];   // one per warp (shuffles, __syncwarp)
 inline float warp_scratch[kMaxCluster][1024];
 inline int warp_scratch_i[kMaxCluster][1024];
+inline double warp_scratch_d[kMaxCluster][2][1024];
 alignas(1024) inline unsigned char dyn_smem[kMaxCluster][kDynSmemBytes];   // dynamic shared memory
 inline unsigned char *dyn_smem_ptr() { return dyn_smem[cta_rank]; }
 

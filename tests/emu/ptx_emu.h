@@ -156,6 +156,11 @@ inline void tma_copy_box(void *smem_dst, const CUtensorMap *map, int32_t c0, int
     }
   *bytes = static_cast<long>(m.box0) * m.box1 * m.esz;
 }
+inline void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) std::abort();   // the hardware faults
+  std::memcpy(smem_dst, gsrc, bytes);
+  emu::mb_complete_tx(bar, bytes);
+}
 inline void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
   long bytes;
   tma_copy_box(smem_dst, map, c0, c1, &bytes);
@@ -324,4 +329,19 @@ inline void mma_commit_pair(uint64_t *bar) {   // one arrival on the barrier at 
 }
 
 }  // namespace ptx
+// mma.sync.aligned.m8n8k4.row.col.f64 (gemm_dmma.cuh): lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and the two accumulators
+// D[l / 4][2 * (l % 4) + {0, 1}]; per output element the four steps of the FMA chain in k order
+inline void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  const unsigned t = emu::t_idx.x, w = t >> 5, r = emu::cta_rank, base = t & ~31u, lane = t & 31u;
+  emu::warp_scratch_d[r][0][t] = a;
+  emu::warp_scratch_d[r][1][t] = b;
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+  const unsigned row = lane >> 2, c0 = 2 * (lane & 3);
+  for (unsigned k = 0; k < 4; ++k) {
+    const double ak = emu::warp_scratch_d[r][0][base + row * 4 + k];
+    d0 = std::fma(ak, emu::warp_scratch_d[r][1][base + c0 * 4 + k], d0);
+    d1 = std::fma(ak, emu::warp_scratch_d[r][1][base + (c0 + 1) * 4 + k], d1);
+  }
+  pthread_barrier_wait(&emu::warp_barrier[r][w]);
+}
 }  // namespace lb200

@@ -5,7 +5,9 @@
 #define LB200_HOST_EMULATION 1
 #include "cuda_emu.h"
 
+#include "ptx_emu.h"
 #include "../../laser_b200/csrc/gemm_simt.cuh"
+#include "../../laser_b200/csrc/gemm_dmma.cuh"
 
 using namespace lb200;
 
@@ -41,6 +43,19 @@ int emu_gemm_simt_f64(int64_t M, int64_t N, int64_t K, double alpha, const doubl
                       const double *B, int64_t rsB, int64_t csB, double beta, double *C, int64_t rsC, int64_t csC,
                       int grid) {
   return run<double, 4, 4, 16>(M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC, grid, nullptr, 0, 0);
+}
+// the fp64 tensor-core kernel (gemm_dmma.cuh), planned and launched as capi.cu: gemm_simt<double> does
+int emu_gemm_dmma_f64(int64_t batch, int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t rsA, int64_t csA,
+                      int64_t bsA, const double *B, int64_t rsB, int64_t csB, int64_t bsB, double beta, double *C, int64_t rsC,
+                      int64_t csC, int64_t bsC, int grid) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return 0;
+  SimtParams<double> p;
+  const int64_t tiles = dmma_plan(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+  if (grid <= 0 || grid > tiles * batch) grid = static_cast<int>(tiles * batch);
+  if (DMMA_SMEM_BYTES > emu::kDynSmemBytes) return -1;
+  emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_dmma_kernel(p); });
+  return static_cast<int>(tiles);
 }
 int emu_gemm_simt_i32(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t *A, int64_t rsA, int64_t csA,
                       const int32_t *B, int64_t rsB, int64_t csB, int32_t beta, int32_t *C, int64_t rsC, int64_t csC,

@@ -46,6 +46,7 @@ struct Args {
   int64_t splitk_ws_floats;
   int *out_k_splits, *out_grid;
   const uint32_t *amax_a, *amax_b;   // SCALED: abs-max words per row of A / column of B (f16_scale.cuh)
+  int tail_min_k;            // TcPlanCfg::tail_min_k (0: the library's default)
   int dyn_sched;             // 1: tiles drawn from an atomic counter (capi.cu: Ctx::sched), 0: static round-robin
 };
 
@@ -58,7 +59,9 @@ static int run(const Args &a) {
   p.C = a.C; p.rsC = a.rsC; p.csC = a.csC; p.zero = 0;
   p.epi.bias = a.bias; p.epi.bias_per_row = a.bias_per_row; p.epi.act = a.act;
   p.amax_a = a.amax_a; p.amax_b = a.amax_b;
-  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, NPASS, PAIR, TcPlanCfg{a.kc_faithful, a.raster_g, a.splitk_enabled != 0, a.sm_count});
+  TcPlanCfg cfg{a.kc_faithful, a.raster_g, a.splitk_enabled != 0, a.sm_count};
+  if (a.tail_min_k > 0) cfg.tail_min_k = a.tail_min_k;
+  tc_plan<ESZ, std::is_same<OutT, float>::value>(p, NPASS, PAIR, cfg);
   if (a.out_k_splits) { a.out_k_splits[0] = p.k_splits; a.out_k_splits[1] = p.n_direct; }
   if (p.k_splits > 1) {   // capi.cu: tc_run -- raw partial sums of the split tiles into the planes, reduced by splitk_tail_reduce_kernel
     if (!a.splitk_ws || a.splitk_ws_floats < tc_split_ws_floats(p, PAIR)) return -2;
@@ -116,9 +119,9 @@ extern "C" int emu_gemm_tc(int kind, int a_mn, int b_mn, int pair, int64_t M, in
                            const void *A0, const void *A1, int64_t ldA, const void *B0, const void *B1, int64_t ldB,
                            void *C, int64_t rsC, int64_t csC, int kc_faithful, int raster_g, int splitk_enabled,
                            int sm_count, const float *bias, int bias_per_row, int act, float *splitk_ws, int64_t splitk_ws_floats, int *out_k_splits,
-                           int *out_grid, const uint32_t *amax_a, const uint32_t *amax_b, int dyn_sched) {
+                           int *out_grid, const uint32_t *amax_a, const uint32_t *amax_b, int dyn_sched, int tail_min_k) {
   Args a{M, N, K, alpha, beta, {A0, A1}, {B0, B1}, ldA, ldB, C, rsC, csC, kc_faithful,
-         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, splitk_ws_floats, out_k_splits, out_grid, amax_a, amax_b, dyn_sched};
+         raster_g, splitk_enabled, sm_count, bias, bias_per_row, act, splitk_ws, splitk_ws_floats, out_k_splits, out_grid, amax_a, amax_b, tail_min_k, dyn_sched};
   switch (kind) {
     case 0: return dispatch<4, ptx::kFmtBF16, 1, float, false>(a_mn, b_mn, pair, a);
     case 1: return dispatch<4, ptx::kFmtBF16, 3, float, false>(a_mn, b_mn, pair, a);

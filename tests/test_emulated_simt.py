@@ -19,7 +19,10 @@ NP = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
 
 @pytest.fixture(scope="module")
 def emu():
-    L = ctypes.CDLL(build_emu("simt_emu", ["gemm_simt.cuh"]))
+    L = ctypes.CDLL(build_emu("simt_emu", ["gemm_simt.cuh", "gemm_simt_kernel.inc", "gemm_dmma.cuh", "ptx.cuh"]))
+    f64 = ctypes.c_double
+    L.emu_gemm_dmma_f64.restype = ci
+    L.emu_gemm_dmma_f64.argtypes = [i64, i64, i64, i64, f64, vp, i64, i64, i64, vp, i64, i64, i64, f64, vp, i64, i64, i64, ci]
     for name, sc in SCALAR.items():
         fn = getattr(L, "emu_gemm_simt_" + name)
         fn.restype = ci
@@ -106,6 +109,38 @@ def test_f64_and_integers(emu):
         O.gemm_strided(M, N, K, 3, ai, K, 1, bi, N, 1, -2, refi, N, 1)
         run(emu, name, M, N, K, 3, ai, 0, K, 1, bi, 0, N, 1, -2, ci_, 0, N, 1, grid=1)
         assert np.array_equal(ci_, refi)     # wrapping arithmetic, as the reference's mullo + add
+
+
+@pytest.mark.parametrize("M,N,K,alpha,beta,layout", [(130, 140, 300, 1.0, 0.0, "nn"), (200, 129, 515, 1.0, 1.0, "tn"),
+                                                     (64, 260, 257, 1.0, -0.5, "nt"), (129, 130, 40, 2.0, 0.0, "tt"),
+                                                     (5, 7, 3, 1.0, 1.0, "nn")])
+def test_f64_tensor_core_kernel_is_the_same_fma_chain(emu, M, N, K, alpha, beta, layout):
+    """gemm_dmma.cuh on the emulator's model of mma.sync.m8n8k4.f64 (per element: four fma steps in k order): bit-identical
+    to the oracle across kc = 256 block boundaries, ragged tiles and all operand layouts; C beyond the view untouched"""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((M, K)); b = rng.standard_normal((K, N)); c0 = rng.standard_normal((M, N + 3))
+    A, rsa, csa = (a, K, 1) if layout[0] == "n" else (np.ascontiguousarray(a.T), 1, M)
+    B, rsb, csb = (b, N, 1) if layout[1] == "n" else (np.ascontiguousarray(b.T), 1, K)
+    ref = c0.copy(); O.gemm_strided(M, N, K, alpha, A, rsa, csa, B, rsb, csb, beta, ref, N + 3, 1)
+    got = c0.copy()
+    if beta == 0.0:
+        got[:, :N] = np.nan
+    tiles = emu.emu_gemm_dmma_f64(1, M, N, K, alpha, at(A, 0), rsa, csa, 0, at(B, 0), rsb, csb, 0, beta, at(got, 0), N + 3, 1, 0, 3)
+    assert tiles == -(-M // 128) * -(-N // 128)
+    if alpha == 1.0:
+        assert np.array_equal(got, ref)
+    else:                                    # alpha != 1: the oracle's compiler may contract C += alpha*AB (1 ulp)
+        assert np.abs(got - ref).max() <= 4e-16 * np.abs(ref).max() and np.array_equal(got[:, N:], ref[:, N:])
+
+
+def test_f64_tensor_core_kernel_batched(emu):
+    batch, M, N, K = 3, 70, 130, 270
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((batch, M, K)); B = rng.standard_normal((K, N)); C = rng.standard_normal((batch, M, N)); ref = C.copy()
+    for i in range(batch):
+        O.gemm_strided(M, N, K, 1.0, A[i], K, 1, B, N, 1, 1.0, ref[i], N, 1)
+    emu.emu_gemm_dmma_f64(batch, M, N, K, 1.0, at(A, 0), K, 1, M * K, at(B, 0), N, 1, 0, 1.0, at(C, 0), N, 1, M * N, 4)
+    assert np.array_equal(C, ref)
 
 
 @pytest.mark.parametrize("per_row,act", [(0, 0), (1, 1), (0, 2), (1, 3)])

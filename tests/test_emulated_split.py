@@ -19,14 +19,16 @@ def emu():
     L = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh"]))
     L.emu_split_rows_tf32.argtypes = [vp, i64, i64, i64, vp, vp, i64, ci]
     L.emu_f16x2_rows_fused.argtypes = [ci, vp, i64, i64, i64, vp, vp, i64, vp, ci]
+    L.emu_f16x2_rows_ring.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp, ci]
+    L.emu_f16x2_rows_ring.restype = ci
     L.emu_absmax_mn.argtypes = [ci, vp, i64, i64, i64, vp, ci]
     L.emu_split_rows_f16x2.argtypes = [ci, vp, i64, i64, i64, vp, vp, i64, vp, ci]
     L.emu_pack_general_f32.argtypes = [ci, vp, i64, i64, i64, i64, vp, vp, i64, ci, ci]
     L.emu_pack_general_u16.argtypes = [vp, i64, i64, i64, i64, vp, i64, ci, ci]
-    L.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
+    L.emu_splitk_tail_reduce.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
     L.emu_fill_uniform_f32.argtypes = [vp, i64, ctypes.c_uint64, f32, f32, ci]
     for n in ("emu_split_rows_tf32", "emu_f16x2_rows_fused", "emu_absmax_mn", "emu_split_rows_f16x2", "emu_pack_general_f32", "emu_pack_general_u16",
-              "emu_splitk_reduce", "emu_fill_uniform_f32"):
+              "emu_splitk_tail_reduce", "emu_fill_uniform_f32"):
         getattr(L, n).restype = None
     return L
 
@@ -61,7 +63,7 @@ def test_split_rows(emu, R, Cc, src_ld):
     assert np.abs((hi[:, :Cc].astype(np.float64) + lo[:, :Cc]) - x).max() <= 2.0 ** -21 * np.abs(x).max()
 
 
-@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100)])
+@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100), (11, 8192, 8196)])
 @pytest.mark.parametrize("per_col", [0, 1])
 def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
     """LASER_B200_PATH_F16X3: one abs-max word per row (K-major operand) or per column (MN-major operand), a power-of-two
@@ -100,6 +102,13 @@ def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
             emu.emu_f16x2_rows_fused(group, p(src), R, Cc, src_ld, p(hb2), p(lb2), ldb, p(w2), grid)
             assert np.array_equal(w2, words)
             assert np.array_equal(hb2[:, :ld], hb[:, :ld]) and np.array_equal(lb2[:, :ld], lb[:, :ld])
+        # ... and its variant with the rows prefetched into a shared-memory ring by bulk copies (long, 16-byte aligned rows)
+        w3 = np.full(n_mn, 77, np.uint32); hb3 = np.full((R, ldb), 9, np.uint16); lb3 = np.full((R, ldb), 9, np.uint16)
+        ran = emu.emu_f16x2_rows_ring(p(src), R, Cc, src_ld, p(hb3), p(lb3), ldb, p(w3), 2)
+        assert ran == int(Cc % 4 == 0 and src_ld % 4 == 0 and 1024 < Cc <= 8192)
+        if ran:
+            assert np.array_equal(w3, words)
+            assert np.array_equal(hb3[:, :ld], hb[:, :ld]) and np.array_equal(lb3[:, :ld], lb[:, :ld])
     mx = np.where(ok, np.abs(xs), 0).max(axis=0 if per_col else 1)
     assert np.all((mx == 0) | ((mx >= 2.0 ** 14) & (mx < 2.0 ** 15)))
     big = ok & (np.abs(xs) >= 2.0 ** -3)           # l = xs - h (<= 2^-11 |xs|) is then rounded at or above fp16's subnormal spacing 2^-24: 22 bits
@@ -146,26 +155,47 @@ def test_pack_general_bf16(emu):
 
 @pytest.mark.parametrize("S,alpha,beta,per_row,act", [(1, 1.0, 0.0, 0, 0), (4, 0.5, -1.25, 0, 0), (3, 1.0, 0.0, 1, 1),
                                                       (5, 2.0, 1.0, 0, 2)])
-def test_splitk_reduce_is_a_fixed_order_sum(emu, S, alpha, beta, per_row, act):
-    M, N, ld = 23, 37, 40
+@pytest.mark.parametrize("n_direct,tile_m", [(0, 128), (3, 256)])
+def test_splitk_tail_reduce_is_a_fixed_order_sum(emu, S, alpha, beta, per_row, act, n_direct, tile_m):
+    """tile-local planes [S][n_tail][tile_m][256] of the tiles n_direct.. (raster order, tc_params.h: tile_coords) -> C;
+    the direct tiles of C are not touched"""
+    M, N, G = 2 * tile_m + 23, 256 + 37, 2              # 3 x 2 tiles, ragged in both directions
+    num_m, num_n = -(-M // tile_m), -(-N // 256)
+    n_tail = num_m * num_n - n_direct
     rng = np.random.default_rng(2)
-    ws = rng.standard_normal((S, M, ld)).astype(np.float32)
+    ws = rng.standard_normal((S, n_tail, tile_m, 256)).astype(np.float32)
     C = rng.standard_normal((N, M)).astype(np.float32)            # column-major C: rsC = 1, csC = M
     bias = rng.standard_normal(M if per_row else N).astype(np.float32) if act else None
     c0 = C.copy()
-    if beta == 0.0:
-        C[:] = np.nan
-    emu.emu_splitk_reduce(p(ws), S, M, N, ld, M * ld, alpha, beta, p(C), 1, M, p(bias) if bias is not None else None,
-                          per_row, act, 3)
-    s = ws[0, :, :N].copy()
-    for k in range(1, S):
-        s = s + ws[k, :, :N]                                        # planes in order 0..S-1, fp32
-    v = np.float32(alpha) * s
-    if beta != 0.0:
-        v = (np.float64(beta) * c0.T.astype(np.float64) + v.astype(np.float64)).astype(np.float32)   # fmaf
-    if act:
-        v = v + (bias[:, None] if per_row else bias[None, :])
-        v = np.maximum(v, 0) if act == 1 else np.tanh(v)
-    assert np.allclose(C.T, v, rtol=1e-6, atol=1e-6)
+    emu.emu_splitk_tail_reduce(p(ws), S, n_tail, n_direct, num_m, num_n, G, tile_m, M, N, alpha, beta, p(C), 1, M,
+                               p(bias) if bias is not None else None, per_row, act, 3)
+    want = c0.T.copy()
+
+    def coords(t):                                                   # tc_params.h: tile_coords
+        per_group = G * num_n
+        g = t // per_group
+        first = g * G
+        gsz = min(G, num_m - first)
+        r = t - g * per_group
+        return first + r % gsz, r // gsz
+    seen = set()
+    for ti in range(n_tail):
+        mb, nb = coords(n_direct + ti)
+        seen.add((mb, nb))
+        r0, c0_ = mb * tile_m, nb * 256
+        rows, cols = min(tile_m, M - r0), min(256, N - c0_)
+        s = ws[0, ti, :rows, :cols].copy()
+        for k in range(1, S):
+            s = s + ws[k, ti, :rows, :cols]                          # planes in order 0..S-1, fp32
+        v = np.float32(alpha) * s
+        if beta != 0.0:
+            old = c0.T[r0:r0 + rows, c0_:c0_ + cols]
+            v = (np.float64(beta) * old.astype(np.float64) + v.astype(np.float64)).astype(np.float32)   # fmaf
+        if act:
+            v = v + (bias[r0:r0 + rows, None] if per_row else bias[None, c0_:c0_ + cols])
+            v = np.maximum(v, 0) if act == 1 else np.tanh(v)
+        want[r0:r0 + rows, c0_:c0_ + cols] = v
+    assert len(seen) == n_tail
+    assert np.allclose(C.T, want, rtol=1e-6, atol=1e-6)
     if S > 1 and beta == 0.0 and not act:
-        assert np.array_equal(C.T, v)
+        assert np.array_equal(C.T, want)

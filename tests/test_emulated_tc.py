@@ -23,14 +23,10 @@ KIND = {"tf32x1": 0, "tf32x3": 1, "bf16": 2, "f16x3": 3}
 
 @pytest.fixture(scope="module")
 def emu():
-    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "tc_params.h", "f16_scale.cuh", "ptx.cuh"]))
+    L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "tc_params.h", "f16_scale.cuh", "ptx.cuh", "split.cuh"]))
     L.emu_gemm_tc.restype = ci
     L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, i64, vp, vp, i64, vp, i64, i64, ci, ci, ci, ci,
-                              vp, ci, ci, vp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp, ci]
-    S = ctypes.CDLL(build_emu("split_emu", ["split.cuh", "f16_scale.cuh", "ptx.cuh"]))
-    S.emu_splitk_reduce.restype = None
-    S.emu_splitk_reduce.argtypes = [vp, ci, i64, i64, i64, i64, f32, f32, vp, i64, i64, vp, ci, ci, ci]
-    L.splitk_reduce = S.emu_splitk_reduce
+                              vp, ci, ci, vp, i64, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp, ci, ci]
     return L
 
 
@@ -57,9 +53,10 @@ def ptr(a):
 
 
 def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=False, pair=False, kc=128, raster=0,
-           splitk=1, sms=4, epi=None, c_base=None, dyn=1):
+           splitk=1, sms=4, epi=None, c_base=None, dyn=1, tail_min_k=0):
     """a: logical (M, K) fp32; b: logical (K, N) fp32; c: flat output buffer (float32, or uint16 for bf16).
-    Returns (expected sum A*B in float64 under the mode's operand model, k_splits, grid)."""
+    Returns (expected sum A*B in float64 under the mode's operand model, k_splits, grid); run_tc.n_direct holds the number
+    of tiles the last launch computed without splitting (tc_params.h)."""
     M, K = a.shape
     N = b.shape[1]
     bt = np.ascontiguousarray(b.T)              # B seen as [n][k]
@@ -96,18 +93,15 @@ def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=F
         arrs["A"][1], _ = lay(la, a_mn, 4); arrs["B"][1], _ = lay(lb_, b_mn, 4)
         exact = ha.astype(f) @ lb_.astype(f).T + la.astype(f) @ hb.astype(f).T + ha.astype(f) @ hb.astype(f).T
     bias, per_row, act = epi if epi else (None, 0, 0)
-    ws = np.zeros(16 * M * (-(-N // 4) * 4), np.float32)
-    ks, grid = ci(0), ci(0)
+    ws = np.full(16 * (-(-M // 256) * 256) * (-(-N // 256) * 256), np.nan, np.float32)   # every tile split 16 ways fits
+    ks, grid = (ci * 2)(0, 0), ci(0)
     rc = emu.emu_gemm_tc(KIND[mode], int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
                          ptr(arrs["A"][0]), ptr(arrs["A"][1]), ld["A"], ptr(arrs["B"][0]), ptr(arrs["B"][1]), ld["B"],
                          ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, kc, raster, splitk, sms,
-                         ptr(bias), per_row, act, ptr(ws), ctypes.byref(ks), ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]), dyn)
-    assert rc == 0
-    if ks.value > 1:     # capi.cu: tc_run -- second kernel of a split-K GEMM
-        ldw = -(-N // 4) * 4
-        emu.splitk_reduce(ptr(ws), ks.value, M, N, ldw, M * ldw, alpha, beta,
-                          ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, ptr(bias), per_row, act, 2)
-    return exact, ks.value, grid.value
+                         ptr(bias), per_row, act, ptr(ws), ws.size, ks, ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]), dyn, tail_min_k)
+    assert rc == 0          # (the harness runs the reduce kernel of a split launch itself, like capi.cu: tc_run)
+    run_tc.n_direct = ks[1]
+    return exact, ks[0], grid.value
 
 
 def rnd(shape, seed, lo=-1.0, hi=1.0):
@@ -195,6 +189,34 @@ def test_split_k(emu, pair, M, mode):
     assert ks >= 2 and grid == (2 * ks if pair else ks)
     want = 0.5 * exact + 2.0 * c0
     assert np.abs(c.reshape(M, N) - want).max() <= 3e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("pair,mode,dyn", [(False, "tf32x3", 1), (True, "f16x3", 1), (True, "tf32x3", 0)])
+@pytest.mark.parametrize("ccol", [False, True])
+def test_split_k_of_the_last_partial_wave(emu, pair, mode, dyn, ccol):
+    """more tiles than persistent CTAs (pairs), the remainder at most half a wave: the full waves are computed directly, the
+    tiles of the remainder as K-ranges through the workspace + reduce kernel (tc_params.h), alpha / beta / bias on both"""
+    tile_m = 256 if pair else 128
+    M, N, K = tile_m + 40, 3 * 256 - 10, 1040         # 2 x 3 = 6 tiles on 4 units: 4 direct, 2 split in two halves of K (>= 512 each)
+    sms = 8 if pair else 4
+    a, b = rnd((M, K), 21), rnd((K, N), 22)
+    c0 = rnd((M, N), 23)
+    bias = rnd((N,), 24)
+    buf = np.ascontiguousarray(c0.T if ccol else c0).reshape(-1).copy()
+    rs, cs = (1, M) if ccol else (N, 1)
+    exact, ks, grid = run_tc(emu, mode, a, b, buf, rs, cs, alpha=0.5, beta=2.0, pair=pair, kc=64, sms=sms, dyn=dyn,
+                             epi=(bias, 0, 1), tail_min_k=256)
+    assert ks == 2 and run_tc.n_direct == 4 and grid == sms
+    want = np.maximum(0.5 * exact + 2.0 * c0 + bias[None, :], 0.0)
+    got = buf.reshape(N, M).T if ccol else buf.reshape(M, N)
+    tol = 2e-3 if mode == "tf32x1" else 3e-6
+    assert np.abs(got - want).max() <= tol * np.abs(want).max()
+    # without the threshold override the same problem runs unsplit (K is short)
+    buf2 = np.ascontiguousarray(c0.T if ccol else c0).reshape(-1).copy()
+    _, ks2, _ = run_tc(emu, mode, a, b, buf2, rs, cs, alpha=0.5, beta=2.0, pair=pair, kc=64, sms=sms, dyn=dyn, epi=(bias, 0, 1))
+    assert ks2 == 1 and run_tc.n_direct == 6
+    got2 = buf2.reshape(N, M).T if ccol else buf2.reshape(M, N)
+    assert np.abs(got2 - want).max() <= tol * np.abs(want).max()
 
 
 @pytest.mark.parametrize("raster", [1, 2, 16])

@@ -101,6 +101,33 @@ def test_simt_bit_exact_other_dtypes(name):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("shape,ab,lay", [((1200, 1100, 700), (1.0, 0.0), ("row", "row", "row")),
+                                          ((1153, 1290, 515), (0.5, -1.25), ("col", "colslice", "padded")),
+                                          ((2048, 1024, 256), (1.0, 1.0), ("row", "col", "col"))])
+def test_f64_dmma_bit_exact(shape, ab, lay):
+    """float64 problems whose 128 x 128 tiles fill half of the SMs run on the fp64 tensor cores (mma.sync.m8n8k4.f64,
+    csrc/gemm_dmma.cuh).  One DMMA performs, per output element, four steps of the reference's k-sequential FMA chain, so the
+    result must equal the oracle's BIT FOR BIT (kc = 256 block boundaries, ragged tiles, strided operands, alpha / beta)."""
+    if EMU:
+        pytest.skip("the emulated library models the kernel in tests/test_emulated_simt.py")
+    M, N, K = shape
+    alpha, beta = ab
+    rng = np.random.default_rng(7)
+    A = rng.uniform(-1, 1, (M, K)); B = rng.uniform(-1, 1, (K, N)); C0 = rng.uniform(-1, 1, (M, N))
+    want = C0.copy(); O.gemm_strided(M, N, K, alpha, A, K, 1, B, N, 1, beta, want, N, 1)
+    n0 = L.lib().laser_b200_debug_f64_dmma_launches()
+    got, after, before, (oc, rsc, csc) = run_dev("f64", M, N, K, alpha, A, lay[0], B, lay[1], beta, C0, lay[2])
+    assert L.lib().laser_b200_debug_f64_dmma_launches() == n0 + 1, "the problem was expected to take the DMMA kernel"
+    if alpha == 1.0:
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    else:      # alpha != 1: the oracle's compiler may contract C += alpha * AB into one fma (1 ulp), as for f32
+        assert np.abs(got - want).max() <= 4e-16 * np.abs(want).max()
+    mask = np.ones(after.shape, bool).reshape(-1)
+    idx = oc + np.arange(M)[:, None] * rsc + np.arange(N)[None, :] * csc
+    mask[idx.reshape(-1)] = False
+    assert np.array_equal(after.reshape(-1)[mask], before.reshape(-1)[mask])      # nothing outside the view changed
+
+
 @pytest.mark.parametrize("la", LAYOUTS)
 @pytest.mark.parametrize("lb", ["row", "col", "colslice", "negrow"])
 @pytest.mark.parametrize("lc", ["row", "col", "padded", "negcol"])
