@@ -102,7 +102,7 @@ struct Ctx {
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
   bool f64_dmma = true;        // env LASER_B200_F64_DMMA=0: fp64 problems stay on the CUDA-core kernel
   bool prep_ring = true;       // env LASER_B200_PREP_RING=0: register-only preparation kernel for K-major operands
-  bool ring_attr_set = false;
+  bool ring_attr_set = false, dmma_attr_set = false;
   int64_t panel_rows = 1024;  // env LASER_B200_PANEL_ROWS: row-panel height of the pipelined host-pointer entry
   bool panel_taper = false;   // env LASER_B200_PANEL_TAPER=1: cut the last row panel finer (shorter PCIe tail)
   bool cta_pair = true;   // env LASER_B200_CTA_PAIR=0 forces the single-CTA kernel
@@ -288,8 +288,31 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
       const int64_t tiles = dmma_plan(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
       if (tiles * batch > 0x7fffffff) return set_error(LASER_B200_EINVAL, "too many tiles");
       p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+      if (!c.dmma_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(DMMA_SMEM_BYTES)));
+        c.dmma_attr_set = true;
+      }
       gemm_dmma_kernel<<<grid_for(c, tiles * batch, 1), 256, DMMA_SMEM_BYTES, s>>>(p);
       g_dmma_launches.fetch_add(1);
+      COUNT_LAUNCH();
+      CHECK_LAUNCH();
+      return LASER_B200_OK;
+    }
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    // few output rows, wide N (the im2col convolution's GEMM): a thread owns 4 columns of all rows, B and C stream once;
+    // the same FMA chain per element as the general kernel (gemm_simt.cuh: gemm_skinny_m_kernel)
+    if (M <= 32 && N >= 1024) {
+      SimtParams<float> p;
+      simt_plan<float, 8, 8>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+      p.bias = epi.bias; p.bias_per_row = epi.bias_per_row; p.act = epi.act;
+      p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+      const int nc = M <= 16 ? 4 : 2;   // columns per thread (gemm_simt.cuh)
+      const int grid = grid_for(c, ((N + 256 * nc - 1) / (256 * nc)) * batch, 2);
+      if (M <= 8) gemm_skinny_m_kernel<8, 4><<<grid, 256, 0, s>>>(p);
+      else if (M <= 16) gemm_skinny_m_kernel<16, 4><<<grid, 256, 0, s>>>(p);
+      else if (M <= 24) gemm_skinny_m_kernel<24, 2><<<grid, 256, 0, s>>>(p);
+      else gemm_skinny_m_kernel<32, 2><<<grid, 256, 0, s>>>(p);
       COUNT_LAUNCH();
       CHECK_LAUNCH();
       return LASER_B200_OK;

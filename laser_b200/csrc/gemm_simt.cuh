@@ -233,4 +233,118 @@ gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict
   }
 }
 
+// ---------------------------------------------------------------------------
+// Few output ROWS, very wide N: the GEMM of the im2col convolution (conv2d_im2col.nim:150-166: M = filters = 20,
+// K = C * kH * kW = 27, N = outH * outW = 49284 per image).  A 128 x 128 tile of the general kernel would compute 84 %
+// padding; here a thread owns 4 consecutive columns of ALL rows: per k one 16-byte load of B (coalesced along n), MT / 4
+// 16-byte broadcast reads of A's k-th column from shared memory and 4 * MT FMAs -- the kernel streams B and C once.
+// Exact: every C[i,j] is the reference's k-sequential FMA chain inside kc = 512 blocks with the reference epilogue per
+// block (same statements as gemm_simt_kernel), so results are bit-identical to the general kernel's.  Batched like it.
+// MT: rows held in registers (M <= MT, a multiple of 4).
+// ---------------------------------------------------------------------------
+constexpr int SKINNY_KCHUNK = 64;   // k-columns of A staged in shared memory at a time
+// NC: columns per thread (4 for MT <= 16, 2 above: MT * NC running sums per thread must leave room for two CTAs per SM)
+template <int MT, int NC>
+__global__ void __launch_bounds__(256, 2)
+gemm_skinny_m_kernel(const SimtParams<float> p) {
+  static_assert(MT % 4 == 0 && MT <= 32 && (NC == 2 || NC == 4), "rows in registers");
+  constexpr int64_t KC = 2048 / 4;   // gemm_tiling.nim:310
+  constexpr int COLS = 256 * NC;     // columns per CTA and iteration
+  __shared__ float4 As4[SKINNY_KCHUNK][MT / 4];   // As[k][m]: the m of one k are contiguous (16-byte broadcast reads)
+  float *As = reinterpret_cast<float *>(As4);
+  const int tid = threadIdx.x;
+  const int64_t nblocks = (p.N + COLS - 1) / COLS;
+  const int64_t total = nblocks * p.batch;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t bi = t / nblocks;
+    const int64_t n0 = (t - bi * nblocks) * COLS + NC * tid;
+    const float *Ab = p.A + bi * p.bsA;
+    const float *Bb = p.B + bi * p.bsB;
+    float *Cb = p.C + bi * p.bsC;
+    const bool vec_b = p.csB == 1 && n0 + NC <= p.N &&
+                       ((reinterpret_cast<uintptr_t>(Bb + n0) | (static_cast<uint64_t>(p.rsB) * 4)) & (4 * NC - 1)) == 0;
+    for (int64_t pc = 0; pc < p.K; pc += KC) {  // reference loop 2 (gemm.nim:150)
+      const int64_t kend = (pc + KC < p.K) ? pc + KC : p.K;
+      float acc[MT][NC];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[i][j] = 0.0f;
+      for (int64_t k0 = pc; k0 < kend; k0 += SKINNY_KCHUNK) {
+        const int kn = static_cast<int>(kend - k0 < SKINNY_KCHUNK ? kend - k0 : SKINNY_KCHUNK);
+        __syncthreads();   // the previous chunk of A is consumed
+        for (int i = tid; i < SKINNY_KCHUNK * MT; i += 256) {
+          const int k = i / MT, m = i - k * MT;
+          As[i] = (m < p.M && k < kn) ? Ab[m * p.rsA + (k0 + k) * p.csA] : 0.0f;
+        }
+        __syncthreads();
+        if (n0 < p.N) {
+          // (k-steps in flight: as many as the register budget of two CTAs per SM allows next to the MT * NC sums)
+#pragma unroll(MT * NC > 48 ? 2 : 4)
+          for (int k = 0; k < kn; ++k) {
+            float b[NC];
+            const float *brow = Bb + (k0 + k) * p.rsB + n0 * p.csB;
+            if (vec_b) {
+              if constexpr (NC == 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(brow);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+              } else {
+                const float2 v = *reinterpret_cast<const float2 *>(brow);
+                b[0] = v.x; b[1] = v.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NC; ++j) b[j] = (n0 + j < p.N) ? brow[j * p.csB] : 0.0f;
+            }
+#pragma unroll
+            for (int i4 = 0; i4 < MT / 4; ++i4) {
+              const float4 a = As4[k][i4];
+              const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[4 * i4 + e][j] = __fmaf_rn(av[e], b[j], acc[4 * i4 + e][j]);
+            }
+          }
+        }
+      }
+      // reference epilogue for this kc block (gemm_ukernel_generic.nim:53-76)
+      const float beta1 = (pc == 0) ? p.beta : 1.0f;
+      if (n0 < p.N) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          if (i >= p.M) break;
+          float *crow = Cb + i * p.rsC + n0 * p.csC;
+          float v[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            if (n0 + j >= p.N) { v[j] = 0.0f; continue; }
+            float x;
+            if (beta1 == 0.0f) x = 0.0f;
+            else if (beta1 != 1.0f) x = __fmul_rn(crow[j * p.csC], beta1);
+            else x = crow[j * p.csC];
+            if (p.alpha == 1.0f) x = __fadd_rn(x, acc[i][j]);
+            else x = __fadd_rn(x, __fmul_rn(p.alpha, acc[i][j]));
+            if (kend == p.K && (p.bias != nullptr || p.act != 0)) {
+              if (p.bias) x += p.bias_per_row ? p.bias[i] : p.bias[n0 + j];
+              if (p.act == 1) x = fmaxf(x, 0.0f);
+              else if (p.act == 2) x = tanhf(x);
+              else if (p.act == 3) x = 1.0f / (1.0f + expf(-x));
+            }
+            v[j] = x;
+          }
+          if (p.csC == 1 && n0 + NC <= p.N && (reinterpret_cast<uintptr_t>(crow) & (4 * NC - 1)) == 0) {
+            if constexpr (NC == 4) *reinterpret_cast<float4 *>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+            else *reinterpret_cast<float2 *>(crow) = make_float2(v[0], v[1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (n0 + j < p.N) crow[j * p.csC] = v[j];
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace lb200

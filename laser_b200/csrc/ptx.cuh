@@ -86,6 +86,14 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "r"(c0), "r"(c1)
       : "memory");
 }
+// cp.async (LDGSTS): 8 bytes global -> shared without passing through registers; `valid` false: eight zero bytes instead
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(valid ? 8u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // contiguous bulk copy global -> shared (16-byte aligned on both sides, bytes a multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <sched.h>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -112,6 +113,9 @@ inline uint32_t atomicMax(uint32_t *p, uint32_t v) {   // shared or global word;
 }
 inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <typename T>
+inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+inline void __nanosleep(unsigned) { sched_yield(); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }

@@ -57,6 +57,22 @@ int emu_gemm_dmma_f64(int64_t batch, int64_t M, int64_t N, int64_t K, double alp
   emu::launch(static_cast<unsigned>(grid), 256, [=]() { gemm_dmma_kernel(p); });
   return static_cast<int>(tiles);
 }
+// few rows, wide N (gemm_simt.cuh: gemm_skinny_m_kernel), launched as capi.cu: gemm_simt<float> does
+int emu_gemm_skinny_m_f32(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t rsA, int64_t csA,
+                          int64_t bsA, const float *B, int64_t rsB, int64_t csB, int64_t bsB, float beta, float *C, int64_t rsC,
+                          int64_t csC, int64_t bsC, int grid, const float *bias, int bias_per_row, int act) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0 || M > 32) return 0;
+  SimtParams<float> p;
+  simt_plan<float, 8, 8>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
+  p.bias = bias; p.bias_per_row = bias_per_row; p.act = act;
+  p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+  if (grid <= 0) grid = 2;
+  if (M <= 8) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<8, 4>(p); });
+  else if (M <= 16) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<16, 4>(p); });
+  else if (M <= 24) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<24, 2>(p); });
+  else emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<32, 2>(p); });
+  return 1;
+}
 int emu_gemm_simt_i32(int64_t M, int64_t N, int64_t K, int32_t alpha, const int32_t *A, int64_t rsA, int64_t csA,
                       const int32_t *B, int64_t rsB, int64_t csB, int32_t beta, int32_t *C, int64_t rsC, int64_t csC,
                       int grid) {

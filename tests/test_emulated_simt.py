@@ -21,6 +21,9 @@ NP = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
 def emu():
     L = ctypes.CDLL(build_emu("simt_emu", ["gemm_simt.cuh", "gemm_simt_kernel.inc", "gemm_dmma.cuh", "ptx.cuh"]))
     f64 = ctypes.c_double
+    L.emu_gemm_skinny_m_f32.restype = ci
+    L.emu_gemm_skinny_m_f32.argtypes = [i64, i64, i64, i64, ctypes.c_float, vp, i64, i64, i64, vp, i64, i64, i64, ctypes.c_float, vp,
+                                        i64, i64, i64, ci, vp, ci, ci]
     L.emu_gemm_dmma_f64.restype = ci
     L.emu_gemm_dmma_f64.argtypes = [i64, i64, i64, i64, f64, vp, i64, i64, i64, vp, i64, i64, i64, f64, vp, i64, i64, i64, ci]
     for name, sc in SCALAR.items():
@@ -131,6 +134,37 @@ def test_f64_tensor_core_kernel_is_the_same_fma_chain(emu, M, N, K, alpha, beta,
         assert np.array_equal(got, ref)
     else:                                    # alpha != 1: the oracle's compiler may contract C += alpha*AB (1 ulp)
         assert np.abs(got - ref).max() <= 4e-16 * np.abs(ref).max() and np.array_equal(got[:, N:], ref[:, N:])
+
+
+@pytest.mark.parametrize("M,N,K,alpha,beta,b_col,batch", [(20, 2500, 27, 1.0, 0.0, False, 3), (7, 1030, 600, 1.0, 1.0, False, 1),
+                                                          (16, 1100, 513, 0.5, -1.25, True, 2), (32, 1029, 70, 1.0, 0.0, False, 1),
+                                                          (1, 2049, 5, 1.0, 1.0, True, 1)])
+def test_skinny_m_kernel_bit_exact(emu, M, N, K, alpha, beta, b_col, batch):
+    """few output rows x wide N (the im2col convolution's GEMM): bit-identical to the oracle across kc = 512 blocks, shared A
+    across the batch, row- and column-major B, ragged N (scalar tail next to the vector path), bias + relu after the last block"""
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bl = rng.standard_normal((batch, K, N)).astype(np.float32)
+    C0 = rng.standard_normal((batch, M, N)).astype(np.float32)
+    bias = rng.standard_normal(M).astype(np.float32)
+    B = np.ascontiguousarray(Bl.transpose(0, 2, 1)) if b_col else Bl
+    rsb, csb = (1, K) if b_col else (N, 1)
+    ref = C0.copy()
+    for i in range(batch):
+        O.gemm_strided(M, N, K, alpha, A, K, 1, B[i], rsb, csb, beta, ref[i], N, 1)
+    ref_epi = np.maximum(ref + bias[None, :, None], 0)
+    for epi in (False, True):
+        got = C0.copy()
+        if beta == 0.0:
+            got[:] = np.nan
+        rc = emu.emu_gemm_skinny_m_f32(batch, M, N, K, alpha, at(A, 0), K, 1, 0, at(B, 0), rsb, csb, K * N, beta, at(got, 0), N, 1,
+                                       M * N, 3, at(bias, 0) if epi else None, 1, 1 if epi else 0)
+        assert rc == 1
+        want = ref_epi if epi else ref
+        if alpha == 1.0:
+            assert np.array_equal(got, want)
+        else:
+            assert np.abs(got - want).max() <= 2e-7 * np.abs(want).max()
 
 
 def test_f64_tensor_core_kernel_batched(emu):

@@ -63,7 +63,7 @@ def test_split_rows(emu, R, Cc, src_ld):
     assert np.abs((hi[:, :Cc].astype(np.float64) + lo[:, :Cc]) - x).max() <= 2.0 ** -21 * np.abs(x).max()
 
 
-@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100), (11, 8192, 8196)])
+@pytest.mark.parametrize("R,Cc,src_ld", [(5, 16, 16), (33, 30, 32), (130, 257, 260), (70, 2100, 2100), (11, 8192, 8196), (300, 2300, 2304)])
 @pytest.mark.parametrize("per_col", [0, 1])
 def test_f16x2_scale_and_split(emu, R, Cc, src_ld, per_col):
     """LASER_B200_PATH_F16X3: one abs-max word per row (K-major operand) or per column (MN-major operand), a power-of-two
