@@ -2,8 +2,9 @@
  * row-sharded entry points (laser_b200/csrc/capi_multi.inc) runs in the CPU suite against the host-emulated library.
  * One process, "devices" are just indices; a broadcast registered inside ncclGroupStart / ncclGroupEnd is performed at
  * GroupEnd: the root's buffer is copied into every other rank's buffer (host memory is device memory in the emulation).
- * Outside a group (the one-rank-per-process usage, played sequentially by the test: the root's call first) the root's call
- * remembers its buffer and every later call of another rank of the same communicator copies from it. */
+ * Outside a group (the one-rank-per-process usage, played sequentially by the test: the root's calls first) every call of the
+ * root appends its buffer to the communicator's queue and the i-th call of another rank copies from the i-th entry (a
+ * row-sharded product may broadcast B in several pieces). */
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,8 +15,10 @@ typedef struct { fakeComm *comm; void *buf; size_t bytes; int root; } PendingOp;
 
 static int g_depth = 0, g_next_group = 1, g_npending = 0, g_calls = 0;
 static PendingOp g_pending[64];
-static const void *g_root_buf[256];   /* by group id: the root's buffer of the broadcast in progress (sequential mode) */
-static size_t g_root_bytes[256];
+#define QLEN 64
+static const void *g_root_buf[256][QLEN];   /* by group id: the root's buffers, in call order (sequential mode) */
+static size_t g_root_bytes[256][QLEN];
+static unsigned g_root_n[256], g_rank_pos[256][16];
 
 int fake_nccl_broadcast_calls(void) { return g_calls; }
 
@@ -42,9 +45,18 @@ int ncclBroadcast(const void *send, void *recv, size_t count, int dtype, int roo
   if (g_depth == 0) {   /* sequential mode */
     const int g = comm->group_id & 255;
     ++g_calls;
-    if (comm->rank == root) { g_root_buf[g] = recv; g_root_bytes[g] = count * 4; return 0; }
-    if (!g_root_buf[g] || g_root_bytes[g] != count * 4) return 5;
-    memcpy(recv, g_root_buf[g], count * 4);
+    if (comm->rank == root) {
+      g_root_buf[g][g_root_n[g] % QLEN] = recv; g_root_bytes[g][g_root_n[g] % QLEN] = count * 4; ++g_root_n[g];
+      return 0;
+    }
+    if (comm->rank < 0 || comm->rank >= 16) return 5;
+    /* a rank that skipped earlier sequences (it joined later) starts at the oldest entry still queued for this size */
+    unsigned *pos = &g_rank_pos[g][comm->rank];
+    if (g_root_n[g] - *pos > QLEN) *pos = g_root_n[g] - QLEN;
+    while (*pos < g_root_n[g] && g_root_bytes[g][*pos % QLEN] != count * 4) ++*pos;
+    if (*pos >= g_root_n[g]) return 5;
+    memcpy(recv, g_root_buf[g][*pos % QLEN], count * 4);
+    ++*pos;
     return 0;
   }
   g_pending[g_npending].comm = comm; g_pending[g_npending].buf = recv; g_pending[g_npending].bytes = count * 4;

@@ -12,7 +12,8 @@ import pytest
 import laser_b200 as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MNEMONICS = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "HMMA", "HGMMA", "ATOMG", "SYNCS", "STG.E.128", "USETMAXREG")
+MNEMONICS = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "DMMA", "HMMA", "HGMMA", "ATOMG", "SYNCS", "STG.E.128",
+             "USETMAXREG")
 
 
 def sass_counts():
@@ -45,15 +46,23 @@ def test_tensor_core_kernels_are_tcgen05_tmem_tma():
         assert c["UTCHMMA"] >= 4 and c["LDTM"] >= 8 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 2, (k, dict(c))
         assert c["USETMAXREG"] == 2, k          # warp-specialised register split
     for k, c in counts.items():
-        assert c["HMMA"] == 0 and c["HGMMA"] == 0, k       # no mma.sync / wgmma anywhere in the library
+        assert c["HMMA"] == 0 and c["HGMMA"] == 0, k       # no half-precision mma.sync / wgmma anywhere in the library
+
+
+def test_fp64_tensor_cores_and_bulk_copies():
+    counts = sass_counts()
+    dmma = [c for k, c in counts.items() if "gemm_dmma_kernel" in k]
+    assert len(dmma) == 1 and dmma[0]["DMMA"] >= 32 and dmma[0]["LDGSTS"] >= 16      # mma.sync.m8n8k4.f64, cp.async staging
+    ring = [c for k, c in counts.items() if "f16x2_rows_ring_kernel" in k]
+    assert len(ring) == 1 and ring[0]["UBLKCP"] >= 2 and ring[0]["SYNCS"] >= 2          # cp.async.bulk rows + mbarrier
 
 
 if __name__ == "__main__":
     counts = sass_counts()
     with open(os.path.join(ROOT, "profiles", "r02_sass_mnemonics.txt"), "w") as f:
         f.write("# cuobjdump -sass laser_b200/lib/liblaser_b200.so: occurrences of the Blackwell mnemonics per tensor-core kernel\n")
-        f.write("# (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor load, UTCBAR = tcgen05.commit)\n")
+        f.write("# (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor load, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk,\n# LDGSTS = cp.async, DMMA = mma.sync.f64)\n")
         for k in sorted(counts):
-            if "gemm_tc_kernel" in k:
+            if "gemm_tc_kernel" in k or "gemm_dmma_kernel" in k or "f16x2_rows_ring_kernel" in k:
                 f.write("%s\n    %s\n" % (k, "  ".join("%s=%d" % (m, counts[k][m]) for m in MNEMONICS if counts[k][m])))
     print("wrote profiles/r02_sass_mnemonics.txt")

@@ -12,17 +12,17 @@ for (M, N, K) in ((256, 512, 513), (256, 512, 4096), (129, 257, 8200), (512, 512
         exact = O.gemm_f32_in_f64(M, N, K, A, K, 1, B, N, 1)
         tA, tB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(); tC = torch.empty(M, N, device="cuda")
         res = {}
-        for pname, path in (("x3", L.PATH_TF32X3), ("mx", L.PATH_TF32_BF16C), ("x1", L.PATH_TF32X1), ("b3", L.PATH_BF16X3), ("f3", L.PATH_F16X3)):
+        for pname, path in (("x3", L.PATH_TF32X3), ("x1", L.PATH_TF32X1), ("f3", L.PATH_F16X3)):
             L.gemm_strided(M, N, K, 1.0, tA, K, 1, tB, N, 1, 0.0, tC, N, 1, path=path); torch.cuda.synchronize()
             got = tC.cpu().numpy()
             res[pname] = (O.max_relative_error(got, want), O.normwise_relative_error(got, want), O.mean_relative_error(got, want),
                           float(np.linalg.norm(got - exact) / np.linalg.norm(exact)), float(np.mean((got - exact) / np.abs(exact).mean())))
         ref_vs_exact = float(np.linalg.norm(want - exact) / np.linalg.norm(exact))
-        print("kc=%s %dx%dx%d %s | x3: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | mixed: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | x1: max %.2e norm %.2e | bf16x3: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | f16x3: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | cpu_ref_vs_exact %.2e"
-              % (kc, M, N, K, name, *res["x3"], *res["mx"], res["x1"][0], res["x1"][1], *res["b3"], *res["f3"], ref_vs_exact))
+        print("kc=%s %dx%dx%d %s | x3: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | x1: max %.2e norm %.2e | f16x3: max %.2e norm %.2e mre %.2e vs_exact %.2e bias %+.2e | cpu_ref_vs_exact %.2e"
+              % (kc, M, N, K, name, *res["x3"], res["x1"][0], res["x1"][1], *res["f3"], ref_vs_exact))
 n = 8192
 a = torch.rand(n, n, device="cuda"); b = torch.rand(n, n, device="cuda"); c = torch.empty(n, n, device="cuda")
-for pname, path in (("x3", L.PATH_TF32X3), ("mixed", L.PATH_TF32_BF16C), ("x1", L.PATH_TF32X1), ("bf16x3", L.PATH_BF16X3), ("f16x3", L.PATH_F16X3)):
+for pname, path in (("x3", L.PATH_TF32X3), ("x1", L.PATH_TF32X1), ("f16x3", L.PATH_F16X3)):
     for _ in range(2): L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1, path=path)
     torch.cuda.synchronize(); ts = []
     for _ in range(5):

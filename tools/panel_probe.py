@@ -11,7 +11,7 @@ def t(fn, it=6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return statistics.median(ts)
-for path, nm in ((L.PATH_TF32_BF16C, "mixed"), (L.PATH_TF32X1, "x1"), (L.PATH_TF32X3, "x3")):
+for path, nm in ((L.PATH_F16X3, "f16x3"), (L.PATH_TF32X1, "x1"), (L.PATH_TF32X3, "x3")):
     print(nm, "full K=8192 beta=0        %.3f ms" % t(lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 0.0, c, n, 1, path=path)))
     print(nm, "full K=8192 beta=1        %.3f ms" % t(lambda: L.gemm_strided(n, n, n, 1.0, a, n, 1, b, n, 1, 1.0, c, n, 1, path=path)))
     print(nm, "view K=4096 beta=0        %.3f ms" % t(lambda: L.gemm_strided(n, n, 4096, 1.0, a[:, :4096], n, 1, b[:4096], n, 1, 0.0, c, n, 1, path=path)))

@@ -2,7 +2,7 @@
 
 bench.py runs this in a CHILD process per mode (with a timeout) after all of its own measurements: the modes were written
 after the round's GPU minutes were spent, so their first run on silicon must not be able to take the bench line down.
-Also usable by hand:  python tools/two_piece_probe.py bf16x3|f16x3 [n] [steps]
+Also usable by hand:  python tools/two_piece_probe.py f16x3|tf32x3|tf32x1 [n] [steps]
 """
 import json
 import os
