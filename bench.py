@@ -426,6 +426,13 @@ def run_ours(args):
         modes["f32_4096_config2"] = {"tflops": 2.0 * n4**3 / ms4 / 1e9, "ms": ms4, "layout": "A, B row-major"}
         modes["f32_4096_At_config3"] = {"tflops": 2.0 * n4**3 / ms4t / 1e9, "ms": ms4t,
                                         "layout": "A given transposed (rowStrideA = 1, colStrideA = M): MN-major TMA tiles, no physical transpose"}
+        # fp64 of the same entry point (gemm.nim:234-246): FP64 tensor cores (mma.sync DMMA), bit-identical to the reference's FMA chain
+        n64 = 4096
+        a64 = torch.rand(n64, n64, dtype=torch.float64, device=dev) - 0.5; b64 = torch.rand(n64, n64, dtype=torch.float64, device=dev) - 0.5
+        c64 = torch.empty(n64, n64, dtype=torch.float64, device=dev)
+        ms64 = timed(lambda: L.gemm_strided(n64, n64, n64, 1.0, a64, n64, 1, b64, n64, 1, 0.0, c64, n64, 1), 3, 1)
+        modes["f64_4096_dmma"] = {"tflops": 2.0 * n64**3 / ms64 / 1e9, "ms": ms64, "note": "float64 gemm_strided on the FP64 tensor cores, bit-exact vs the oracle"}
+        del a64, b64, c64
         del A, C
 
     # ---- e2e: the drop-in call with HOST buffers, copies inside the timed region ----------------

@@ -100,6 +100,7 @@ struct Ctx {
   int map_cache_next = 0;
   int raster_g = 0;       // env LASER_B200_RASTER (0 = default)
   bool splitk_enabled = true;  // env LASER_B200_SPLITK=0 disables split-K
+  bool c_tma = true;           // env LASER_B200_C_TMA=0: the tensor-core epilogue stores C with plain 16-byte stores
   bool f64_dmma = true;        // env LASER_B200_F64_DMMA=0: fp64 problems stay on the CUDA-core kernel
   bool prep_ring = true;       // env LASER_B200_PREP_RING=0: register-only preparation kernel for K-major operands
   bool ring_attr_set = false, dmma_attr_set = false;
@@ -191,6 +192,7 @@ int get_ctx(Ctx **out) {
       if (const char *sk = getenv("LASER_B200_SPLITK")) c.splitk_enabled = atoi(sk) != 0;
       if (const char *pr = getenv("LASER_B200_PREP_RING")) c.prep_ring = atoi(pr) != 0;
       if (const char *dm = getenv("LASER_B200_F64_DMMA")) c.f64_dmma = atoi(dm) != 0;
+      if (const char *ct = getenv("LASER_B200_C_TMA")) c.c_tma = atoi(ct) != 0;
       if (const char *pt = getenv("LASER_B200_PANEL_TAPER")) c.panel_taper = atoi(pt) != 0;
       if (const char *ds = getenv("LASER_B200_DYNSCHED")) c.dyn_sched = atoi(ds) != 0;
       if (const char *pd = getenv("LASER_B200_PDL")) c.pdl = atoi(pd) != 0;
@@ -558,6 +560,16 @@ int tc_run(Ctx &c, TcKind kind, int64_t M, int64_t N, int64_t K, float alpha, co
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta;
   p.C = C; p.rsC = rsC; p.csC = csC; p.zero = 0; p.epi = epi;
   if (f16) { p.amax_a = f16->a; p.amax_b = f16->b; }
+  std::memset(&l.c, 0, sizeof l.c);
+  if constexpr (std::is_same<OutT, float>::value) {
+    // C leaves through TMA (smem-staged cp.async.bulk.tensor stores of 32 x 32 boxes) when the copy engine can address it:
+    // unit column stride, 16-byte aligned base and row pitch (LASER_B200_C_TMA=0: plain 16-byte stores)
+    if (c.c_tma && csC == 1 && rsC >= N && (rsC * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && N >= 32 && M >= 1) {
+      const int rc_map = encode_map(c, &l.c, 4, C, N, M, rsC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc_map) return rc_map;
+      p.c_tma = 1;
+    }
+  }
   const int npass = (kind == TC_TF32X3 || kind == TC_F16X3) ? 3 : 1;
   const TcPlanCfg cfg{c.kc_faithful, c.raster_g, c.splitk_enabled, c.sm_count};
   if (kind == TC_BF16 || kind == TC_F16X3) tc_plan<2, std::is_same<OutT, float>::value>(p, npass, pair, cfg);

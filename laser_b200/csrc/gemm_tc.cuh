@@ -72,7 +72,8 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 template <int ESZ, uint32_t FMT16, int NPASS, bool A_MN, bool B_MN, typename OutT, bool PAIR, bool SCALED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapC, const TcParams p) {
   static_assert(NPASS == 1 || NPASS == 3, "one pass, or the three passes of a two-piece product");
   using Cfg = TcCfg<NPASS, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
@@ -86,7 +87,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   LB200_DYN_SMEM(uint8_t, smem_raw);
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t *store_staging = smem + STAGES * Cfg::STAGE_BYTES;   // 4 KB per epilogue warp (1024-byte aligned: TMA swizzle atoms)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(store_staging + Cfg::STORE_STAGING_BYTES);
   uint64_t *full_bar = bars;                        // [STAGES]
   uint64_t *empty_bar = bars + STAGES;              // [STAGES]
   uint64_t *tmem_full = bars + 2 * STAGES;          // [TC_ACC_STAGES]
@@ -137,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       ptx::prefetch_tensormap(&mapA1);
       ptx::prefetch_tensormap(&mapB1);
     }
+    if (p.c_tma) ptx::prefetch_tensormap(&mapC);
   }
   if (threadIdx.x == 32) {
     for (int i = 0; i < STAGES; ++i) {
@@ -435,10 +438,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (vec_ok && ncols >= TC_EPI_COLS) {
           if constexpr (sizeof(OutT) == 4) {
             float4 *dst = reinterpret_cast<float4 *>(crow_base);
+            // Direct tiles of a TMA-addressable C leave through shared memory: the warp's 32 rows x 32 columns go, 128B-
+            // swizzled, into its 4 KB staging buffer and one cp.async.bulk.tensor store writes them as 32 full 128-byte
+            // lines (a plain 16-byte store per thread touches 32 different lines per warp instruction); the copy engine
+            // clips rows past M.  The buffer is reused once the previous store has READ it (wait_group.read).
+            const bool via_tma = p.c_tma != 0 && !split_unit;
+            uint8_t *stage_buf = store_staging + (warp_idx - 4) * 4096;
+            const int row_in_warp_tile = static_cast<int>(mb) * TILE_M + static_cast<int>(cta_rank) * TC_BLOCK_M + q * 32;
             // batches of 4 x 16 B: with beta != 0 the four loads of a batch are in flight
             // together (the old C lines were prefetched into L2 when the tile started)
 #pragma unroll
             for (int b8 = 0; b8 < TC_EPI_COLS / 16; ++b8) {
+              if (via_tma && (b8 & 1) == 0) {   // a new 32-column chunk: the staging buffer must have been read
+                if (lane == 0) ptx::tma_store_wait_read<0>();
+                __syncwarp();
+              }
               float4 o[4];
               if (beta_u != 0.0f && row_ok) {
 #pragma unroll
@@ -476,7 +490,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   v.z = epi_act(v.z + bv.z, p.epi.act);
                   v.w = epi_act(v.w + bv.w, p.epi.act);
                 }
-                if (row_ok) dst[v4] = v;
+                if (via_tma) {
+                  const int j = v4 & 7;   // 16-byte chunk of this thread's 128-byte staging row
+                  *reinterpret_cast<float4 *>(stage_buf + lane * 128 + ptx::sw128_chunk(lane, j) * 16) = v;
+                } else if (row_ok) {
+                  dst[v4] = v;
+                }
+              }
+              if (via_tma && (b8 & 1) == 1) {   // 32 columns staged: hand them to the copy engine
+                ptx::fence_proxy_async_smem();  // the generic-proxy writes above become visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                  ptx::tma_store_2d(&mapC, stage_buf, static_cast<int>(col0) + (b8 >> 1) * 32, row_in_warp_tile);
+                  ptx::tma_store_commit();
+                }
               }
             }
           } else {
@@ -537,6 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   }
 
+  if (warp_idx >= 4 && lane == 0) ptx::tma_store_wait<0>();   // the tile stores of this warp have left shared memory and landed
   __syncwarp();
   ptx::tc_fence_before_sync();
   if constexpr (PAIR) ptx::cluster_sync();  // neither CTA may leave while its peer still uses its smem/TMEM

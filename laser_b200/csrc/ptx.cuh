@@ -100,6 +100,8 @@ __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, u
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// position of 16-byte chunk j of row `row` inside a 128B-swizzled tile of 128-byte rows (what TMA expects to find / leaves)
+__device__ __forceinline__ int sw128_chunk(int row, int j) { return j ^ (row & 7); }
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src,
                                              int32_t c0, int32_t c1) {

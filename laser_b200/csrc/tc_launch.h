@@ -11,6 +11,7 @@ namespace lb200 {
 
 struct TcLaunch {
   CUtensorMap a0, a1, b0, b1;   // piece 0 (hi / the operand itself) and piece 1 (lo) of A and B
+  CUtensorMap c;                // C as a tensor of 32 x 32 boxes (used when p.c_tma; zero-initialised otherwise)
   TcParams p;
   bool a_mn = false, b_mn = false;   // operand major-ness
   bool pair = false;                 // clusters of two CTAs (cta_group::2)

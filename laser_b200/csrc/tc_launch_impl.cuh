@@ -44,7 +44,7 @@ int launch_tc_one(const TcLaunch &l) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set.fetch_or(1u << l.dev, std::memory_order_release);
   }
-  return static_cast<int>(LB200_LAUNCH_EX(&cfg, kfn, l.a0, l.a1, l.b0, l.b1, l.p));
+  return static_cast<int>(LB200_LAUNCH_EX(&cfg, kfn, l.a0, l.a1, l.b0, l.b1, l.c, l.p));
 }
 
 template <int ESZ, uint32_t FMT16, int NPASS, typename OutT, bool SCALED>

@@ -28,7 +28,10 @@ template <int NPASS, bool PAIR> struct TcCfg {
 #else
   static constexpr int STAGES = (NPASS == 3) ? (PAIR ? 3 : 2) : (PAIR ? 6 : 4);   // 192 KB of tiles in every variant
 #endif
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, scheduler slot*/;
+  // after the operand stages: one 4 KB staging buffer per epilogue warp (32 rows x 128 B, 128B-swizzled) from which the
+  // tile leaves through cp.async.bulk.tensor stores, then the barriers
+  static constexpr int STORE_STAGING_BYTES = 8 * 32 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGING_BYTES + 1024 /*align*/ + 512 /*barriers, scheduler slot*/;
 };
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512: all of TMEM
@@ -67,6 +70,9 @@ struct TcParams {
   int kb_per_split;      // k-tiles per split
   float *split_ws = nullptr;   // [k_splits][split tiles][tile rows][TC_BLOCK_N] fp32
   int num_m_blocks, num_n_blocks;  // output tiles: 128 x 256, or 256 x 256 per CTA pair
+  // fp32 C with unit column stride and 16-byte aligned rows leaves through TMA (mapC of the launch: box 32 columns x 32 rows,
+  // 128B swizzle; rows / columns past M / N are clipped by the copy engine); otherwise, and for split units, plain stores
+  int c_tma = 0;
   // SCALED: fp32 bits of the largest finite |a| of row i of A / |b| of column j of B (f16_scale.cuh)
   const uint32_t *amax_a = nullptr, *amax_b = nullptr;
   // tile scheduler: word 0 = next unit (atomicAdd), word 1 = pairs that have drawn their last unit (the last one zeroes

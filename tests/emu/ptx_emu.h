@@ -162,6 +162,30 @@ inline void cp_async_8(void *smem_dst, const void *gsrc, bool valid) {   // comp
 }
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
+inline int sw128_chunk(int, int j) { return j; }      // the model keeps tiles unswizzled on both sides
+// cp.async.bulk.tensor store: the box leaves at once (commit / wait have nothing to track); elements outside the tensor are
+// not written
+inline void tma_store_2d(const CUtensorMap *map, const void *smem_src, int32_t c0, int32_t c1) {
+  emu::TensorMap2D m;
+  std::memcpy(&m, map, sizeof m);
+  if (m.magic != emu::kMapMagic) { std::fprintf(stderr, "emu: not an emulated tensor map\n"); std::abort(); }
+  const unsigned char *src = static_cast<const unsigned char *>(smem_src);
+  const unsigned char *lo = emu::dyn_smem[emu::cta_rank];
+  const size_t box_bytes = static_cast<size_t>(m.box0) * m.box1 * m.esz;
+  if (src < lo || src + box_bytes > lo + emu::kDynSmemBytes || ((src - lo) & 1023)) {
+    std::fprintf(stderr, "emu: TMA store source outside this CTA's shared memory or not 1024-byte aligned\n");
+    std::abort();
+  }
+  for (int r = 0; r < m.box1; ++r)
+    for (int e = 0; e < m.box0; ++e) {
+      const int64_t i0 = static_cast<int64_t>(c0) + e, i1 = static_cast<int64_t>(c1) + r;
+      if (i0 >= 0 && i0 < m.dim0 && i1 >= 0 && i1 < m.dim1)
+        std::memcpy(const_cast<unsigned char *>(m.base) + i1 * m.stride1_bytes + i0 * m.esz, src + (static_cast<size_t>(r) * m.box0 + e) * m.esz, m.esz);
+    }
+}
+inline void tma_store_commit() {}
+template <int N> inline void tma_store_wait_read() {}
+template <int N> inline void tma_store_wait() {}
 inline void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
   if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) std::abort();   // the hardware faults
   std::memcpy(smem_dst, gsrc, bytes);

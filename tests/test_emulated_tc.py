@@ -26,7 +26,7 @@ def emu():
     L = ctypes.CDLL(build_emu("tc_emu", ["gemm_tc.cuh", "tc_params.h", "f16_scale.cuh", "ptx.cuh", "split.cuh"]))
     L.emu_gemm_tc.restype = ci
     L.emu_gemm_tc.argtypes = [ci, ci, ci, ci, i64, i64, i64, f32, f32, vp, vp, i64, vp, vp, i64, vp, i64, i64, ci, ci, ci, ci,
-                              vp, ci, ci, vp, i64, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp, ci, ci]
+                              vp, ci, ci, vp, i64, ctypes.POINTER(ci), ctypes.POINTER(ci), vp, vp, ci, ci, ci]
     return L
 
 
@@ -53,7 +53,7 @@ def ptr(a):
 
 
 def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=False, pair=False, kc=128, raster=0,
-           splitk=1, sms=4, epi=None, c_base=None, dyn=1, tail_min_k=0):
+           splitk=1, sms=4, epi=None, c_base=None, dyn=1, tail_min_k=0, c_tma=1):
     """a: logical (M, K) fp32; b: logical (K, N) fp32; c: flat output buffer (float32, or uint16 for bf16).
     Returns (expected sum A*B in float64 under the mode's operand model, k_splits, grid); run_tc.n_direct holds the number
     of tiles the last launch computed without splitting (tc_params.h)."""
@@ -98,7 +98,7 @@ def run_tc(emu, mode, a, b, c, rsC, csC, alpha=1.0, beta=0.0, a_mn=False, b_mn=F
     rc = emu.emu_gemm_tc(KIND[mode], int(a_mn), int(b_mn), int(pair), M, N, K, alpha, beta,
                          ptr(arrs["A"][0]), ptr(arrs["A"][1]), ld["A"], ptr(arrs["B"][0]), ptr(arrs["B"][1]), ld["B"],
                          ctypes.c_void_p(c.ctypes.data + (c_base or 0) * c.itemsize), rsC, csC, kc, raster, splitk, sms,
-                         ptr(bias), per_row, act, ptr(ws), ws.size, ks, ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]), dyn, tail_min_k)
+                         ptr(bias), per_row, act, ptr(ws), ws.size, ks, ctypes.byref(grid), ptr(amax["A"]), ptr(amax["B"]), dyn, tail_min_k, c_tma)
     assert rc == 0          # (the harness runs the reduce kernel of a split launch itself, like capi.cu: tc_run)
     run_tc.n_direct = ks[1]
     return exact, ks[0], grid.value
@@ -217,6 +217,28 @@ def test_split_k_of_the_last_partial_wave(emu, pair, mode, dyn, ccol):
     assert ks2 == 1 and run_tc.n_direct == 6
     got2 = buf2.reshape(N, M).T if ccol else buf2.reshape(M, N)
     assert np.abs(got2 - want).max() <= tol * np.abs(want).max()
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("mode", ["f16x3", "tf32x1"])
+def test_c_through_tma_stores_equals_plain_stores(emu, pair, mode):
+    """fp32 C with unit column stride and 16-byte aligned rows leaves through shared-memory staging + cp.async.bulk.tensor
+    stores (32 x 32 boxes, rows past M and columns past N clipped by the copy engine); bit-identical to the plain-store
+    epilogue, C beyond the view untouched, beta / bias / activation included; a padded C (ldc > N) too"""
+    M, N, K = 300, 520, 96                       # ragged rows; the last column block (8 columns) takes the scalar path
+    a, b = rnd((M, K), 31), rnd((K, N), 32)
+    ldc = N + 8
+    c0 = rnd((M, ldc), 33)
+    bias = rnd((N,), 34)
+    outs = []
+    for c_tma in (1, 0):
+        buf = c0.reshape(-1).copy()
+        exact, _, _ = run_tc(emu, mode, a, b, buf, ldc, 1, alpha=0.5, beta=2.0, pair=pair, sms=4, epi=(bias, 0, 1), c_tma=c_tma)
+        outs.append(buf.reshape(M, ldc))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0][:, N:], c0[:, N:])                 # the padding of C is not written
+    want = np.maximum(0.5 * exact + 2.0 * c0[:, :N] + bias[None, :], 0.0)
+    assert np.abs(outs[0][:, :N] - want).max() <= (2e-3 if mode == "tf32x1" else 3e-6) * np.abs(want).max()
 
 
 @pytest.mark.parametrize("raster", [1, 2, 16])

@@ -16,8 +16,12 @@ MNEMONICS = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGST
              "USETMAXREG")
 
 
+import functools
+
+
+@functools.lru_cache(maxsize=1)
 def sass_counts():
-    """{kernel symbol: Counter(mnemonic -> count)} of the tensor-core kernels in liblaser_b200.so"""
+    """{kernel symbol: Counter(mnemonic -> count)} of the tensor-core kernels in liblaser_b200.so (one disassembly per run)"""
     exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(exe):
         pytest.skip("cuobjdump not installed")

@@ -21,4 +21,22 @@ tC = torch.zeros(256, 256, device="cuda"); a2 = torch.rand(256, 4096, device="cu
 L.gemm_strided(256, 256, 4096, 1.0, a2, 4096, 1, b2, 256, 1, 0.0, tC, 256, 1)                # split-K + reduce
 y = torch.zeros(2000, 3, device="cuda"); v = torch.rand(K, 3, device="cuda"); big = torch.rand(2000, K, device="cuda")
 L.gemm_strided(2000, 3, K, 1.0, big, K, 1, v, 3, 1, 0.0, y, 3, 1)                            # GEMV
+# ---- kernels of round 2
+a3 = torch.rand(600, 2048, device="cuda"); b3 = torch.rand(2048, 512, device="cuda"); c3 = torch.zeros(600, 512, device="cuda")
+L.gemm_strided(600, 512, 2048, 1.0, a3, 2048, 1, b3, 512, 1, 0.0, c3, 512, 1)                # ring-buffered preparation (rows of 2048 floats)
+err = ((c3 - a3 @ b3).abs().max() / (a3 @ b3).abs().max()).item(); print("ring prep", err); assert err < 1e-4
+a4 = torch.rand(2560, 2048, device="cuda"); b4 = torch.rand(2048, 2304, device="cuda"); c4 = torch.zeros(2560, 2304, device="cuda")
+n0 = L.launch_count()
+L.gemm_strided(2560, 2304, 2048, 1.0, a4, 2048, 1, b4, 2304, 1, 0.0, c4, 2304, 1)            # 90 pair-tiles on 74 pairs: split-K of the last wave
+print("tail split launches", L.launch_count() - n0)
+err = ((c4 - a4 @ b4).abs().max() / (a4 @ b4).abs().max()).item(); print("tail split", err); assert err < 1e-4
+a5 = torch.rand(1152, 96, device="cuda", dtype=torch.float64); b5 = torch.rand(96, 1280, device="cuda", dtype=torch.float64)
+c5 = torch.zeros(1152, 1280, device="cuda", dtype=torch.float64)
+d0 = L.lib().laser_b200_debug_f64_dmma_launches()
+L.gemm_strided(1152, 1280, 96, 1.0, a5, 96, 1, b5, 1280, 1, 0.0, c5, 1280, 1)                 # fp64 tensor cores (cp.async staging)
+assert L.lib().laser_b200_debug_f64_dmma_launches() == d0 + 1
+err = ((c5 - a5 @ b5).abs().max() / (a5 @ b5).abs().max()).item(); print("dmma", err); assert err < 1e-14
+a6 = torch.rand(20, 27, device="cuda"); b6 = torch.rand(27, 5001, device="cuda"); c6 = torch.zeros(20, 5001, device="cuda")
+L.gemm_strided(20, 5001, 27, 1.0, a6, 27, 1, b6, 5001, 1, 0.0, c6, 5001, 1, path=L.PATH_SIMT)  # few-rows kernel, ragged N
+err = ((c6 - a6 @ b6).abs().max() / (a6 @ b6).abs().max()).item(); print("few rows", err); assert err < 1e-5
 torch.cuda.synchronize(); print("done")
