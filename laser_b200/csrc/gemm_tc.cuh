@@ -449,10 +449,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // together (the old C lines were prefetched into L2 when the tile started)
 #pragma unroll
             for (int b8 = 0; b8 < TC_EPI_COLS / 16; ++b8) {
-              if (via_tma && (b8 & 1) == 0) {   // a new 32-column chunk: the staging buffer must have been read
-                if (lane == 0) ptx::tma_store_wait_read<0>();
-                __syncwarp();
-              }
               float4 o[4];
               if (beta_u != 0.0f && row_ok) {
 #pragma unroll
@@ -490,14 +486,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                   v.z = epi_act(v.z + bv.z, p.epi.act);
                   v.w = epi_act(v.w + bv.w, p.epi.act);
                 }
-                if (via_tma) {
-                  const int j = v4 & 7;   // 16-byte chunk of this thread's 128-byte staging row
-                  *reinterpret_cast<float4 *>(stage_buf + lane * 128 + ptx::sw128_chunk(lane, j) * 16) = v;
+                if (via_tma) {   // the finished values replace the sums they came from until the chunk is complete
+                  run[4 * v4 + 0] = v.x; run[4 * v4 + 1] = v.y; run[4 * v4 + 2] = v.z; run[4 * v4 + 3] = v.w;
                 } else if (row_ok) {
                   dst[v4] = v;
                 }
               }
-              if (via_tma && (b8 & 1) == 1) {   // 32 columns staged: hand them to the copy engine
+              if (via_tma && (b8 & 1) == 1) {   // 32 columns finished: stage them and hand them to the copy engine
+                // (the arithmetic above ran while the previous store was still reading the staging buffer)
+                if (lane == 0) ptx::tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {   // 16-byte chunk j of this thread's 128-byte staging row
+                  const int v4 = (b8 - 1) * 4 + j;
+                  *reinterpret_cast<float4 *>(stage_buf + lane * 128 + ptx::sw128_chunk(lane, j) * 16) =
+                      make_float4(run[4 * v4 + 0], run[4 * v4 + 1], run[4 * v4 + 2], run[4 * v4 + 3]);
+                }
                 ptx::fence_proxy_async_smem();  // the generic-proxy writes above become visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {

@@ -150,9 +150,31 @@ def source_hot(pre, tag):
     print("wrote", dst)
 
 
+def copies(pre, tag):
+    """plain copies of the small text artefacts of the session"""
+    import shutil
+    for src, dst in (("bench_n1.json", "bench_n1.json"), ("bench_ref.json", "bench_reference.json"), ("layouts.log", "layouts.log"),
+                     ("probes.jsonl", "probes.jsonl"), ("pytest.log", "pytest.log"), ("smi.txt", "smi.txt"), ("f64.jsonl", "f64_dmma.jsonl"),
+                     ("layers_bench.txt", "layers_bench.txt")):
+        a = os.path.join(G, "%s_%s" % (pre, src))
+        if os.path.exists(a):
+            shutil.copy(a, os.path.join(P, "%s_%s" % (tag, dst)))
+    with open(os.path.join(P, tag + "_compute_sanitizer.txt"), "w") as f:
+        f.write("# compute-sanitizer on tools/sanitizer_target.py (every kernel family once, incl. the kernels of round 2)\n")
+        for tool in ("memcheck", "racecheck"):
+            a = os.path.join(G, "%s_sanitizer_%s.log" % (pre, tool))
+            if os.path.exists(a):
+                f.write("## --tool %s\n" % tool)
+                for ln in open(a, errors="replace"):
+                    if re.search(r"SUMMARY|Error|error|hazard|done|ring prep|tail split|dmma|few rows|simt|f16x3|tf32", ln):
+                        f.write(ln)
+
+
 if __name__ == "__main__":
     pre, tag = sys.argv[1], sys.argv[2]
     launches(pre, tag); single_pass(pre, tag)
     full(pre, tag, "full", "gemm_tc_kernel (F16X3 default fp32 mode, CTA pair) at 8192^3, second launch of tools/r2_ncu_f16_target.py")
     full(pre, tag, "prep", "operand preparation kernels of the F16X3 mode at 8192^3")
+    full(pre, tag, "aux", "fp64 DMMA kernel, 4096^3 with split-K of the last wave (+ tail reduce), im2col + few-rows kernel (conv2d 16x3x224x224 -> 20), transpose 8192^2: tools/ncu_r2_aux_target.py")
     source_hot(pre, tag)
+    copies(pre, tag)
