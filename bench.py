@@ -374,6 +374,10 @@ def run_ours(args):
                     "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 2 = fp32 (TF32-rate) tensor peak, of %s" % peaks["source"],
                     "tensor_pipe_frac": 1.5 * achieved / tf32_peak,
+                    "frac_of_sustained_peak": achieved / (peaks["bf16_sustained"] / 2.0),
+                    "sustained_note": "kernel_ms is the CUDA-event time of the kernel inside a long back-to-back sequence (the part is at its power "
+                                      "cap by then); B200_PROFILING.md pairs such a time with the SUSTAINED cuBLAS figure (bf16_tflops_sustained / 2): "
+                                      "frac_of_sustained_peak.  `frac` keeps the stricter burst denominator used in round 1",
                     "note": "achieved counts ALGORITHMIC flops 2MNK; the default mode issues three fp16 MMAs (K = 16 each, the bf16 "
                             "rate) per useful MAC = 1.5 TF32-equivalents, so frac <= 2/3 by construction and tensor_pipe_frac = "
                             "1.5 * frac is the tensor-pipe utilisation; traffic = ncu dram bytes read + written per launch "

@@ -2,6 +2,7 @@
 
 One object per translation unit, compiled in parallel (the tcgen05 kernel families are the slow ones), then one link."""
 import concurrent.futures
+import fcntl
 import os
 import shutil
 import subprocess
@@ -49,29 +50,47 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into the in-tree shared library. Returns its path."""
+    """Compile every CUDA source into the in-tree shared library. Returns its path.
+
+    Safe when several processes ask at once (one rank per GPU importing the package on a box whose snapshot made the
+    library look stale): one of them builds under a file lock -- objects and the library are written under temporary names
+    and renamed when complete -- the others wait for the lock and find the result up to date."""
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():     # another process built it while this one waited
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     nvcc = _nvcc()
     hdr_t = _newest_header()
+    tag = ".tmp%d" % os.getpid()
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
         path = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(path)):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj + tag]
         subprocess.check_call(cmd, env=env)
+        os.replace(obj + tag, obj)
         return obj
 
     srcs = _sources()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, srcs))
-    subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs, env=env)
+    subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", LIB_PATH + tag] + objs, env=env)
+    os.replace(LIB_PATH + tag, LIB_PATH)
     return LIB_PATH
 
 

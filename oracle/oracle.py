@@ -29,7 +29,14 @@ ISA_NAMES = {1: "generic 2x1", 2: "avx+fma 6x16", 3: "avx512 14x32"}
 def build(force=False):
     """Compile the oracle with its Makefile (gcc only; no GPU, no reference sources)."""
     if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-s", "-C", _HERE])
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:      # one process builds, the others of a multi-rank job wait
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or not os.path.exists(_LIB_PATH):
+                    subprocess.check_call(["make", "-s", "-C", _HERE])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB_PATH
 
 
