@@ -309,6 +309,26 @@ int gemm_simt(Ctx &c, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int6
       simt_plan<float, 8, 8>(p, M, N, K, alpha, A, rsA, csA, B, rsB, csB, beta, C, rsC, csC);
       p.bias = epi.bias; p.bias_per_row = epi.bias_per_row; p.act = epi.act;
       p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
+      // B with unit column stride and 16-byte aligned rows streams through shared memory (cp.async FIFO per thread)
+      const bool async_ok = csB == 1 && rsB % 4 == 0 && (batch == 1 || bsB % 4 == 0) && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+      if (async_ok) {
+        const int grid = grid_for(c, ((N + 1023) / 1024) * batch, 1);
+#define LB200_SKA(MT)                                                                                                  \
+  do {                                                                                                                 \
+    static std::atomic<uint32_t> attr_set{0};                                                                          \
+    if (!(attr_set.load(std::memory_order_acquire) & (1u << c.dev))) {                                                 \
+      CUDA_TRY(cudaFuncSetAttribute(gemm_skinny_m_async_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    static_cast<int>(ska_smem_bytes<MT>())));                                          \
+      attr_set.fetch_or(1u << c.dev, std::memory_order_release);                                                       \
+    }                                                                                                                  \
+    gemm_skinny_m_async_kernel<MT><<<grid, 256, ska_smem_bytes<MT>(), s>>>(p);                                         \
+  } while (0)
+        if (M <= 8) LB200_SKA(8); else if (M <= 16) LB200_SKA(16); else if (M <= 24) LB200_SKA(24); else LB200_SKA(32);
+#undef LB200_SKA
+        COUNT_LAUNCH();
+        CHECK_LAUNCH();
+        return LASER_B200_OK;
+      }
       const int nc = M <= 16 ? 4 : 2;   // columns per thread (gemm_simt.cuh)
       const int grid = grid_for(c, ((N + 256 * nc - 1) / (256 * nc)) * batch, 2);
       if (M <= 8) gemm_skinny_m_kernel<8, 4><<<grid, 256, 0, s>>>(p);

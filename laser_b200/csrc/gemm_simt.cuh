@@ -23,6 +23,8 @@
 
 #include <type_traits>
 
+#include "ptx.cuh"
+
 namespace lb200 {
 
 template <typename T> struct SimtOps;
@@ -242,6 +244,20 @@ gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict
 // block (same statements as gemm_simt_kernel), so results are bit-identical to the general kernel's.  Batched like it.
 // MT: rows held in registers (M <= MT, a multiple of 4).
 // ---------------------------------------------------------------------------
+// bias + activation of the fused epilogue, out of line: inlined into the unrolled MT x NC store loops the tanhf / expf bodies
+// made the kernels several times larger than the instruction cache (ncu: 58 % of the stall samples "no instruction")
+#ifndef LB200_HOST_EMULATION
+__device__ __noinline__
+#else
+inline
+#endif
+float skinny_epilogue(float x, const float *bias, int bias_per_row, int act, int row, int64_t col) {
+  if (bias) x += bias_per_row ? bias[row] : bias[col];
+  if (act == 1) x = fmaxf(x, 0.0f);
+  else if (act == 2) x = tanhf(x);
+  else if (act == 3) x = 1.0f / (1.0f + expf(-x));
+  return x;
+}
 constexpr int SKINNY_KCHUNK = 64;   // k-columns of A staged in shared memory at a time
 // NC: columns per thread (4 for MT <= 16, 2 above: MT * NC running sums per thread must leave room for two CTAs per SM)
 template <int MT, int NC>
@@ -310,6 +326,7 @@ gemm_skinny_m_kernel(const SimtParams<float> p) {
       }
       // reference epilogue for this kc block (gemm_ukernel_generic.nim:53-76)
       const float beta1 = (pc == 0) ? p.beta : 1.0f;
+      const bool has_epi = kend == p.K && (p.bias != nullptr || p.act != 0);
       if (n0 < p.N) {
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
@@ -325,12 +342,7 @@ gemm_skinny_m_kernel(const SimtParams<float> p) {
             else x = crow[j * p.csC];
             if (p.alpha == 1.0f) x = __fadd_rn(x, acc[i][j]);
             else x = __fadd_rn(x, __fmul_rn(p.alpha, acc[i][j]));
-            if (kend == p.K && (p.bias != nullptr || p.act != 0)) {
-              if (p.bias) x += p.bias_per_row ? p.bias[i] : p.bias[n0 + j];
-              if (p.act == 1) x = fmaxf(x, 0.0f);
-              else if (p.act == 2) x = tanhf(x);
-              else if (p.act == 3) x = 1.0f / (1.0f + expf(-x));
-            }
+            if (has_epi) x = skinny_epilogue(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
             v[j] = x;
           }
           if (p.csC == 1 && n0 + NC <= p.N && (reinterpret_cast<uintptr_t>(crow) & (4 * NC - 1)) == 0) {
@@ -346,5 +358,141 @@ gemm_skinny_m_kernel(const SimtParams<float> p) {
     }
   }
 }
+
+// The same product with B streamed through shared memory by cp.async: thread t copies exactly the 16 bytes (its 4 columns) of
+// each k-row it will consume into a private FIFO of SKA_STAGES x SKA_K rows -- no registers hold data in flight and no barrier
+// guards it, so ~100 KB per SM are on their way from HBM at any time (the register-only kernel above keeps 16 KB in flight and
+// runs at 1.1 TB/s).  Needs unit column stride and 16-byte aligned rows of B (the host checks); same FMA chains, same results.
+constexpr int SKA_K = 8, SKA_STAGES = 4;
+template <int MT>
+__global__ void __launch_bounds__(256, 1)
+gemm_skinny_m_async_kernel(const SimtParams<float> p) {
+  static_assert(MT % 4 == 0 && MT <= 32, "rows in registers");
+  static_assert(SKINNY_KCHUNK % SKA_K == 0, "whole FIFO stages per chunk of A");
+  constexpr int64_t KC = 2048 / 4;   // gemm_tiling.nim:310 (a multiple of SKA_K: stages never straddle a kc block)
+  LB200_DYN_SMEM(float4, ska_smem);  // [SKA_STAGES][SKA_K][256] float4 of B, then As4[SKINNY_KCHUNK][MT / 4]
+  float4 *Bf = ska_smem;
+  float4 *As4 = ska_smem + SKA_STAGES * SKA_K * 256;
+  float *As = reinterpret_cast<float *>(As4);
+  const int tid = threadIdx.x;
+  const int64_t nblocks = (p.N + 1023) / 1024;
+  const int64_t total = nblocks * p.batch;
+  // The CTA's tiles (1024 columns of one problem each) form ONE stream of FIFO stages, SKA_K k-rows each: the copies of the
+  // next tile are in flight while this one is multiplied and stored (with K = 27 a tile is only four stages long)
+  const int64_t st_per_tile = (p.K + SKA_K - 1) / SKA_K;
+  const int64_t my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total_stages = my_tiles * st_per_tile;
+  auto issue = [&](int64_t g) {   // one commit group per call (possibly empty)
+    if (g < total_stages) {
+      const int64_t it = g / st_per_tile, s = g - it * st_per_tile;
+      const int64_t t = blockIdx.x + it * gridDim.x;
+      const int64_t bi = t / nblocks;
+      const int64_t n0 = (t - bi * nblocks) * 1024 + 4 * tid;
+      if (n0 < p.N) {
+        const uint32_t src_bytes = static_cast<uint32_t>((p.N - n0 < 4 ? p.N - n0 : 4) * 4);   // ragged right edge: zero fill
+        const float *Bb = p.B + bi * p.bsB + n0;
+        float4 *dst = Bf + ((g % SKA_STAGES) * SKA_K) * 256 + tid;
+#pragma unroll
+        for (int r = 0; r < SKA_K; ++r) {
+          const int64_t k = s * SKA_K + r;
+          if (k < p.K) ptx::cp_async_16(dst + r * 256, Bb + k * p.rsB, src_bytes);
+        }
+      }
+    }
+    ptx::cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < SKA_STAGES - 1; ++s) issue(s);
+  int64_t g = 0;   // stage being consumed
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t bi = t / nblocks;
+    const int64_t n0 = (t - bi * nblocks) * 1024 + 4 * tid;
+    const float *Ab = p.A + bi * p.bsA;
+    float *Cb = p.C + bi * p.bsC;
+    const bool live = n0 < p.N;
+    for (int64_t pc = 0; pc < p.K; pc += KC) {  // reference loop 2 (gemm.nim:150)
+      const int64_t kend = (pc + KC < p.K) ? pc + KC : p.K;
+      float acc[MT][4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+      for (int64_t k0 = pc; k0 < kend; k0 += SKINNY_KCHUNK) {
+        const int kn = static_cast<int>(kend - k0 < SKINNY_KCHUNK ? kend - k0 : SKINNY_KCHUNK);
+        __syncthreads();   // the previous chunk of A is consumed
+        for (int i = tid; i < SKINNY_KCHUNK * MT; i += 256) {
+          const int k = i / MT, m = i - k * MT;
+          As[i] = (m < p.M && k < kn) ? Ab[m * p.rsA + (k0 + k) * p.csA] : 0.0f;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kn; kk += SKA_K, ++g) {
+          ptx::cp_async_wait<SKA_STAGES - 2>();   // this thread's copies of stage g have landed (nobody else reads them)
+          const float4 *bs = Bf + ((g % SKA_STAGES) * SKA_K) * 256 + tid;
+          const int kr = kn - kk < SKA_K ? kn - kk : SKA_K;
+          if (live) {
+#pragma unroll
+            for (int r = 0; r < SKA_K; ++r) {
+              if (r < kr) {
+                const float4 bv = bs[r * 256];
+                const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int i4 = 0; i4 < MT / 4; ++i4) {
+                  const float4 a = As4[(kk + r) * (MT / 4) + i4];
+                  const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[4 * i4 + e][j] = __fmaf_rn(av[e], b[j], acc[4 * i4 + e][j]);
+                }
+              }
+            }
+          }
+          issue(g + SKA_STAGES - 1);   // refill the slot consumed one iteration ago (it may belong to the next tile)
+        }
+      }
+      // reference epilogue for this kc block (gemm_ukernel_generic.nim:53-76)
+      const float beta1 = (pc == 0) ? p.beta : 1.0f;
+      const bool has_epi = kend == p.K && (p.bias != nullptr || p.act != 0);
+      // the common case of the convolution (alpha = 1, beta = 0, nothing fused, whole float4 inside C): 0 + sum, one vector
+      // store per row -- a few hundred instructions instead of the general store loop below (instruction-cache footprint)
+      const bool plain = beta1 == 0.0f && p.alpha == 1.0f && !has_epi && p.csC == 1 && n0 + 4 <= p.N &&
+                         ((reinterpret_cast<uintptr_t>(Cb + n0) | (static_cast<uint64_t>(p.rsC) * 4)) & 15) == 0;
+      if (live && plain) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          if (i < p.M)
+            *reinterpret_cast<float4 *>(Cb + i * p.rsC + n0) =
+                make_float4(__fadd_rn(0.0f, acc[i][0]), __fadd_rn(0.0f, acc[i][1]), __fadd_rn(0.0f, acc[i][2]), __fadd_rn(0.0f, acc[i][3]));
+        }
+      } else if (live) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          if (i >= p.M) break;
+          float *crow = Cb + i * p.rsC + n0 * p.csC;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + j >= p.N) { v[j] = 0.0f; continue; }
+            float x;
+            if (beta1 == 0.0f) x = 0.0f;
+            else if (beta1 != 1.0f) x = __fmul_rn(crow[j * p.csC], beta1);
+            else x = crow[j * p.csC];
+            if (p.alpha == 1.0f) x = __fadd_rn(x, acc[i][j]);
+            else x = __fadd_rn(x, __fmul_rn(p.alpha, acc[i][j]));
+            if (has_epi) x = skinny_epilogue(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
+            v[j] = x;
+          }
+          if (p.csC == 1 && n0 + 4 <= p.N && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+            *reinterpret_cast<float4 *>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n0 + j < p.N) crow[j * p.csC] = v[j];
+          }
+        }
+      }
+    }
+  }
+  ptx::cp_async_wait<0>();
+}
+template <int MT> constexpr size_t ska_smem_bytes() { return (static_cast<size_t>(SKA_STAGES) * SKA_K * 256 + SKINNY_KCHUNK * (MT / 4)) * sizeof(float4); }
 
 }  // namespace lb200

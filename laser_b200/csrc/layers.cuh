@@ -91,7 +91,8 @@ struct Im2colParams {
   int64_t rows;  // K * images
   int64_t in_image_stride, ws_image_stride;  // elements
   int tx_log2;   // threads along the columns = 1 << tx_log2 (each owns 4 consecutive columns)
-  int chunks;    // column chunks of (4 << tx_log2) per row
+  int chunks;    // column chunks of (4 * quads_per_thread << tx_log2) per row
+  int quads_per_thread;   // consecutive groups of 4 columns one thread writes (row and column decoded once for all of them)
 };
 
 // host side: launch geometry.  geom = {C, H, W, kH, kW, pH, pW, sH, sW, outH, outW} (all < 2^31).
@@ -110,14 +111,16 @@ inline int64_t im2col_plan(const int64_t geom[11], int64_t images, const void *w
   int tx_log2 = 0;
   while ((1 << tx_log2) < quads && tx_log2 < 8) ++tx_log2;
   p->tx_log2 = tx_log2;
-  p->chunks = (quads + (1 << tx_log2) - 1) >> tx_log2;
+  p->quads_per_thread = quads >= 1024 ? 4 : 1;
+  const int per_chunk = p->quads_per_thread << tx_log2;
+  p->chunks = (quads + per_chunk - 1) / per_chunk;
   const int rows_per_block = 256 >> tx_log2;
   *vec4 = (p->outHW % 4 == 0) && (reinterpret_cast<uintptr_t>(workspace) % 16 == 0);
   return ((p->rows + rows_per_block - 1) / rows_per_block) * p->chunks;
 }
 
-// thread (tx, ty): row = block_row_group * rows_per_block + ty, columns 4*(chunk*TX + tx) .. +3.
-// The row is decoded once per thread (kk -> c, krow, kcol), the column once per 4 outputs.
+// thread (tx, ty): row = block_row_group * rows_per_block + ty, columns 4*((chunk*U + u)*TX + tx) .. +3 for u < U =
+// quads_per_thread.  The row is decoded once per thread (kk -> c, krow, kcol), the column once per 4 outputs.
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
 im2col_kernel(float *__restrict__ ws, const float *__restrict__ in, Im2colParams p) {
@@ -132,26 +135,30 @@ im2col_kernel(float *__restrict__ ws, const float *__restrict__ in, Im2colParams
   const int khw = p.kH * p.kW;
   const int c = kk / khw, r2 = kk - c * khw;
   const int krow = r2 / p.kW, kcol = r2 - krow * p.kW;
-  const int p0 = ((chunk << p.tx_log2) + tx) * 4;
-  if (p0 >= p.outHW) return;
-  int oh = p0 / p.outW, ow = p0 - oh * p.outW;
   const float *src = in + img * p.in_image_stride + static_cast<int64_t>(c) * p.H * p.W;
-  float *dst = ws + img * p.ws_image_stride + static_cast<int64_t>(kk) * p.outHW + p0;
-  float v[4];
+  float *wrow = ws + img * p.ws_image_stride + static_cast<int64_t>(kk) * p.outHW;
+  // quad u of this thread: lanes stay next to each other in every store instruction (the row was decoded once above)
+  for (int u = 0; u < p.quads_per_thread; ++u) {
+    const int p0 = (((chunk * p.quads_per_thread + u) << p.tx_log2) + tx) * 4;
+    if (p0 >= p.outHW) return;
+    int oh = p0 / p.outW, ow = p0 - oh * p.outW;
+    float *dst = wrow + p0;
+    float v[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int r = oh * p.sH - p.pH + krow, cc = ow * p.sW - p.pW + kcol;
-    const bool inside = (p0 + e < p.outHW) && static_cast<unsigned>(r) < static_cast<unsigned>(p.H) &&
-                        static_cast<unsigned>(cc) < static_cast<unsigned>(p.W);
-    v[e] = inside ? src[static_cast<int64_t>(r) * p.W + cc] : 0.0f;
-    if (++ow == p.outW) { ow = 0; ++oh; }
-  }
-  if constexpr (VEC4) {
-    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
+    for (int e = 0; e < 4; ++e) {
+      const int r = oh * p.sH - p.pH + krow, cc = ow * p.sW - p.pW + kcol;
+      const bool inside = (p0 + e < p.outHW) && static_cast<unsigned>(r) < static_cast<unsigned>(p.H) &&
+                          static_cast<unsigned>(cc) < static_cast<unsigned>(p.W);
+      v[e] = inside ? src[static_cast<int64_t>(r) * p.W + cc] : 0.0f;
+      if (++ow == p.outW) { ow = 0; ++oh; }
+    }
+    if constexpr (VEC4) {
+      *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (p0 + e < p.outHW) dst[e] = v[e];
+      for (int e = 0; e < 4; ++e)
+        if (p0 + e < p.outHW) dst[e] = v[e];
+    }
   }
 }
 

@@ -91,6 +91,11 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc, boo
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(valid ? 8u : 0u) : "memory");
 }
+// 16 bytes, bypassing L1 (streaming); src_bytes < 16: the rest of the destination is zero-filled
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -160,6 +160,11 @@ inline void cp_async_8(void *smem_dst, const void *gsrc, bool valid) {   // comp
   if (valid) std::memcpy(smem_dst, gsrc, 8);
   else std::memset(smem_dst, 0, 8);
 }
+inline void cp_async_16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
+  if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gsrc)) & 15u) std::abort();   // the hardware faults
+  std::memset(smem_dst, 0, 16);
+  if (src_bytes) std::memcpy(smem_dst, gsrc, src_bytes);
+}
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
 inline int sw128_chunk(int, int j) { return j; }      // the model keeps tiles unswizzled on both sides

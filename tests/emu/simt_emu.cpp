@@ -67,6 +67,15 @@ int emu_gemm_skinny_m_f32(int64_t batch, int64_t M, int64_t N, int64_t K, float 
   p.bias = bias; p.bias_per_row = bias_per_row; p.act = act;
   p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   if (grid <= 0) grid = 2;
+  // capi.cu: gemm_simt<float> -- B with unit column stride and 16-byte aligned rows takes the cp.async-staged kernel
+  const bool async_ok = csB == 1 && rsB % 4 == 0 && (batch == 1 || bsB % 4 == 0) && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+  if (async_ok && ska_smem_bytes<32>() <= emu::kDynSmemBytes) {
+    if (M <= 8) emu::launch(grid, 256, [=]() { gemm_skinny_m_async_kernel<8>(p); });
+    else if (M <= 16) emu::launch(grid, 256, [=]() { gemm_skinny_m_async_kernel<16>(p); });
+    else if (M <= 24) emu::launch(grid, 256, [=]() { gemm_skinny_m_async_kernel<24>(p); });
+    else emu::launch(grid, 256, [=]() { gemm_skinny_m_async_kernel<32>(p); });
+    return 2;
+  }
   if (M <= 8) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<8, 4>(p); });
   else if (M <= 16) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<16, 4>(p); });
   else if (M <= 24) emu::launch(grid, 256, [=]() { gemm_skinny_m_kernel<24, 2>(p); });

@@ -138,7 +138,8 @@ def test_f64_tensor_core_kernel_is_the_same_fma_chain(emu, M, N, K, alpha, beta,
 
 @pytest.mark.parametrize("M,N,K,alpha,beta,b_col,batch", [(20, 2500, 27, 1.0, 0.0, False, 3), (7, 1030, 600, 1.0, 1.0, False, 1),
                                                           (16, 1100, 513, 0.5, -1.25, True, 2), (32, 1029, 70, 1.0, 0.0, False, 1),
-                                                          (1, 2049, 5, 1.0, 1.0, True, 1)])
+                                                          (1, 2049, 5, 1.0, 1.0, True, 1), (24, 2052, 530, 0.5, 2.0, False, 2),
+                                                          (9, 1500, 65, 1.0, 0.0, False, 1)])
 def test_skinny_m_kernel_bit_exact(emu, M, N, K, alpha, beta, b_col, batch):
     """few output rows x wide N (the im2col convolution's GEMM): bit-identical to the oracle across kc = 512 blocks, shared A
     across the batch, row- and column-major B, ragged N (scalar tail next to the vector path), bias + relu after the last block"""
@@ -147,8 +148,11 @@ def test_skinny_m_kernel_bit_exact(emu, M, N, K, alpha, beta, b_col, batch):
     Bl = rng.standard_normal((batch, K, N)).astype(np.float32)
     C0 = rng.standard_normal((batch, M, N)).astype(np.float32)
     bias = rng.standard_normal(M).astype(np.float32)
-    B = np.ascontiguousarray(Bl.transpose(0, 2, 1)) if b_col else Bl
-    rsb, csb = (1, K) if b_col else (N, 1)
+    ldb = -(-N // 4) * 4                     # row-major B is stored with a 16-byte multiple pitch (padding columns hold junk)
+    if b_col:
+        B = np.ascontiguousarray(Bl.transpose(0, 2, 1)); rsb, csb, bsb = 1, K, K * N
+    else:
+        B = np.full((batch, K, ldb), 7e30, np.float32); B[:, :, :N] = Bl; rsb, csb, bsb = ldb, 1, K * ldb
     ref = C0.copy()
     for i in range(batch):
         O.gemm_strided(M, N, K, alpha, A, K, 1, B[i], rsb, csb, beta, ref[i], N, 1)
@@ -157,9 +161,10 @@ def test_skinny_m_kernel_bit_exact(emu, M, N, K, alpha, beta, b_col, batch):
         got = C0.copy()
         if beta == 0.0:
             got[:] = np.nan
-        rc = emu.emu_gemm_skinny_m_f32(batch, M, N, K, alpha, at(A, 0), K, 1, 0, at(B, 0), rsb, csb, K * N, beta, at(got, 0), N, 1,
+        rc = emu.emu_gemm_skinny_m_f32(batch, M, N, K, alpha, at(A, 0), K, 1, 0, at(B, 0), rsb, csb, bsb, beta, at(got, 0), N, 1,
                                        M * N, 3, at(bias, 0) if epi else None, 1, 1 if epi else 0)
-        assert rc == 1
+        # 2: the cp.async-staged kernel (B with unit column stride, 16-byte aligned rows), 1: the register-only kernel
+        assert rc == (1 if b_col else 2), rc      # (the ragged right edge of a padded B arrives zero-filled)
         want = ref_epi if epi else ref
         if alpha == 1.0:
             assert np.array_equal(got, want)
