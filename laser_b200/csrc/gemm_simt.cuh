@@ -98,6 +98,20 @@ inline int64_t simt_plan(SimtParams<T> &p, int64_t M, int64_t N, int64_t K, T al
   return mblocks * nblocks;
 }
 
+// bias + activation of the fused epilogue, out of line: inlined into the unrolled MT x NC store loops the tanhf / expf bodies
+// made the kernels several times larger than the instruction cache (ncu: 58 % of the stall samples "no instruction")
+#ifndef LB200_HOST_EMULATION
+static __device__ __noinline__
+#else
+inline
+#endif
+float simt_bias_act(float x, const float *bias, int bias_per_row, int act, int64_t row, int64_t col) {
+  if (bias) x += bias_per_row ? bias[row] : bias[col];
+  if (act == 1) x = fmaxf(x, 0.0f);
+  else if (act == 2) x = tanhf(x);
+  else if (act == 3) x = 1.0f / (1.0f + expf(-x));
+  return x;
+}
 #ifndef LB200_SIMT_MINB
 #define LB200_SIMT_MINB 1
 #endif
@@ -244,20 +258,6 @@ gemv_warp_smem_kernel(int64_t M, int64_t K, float alpha, const float *__restrict
 // block (same statements as gemm_simt_kernel), so results are bit-identical to the general kernel's.  Batched like it.
 // MT: rows held in registers (M <= MT, a multiple of 4).
 // ---------------------------------------------------------------------------
-// bias + activation of the fused epilogue, out of line: inlined into the unrolled MT x NC store loops the tanhf / expf bodies
-// made the kernels several times larger than the instruction cache (ncu: 58 % of the stall samples "no instruction")
-#ifndef LB200_HOST_EMULATION
-__device__ __noinline__
-#else
-inline
-#endif
-float skinny_epilogue(float x, const float *bias, int bias_per_row, int act, int row, int64_t col) {
-  if (bias) x += bias_per_row ? bias[row] : bias[col];
-  if (act == 1) x = fmaxf(x, 0.0f);
-  else if (act == 2) x = tanhf(x);
-  else if (act == 3) x = 1.0f / (1.0f + expf(-x));
-  return x;
-}
 constexpr int SKINNY_KCHUNK = 64;   // k-columns of A staged in shared memory at a time
 // NC: columns per thread (4 for MT <= 16, 2 above: MT * NC running sums per thread must leave room for two CTAs per SM)
 template <int MT, int NC>
@@ -342,7 +342,7 @@ gemm_skinny_m_kernel(const SimtParams<float> p) {
             else x = crow[j * p.csC];
             if (p.alpha == 1.0f) x = __fadd_rn(x, acc[i][j]);
             else x = __fadd_rn(x, __fmul_rn(p.alpha, acc[i][j]));
-            if (has_epi) x = skinny_epilogue(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
+            if (has_epi) x = simt_bias_act(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
             v[j] = x;
           }
           if (p.csC == 1 && n0 + NC <= p.N && (reinterpret_cast<uintptr_t>(crow) & (4 * NC - 1)) == 0) {
@@ -423,6 +423,7 @@ gemm_skinny_m_async_kernel(const SimtParams<float> p) {
           As[i] = (m < p.M && k < kn) ? Ab[m * p.rsA + (k0 + k) * p.csA] : 0.0f;
         }
         __syncthreads();
+#pragma unroll 1
         for (int kk = 0; kk < kn; kk += SKA_K, ++g) {
           ptx::cp_async_wait<SKA_STAGES - 2>();   // this thread's copies of stage g have landed (nobody else reads them)
           const float4 *bs = Bf + ((g % SKA_STAGES) * SKA_K) * 256 + tid;
@@ -477,7 +478,7 @@ gemm_skinny_m_async_kernel(const SimtParams<float> p) {
             else x = crow[j * p.csC];
             if (p.alpha == 1.0f) x = __fadd_rn(x, acc[i][j]);
             else x = __fadd_rn(x, __fmul_rn(p.alpha, acc[i][j]));
-            if (has_epi) x = skinny_epilogue(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
+            if (has_epi) x = simt_bias_act(x, p.bias, p.bias_per_row, p.act, i, n0 + j);
             v[j] = x;
           }
           if (p.csC == 1 && n0 + 4 <= p.N && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {

@@ -51,7 +51,13 @@
 
 namespace lb200 {
 
-__device__ __forceinline__ float epi_act(float v, int act) {
+// (out of line: inlined into the 128 unrolled stores of each of the three store paths the tanhf / expf bodies made the kernel
+// 370 KB -- the epilogue warps then miss the 32 KB instruction cache on every tile)
+#ifndef LB200_HOST_EMULATION
+static __device__ __noinline__ float epi_act(float v, int act) {
+#else
+inline float epi_act(float v, int act) {
+#endif
   if (act == 1) return fmaxf(v, 0.0f);
   if (act == 2) return tanhf(v);
   if (act == 3) return 1.0f / (1.0f + expf(-v));
