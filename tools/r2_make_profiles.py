@@ -155,7 +155,7 @@ def copies(pre, tag):
     import shutil
     for src, dst in (("bench_n1.json", "bench_n1.json"), ("bench_ref.json", "bench_reference.json"), ("layouts.log", "layouts.log"),
                      ("probes.jsonl", "probes.jsonl"), ("pytest.log", "pytest.log"), ("smi.txt", "smi.txt"), ("f64.jsonl", "f64_dmma.jsonl"),
-                     ("layers_bench.txt", "layers_bench.txt")):
+                     ("layers_bench.txt", "layers_bench.txt"), ("large_shapes.txt", "large_shapes.txt")):
         a = os.path.join(G, "%s_%s" % (pre, src))
         if os.path.exists(a):
             shutil.copy(a, os.path.join(P, "%s_%s" % (tag, dst)))

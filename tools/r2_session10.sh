@@ -15,6 +15,7 @@ echo "=== probes"
 for v in "X=1" "LASER_B200_KC=256"; do
   echo "--- $v"; env $v timeout 200 python tools/two_piece_probe.py f16x3 8192 10 2>>$O/${P}_err.log | tee -a $O/${P}_probes.jsonl | cut -c1-900; done
 echo "=== layouts"; timeout 400 python tools/r2_probe_f16.py 2>&1 | tee $O/${P}_layouts.log
+echo "=== large / skewed shapes"; timeout 600 python tools/large_shapes.py 2>&1 | tee $O/${P}_large_shapes.txt | tail -14
 echo "=== f64"; timeout 600 python tools/f64_probe.py 2048 4096 8192 2>&1 | tee $O/${P}_f64.jsonl
 echo "=== layers bench"; timeout 600 python tools/layers_bench.py 2>&1 | tee $O/${P}_layers_bench.txt | tail -12
 echo "=== bench reference arm"; LASER_B200_REF_BUDGET_S=12 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>$O/${P}_bench_ref_err.log | tee $O/${P}_bench_ref.json | cut -c1-300
