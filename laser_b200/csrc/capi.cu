@@ -840,6 +840,10 @@ int resolve_auto(int64_t M, int64_t N, int64_t K, const Epilogue &epi) {
   const int mode = g_f32_mode.load();
   if (mode == LASER_B200_PATH_SIMT) return LASER_B200_PATH_SIMT;
   if (N <= 4 && M >= 1024 && !epi.bias && !epi.act) return -1;
+  // few output rows, wide N (the im2col convolution's product): the exact few-rows kernel streams B once; a tensor-core
+  // call would first spend three passes over B preparing it and then compute 84+ % padding (20 x 788544 x 27: 0.08 ms
+  // against 0.28 ms, profiles/r02_large_shapes.txt) -- and exact is at least as accurate as any tensor-core mode
+  if (M <= 32 && N >= 1024) return LASER_B200_PATH_SIMT;
   return mode < 0 ? kDefaultF32Mode : mode;
 }
 

@@ -276,6 +276,12 @@ def test_auto_path_selection():
     assert L.last_path() == L.PATH_F16X3
     sync()
     assert np.all(c.cpu().numpy() == 256.0)
+    # few output rows, wide N (the im2col convolution's product): exact few-rows kernel, whatever the tensor-core mode
+    a = dev(np.ones(20 * 300, np.float32)); b = dev(np.ones(300 * 2048, np.float32)); c = dev(np.zeros(20 * 2048, np.float32))
+    L.gemm_strided(20, 2048, 300, 1.0, dptr(a, 0, "f32"), 300, 1, dptr(b, 0, "f32"), 2048, 1, 0.0, dptr(c, 0, "f32"), 2048, 1)
+    assert L.last_path() == L.PATH_SIMT
+    sync()
+    assert np.all(c.cpu().numpy() == 300.0)
 
 
 @pytest.mark.parametrize("K", [777, 776])      # 776: the 16-byte vectorised variant
