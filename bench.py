@@ -7,8 +7,8 @@
 A "step" is one pass of the hot path: C <- A x B, fp32, row-major, alpha=1, beta=0 (the call the reference's bench
 makes, benchmarks/gemm/gemm_bench_float32.nim:184-189), through the C ABI of liblaser_b200.so in its DEFAULT fp32 mode
 (F16X3: tcgen05 kind::f16 over two fp16 pieces of the scaled operands, three passes, parity-gated at 1e-4).  At N GPUs
-the headline line is weak-scaling: every rank owns 8192 rows of A and C, and each step includes the NCCL broadcast of B
-from rank 0, issued by the library itself (laser_b200_gemm_rowsharded_f32_dev).
+the headline line is weak-scaling: every rank owns 8192 rows of A and C, and each step includes B travelling over NCCL from
+rank 0 (prepared there, sent in column panels), issued by the library itself (laser_b200_gemm_rowsharded_f32_dev).
 
 One JSON line on stdout (rank 0).  Extra keys beyond the driver's contract:
   roofline       dominant kernel (gemm_tc_kernel, F16X3) against the tensor roofline
@@ -307,7 +307,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         rows = np.unique(np.random.default_rng(1234 + rank).integers(0, M_local, rows_per_rank))
         idx = torch.as_tensor(rows, device=dev)
-        a = np.ascontiguousarray(A.view(M_local, K)[idx].cpu().numpy()); b = B.view(K, N).cpu().numpy()
+        a = np.ascontiguousarray(A.view(M_local, K)[idx].cpu().numpy())
+        # B is an input that lives on rank 0 (the library sends it prepared, in panels): the checker fetches the root's copy
+        Bchk = B.clone()
+        if world > 1:
+            dist.broadcast(Bchk, src=0)
+        b = Bchk.view(K, N).cpu().numpy()
+        del Bchk
         got = C.view(M_local, N)[idx].cpu().numpy()
         want = np.zeros((len(rows), N), np.float32)
         O.cpu_gemm_strided_f32(len(rows), N, K, 1.0, a.reshape(-1), K, 1, b.reshape(-1), N, 1, 0.0, want.reshape(-1), N, 1)
@@ -322,7 +328,7 @@ def run_ours(args):
         if bad != 0.0:
             nw = mre = None      # non-finite output (or B never arrived): strict JSON has no Infinity
         return {"rows_per_rank": int(len(rows)), "ranks": world, "normwise": nw, "mean_relative_error": mre, "ok": bool(ok),
-                "gates": "normwise < 2e-6, mean_relative_error <= 1e-5 (gemm_bench_float32.nim:365-367), B delivered to every rank",
+                "gates": "normwise < 2e-6, mean_relative_error <= 1e-5 (gemm_bench_float32.nim:365-367) on every rank's rows",
                 "against": "oracle/laser_cpu_gemm.c (CPU restatement of the reference, bit-equal to the numerics oracle)"}
 
     # ---- the metric: device-resident, default (fp32-faithful) mode, 8192 rows per rank ------------
@@ -402,7 +408,7 @@ def run_ours(args):
     strong = {"global_M": STRONG_M, "N": N, "K": K, "rows_per_rank": Ms, "ms_per_step": ms_strong, "steps": s_steps,
               "value": 2.0 * STRONG_M * N * K / (ms_strong * 1e-3) / 1e12, "unit": UNIT, "scaling": "strong",
               "parity": strong_parity,
-              "note": "same call as the headline (row-sharded, one NCCL broadcast of B per step at N > 1); speed-up at N GPUs = "
+              "note": "same call as the headline (row-sharded, B travels over NCCL from rank 0 every step at N > 1); speed-up at N GPUs = "
                       "this value at --gpus N / this value at --gpus 1"}
     del As, Cs
 
@@ -445,7 +451,9 @@ def run_ours(args):
     gA = torch.empty(M * K, dtype=torch.float32, device=dev)
     L.fill_uniform_f32(gA, M * K, 42 + rank, -0.1, 0.1)
     hA.copy_(gA.cpu()); del gA
-    hB.copy_(B.cpu())              # (delivered to every rank by the broadcasts above)
+    if world > 1:
+        dist.broadcast(B, src=0)   # every rank's own host-pointer call needs a valid B (the row-sharded steps above do not deliver it)
+    hB.copy_(B.cpu())
     nA, nB, nC = hA.numpy(), hB.numpy(), hC.numpy()
     e2e_steps = max(2, min(args.steps, 5))
     L.gemm_strided(M, N, K, 1.0, nA, K, 1, nB, N, 1, 0.0, nC, N, 1)     # warm-up (staging buffers)
@@ -471,7 +479,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic U(-0.1,0.1), counter-based generator, seed 42 (device-generated)",
             "config": {"workload": "SGEMM fp32 C=A*B, per-GPU M=8192 N=K=8192 row-major, alpha=1 beta=0"
-                                   + ("" if world == 1 else "; row-sharded: total M=%d, one NCCL broadcast of B from rank 0 every step "
+                                   + ("" if world == 1 else "; row-sharded: total M=%d, B travels over NCCL from rank 0 every step (prepared fp16 pieces + scales, column panels) "
                                                             "(laser_b200_gemm_rowsharded_f32_dev)" % (M * world)),
                        "global_M": M * world, "N": N, "K": K, "parallelism": "rowshard%d" % world,
                        "f32_mode": "f16x3 (fp32-faithful, default)", "l2": "inputs larger than L2 (A+B+C = 805 MB vs 126 MB)",

@@ -202,9 +202,13 @@ int laser_b200_gemm_packedB_f32_dev(int64_t M, int64_t N, int64_t K, float alpha
 /* ---- row panels of C across the GPUs of one box ---------------------------------
  * The reference parallelises this split inside gemm_strided itself: its `ic` loop hands every worker a row block of A
  * and C while all workers share one packed panel of B (gemm.nim:160-176).  Here a worker is a GPU: rank r owns rows of
- * A and C (never moved); B lives on `root` and is broadcast ONCE per product over NCCL (NVLink 5 / NVSwitch) on a
+ * A and C (never moved); B lives on `root` and travels ONCE per product over NCCL (NVLink 5 / NVSwitch) on a
  * communication stream, while the rank's rows of A are already being prepared; no collective inside the MMA loop, no
- * reduction.  NCCL is bound at run time (dlopen of libnccl.so.2); without it these entries return LASER_B200_EUNSUPPORTED.
+ * reduction.  In the default fp32 mode a row- or column-major B travels PREPARED -- the fp16 pieces and scale words the
+ * tensor-core kernel reads, the same 4 bytes per element -- in LASER_B200_ROWSHARD_PANELS column panels (default 1; with more, the
+ * root prepares panel p + 1 while panel p is on the wire and every rank multiplies its rows by panel p as soon as it is
+ * there); only the root ever prepares B, and while the other ranks still multiply it is already preparing the next product's.  Otherwise (other modes, general strides, LASER_B200_ROWSHARD_PANELS=0) B itself
+ * is broadcast and every rank prepares it.  NCCL is bound at run time (dlopen of libnccl.so.2); without it these entries return LASER_B200_EUNSUPPORTED.
  *
  *   comm_get_unique_id / comm_init_rank   one process (or thread) per GPU: rank 0 obtains the 128-byte id, hands it to
  *                                         the others by any means, every rank calls init_rank with ITS device current
@@ -212,7 +216,8 @@ int laser_b200_gemm_packedB_f32_dev(int64_t M, int64_t N, int64_t K, float alpha
  *   rowshard_partition                    the row range of a rank: ceil(M / nranks) rounded up to the 256-row tile
  *   gemm_rowsharded_f32_dev               per-rank entry, DEVICE pointers on the communicator's device, asynchronous on
  *                                         `stream`: C_local <- alpha * A_local * B + beta * C_local with B (K x N, dense in
- *                                         memory) valid on `root` and overwritten by the broadcast on every other rank
+ *                                         memory) an input on `root`; on every other rank the buffer is scratch (filled
+ *                                         with B by the raw broadcast, left alone when B travels prepared)
  *   gemm_rowsharded_f32                   the reference signature with HOST pointers on `ngpus` devices of this process:
  *                                         row panels of A (and of C when beta != 0) go to their device, B to device 0,
  *                                         one broadcast, every device its rows, C comes back; synchronous */

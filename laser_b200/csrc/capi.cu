@@ -126,6 +126,7 @@ struct Ctx {
   Buffer gather[2];  // F16X3: compact fp32 copy of a general-stride operand (A, B) before it is scaled and split
   Buffer stage[3];   // device staging of host A, B, C spans
   Buffer splitk;     // split-K partial-sum planes
+  Buffer bpanels;    // row-sharded products: B prepared, panel-major (capi_multi.inc: rowshard_prepared)
   Buffer layer_ws;   // im2col workspace of the host-pointer convolution
   Buffer f16s;       // F16X3 mode: fp32 bits of max_k |a| per row of A (words [0, M)) and of max_k |b| per column of B (from
                      // f16_b_off on), written and read on the device
@@ -457,6 +458,41 @@ int f16x2_prepare(Ctx &c, const float *src, int64_t R, int64_t Cc, int64_t src_l
     f16x2_rows_ring_kernel<<<grid_for(c, R, 2), 256, smem, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
   } else {
     f16x2_rows_fused_kernel<256><<<grid_for(c, R, 4), 256, 0, s>>>(src, R, Cc, src_ld, xb, lb, ld_b, words);
+  }
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+
+// capi_multi.inc (rowshard_prepared): the root prepares B panel by panel into a panel-major buffer.
+// Scale words of every column of a row-major B [K][N] (a column's scale needs the whole column):
+int f16x2_absmax_cols(Ctx &c, const float *B, int64_t K, int64_t N, int64_t ld, uint32_t *words, cudaStream_t s) {
+  CUDA_TRY(cudaMemsetAsync(words, 0, static_cast<size_t>(N) * sizeof(uint32_t), s));
+  const int64_t items = ((N + 3) / 4) * ((K + ABSMAX_COL_ROWS - 1) / ABSMAX_COL_ROWS);
+  absmax_mn_kernel<true><<<grid_for(c, (items + 255) / 256, 8), 256, 0, s>>>(B, K, N, ld, words);
+  COUNT_LAUNCH();
+  CHECK_LAUNCH();
+  return LASER_B200_OK;
+}
+// One column panel (w columns) of B into its two fp16 pieces.  Row-major B: Bp = first column of the panel, ld = row
+// pitch, pieces [K][w] (MN-major), `words` already hold the panel's scales.  Column-major B: Bp = first column (a contiguous
+// row of K floats), ld = column pitch, pieces [w][K] (K-major), scale words written in the same pass.
+int f16x2_prepare_panel(Ctx &c, bool row_major, const float *Bp, int64_t K, int64_t w, int64_t ld, uint16_t *hi, uint16_t *lo,
+                        uint32_t *words, cudaStream_t s) {
+  if (row_major) {
+    const int64_t split_items = ((w + 255) / 256) * ((K + SPLIT_ROWS - 1) / SPLIT_ROWS);
+    split_rows_f16x2_kernel<true><<<grid_for(c, split_items, 8), 256, 0, s>>>(Bp, K, w, ld, hi, lo, w, words);
+  } else if (K <= 4 * 32 * F16ROWS_MAXV) {
+    f16x2_rows_fused_kernel<32><<<grid_for(c, (w + 7) / 8, 4), 256, 0, s>>>(Bp, w, K, ld, hi, lo, K, words);
+  } else if (c.prep_ring && f16x2_rows_ring_ok(Bp, K, ld)) {
+    if (!c.ring_attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(f16x2_rows_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(f16x2_rows_ring_smem(4 * 256 * F16ROWS_MAXV))));
+      c.ring_attr_set = true;
+    }
+    f16x2_rows_ring_kernel<<<grid_for(c, w, 2), 256, f16x2_rows_ring_smem(K), s>>>(Bp, w, K, ld, hi, lo, K, words);
+  } else {
+    f16x2_rows_fused_kernel<256><<<grid_for(c, w, 4), 256, 0, s>>>(Bp, w, K, ld, hi, lo, K, words);
   }
   COUNT_LAUNCH();
   CHECK_LAUNCH();
@@ -1144,6 +1180,7 @@ void laser_b200_shutdown(void) {
     for (auto &b : c.ws) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     for (auto &b : c.stage) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }
     if (c.splitk.ptr) { cudaFree(c.splitk.ptr); c.splitk = Buffer(); }
+    if (c.bpanels.ptr) { cudaFree(c.bpanels.ptr); c.bpanels = Buffer(); }
     if (c.layer_ws.ptr) { cudaFree(c.layer_ws.ptr); c.layer_ws = Buffer(); }
     if (c.f16s.ptr) { cudaFree(c.f16s.ptr); c.f16s = Buffer(); }
     for (auto &b : c.gather) { if (b.ptr) cudaFree(b.ptr); b = Buffer(); }

@@ -99,8 +99,9 @@ def comm_from_torch_distributed(group=None):
 def gemm_rowsharded(M_local, N, K, alpha, A_local, B, beta, C_local, src=0, comm=None, group=None, stream=None, gemm_fn=None):
     """C_local <- alpha * A_local @ B + beta * C_local on every rank (device buffers on this rank's GPU).
 
-    A_local: (M_local, K) view (any strides), C_local: (M_local, N) view, B: (K, N) dense tensor on every rank, valid on
-    `src` only -- the other ranks' copies are overwritten by the broadcast.  gemm_fn (tests of the host logic only): a
+    A_local: (M_local, K) view (any strides), C_local: (M_local, N) view, B: (K, N) dense tensor on every rank, an INPUT
+    that needs to be valid on `src` only.  On the other ranks the buffer is scratch: the library may fill it with B (raw
+    broadcast) or leave it alone (default fp32 mode, row- or column-major B: B travels prepared, in column panels).  gemm_fn (tests of the host logic only): a
     gemm_strided-like callable that stands in for the library, with torch.distributed doing the broadcast."""
     rsA, csA = (A_local.stride(0), A_local.stride(1)) if M_local > 0 else (K, 1)
     rsC, csC = (C_local.stride(0), C_local.stride(1)) if M_local > 0 else (N, 1)

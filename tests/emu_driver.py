@@ -352,16 +352,17 @@ def rowsharded():
     for r, (lo, hi) in enumerate(parts):
         assert np.array_equal(Bs[r], bfull), r
         assert hi == lo or np.abs(Cs[r] - ref[lo:hi]).max() <= 1e-5 * np.abs(ref).max(), r     # (a rank may own no rows)
-    # B in pieces (LASER_B200_ROWSHARD_PANELS > 1): K-panels of a row-major B accumulate, column panels of a column-major B
-    # fill their own columns of C; every piece is one broadcast per rank
-    P = int(os.environ.get("LASER_B200_ROWSHARD_PANELS", "1"))
-    if P > 1:
-        for by_k in (True, False):
-            M, N, K = (300, 72, 1280) if by_k else (300, 1280, 72)
+    # default fp32 mode, B row- or column-major, N >= 512: B travels PREPARED in column panels (capi_multi.inc:
+    # rowshard_prepared) -- the root prepares and sends panel after panel, every rank multiplies its rows by each panel as it
+    # arrives; B of the other ranks is not touched
+    P = int(os.environ.get("LASER_B200_ROWSHARD_PANELS", "2"))
+    if P >= 1:
+        for row_major in (True, False):
+            M, N, K = 300, 2304, 96
             a, bfull, c0 = rnd((M, K), 76), rnd((K, N), 77), rnd((M, N), 78)
             parts = RS.partition_rows(M, ndev)
-            stored = bfull if by_k else np.ascontiguousarray(bfull.T)        # row-major [K][N] or column-major (= [N][K])
-            rsb, csb = (N, 1) if by_k else (1, K)
+            stored = bfull if row_major else np.ascontiguousarray(bfull.T)        # row-major [K][N] or column-major (= [N][K])
+            rsb, csb = (N, 1) if row_major else (1, K)
             Bs = [stored.copy() if r == 0 else np.full(stored.shape, np.nan, np.float32) for r in range(ndev)]
             Cs = [c0[lo:hi].copy() for lo, hi in parts]
             calls0 = fake.fake_nccl_broadcast_calls()
@@ -371,12 +372,15 @@ def rowsharded():
                 RS.gemm_rowsharded_dev(comms[r], hi - lo, N, K, 0.5, D(a[lo:hi]) if hi > lo else None, K, 1, D(Bs[r]), rsb, csb, 0,
                                        -1.25, D(Cs[r]) if hi > lo else None, N, 1, stream=1)
             cudart_set(0)
-            pieces = min(P, 1280 // 512)
-            assert fake.fake_nccl_broadcast_calls() - calls0 == ndev * pieces, (fake.fake_nccl_broadcast_calls() - calls0, pieces)
+            W = -(-(-(-N // min(P, N // 1024)) ) // 256) * 256
+            panels = -(-N // W)
+            per_rank = (1 + panels) if row_major else 2 * panels
+            assert fake.fake_nccl_broadcast_calls() - calls0 == ndev * per_rank, (fake.fake_nccl_broadcast_calls() - calls0, panels)
             ref = ref_gemm(M, N, K, 0.5, a, bfull, -1.25, c0)
+            assert np.array_equal(Bs[0], stored)
             for r, (lo, hi) in enumerate(parts):
-                assert np.array_equal(Bs[r], stored), r
-                assert hi == lo or np.abs(Cs[r] - ref[lo:hi]).max() <= 2e-5 * np.abs(ref).max(), (by_k, r)
+                assert r == 0 or np.isnan(Bs[r]).all(), r                       # B of the other ranks: not an output
+                assert hi == lo or np.abs(Cs[r] - ref[lo:hi]).max() <= 2e-5 * np.abs(ref).max(), (row_major, r)
             n += 1
     for cm in comms:
         cm.destroy()

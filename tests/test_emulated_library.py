@@ -53,11 +53,11 @@ def test_host_entry_under_configuration(emulated_lib, env):
     run(emulated_lib, "host_entry", **env)
 
 
-@pytest.mark.parametrize("ndev,panels", [(2, 1), (3, 1), (2, 2), (3, 4)])
+@pytest.mark.parametrize("ndev,panels", [(2, 0), (3, 1), (2, 2), (3, 2)])
 def test_rowsharded_entry_points_with_a_stand_in_nccl(emulated_lib, ndev, panels):
     """laser_b200_gemm_rowsharded_f32 / _f32_dev on 2 and 3 emulated devices (3: uneven row panels, the last rank short);
-    panels > 1: B travels in pieces (K-panels of a row-major B accumulate into C, column panels of a column-major B fill
-    their own columns), the partial products follow their pieces"""
+    panels >= 1: wide products in the default fp32 mode send B PREPARED in column panels, every rank multiplying its rows
+    by each panel as it arrives (panels = 0: raw B in one broadcast)"""
     run(emulated_lib, "rowsharded", LASER_B200_EMU_DEVICES=ndev, LASER_B200_NCCL_LIB=build_fake_nccl(),
         LASER_B200_ROWSHARD_PANELS=panels)
 

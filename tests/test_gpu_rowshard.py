@@ -10,15 +10,19 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.timeout(600)
-def test_rowsharded_nccl():
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("env", [{}, {"RS_COLMAJOR": "1"}, {"LASER_B200_ROWSHARD_PANELS": "0"}, {"LASER_B200_ROWSHARD_PANELS": "4", "RS_M": "5000"}],
+                         ids=["prepared-panels", "column-major-B", "raw-broadcast", "four-panels-uneven-rows"])
+def test_rowsharded_nccl(env):
+    """every rank checks sampled rows of its C panel against the oracle: B prepared on the root and sent in column panels
+    (row- and column-major B), and the raw broadcast of B"""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     n = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "rowshard_check.py")]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=550)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=550, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("max_rel_err") == n
 

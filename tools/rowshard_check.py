@@ -17,18 +17,18 @@ lo, hi = partition_rows(M, world)[rank]
 Ml = hi - lo
 A = torch.empty(M * K, dtype=torch.float32, device="cuda"); L.fill_uniform_f32(A, M * K, 7, 0, 1)
 A = A.view(M, K)[lo:hi]
-B = torch.empty(K * N, dtype=torch.float32, device="cuda")
-if rank == 0:
-    L.fill_uniform_f32(B, K * N, 8, 0, 1)
-else:
-    B.fill_(float("nan"))
-B = B.view(K, N)
+Bref = torch.empty(K * N, dtype=torch.float32, device="cuda"); L.fill_uniform_f32(Bref, K * N, 8, 0, 1)   # what the root holds
+Bref = Bref.view(K, N)
+colmajor = os.environ.get("RS_COLMAJOR", "0") == "1"       # B stored column-major (= [N][K] row-major), passed with strides (1, K)
+stored = Bref.t().contiguous() if colmajor else Bref.clone()
+if rank != 0:
+    stored.fill_(float("nan"))                             # B is an input that lives on the root only
+B = stored.t() if colmajor else stored
 C = torch.full((Ml, N), 3.0, dtype=torch.float32, device="cuda")
-gemm_rowsharded(Ml, N, K, 0.5, A, B, -1.25, C, src=0)      # the C ABI: NCCL broadcast of B + this rank's rows
+gemm_rowsharded(Ml, N, K, 0.5, A, B, -1.25, C, src=0)      # the C ABI: B travels over NCCL (prepared panels or raw) + this rank's rows
 torch.cuda.synchronize()
-assert not torch.isnan(B).any(), "broadcast of B incomplete"
 rows = np.unique(np.random.default_rng(rank).integers(0, Ml, 24))
-a = A[rows].cpu().numpy(); b = B.cpu().numpy()
+a = A[rows].cpu().numpy(); b = Bref.cpu().numpy()
 want = np.full((len(rows), N), 3.0, np.float32)
 O.gemm_strided(len(rows), N, K, 0.5, a, K, 1, b, N, 1, -1.25, want, N, 1)
 err = O.max_relative_error(C[rows].cpu().numpy(), want)
