@@ -264,8 +264,8 @@ proc conv2d_im2col*(output: ptr float32, oshape: TensorShape, input: ptr float32
                     kernel: ptr float32, kshape: KernelShape, padding: Padding, strides: Strides) =
   ## conv2d_im2col.nim:95-166 without the caller-provided workspace (owned by the library)
   var
-    ish = [ishape.n.int64, ishape.c, ishape.h, ishape.w]
-    ksh = [kshape.c_out.int64, kshape.c_in, kshape.kH, kshape.kW]
-    pad = [padding.h.int64, padding.w]
-    st = [strides.h.int64, strides.w]
+    ish = [ishape.n.int64, ishape.c.int64, ishape.h.int64, ishape.w.int64]
+    ksh = [kshape.c_out.int64, kshape.c_in.int64, kshape.kH.int64, kshape.kW.int64]
+    pad = [padding.h.int64, padding.w.int64]
+    st = [strides.h.int64, strides.w.int64]
   check laser_b200_conv2d_im2col_f32(output, input, ish.addr, kernel, ksh.addr, pad.addr, st.addr)

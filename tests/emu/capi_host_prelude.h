@@ -33,6 +33,7 @@ inline cudaError_t emu_launch_ex(const cudaLaunchConfig_t *cfg, void (*kernel)(K
   for (unsigned i = 0; i < cfg->numAttrs; ++i)
     if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = cfg->attrs[i].val.clusterDim.x;
   if (cfg->dynamicSmemBytes > emu::kDynSmemBytes) return cudaErrorInvalidValue;
+  std::lock_guard<std::recursive_mutex> device_lk(emu::launch_mu);   // reset + launch are one step of the one emulated device
   emu::reset_state();
   emu::launch(cfg->gridDim.x, cfg->blockDim.x, [=]() { kernel(static_cast<KArgs>(args)...); }, cluster);
   return cudaSuccess;

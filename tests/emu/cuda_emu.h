@@ -16,6 +16,7 @@
 #include <cmath>
 #include <sched.h>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -54,11 +55,16 @@ inline int warp_scratch_i[kMaxCluster][1024];
 inline double warp_scratch_d[kMaxCluster][2][1024];
 alignas(1024) inline unsigned char dyn_smem[kMaxCluster][kDynSmemBytes];   // dynamic shared memory
 inline unsigned char *dyn_smem_ptr() { return dyn_smem[cta_rank]; }
+// ONE emulated device: everything above is global, so kernels launched by concurrent host threads (the library's
+// thread-safety test, tests/c_harness/threads_harness.c) run one after the other -- the host code around the launches
+// (workspace, tensor-map cache, dispatch state) still runs concurrently, which is what that test is about
+inline std::recursive_mutex launch_mu;
 
 // grid = number of CTAs (a multiple of `cluster`); block a multiple of 32 (or < 32 without warp ops).
 // Every thread of a CTA must reach every __syncthreads of the kernel (true for the product's kernels).
 template <typename Body>
 void launch(unsigned grid, unsigned block, Body body, unsigned cluster = 1) {
+  std::lock_guard<std::recursive_mutex> device_lk(launch_mu);
   g_dim = Idx{grid, 1, 1};
   b_dim = Idx{block, 1, 1};
   cluster_size = cluster;

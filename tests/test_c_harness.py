@@ -12,11 +12,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "c_harness", "gemm_harness.c")
 
 
-def build(tmp_path, src=SRC, name="gemm_harness"):
+THREADS_SRC = os.path.join(ROOT, "tests", "c_harness", "threads_harness.c")
+
+
+def build(tmp_path, src=SRC, name="gemm_harness", lib=None):
+    """lib: link against this shared library by path instead of the in-tree liblaser_b200.so (the host-emulated build)"""
     exe = str(tmp_path / name)
-    libdir = os.path.dirname(L.lib_path())
-    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
-                           "-o", exe, "-L", libdir, "-llaser_b200", "-lm", "-Wl,-rpath," + libdir])
+    libdir = os.path.dirname(lib or L.lib_path())
+    link = [lib] if lib else ["-L", libdir, "-llaser_b200"]
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-pthread", "-I", os.path.join(ROOT, "include"), src,
+                           "-o", exe] + link + ["-lm", "-Wl,-rpath," + libdir])
     return exe
 
 
@@ -54,3 +59,27 @@ def test_c_caller_row_shards_over_two_gpus(tmp_path):
         out = subprocess.run([exe, str(g)], capture_output=True, text=True, timeout=600, env=env)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "max error relative" in out.stdout
+
+
+def test_concurrent_callers_host_logic(tmp_path):
+    """SURVEY.md 8(b) "Threading": four threads issue a mix of products (exact kernel, tensor cores, fp64, int64, host and
+    device entries) at once and every result must be bit-identical to the serial run.  Here against the host-emulated
+    build of capi.cu (tests/emu/: kernels run one at a time on the one emulated device, the host code around them --
+    context creation, workspace growth, tensor-map cache, dispatch state -- runs concurrently)."""
+    from emu_build import build_capi_host_emu
+    emu = build_capi_host_emu()
+    exe = build(tmp_path, THREADS_SRC, "threads_harness_emu", lib=emu)
+    out = subprocess.run([exe, "4", "1"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches" in out.stdout
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_on_gpu(tmp_path):
+    """the same harness on the B200: each thread launches on its own stream (cudaStreamPerThread), so the shared workspace
+    is handed from stream to stream by the library's events while kernels of different callers overlap"""
+    exe = build(tmp_path, THREADS_SRC, "threads_harness")
+    for argv in (["4", "3", "1"], ["6", "2", "4"]):     # scale 4: shapes up to 1200 x 1040 x 288 and 512 x 512 x 4096
+        out = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert " 0 mismatches" in out.stdout
