@@ -3,6 +3,7 @@
 One object per translation unit, compiled in parallel (the tcgen05 kernel families are the slow ones), then one link."""
 import concurrent.futures
 import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -42,9 +43,45 @@ def _newest_header():
     return max((os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h))), default=0.0)
 
 
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def _src_digest():
+    """sha256 over the flags and the contents of every source the library is made of"""
+    h = hashlib.sha256(repr((NVCC_FLAGS, LINK_FLAGS)).encode())
+    for name in _sources() + HEADERS:
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            h.update(name.encode() + b"\0")
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp():
+    try:
+        with open(STAMP_PATH) as f:
+            return f.read().strip()
+    except OSError:
+        return None
+
+
+def _write_stamp():
+    tmp = "%s.tmp%d" % (STAMP_PATH, os.getpid())
+    with open(tmp, "w") as f:
+        f.write(_src_digest() + "\n")
+    os.replace(tmp, STAMP_PATH)
+
+
 def needs_build():
+    """The library is current when the digest recorded next to it matches the sources -- a copy of the tree (the snapshot
+    that travels to a GPU box) keeps contents, not modification times.  A library without a digest file falls back to
+    modification times."""
     if not os.path.exists(LIB_PATH):
         return True
+    stamp = _stamp()
+    if stamp is not None:
+        return stamp != _src_digest()
     t = os.path.getmtime(LIB_PATH)
     return _newest_header() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in _sources())
 
@@ -56,6 +93,11 @@ def build(force=False, verbose=False):
     library look stale): one of them builds under a file lock -- objects and the library are written under temporary names
     and renamed when complete -- the others wait for the lock and find the result up to date."""
     if not force and not needs_build():
+        if _stamp() is None:
+            try:
+                _write_stamp()       # built before digests existed and current by modification time: record it
+            except OSError:
+                pass
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
@@ -91,6 +133,7 @@ def _build_locked(force, verbose):
         objs = list(pool.map(compile_one, srcs))
     subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", LIB_PATH + tag] + objs, env=env)
     os.replace(LIB_PATH + tag, LIB_PATH)
+    _write_stamp()
     return LIB_PATH
 
 

@@ -50,3 +50,30 @@ def test_prepack_sizes():
     assert 2 * M * 520 * 2 + M * 4 <= need_a <= 2 * M * 520 * 2 + M * 4 + 3 * 256 and need_a % 256 == 0
     assert 2 * N * 520 * 2 + N * 4 <= need_b <= 2 * N * 520 * 2 + N * 4 + 3 * 256 and need_b % 256 == 0
     assert L.gemm_prepackA_mem_required(0, N, K) == 0
+
+
+def test_library_is_current_by_content_not_by_modification_time(tmp_path):
+    """The tree that travels to a GPU box is a COPY: contents survive, modification times do not.  The build records a
+    digest of the sources next to the library; a touched source must not trigger a rebuild (8 ranks importing the
+    package on such a box once raced 8 rebuilds), an edited one must."""
+    import os
+    from laser_b200 import _build as B
+    B.build()
+    assert B._stamp() == B._src_digest() and not B.needs_build()
+    src = os.path.join(B.CSRC, "capi.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src)                                   # newer than the library now
+        assert os.path.getmtime(src) > os.path.getmtime(B.LIB_PATH)
+        assert not B.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    saved = B._stamp()
+    try:
+        with open(B.STAMP_PATH, "w") as f:
+            f.write("0" * 64 + "\n")                    # what an edited source looks like
+        assert B.needs_build()
+    finally:
+        with open(B.STAMP_PATH, "w") as f:
+            f.write(saved + "\n")
+    assert not B.needs_build()
